@@ -1,0 +1,395 @@
+/*
+ * rfnet_oracle.c -- CPU restatement of the reference's point-cloud operators.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA kernels in rfnet_b200/csrc.  Only tests/,
+ * __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py may load it.  The product
+ * (rfnet_b200/) never links, loads or falls back to it.
+ *
+ * Parity status: PINNED.  The reference holds no golden vectors for this path, so the oracle is
+ * pinned against the reference itself: tests/test_oracle_vs_ref.py compares every function below with the reference's
+ * own OpKernels compiled unmodified into oracle/_ref/ (CPU kernels here; the reference CUDA kernels, recompiled for
+ * sm_100a, on the GPU box), and tests/golden/ holds outputs generated from oracle/_ref by tests/golden/make_golden.py.
+ *
+ * Each function cites the reference lines it restates.  Paths are relative to the reference repository root.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off (see Makefile).  Contraction is OFF so that every fused multiply-add in
+ * this file is an explicit fmaf(): "fused" mode reproduces what nvcc emits for the reference's CUDA kernels
+ * (mul(dy,dy); fma(dx,dx,.); fma(dz,dz,.) -- checked in the sm_100a PTX of tf_nndistance_g.cu, tf_sampling_g.cu,
+ * tf_grouping_g.cu and tf_approxmatch.cu), "unfused" mode reproduces the reference's CPU build (g++ -O2, no -mfma).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RFO_API __attribute__((visibility("default")))
+
+/* Squared distance between candidate c and query q, evaluated the way the reference evaluates x*x+y*y+z*z with
+ * x = c.x - q.x etc.:  fused   = fma(dz,dz, fma(dx,dx, dy*dy))      (GPU kernels, nvcc -fmad=true)
+ *                      unfused = ((dx*dx) + (dy*dy)) + (dz*dz)      (CPU kernels, g++ without FMA)            */
+static inline float sqdist(const float *c, const float *q, int fused) {
+    float dx = c[0] - q[0], dy = c[1] - q[1], dz = c[2] - q[2];
+    if (fused) return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * nn_distance.   pc_distance/tf_nndistance.cpp:21-43 (nnsearch, CPU) and tf_ops/CD/tf_nndistance_g.cu:4-126 (GPU).
+ * For every query j of cloud i: smallest squared distance to the m candidates and the FIRST index attaining it
+ * (strict '<', seeded by k==0: .cpp:34, _g.cu:28,38,118).
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_nnsearch(int b, int n, int m, const float *queries, const float *cands, float *dist, int *idx, int fused) {
+    for (int i = 0; i < b; i++) {
+        const float *Q = queries + (size_t)i * n * 3, *C = cands + (size_t)i * m * 3;
+        for (int j = 0; j < n; j++) {
+            float best = 0.0f;
+            int besti = 0;
+            for (int k = 0; k < m; k++) {
+                float d = sqdist(C + 3 * k, Q + 3 * j, fused);
+                if (k == 0 || d < best) { best = d; besti = k; }
+            }
+            dist[(size_t)i * n + j] = best;
+            idx[(size_t)i * n + j] = besti;
+        }
+    }
+}
+
+/* NnDistanceOp::Compute calls the search once per direction: tf_nndistance.cpp:79-80; GPU launcher _g.cu:127-130. */
+RFO_API void rfo_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                             float *dist2, int *idx2, int fused) {
+    rfo_nnsearch(b, n, m, xyz1, xyz2, dist1, idx1, fused);
+    rfo_nnsearch(b, m, n, xyz2, xyz1, dist2, idx2, fused);
+}
+
+/* NnDistanceGrad.  pc_distance/tf_nndistance.cpp:122-163 (CPU, sequential) / tf_nndistance_g.cu:131-156 (GPU, atomics).
+ * g = 2*grad_dist[j]; grad_self[j] += g*(p - nn); grad_other[nn_idx] -= g*(p - nn); both directions.               */
+static void nn_grad_one_dir(int n, int m, const float *P, const float *O, const float *gd, const int *idx, float *gP, float *gO) {
+    (void)m;
+    for (int j = 0; j < n; j++) {
+        int j2 = idx[j];
+        float g = gd[j] * 2;
+        for (int c = 0; c < 3; c++) {
+            float t = g * (P[j * 3 + c] - O[j2 * 3 + c]);
+            gP[j * 3 + c] += t;
+            gO[j2 * 3 + c] -= t;
+        }
+    }
+}
+RFO_API void rfo_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                                  const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2) {
+    memset(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3);
+    memset(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3);
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3;
+        float *gA = grad_xyz1 + (size_t)i * n * 3, *gB = grad_xyz2 + (size_t)i * m * 3;
+        nn_grad_one_dir(n, m, A, B, grad_dist1 + (size_t)i * n, idx1 + (size_t)i * n, gA, gB);
+        nn_grad_one_dir(m, n, B, A, grad_dist2 + (size_t)i * m, idx2 + (size_t)i * m, gB, gA);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * approx_match, GPU contract.  pc_distance/tf_approxmatch.cu:1-179.
+ * float arithmetic, levels j = start_level .. -2 (the GPU runs start_level = 7, .cu:21; the CPU twin 8, .cpp:31),
+ * level = -4^j except 0 at j = -2 (.cu:22-25), match laid out (m, n): match[l*n + k] (.cu:152).
+ * multiL/multiR use integer division (.cu:4-10).  __expf(x) is ex2.approx(x*log2e); expf() is used here, the two
+ * differ by a few ulp which the 1e-4 EMD tolerance absorbs.
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, int start_level) {
+    float *remainL = malloc(sizeof(float) * (size_t)(n + m) * 2);
+    float *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+    float multiL, multiR;
+    if (n >= m) { multiL = 1; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1; }
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3;
+        float *M = match + (size_t)i * n * m;
+        memset(M, 0, sizeof(float) * (size_t)n * m);
+        for (int k = 0; k < n; k++) remainL[k] = multiL;
+        for (int l = 0; l < m; l++) remainR[l] = multiR;
+        for (int j = start_level; j >= -2; j--) {
+            float level = -powf(4.0f, (float)j);
+            if (j == -2) level = 0;
+            /* pass 1 (.cu:26-59): ratioL[k] = remainL[k] / (1e-9 + sum_l e(k,l) * remainR[l]) */
+            for (int k = 0; k < n; k++) {
+                float suml = 1e-9f;
+                for (int l = 0; l < m; l++) suml += expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * remainR[l];
+                ratioL[k] = remainL[k] / suml;
+            }
+            /* pass 2 (.cu:75-108): column sums with ratioL, consumption clamp, remainR update */
+            for (int l = 0; l < m; l++) {
+                float sumr = 0;
+                for (int k = 0; k < n; k++) sumr += expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * ratioL[k];
+                sumr *= remainR[l];
+                float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmaxf(0.0f, remainR[l] - sumr);
+            }
+            /* pass 3 (.cu:127-160): match += e * ratioL[k] * ratioR[l]; remainL update */
+            for (int k = 0; k < n; k++) {
+                float suml = 0;
+                for (int l = 0; l < m; l++) {
+                    float w = expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * ratioL[k] * ratioR[l];
+                    M[(size_t)l * n + k] += w;
+                    suml += w;
+                }
+                remainL[k] = fmaxf(0.0f, remainL[k] - suml);
+            }
+        }
+    }
+    free(remainL);
+}
+
+/* approx_match, CPU twin.  pc_distance/tf_approxmatch.cpp:23-84: double accumulation, 11 levels (j = 8..-2),
+ * match laid out (n, m): match[k*m + l] (.cpp:44,75).  Keeps the reference's n*m double weight matrix.          */
+RFO_API void rfo_approxmatch_cpu_twin(int b, int n, int m, const float *xyz1, const float *xyz2, float *match) {
+    int big = n > m ? n : m;
+    double *satl = malloc(sizeof(double) * (size_t)(n + 3 * m + n));
+    double *satr = satl + n, *ss = satr + m, *ss2 = ss + m, *rows = ss2 + m;
+    double *w = malloc(sizeof(double) * (size_t)n * m);
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3;
+        float *M = match + (size_t)i * n * m;
+        for (int k = 0; k < n; k++) satl[k] = (double)(big / n);
+        for (int l = 0; l < m; l++) satr[l] = (double)(big / m);
+        memset(M, 0, sizeof(float) * (size_t)n * m);
+        for (int j = 8; j >= -2; j--) {
+            double level = -powf(4.0f, (float)j);
+            if (j == -2) level = 0;
+            for (int k = 0; k < n; k++) {
+                double x1 = A[k * 3], y1 = A[k * 3 + 1], z1 = A[k * 3 + 2];
+                for (int l = 0; l < m; l++) {
+                    double x2 = B[l * 3], y2 = B[l * 3 + 1], z2 = B[l * 3 + 2];
+                    /* .cpp:44: expf() of a double argument narrows to float first */
+                    w[(size_t)k * m + l] = expf((float)(level * ((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2)))) * satr[l];
+                }
+            }
+            for (int l = 0; l < m; l++) ss[l] = 1e-9;
+            for (int k = 0; k < n; k++) {
+                double s = 1e-9;
+                for (int l = 0; l < m; l++) s += w[(size_t)k * m + l];
+                for (int l = 0; l < m; l++) w[(size_t)k * m + l] = w[(size_t)k * m + l] / s * satl[k];
+                for (int l = 0; l < m; l++) ss[l] += w[(size_t)k * m + l];
+            }
+            for (int l = 0; l < m; l++) { double r = satr[l] / ss[l]; ss[l] = r < 1.0 ? r : 1.0; }
+            for (int l = 0; l < m; l++) ss2[l] = 0;
+            for (int k = 0; k < n; k++) {
+                double s = 0;
+                for (int l = 0; l < m; l++) {
+                    w[(size_t)k * m + l] *= ss[l];
+                    s += w[(size_t)k * m + l];
+                    ss2[l] += w[(size_t)k * m + l];
+                }
+                rows[k] = s;
+            }
+            for (int k = 0; k < n; k++) { double v = satl[k] - rows[k]; satl[k] = v > 0 ? v : 0; }
+            for (size_t t = 0; t < (size_t)n * m; t++) M[t] = (float)((double)M[t] + w[t]);   /* float += double, .cpp:75 */
+            for (int l = 0; l < m; l++) { double v = satr[l] - ss2[l]; satr[l] = v > 0 ? v : 0; }
+        }
+    }
+    free(w);
+    free(satl);
+}
+
+/* match_cost, GPU contract.  pc_distance/tf_approxmatch.cu:183-225: cost[i] = sum_{k,l} sqrtf(d2(k,l)) * match[l*n+k].
+ * The reference reduces per-thread partial sums with a tree; here accumulation is in double so the oracle is the
+ * more accurate side of a 1e-4 comparison.                                                                      */
+RFO_API void rfo_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *cost) {
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3, *M = match + (size_t)i * n * m;
+        double s = 0;
+        for (int l = 0; l < m; l++)
+            for (int k = 0; k < n; k++) s += (double)(sqrtf(sqdist(B + 3 * l, A + 3 * k, 1)) * M[(size_t)l * n + k]);
+        cost[i] = (float)s;
+    }
+}
+
+/* match_cost grad, GPU contract.  pc_distance/tf_approxmatch.cu:229-295.
+ * grad1[k] = sum_l match[l*n+k] * (p1_k - p2_l) * rsqrt(max(d2, 1e-20))   (matchcostgrad1, .cu:270-291)
+ * grad2[l] = sum_k match[l*n+k] * (p2_l - p1_k) * rsqrt(max(d2, 1e-20))   (matchcostgrad2, .cu:229-269)        */
+RFO_API void rfo_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2) {
+    double *g1 = malloc(sizeof(double) * (size_t)n * 3);
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3, *M = match + (size_t)i * n * m;
+        for (int t = 0; t < n * 3; t++) g1[t] = 0;
+        for (int l = 0; l < m; l++) {
+            double g2[3] = {0, 0, 0};
+            for (int k = 0; k < n; k++) {
+                float dx = A[3 * k] - B[3 * l], dy = A[3 * k + 1] - B[3 * l + 1], dz = A[3 * k + 2] - B[3 * l + 2];
+                float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                float s = M[(size_t)l * n + k] * (1.0f / sqrtf(fmaxf(d2, 1e-20f)));
+                g1[3 * k] += dx * s; g1[3 * k + 1] += dy * s; g1[3 * k + 2] += dz * s;
+                g2[0] -= dx * s; g2[1] -= dy * s; g2[2] -= dz * s;
+            }
+            for (int c = 0; c < 3; c++) grad2[((size_t)i * m + l) * 3 + c] = (float)g2[c];
+        }
+        for (int t = 0; t < n * 3; t++) grad1[(size_t)i * n * 3 + t] = (float)g1[t];
+    }
+    free(g1);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * farthest_point_sample.  tf_ops/sampling/tf_sampling_g.cu:105-170 (GPU only; there is no reference CPU code).
+ * idx[0] = 0; running min-distance temp[k] starts at 1e38 (:118-119); each round updates temp against the last pick
+ * (fused d2, :142-145) and takes the arg-max.  Tie rule of the 512-thread block (:146-163): thread t = k mod 512 keeps
+ * its first strict maximum starting from (best=-1, besti=0); the tree keeps the LOWER slot unless strictly smaller,
+ * so among equal maxima the lowest thread id wins, and within a thread the lowest k.
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_farthest_point_sample(int b, int n, int m, const float *inp, int *idx) {
+    enum { BLOCK = 512 };
+    if (m <= 0) return;
+    float *temp = malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < b; i++) {
+        const float *P = inp + (size_t)i * n * 3;
+        int old = 0;
+        idx[(size_t)i * m] = 0;
+        for (int k = 0; k < n; k++) temp[k] = 1e38f;
+        for (int j = 1; j < m; j++) {
+            float tbest[BLOCK];
+            int tbesti[BLOCK];
+            for (int t = 0; t < BLOCK; t++) { tbest[t] = -1; tbesti[t] = 0; }
+            for (int k = 0; k < n; k++) {
+                float d = sqdist(P + 3 * k, P + 3 * old, 1);
+                float d2 = fminf(d, temp[k]);
+                temp[k] = d2;
+                int t = k % BLOCK;
+                if (d2 > tbest[t]) { tbest[t] = d2; tbesti[t] = k; }
+            }
+            float best = tbest[0];
+            int besti = tbesti[0];
+            for (int t = 1; t < BLOCK; t++)
+                if (best < tbest[t]) { best = tbest[t]; besti = tbesti[t]; }
+            old = besti;
+            idx[(size_t)i * m + j] = old;
+        }
+    }
+    free(temp);
+}
+
+/* gather_point / its gradient.  tf_ops/sampling/tf_sampling_g.cu:172-192 (+ cudaMemset at tf_sampling.cpp:174). */
+RFO_API void rfo_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out) {
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < m; j++) {
+            int a = idx[(size_t)i * m + j];
+            for (int c = 0; c < 3; c++) out[((size_t)i * m + j) * 3 + c] = inp[((size_t)i * n + a) * 3 + c];
+        }
+}
+RFO_API void rfo_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g) {
+    memset(inp_g, 0, sizeof(float) * (size_t)b * n * 3);
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < m; j++) {
+            int a = idx[(size_t)i * m + j];
+            for (int c = 0; c < 3; c++) inp_g[((size_t)i * n + a) * 3 + c] += out_g[((size_t)i * m + j) * 3 + c];
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * query_ball_point.  tf_ops/grouping/tf_grouping_g.cu:3-36 (GPU) / tf_ops/grouping/query_ball_point.cpp:19-47 (CPU
+ * prototype, no pts_cnt).  xyz1 = dataset (b,n,3), xyz2 = queries (b,m,3).  Scan dataset in index order, keep the first
+ * nsample with max(sqrtf(d2),1e-20f) < radius[0]; the first hit fills the whole row (:26-29).  Rows without a hit are
+ * left untouched by the reference (allocator garbage); this oracle writes fill_empty there so tests can mask them.
+ * d2 is fused with (query - dataset) differences (:24, PTX above).
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_query_ball_point(int b, int n, int m, const float *radius, int nsample, const float *xyz1, const float *xyz2,
+                                  int *idx, int *pts_cnt, int fill_empty) {
+    float r = radius[0];
+    for (int i = 0; i < b; i++) {
+        const float *D = xyz1 + (size_t)i * n * 3, *Q = xyz2 + (size_t)i * m * 3;
+        for (int j = 0; j < m; j++) {
+            int *row = idx + ((size_t)i * m + j) * nsample;
+            int cnt = 0;
+            for (int k = 0; k < n && cnt < nsample; k++) {
+                float d = fmaxf(sqrtf(sqdist(Q + 3 * j, D + 3 * k, 1)), 1e-20f);
+                if (d < r) {
+                    if (cnt == 0)
+                        for (int l = 0; l < nsample; l++) row[l] = k;
+                    row[cnt++] = k;
+                }
+            }
+            if (cnt == 0)
+                for (int l = 0; l < nsample; l++) row[l] = fill_empty;
+            pts_cnt[(size_t)i * m + j] = cnt;
+        }
+    }
+}
+
+/* group_point / grad.  tf_ops/grouping/tf_grouping_g.cu:40-78 (+ cudaMemset tf_grouping.cpp:208);
+ * CPU prototypes tf_ops/grouping/query_ball_point.cpp:52-84.                                                    */
+RFO_API void rfo_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out) {
+    for (int i = 0; i < b; i++)
+        for (size_t t = 0; t < (size_t)m * nsample; t++) {
+            int ii = idx[(size_t)i * m * nsample + t];
+            memcpy(out + ((size_t)i * m * nsample + t) * c, points + ((size_t)i * n + ii) * c, sizeof(float) * c);
+        }
+}
+RFO_API void rfo_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx, float *grad_points) {
+    memset(grad_points, 0, sizeof(float) * (size_t)b * n * c);
+    for (int i = 0; i < b; i++)
+        for (size_t t = 0; t < (size_t)m * nsample; t++) {
+            int ii = idx[(size_t)i * m * nsample + t];
+            for (int l = 0; l < c; l++) grad_points[((size_t)i * n + ii) * c + l] += grad_out[((size_t)i * m * nsample + t) * c + l];
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * three_nn / three_interpolate (+grad).  tf_ops/interpolation/tf_interpolate.cpp:60-153 -- CPU-only ops in the reference.
+ * three_nn: the reference's CPU build evaluates d2 UNFUSED in float ((x2-x1)^2 + ... with float operands, widened to
+ * double only for the comparisons, :75), keeps the three smallest with strict '<' insertion (:76-92), init 1e40 / 0.
+ * xyz1 = unknown (b,n,3) are the queries, xyz2 = known (b,m,3) the candidates.  `fused` selects the contraction so the
+ * same oracle can also be asked what a GPU-style evaluation would give.
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, int fused) {
+    for (int i = 0; i < b; i++) {
+        const float *U = xyz1 + (size_t)i * n * 3, *K = xyz2 + (size_t)i * m * 3;
+        for (int j = 0; j < n; j++) {
+            double b1 = 1e40, b2 = 1e40, b3 = 1e40;
+            int i1 = 0, i2 = 0, i3 = 0;
+            for (int k = 0; k < m; k++) {
+                double d = sqdist(K + 3 * k, U + 3 * j, fused);
+                if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+                else if (d < b3) { b3 = d; i3 = k; }
+            }
+            float *dd = dist + ((size_t)i * n + j) * 3;
+            int *ii = idx + ((size_t)i * n + j) * 3;
+            dd[0] = (float)b1; dd[1] = (float)b2; dd[2] = (float)b3;   /* (float)1e40 == +inf, as in the reference */
+            ii[0] = i1; ii[1] = i2; ii[2] = i3;
+        }
+    }
+}
+
+/* tf_interpolate.cpp:107-127: out[j,:] = p[i1,:]*w1 + p[i2,:]*w2 + p[i3,:]*w3 (left to right, unfused on the CPU). */
+RFO_API void rfo_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight, float *out) {
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < n; j++) {
+            const float *w = weight + ((size_t)i * n + j) * 3;
+            const int *id = idx + ((size_t)i * n + j) * 3;
+            const float *P = points + (size_t)i * m * c;
+            for (int l = 0; l < c; l++)
+                out[((size_t)i * n + j) * c + l] = (P[(size_t)id[0] * c + l] * w[0] + P[(size_t)id[1] * c + l] * w[1]) + P[(size_t)id[2] * c + l] * w[2];
+        }
+}
+
+/* tf_interpolate.cpp:131-153 (+ memset :258): grad_points[i_t,:] += grad_out[j,:] * w_t, j ascending. */
+RFO_API void rfo_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points) {
+    memset(grad_points, 0, sizeof(float) * (size_t)b * m * c);
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < n; j++) {
+            const float *w = weight + ((size_t)i * n + j) * 3;
+            const int *id = idx + ((size_t)i * n + j) * 3;
+            float *G = grad_points + (size_t)i * m * c;
+            for (int l = 0; l < c; l++) {
+                float g = grad_out[((size_t)i * n + j) * c + l];
+                G[(size_t)id[0] * c + l] += g * w[0];
+                G[(size_t)id[1] * c + l] += g * w[1];
+                G[(size_t)id[2] * c + l] += g * w[2];
+            }
+        }
+}
+
+/* Smallest float T such that sqrtf(T) >= r, i.e. (max(sqrtf(d2),1e-20f) < r)  <=>  (d2 < T) for r > 1e-20f.
+ * Used by tests to check the sqrt-free ball-query predicate of the CUDA kernel. */
+RFO_API float rfo_ball_threshold(float r) {
+    float t = r * r;
+    while (sqrtf(t) >= r && t > 0) t = nextafterf(t, 0.0f);
+    while (sqrtf(t) < r) t = nextafterf(t, INFINITY);
+    return t;
+}
