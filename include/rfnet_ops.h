@@ -1,0 +1,128 @@
+/*
+ * rfnet_ops.h -- C ABI of librfnet_ops.so: B200 (sm_100a) kernels for RFNet's point-cloud operators.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one of the C++ launcher functions that the reference's
+ * TensorFlow OpKernels call (file:line given per function, paths relative to the reference repository).  Argument
+ * ORDER and MEANING are the reference's; three things are added, always at the end:
+ *     - scratch that the reference obtained with allocate_temp is passed as (workspace, workspace_bytes); ask
+ *       rfnet_<op>_workspace_bytes() for the size.  Kernels never allocate.
+ *     - a CUDA stream (the reference launched everything on the legacy default stream);
+ *     - an int return: 0 on success, otherwise a cudaError_t value (1 = cudaErrorInvalidValue for bad arguments).
+ *       Nothing is thrown across this boundary and nothing synchronises the host.
+ *
+ * All pointers are DEVICE pointers unless the function name ends in _host.  Clouds are row-major float32 (b, n, 3),
+ * indices int32.  Offsets are 64-bit internally, so b*n*m may exceed 2^31 (the reference's approxmatch cannot:
+ * pc_distance/tf_approxmatch.cu:15).  Calls are re-entrant and stream-ordered; there is no global state.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef RFNET_OPS_H_
+#define RFNET_OPS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *rfnet_stream_t; /* == cudaStream_t */
+
+/* Library version (major*10000 + minor*100 + patch) and a printable name for a return code. */
+int rfnet_version(void);
+const char *rfnet_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * nn_distance (Chamfer).  Replaces NmDistanceKernelLauncher, pc_distance/tf_nndistance.cpp:168 (defined
+ * tf_ops/CD/tf_nndistance_g.cu:127-130).  dist1[i,j] = min_k d2(xyz1[i,j], xyz2[i,k]), idx1 = first arg-min; same for
+ * direction 2.  d2 is evaluated as fma(dz,dz, fma(dx,dx, dy*dy)) -- the contraction of the reference's GPU binary --
+ * unless RFNET_NN_UNFUSED is set in flags, which gives ((dx*dx)+(dy*dy))+(dz*dz) as in the reference's CPU build
+ * (pc_distance/tf_nndistance.cpp:21-43).  workspace may be NULL when rfnet_nn_distance_workspace_bytes() returns 0.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RFNET_NN_UNFUSED 1
+size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m);
+int rfnet_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
+                      int *idx2, void *workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream);
+
+/* Replaces NmDistanceGradKernelLauncher, pc_distance/tf_nndistance.cpp:208 (tf_nndistance_g.cu:151-156).
+ * grad_xyz1 / grad_xyz2 are fully overwritten (the launcher zero-fills them itself, as the reference does). */
+int rfnet_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                           const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                           float *grad_xyz2, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * approx_match / match_cost (EMD).  Replace approxmatchLauncher, matchcostLauncher, matchcostgradLauncher,
+ * pc_distance/tf_approxmatch.cpp:141-143 (defined pc_distance/tf_approxmatch.cu:180-182,226-228,292-295).
+ * match is (b, m, n): match[i, l, k] pairs xyz2[i,l] with xyz1[i,k] (tf_approxmatch.cu:152).  `temp` of the reference
+ * ((b, 2(n+m)) floats, tf_approxmatch.cpp:168) becomes workspace.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m);
+int rfnet_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace,
+                      size_t workspace_bytes, rfnet_stream_t stream);
+size_t rfnet_matchcost_workspace_bytes(int b, int n, int m);
+int rfnet_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,
+                    void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+size_t rfnet_matchcostgrad_workspace_bytes(int b, int n, int m);
+int rfnet_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1,
+                        float *grad2, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * sampling.  Replace farthestpointsamplingLauncher, gatherpointLauncher, scatteraddpointLauncher,
+ * tf_ops/sampling/tf_sampling.cpp:94,125,150 (defined tf_ops/sampling/tf_sampling_g.cu:203-211).
+ * FPS: out (b, m) int32, first index 0, ties broken exactly as the reference's 512-thread block does.
+ * scatteraddpoint zero-fills inp_g itself (the reference's OpKernel did it, tf_sampling.cpp:174).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t rfnet_farthestpointsampling_workspace_bytes(int b, int n, int m);
+int rfnet_farthestpointsampling(int b, int n, int m, const float *inp, void *workspace, size_t workspace_bytes,
+                                int *out, rfnet_stream_t stream);
+int rfnet_gatherpoint(int b, int n, int m, const float *inp, const int *idx, float *out, rfnet_stream_t stream);
+int rfnet_scatteraddpoint(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * grouping.  Replace queryBallPointLauncher, groupPointLauncher, groupPointGradLauncher,
+ * tf_ops/grouping/tf_grouping.cpp:67,146,177 (defined tf_ops/grouping/tf_grouping_g.cu:125-141).
+ * radius is a DEVICE pointer to one float, as in the reference (tf_grouping.cpp:93-95).  Rows with no point in the
+ * ball are filled with 0 (the reference leaves them uninitialised) and get pts_cnt 0.
+ * groupPointGrad zero-fills grad_points itself (reference: tf_grouping.cpp:208).
+ * ------------------------------------------------------------------------------------------------------------- */
+int rfnet_query_ball_point(int b, int n, int m, const float *radius, int nsample, const float *xyz1,
+                           const float *xyz2, int *idx, int *pts_cnt, rfnet_stream_t stream);
+int rfnet_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      rfnet_stream_t stream);
+int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * interpolation.  The reference has CPU code only: threenn_cpu, threeinterpolate_cpu, threeinterpolate_grad_cpu,
+ * tf_ops/interpolation/tf_interpolate.cpp:60,107,131.  Same argument orders.  three_nn evaluates d2 UNFUSED, as the
+ * reference's CPU build does, so indices match it bit for bit.  three_interpolate_grad zero-fills grad_points
+ * (reference: tf_interpolate.cpp:258).
+ * ------------------------------------------------------------------------------------------------------------- */
+int rfnet_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                   rfnet_stream_t stream);
+int rfnet_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, rfnet_stream_t stream);
+int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                 const float *weight, float *grad_points, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-buffer entry points: what a CPU-side caller (e.g. the reference's DEVICE_CPU OpKernels,
+ * pc_distance/tf_nndistance.cpp:60-81, pc_distance/tf_approxmatch.cpp:175-199) binds.  Pointers are HOST memory
+ * (pinned memory makes the copies asynchronous); the call copies in, runs on `device`, copies out and returns when the
+ * outputs are complete.  Device scratch comes from the CUDA stream-ordered pool of that device.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rfnet_nn_distance_host(int device, int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1,
+                           int *idx1, float *dist2, int *idx2, int flags);
+int rfnet_emd_host(int device, int b, int n, int m, const float *xyz1, const float *xyz2, float *match_or_null,
+                   float *cost);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Measurement helper (used by bench.py only): runs a dependent-free FP32 FFMA2 stream on every SM for `iters` rounds
+ * and returns lane-operations executed in *lane_ops, so the bench can report a MEASURED FP32 pipe peak next to the
+ * architectural one.  Not part of the reference's interface.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rfnet_probe_fp32(int iters, float *sink, unsigned long long *lane_ops, rfnet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFNET_OPS_H_ */

@@ -1,0 +1,137 @@
+// Library-level entry points of librfnet_ops.so: version, error strings, the host-buffer variants and the FP32 probe.
+#include <mutex>
+
+#include "common.cuh"
+#include "rfnet_ops.h"
+
+namespace rfnet {
+
+// Dependency-free FFMA2 stream: 8 independent packed chains per thread, 64 lane-ops per thread per round.
+__global__ void __launch_bounds__(512) probe_fp32_kernel(int iters, float* __restrict__ sink) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(1.0f + i + threadIdx.x * 1e-6f, 1.0f - i);
+    const float2 c = make_float2(0.999999f, 1e-7f);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], c, make_float2(c.y, c.y));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chains alive
+}
+
+struct DeviceStreams {
+    std::mutex mu;
+    cudaStream_t s[64] = {};
+};
+static DeviceStreams g_streams;
+
+static int host_stream(int device, cudaStream_t* out) {
+    if (device < 0 || device >= 64) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> g(g_streams.mu);
+    if (!g_streams.s[device]) RFNET_CUDA(cudaStreamCreateWithFlags(&g_streams.s[device], cudaStreamNonBlocking));
+    *out = g_streams.s[device];
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    int set(int device) {
+        RFNET_CUDA(cudaGetDevice(&prev));
+        RFNET_CUDA(cudaSetDevice(device));
+        return 0;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace rfnet
+
+using namespace rfnet;
+
+extern "C" int rfnet_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char* rfnet_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+extern "C" int rfnet_probe_fp32(int iters, float* sink, unsigned long long* lane_ops, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(iters > 0 && sink && lane_ops);
+    const int blocks = kNumSMs * 4, threads = 512;
+    probe_fp32_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+    *lane_ops = (unsigned long long)blocks * threads * (unsigned long long)iters * 64ull;
+    return launch_status();
+}
+
+#define HOST_TRY(expr)            \
+    do {                          \
+        rc = (expr);              \
+        if (rc) goto done;        \
+    } while (0)
+
+extern "C" int rfnet_nn_distance_host(int device, int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1,
+                                      float* dist2, int* idx2, int flags) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0 || (n == 0 && m == 0)) return 0;
+    DeviceGuard guard;
+    int rc = guard.set(device);
+    if (rc) return rc;
+    cudaStream_t s;
+    rc = host_stream(device, &s);
+    if (rc) return rc;
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    const size_t wsb = rfnet_nn_distance_workspace_bytes(b, n, m);
+    // one pooled allocation: xyz1 | xyz2 | dist1 | idx1 | dist2 | idx2 | workspace
+    const size_t o_x2 = bn * 12, o_d1 = o_x2 + bm * 12, o_i1 = o_d1 + bn * 4, o_d2 = o_i1 + bn * 4, o_i2 = o_d2 + bm * 4;
+    const size_t o_ws = (o_i2 + bm * 4 + 255) & ~(size_t)255;
+    char* d = nullptr;
+    HOST_TRY((int)cudaMallocAsync((void**)&d, o_ws + wsb + 256, s));
+    if (bn) HOST_TRY((int)cudaMemcpyAsync(d, xyz1, bn * 12, cudaMemcpyHostToDevice, s));
+    if (bm) HOST_TRY((int)cudaMemcpyAsync(d + o_x2, xyz2, bm * 12, cudaMemcpyHostToDevice, s));
+    HOST_TRY(rfnet_nn_distance(b, n, (const float*)d, m, (const float*)(d + o_x2), (float*)(d + o_d1), (int*)(d + o_i1), (float*)(d + o_d2),
+                               (int*)(d + o_i2), d + o_ws, wsb, flags, (rfnet_stream_t)s));
+    if (bn) {
+        HOST_TRY((int)cudaMemcpyAsync(dist1, d + o_d1, bn * 4, cudaMemcpyDeviceToHost, s));
+        HOST_TRY((int)cudaMemcpyAsync(idx1, d + o_i1, bn * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (bm) {
+        HOST_TRY((int)cudaMemcpyAsync(dist2, d + o_d2, bm * 4, cudaMemcpyDeviceToHost, s));
+        HOST_TRY((int)cudaMemcpyAsync(idx2, d + o_i2, bm * 4, cudaMemcpyDeviceToHost, s));
+    }
+done:
+    if (d) cudaFreeAsync(d, s);
+    const int rc2 = (int)cudaStreamSynchronize(s);
+    return rc ? rc : rc2;
+}
+
+extern "C" int rfnet_emd_host(int device, int b, int n, int m, const float* xyz1, const float* xyz2, float* match_or_null, float* cost) {
+    RFNET_CHECK_ARG(b >= 0 && n > 0 && m > 0 && cost);
+    if (b == 0) return 0;
+    DeviceGuard guard;
+    int rc = guard.set(device);
+    if (rc) return rc;
+    cudaStream_t s;
+    rc = host_stream(device, &s);
+    if (rc) return rc;
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m, nm = (size_t)b * n * m;
+    size_t wsb = rfnet_approxmatch_workspace_bytes(b, n, m);
+    const size_t wsc = rfnet_matchcost_workspace_bytes(b, n, m);
+    if (wsc > wsb) wsb = wsc;
+    const size_t o_x2 = (bn * 12 + 255) & ~(size_t)255, o_cost = (o_x2 + bm * 12 + 255) & ~(size_t)255;
+    const size_t o_match = (o_cost + (size_t)b * 4 + 255) & ~(size_t)255, o_ws = (o_match + nm * 4 + 255) & ~(size_t)255;
+    char* d = nullptr;
+    HOST_TRY((int)cudaMallocAsync((void**)&d, o_ws + wsb + 256, s));
+    HOST_TRY((int)cudaMemcpyAsync(d, xyz1, bn * 12, cudaMemcpyHostToDevice, s));
+    HOST_TRY((int)cudaMemcpyAsync(d + o_x2, xyz2, bm * 12, cudaMemcpyHostToDevice, s));
+    HOST_TRY(rfnet_approxmatch(b, n, m, (const float*)d, (const float*)(d + o_x2), (float*)(d + o_match), d + o_ws, wsb, (rfnet_stream_t)s));
+    HOST_TRY(rfnet_matchcost(b, n, m, (const float*)d, (const float*)(d + o_x2), (const float*)(d + o_match), (float*)(d + o_cost), d + o_ws, wsb,
+                             (rfnet_stream_t)s));
+    HOST_TRY((int)cudaMemcpyAsync(cost, d + o_cost, (size_t)b * 4, cudaMemcpyDeviceToHost, s));
+    if (match_or_null) HOST_TRY((int)cudaMemcpyAsync(match_or_null, d + o_match, nm * 4, cudaMemcpyDeviceToHost, s));
+done:
+    if (d) cudaFreeAsync(d, s);
+    const int rc2 = (int)cudaStreamSynchronize(s);
+    return rc ? rc : rc2;
+}

@@ -1,0 +1,440 @@
+// approx_match (approximate EMD transport plan), match_cost and match_cost gradient for sm_100a.
+//
+// Replaces approxmatch / matchcost / matchcostgrad1 / matchcostgrad2 (pc_distance/tf_approxmatch.cu:1-295).
+//
+// The reference runs ONE 512-thread block per cloud through 10 levels x 3 dependent n*m passes and read-modify-writes the
+// n*m match matrix once per level (80 B of HBM traffic per pair).  Here:
+//   * every pass is the same reduction  S[row] = sum_c exp(level * d2(row, c)) * w[c]  ("weighted exp-sum sweep") with the
+//     roles of the two clouds swapped between passes; it runs on the whole chip: grid = clouds x row tiles x candidate
+//     splits, rows in registers as packed pairs (FADD2/FMUL2/FFMA2), candidates + weights broadcast from shared memory,
+//     one MUFU.EX2 per pair; partial sums go to a small buffer and a tiny epilogue kernel applies the pass's update rule
+//     (ratioL / consumption+ratioR / remainL) -- deterministic, no atomics;
+//   * match is NOT accumulated level by level.  The per-level factors ratioL_j[k], ratioR_j[l] are kept (10*(n+m) floats per
+//     cloud) and match[l,k] = sum_j e_j(k,l) * ratioL_j[k] * ratioR_j[l] is written ONCE at the end: 4 B/pair of HBM
+//     traffic instead of 80, at the price of 9 more ex2 per pair (the j = -2 level has e = 1).
+// exp(x) is ex2.approx(x * log2e) exactly as __expf in the reference; level * log2e is folded into one constant, which is
+// bit-identical because level is a power of two.  d2 is the reference's fused expression.  Offsets are 64-bit.
+#include "common.cuh"
+#include "rfnet_ops.h"
+
+namespace rfnet {
+
+constexpr int EMD_LEVELS = 10;   // j = 7 .. -2   (tf_approxmatch.cu:21)
+constexpr int EMD_THREADS = 128;
+constexpr int EMD_Q = 8;         // rows per thread in the sweep (4 packed pairs)
+constexpr int EMD_TC = 512;      // candidates per shared-memory chunk (float4 each: 8 KiB)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ inline float emd_level(int li) {  // li = 0..9  ->  j = 7..-2 ; level = -4^j, 0 at j = -2
+    const int j = 7 - li;
+    if (j == -2) return 0.0f;
+    float v = 1.0f;
+    for (int i = 0; i < (j < 0 ? -j : j); ++i) v *= 4.0f;
+    return j >= 0 ? -v : -1.0f / v;
+}
+
+// Workspace layout (floats), per call:
+//   remainL [b*n] remainR [b*m] ratioL [b*n] ratioR [b*m]                      running state of the current level
+//   facL [EMD_LEVELS][b*n]  facR [EMD_LEVELS][b*m]                             per-level factors for the final materialisation
+//   partial [b * max(n,m) * max_split]                                         sweep partial sums
+struct EmdWs {
+    float *remainL, *remainR, *ratioL, *ratioR, *facL, *facR, *partial;
+};
+static int emd_max_split(int b, int n, int m) {
+    // enough CTAs per sweep to give every SM ~8 at the smallest batch; bounded by the number of candidate chunks
+    const int rows = n < m ? n : m, cands = n < m ? m : n;
+    (void)rows;
+    int chunks = (cands + EMD_TC - 1) / EMD_TC;
+    int s = chunks < 32 ? chunks : 32;
+    return s < 1 ? 1 : s;
+}
+static size_t emd_ws_floats(int b, int n, int m) {
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    return 2 * (bn + bm) + (size_t)EMD_LEVELS * (bn + bm) + (size_t)b * (n > m ? n : m) * emd_max_split(b, n, m);
+}
+static EmdWs emd_carve(float* w, int b, int n, int m) {
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    EmdWs s;
+    s.remainL = w; w += bn;
+    s.remainR = w; w += bm;
+    s.ratioL = w; w += bn;
+    s.ratioR = w; w += bm;
+    s.facL = w; w += EMD_LEVELS * bn;
+    s.facR = w; w += EMD_LEVELS * bm;
+    s.partial = w;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weighted exp-sum sweep:  partial[cloud][split][row] = sum_{c in split} ex2(lvl2 * d2(row, c)) * w[c]
+//   rows: (b, nr, 3), cands: (b, nc, 3), w: (b, nc).  grid.x = b * nrt * nsplit.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2,
+                                                               const float* __restrict__ rows, const float* __restrict__ cands,
+                                                               const float* __restrict__ w, float* __restrict__ partial) {
+    __shared__ __align__(16) float4 sC[EMD_TC];
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int split = bid % nsplit;
+    const int tile = (bid / nsplit) % nrt;
+    const int cloud = bid / (nsplit * nrt);
+    const float* __restrict__ rbase = rows + (size_t)cloud * nr * 3;
+    const float* __restrict__ cbase = cands + (size_t)cloud * nc * 3;
+    const float* __restrict__ wbase = w + (size_t)cloud * nc;
+
+    const int r0 = tile * (EMD_THREADS * EMD_Q) + tid;
+    float2 rx[EMD_Q / 2], ry[EMD_Q / 2], rz[EMD_Q / 2], acc[EMD_Q / 2];
+#pragma unroll
+    for (int h = 0; h < EMD_Q / 2; ++h) {
+        const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
+        const bool va = ia < nr, vb = ib < nr;
+        // rows are kept NEGATED so that (cand - row) is one FADD2 with a broadcast scalar: c + (-r) == c - r exactly
+        rx[h].x = va ? -rbase[(size_t)ia * 3 + 0] : 0.f; ry[h].x = va ? -rbase[(size_t)ia * 3 + 1] : 0.f; rz[h].x = va ? -rbase[(size_t)ia * 3 + 2] : 0.f;
+        rx[h].y = vb ? -rbase[(size_t)ib * 3 + 0] : 0.f; ry[h].y = vb ? -rbase[(size_t)ib * 3 + 1] : 0.f; rz[h].y = vb ? -rbase[(size_t)ib * 3 + 2] : 0.f;
+        acc[h] = make_float2(0.f, 0.f);
+    }
+    const float2 L2 = make_float2(lvl2, lvl2);
+
+    const int c_begin = split * cps * EMD_TC;
+    const int c_end = min(nc, c_begin + cps * EMD_TC);
+    for (int c0 = c_begin; c0 < c_end; c0 += EMD_TC) {
+        const int len = min(EMD_TC, c_end - c0);
+        __syncthreads();
+        for (int i = tid; i < EMD_TC; i += EMD_THREADS) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padded candidates carry weight 0
+            if (i < len) {
+                const float* c = cbase + (size_t)(c0 + i) * 3;
+                v = make_float4(c[0], c[1], c[2], wbase[c0 + i]);
+            }
+            sC[i] = v;
+        }
+        __syncthreads();
+        const int len2 = (len + 1) & ~1;
+#pragma unroll 2
+        for (int k = 0; k < len2; ++k) {
+            const float4 c = sC[k];
+#pragma unroll
+            for (int h = 0; h < EMD_Q / 2; ++h) {
+                const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // cand - row, as tf_approxmatch.cu:51
+                const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
+                const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
+                const float2 a = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
+                const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                acc[h] = __ffma2_rn(e, make_float2(c.w, c.w), acc[h]);
+            }
+        }
+    }
+    float* __restrict__ out = partial + ((size_t)cloud * nsplit + split) * nr;
+#pragma unroll
+    for (int h = 0; h < EMD_Q / 2; ++h) {
+        const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
+        if (ia < nr) out[ia] = acc[h].x;
+        if (ib < nr) out[ib] = acc[h].y;
+    }
+}
+
+// ---- epilogues: one thread per row; sum the split partials in fixed order, then the pass's update rule -----------
+__device__ __forceinline__ float emd_sum_partials(const float* __restrict__ partial, size_t cloud, int nsplit, int nr, int r) {
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[(cloud * nsplit + sp) * nr + r];
+    return s;
+}
+__global__ void emd_init_kernel(size_t bn, size_t bm, float multiL, float multiR, float* __restrict__ remainL, float* __restrict__ remainR) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < bn) remainL[t] = multiL;                     // tf_approxmatch.cu:17-20
+    else if (t < bn + bm) remainR[t - bn] = multiR;
+}
+// pass 1 (tf_approxmatch.cu:26-59): ratioL[k] = remainL[k] / (1e-9 + sum)
+__global__ void emd_epi1_kernel(int n, int nsplit, size_t bn, const float* __restrict__ partial, const float* __restrict__ remainL,
+                                float* __restrict__ ratioL, float* __restrict__ facL) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bn) return;
+    const float suml = 1e-9f + emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));
+    const float r = remainL[t] / suml;
+    ratioL[t] = r;
+    facL[t] = r;
+}
+// pass 2 (tf_approxmatch.cu:75-108)
+__global__ void emd_epi2_kernel(int m, int nsplit, size_t bm, const float* __restrict__ partial, float* __restrict__ remainR,
+                                float* __restrict__ ratioR, float* __restrict__ facR) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bm) return;
+    const float rem = remainR[t];
+    const float sumr = emd_sum_partials(partial, t / m, nsplit, m, (int)(t % m)) * rem;
+    const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+    const float r = consumption * rem;
+    ratioR[t] = r;
+    facR[t] = r;
+    remainR[t] = fmaxf(0.0f, rem - sumr);
+}
+// pass 3 (tf_approxmatch.cu:127-160), without the match write: remainL[k] = max(0, remainL[k] - ratioL[k] * sum_l e*ratioR[l])
+__global__ void emd_epi3_kernel(int n, int nsplit, size_t bn, const float* __restrict__ partial, const float* __restrict__ ratioL,
+                                float* __restrict__ remainL) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bn) return;
+    const float suml = ratioL[t] * emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));
+    remainL[t] = fmaxf(0.0f, remainL[t] - suml);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Final materialisation: match[cloud, l, k] = sum_j ex2(lvl2_j * d2(k,l)) * facL_j[k] * facR_j[l]   (k contiguous)
+// CTA = 128 k's x MT_L l's; thread owns one k (point + 10 factors in registers), l's come from shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MT_THREADS = 128;
+constexpr int MT_L = 64;
+struct EmdLevels { float lvl2[EMD_LEVELS]; };
+__global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int m, size_t bn, size_t bm, EmdLevels lv,
+                                                                     const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                                     const float* __restrict__ facL, const float* __restrict__ facR,
+                                                                     float* __restrict__ match) {
+    __shared__ float sP[MT_L][4];
+    __shared__ float sF[MT_L][EMD_LEVELS];
+    const int cloud = blockIdx.z;
+    const int k = blockIdx.x * MT_THREADS + threadIdx.x;
+    const int l0 = blockIdx.y * MT_L;
+    const int nl = min(MT_L, m - l0);
+    for (int i = threadIdx.x; i < nl * 3; i += MT_THREADS) sP[i / 3][i % 3] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    for (int i = threadIdx.x; i < nl * EMD_LEVELS; i += MT_THREADS) {
+        const int l = i / EMD_LEVELS, j = i % EMD_LEVELS;
+        sF[l][j] = facR[(size_t)j * bm + (size_t)cloud * m + l0 + l];
+    }
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f, fl[EMD_LEVELS];
+    const bool valid = k < n;
+    if (valid) {
+        const float* p = xyz1 + ((size_t)cloud * n + k) * 3;
+        x1 = p[0]; y1 = p[1]; z1 = p[2];
+    }
+#pragma unroll
+    for (int j = 0; j < EMD_LEVELS; ++j) fl[j] = valid ? facL[(size_t)j * bn + (size_t)cloud * n + k] : 0.f;
+    __syncthreads();
+    if (!valid) return;
+    float* __restrict__ out = match + ((size_t)cloud * m + l0) * n + k;
+    for (int l = 0; l < nl; ++l) {
+        const float d2 = sqdist3<true>(sP[l][0] - x1, sP[l][1] - y1, sP[l][2] - z1);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < EMD_LEVELS - 1; ++j) acc = __fmaf_rn(__fmul_rn(ex2_approx(__fmul_rn(d2, lv.lvl2[j])), fl[j]), sF[l][j], acc);
+        acc = __fmaf_rn(fl[EMD_LEVELS - 1], sF[l][EMD_LEVELS - 1], acc);  // j = -2: level 0, e = 1
+        out[(size_t)l * n] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// match_cost: cost[i] = sum_{l,k} sqrtf(d2(k,l)) * match[i,l,k]                     (tf_approxmatch.cu:183-225)
+// One streaming pass over match.  CTA = 256 k's x MC_L l's -> one partial per CTA, then a fixed-order final sum.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MC_THREADS = 256;
+constexpr int MC_L = 128;
+__global__ void __launch_bounds__(MC_THREADS) matchcost_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                               const float* __restrict__ match, float* __restrict__ partial) {
+    __shared__ float sP[MC_L * 3];
+    __shared__ float sW[MC_THREADS / 32];
+    const int cloud = blockIdx.z;
+    const int k = blockIdx.x * MC_THREADS + threadIdx.x;
+    const int l0 = blockIdx.y * MC_L;
+    const int nl = min(MC_L, m - l0);
+    for (int i = threadIdx.x; i < nl * 3; i += MC_THREADS) sP[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    __syncthreads();
+    float sum = 0.f;
+    if (k < n) {
+        const float* p = xyz1 + ((size_t)cloud * n + k) * 3;
+        const float x1 = p[0], y1 = p[1], z1 = p[2];
+        const float* __restrict__ mp = match + ((size_t)cloud * m + l0) * n + k;
+#pragma unroll 4
+        for (int l = 0; l < nl; ++l) {
+            const float d2 = sqdist3<true>(sP[l * 3] - x1, sP[l * 3 + 1] - y1, sP[l * 3 + 2] - z1);
+            sum = __fmaf_rn(__fsqrt_rn(d2), __ldg(mp + (size_t)l * n), sum);
+        }
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < MC_THREADS / 32; ++i) s += sW[i];
+        partial[((size_t)cloud * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+__global__ void reduce_partials_kernel(int per_cloud, const float* __restrict__ partial, float* __restrict__ out) {
+    __shared__ float sW[8];
+    const int cloud = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < per_cloud; i += blockDim.x) s += partial[(size_t)cloud * per_cloud + i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sW[i];
+        out[cloud] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// match_cost gradient.                                                              (tf_approxmatch.cu:229-291)
+//   grad1[k] = sum_l match[l,k] * (p1_k - p2_l) * rsqrt(max(d2, 1e-20))   thread per k, l-range per CTA, partials
+//   grad2[l] = sum_k match[l,k] * (p2_l - p1_k) * rsqrt(max(d2, 1e-20))   warp per l, lanes stride k, shuffle reduce
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int G1_THREADS = 128;
+constexpr int G1_L = 512;
+__global__ void __launch_bounds__(G1_THREADS) matchcostgrad1_kernel(int n, int m, int nlt, const float* __restrict__ xyz1,
+                                                                    const float* __restrict__ xyz2, const float* __restrict__ match,
+                                                                    float* __restrict__ partial) {
+    __shared__ float sP[G1_L * 3];
+    const int cloud = blockIdx.z;
+    const int k = blockIdx.x * G1_THREADS + threadIdx.x;
+    const int l0 = blockIdx.y * G1_L;
+    const int nl = min(G1_L, m - l0);
+    for (int i = threadIdx.x; i < nl * 3; i += G1_THREADS) sP[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    __syncthreads();
+    if (k >= n) return;
+    const float* p = xyz1 + ((size_t)cloud * n + k) * 3;
+    const float x1 = p[0], y1 = p[1], z1 = p[2];
+    const float* __restrict__ mp = match + ((size_t)cloud * m + l0) * n + k;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 4
+    for (int l = 0; l < nl; ++l) {
+        const float dx = x1 - sP[l * 3], dy = y1 - sP[l * 3 + 1], dz = z1 - sP[l * 3 + 2];
+        const float s = __ldg(mp + (size_t)l * n) * rsqrtf(fmaxf(sqdist3<true>(dx, dy, dz), 1e-20f));
+        gx = __fmaf_rn(dx, s, gx); gy = __fmaf_rn(dy, s, gy); gz = __fmaf_rn(dz, s, gz);
+    }
+    float* o = partial + (((size_t)cloud * nlt + blockIdx.y) * n + k) * 3;
+    o[0] = gx; o[1] = gy; o[2] = gz;
+}
+__global__ void matchcostgrad1_reduce_kernel(int n, int nlt, size_t bn, const float* __restrict__ partial, float* __restrict__ grad1) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over bn*3
+    if (t >= bn * 3) return;
+    const size_t cloud = t / ((size_t)n * 3), r = t % ((size_t)n * 3);
+    float s = 0.f;
+    for (int i = 0; i < nlt; ++i) s += partial[((size_t)cloud * nlt + i) * n * 3 + r];
+    grad1[t] = s;
+}
+constexpr int G2_WARPS = 8;
+__global__ void __launch_bounds__(G2_WARPS * 32) matchcostgrad2_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                                       const float* __restrict__ match, float* __restrict__ grad2) {
+    const int cloud = blockIdx.y;
+    const int l = blockIdx.x * G2_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (l >= m) return;
+    const float* q = xyz2 + ((size_t)cloud * m + l) * 3;
+    const float x2 = q[0], y2 = q[1], z2 = q[2];
+    const float* __restrict__ a = xyz1 + (size_t)cloud * n * 3;
+    const float* __restrict__ mp = match + ((size_t)cloud * m + l) * n;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int k = lane; k < n; k += 32) {
+        const float dx = x2 - a[(size_t)k * 3], dy = y2 - a[(size_t)k * 3 + 1], dz = z2 - a[(size_t)k * 3 + 2];
+        const float s = __ldg(mp + k) * rsqrtf(fmaxf(sqdist3<true>(dx, dy, dz), 1e-20f));
+        gx = __fmaf_rn(dx, s, gx); gy = __fmaf_rn(dy, s, gy); gz = __fmaf_rn(dz, s, gz);
+    }
+    gx = warp_sum(gx); gy = warp_sum(gy); gz = warp_sum(gz);
+    if (lane == 0) {
+        float* o = grad2 + ((size_t)cloud * m + l) * 3;
+        o[0] = gx; o[1] = gy; o[2] = gz;
+    }
+}
+
+static void emd_sweep(int b, int nr, int nc, float lvl2, const float* rows, const float* cands, const float* w, float* partial, int& nsplit_out,
+                      cudaStream_t s) {
+    const int nrt = (nr + EMD_THREADS * EMD_Q - 1) / (EMD_THREADS * EMD_Q);
+    const int chunks = (nc + EMD_TC - 1) / EMD_TC;
+    // aim for >= 32 CTAs per SM (several waves, small tail); never more splits than emd_max_split() reserved room for
+    long want = ((long)kNumSMs * 32 + (long)b * nrt - 1) / ((long)b * nrt);
+    int nsplit = (int)(want < 1 ? 1 : want);
+    if (nsplit > chunks) nsplit = chunks;
+    if (nsplit > 32) nsplit = 32;
+    const int cps = (chunks + nsplit - 1) / nsplit;
+    nsplit = (chunks + cps - 1) / cps;
+    nsplit_out = nsplit;
+    emd_sweep_kernel<<<(unsigned)(b * nrt * nsplit), EMD_THREADS, 0, s>>>(nr, nc, nrt, nsplit, cps, lvl2, rows, cands, w, partial);
+}
+
+}  // namespace rfnet
+
+using namespace rfnet;
+
+extern "C" size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return emd_ws_floats(b, n, m) * sizeof(float);
+}
+
+extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, void* workspace,
+                                 size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0 || n == 0 || m == 0) return 0;
+    RFNET_CHECK_ARG(xyz1 && xyz2 && match && workspace && workspace_bytes >= rfnet_approxmatch_workspace_bytes(b, n, m));
+    RFNET_CHECK_ARG(b <= 65535);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    EmdWs ws = emd_carve((float*)workspace, b, n, m);
+    const float multiL = n >= m ? 1.0f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.0f;  // integer division, tf_approxmatch.cu:4-10
+    emd_init_kernel<<<(unsigned)((bn + bm + 255) / 256), 256, 0, s>>>(bn, bm, multiL, multiR, ws.remainL, ws.remainR);
+    EmdLevels lv;
+    for (int li = 0; li < EMD_LEVELS; ++li) {
+        const float lvl2 = emd_level(li) * LOG2E;
+        lv.lvl2[li] = lvl2;
+        int ns;
+        // pass 1: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR
+        emd_sweep(b, n, m, lvl2, xyz1, xyz2, ws.remainR, ws.partial, ns, s);
+        emd_epi1_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn);
+        // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL
+        emd_sweep(b, m, n, lvl2, xyz2, xyz1, ws.ratioL, ws.partial, ns, s);
+        emd_epi2_kernel<<<(unsigned)((bm + 255) / 256), 256, 0, s>>>(m, ns, bm, ws.partial, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm);
+        // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR
+        emd_sweep(b, n, m, lvl2, xyz1, xyz2, ws.ratioR, ws.partial, ns, s);
+        emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.ratioL, ws.remainL);
+    }
+    dim3 grid((unsigned)((n + MT_THREADS - 1) / MT_THREADS), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
+    RFNET_CHECK_ARG(grid.y <= 65535);
+    emd_materialise_kernel<<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, match);
+    return launch_status();
+}
+
+extern "C" size_t rfnet_matchcost_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return sizeof(float) * (size_t)b * ((n + MC_THREADS - 1) / MC_THREADS) * ((m + MC_L - 1) / MC_L);
+}
+
+extern "C" int rfnet_matchcost(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match, float* out, void* workspace,
+                               size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0) return 0;
+    RFNET_CHECK_ARG(out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        RFNET_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * b, s));
+        return 0;
+    }
+    RFNET_CHECK_ARG(xyz1 && xyz2 && match && workspace && workspace_bytes >= rfnet_matchcost_workspace_bytes(b, n, m) && b <= 65535);
+    dim3 grid((unsigned)((n + MC_THREADS - 1) / MC_THREADS), (unsigned)((m + MC_L - 1) / MC_L), (unsigned)b);
+    RFNET_CHECK_ARG(grid.y <= 65535);
+    matchcost_kernel<<<grid, MC_THREADS, 0, s>>>(n, m, xyz1, xyz2, match, (float*)workspace);
+    reduce_partials_kernel<<<b, 256, 0, s>>>((int)(grid.x * grid.y), (const float*)workspace, out);
+    return launch_status();
+}
+
+extern "C" size_t rfnet_matchcostgrad_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return sizeof(float) * 3 * (size_t)b * n * ((m + G1_L - 1) / G1_L);
+}
+
+extern "C" int rfnet_matchcostgrad(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match, float* grad1, float* grad2,
+                                   void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        if (n) RFNET_CUDA(cudaMemsetAsync(grad1, 0, sizeof(float) * 3 * (size_t)b * n, s));
+        if (m) RFNET_CUDA(cudaMemsetAsync(grad2, 0, sizeof(float) * 3 * (size_t)b * m, s));
+        return 0;
+    }
+    RFNET_CHECK_ARG(xyz1 && xyz2 && match && grad1 && grad2 && workspace && workspace_bytes >= rfnet_matchcostgrad_workspace_bytes(b, n, m) && b <= 65535);
+    const int nlt = (m + G1_L - 1) / G1_L;
+    RFNET_CHECK_ARG(nlt <= 65535);
+    const size_t bn = (size_t)b * n;
+    dim3 g1((unsigned)((n + G1_THREADS - 1) / G1_THREADS), (unsigned)nlt, (unsigned)b);
+    matchcostgrad1_kernel<<<g1, G1_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
+    matchcostgrad1_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, nlt, bn, (const float*)workspace, grad1);
+    dim3 g2((unsigned)((m + G2_WARPS - 1) / G2_WARPS), (unsigned)b);
+    matchcostgrad2_kernel<<<g2, G2_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
+    return launch_status();
+}

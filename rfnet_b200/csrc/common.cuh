@@ -1,0 +1,108 @@
+// Shared device helpers for the rfnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "rfnet_b200 kernels are written for sm_100a (Blackwell) only"
+#endif
+
+namespace rfnet {
+
+constexpr int kNumSMs = 148;  // B200
+
+#define RFNET_CHECK_ARG(cond) \
+    do {                      \
+        if (!(cond)) return (int)cudaErrorInvalidValue; \
+    } while (0)
+
+#define RFNET_CUDA(call)                     \
+    do {                                     \
+        cudaError_t _e = (call);             \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+static inline int launch_status() { return (int)cudaGetLastError(); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Squared distance in the reference's operand order.  Explicit intrinsics so -fmad never decides the contraction.
+//   fused   : fma(dz,dz, fma(dx,dx, dy*dy))     what nvcc emits for x*x+y*y+z*z in every reference CUDA kernel
+//   unfused : ((dx*dx)+(dy*dy))+(dz*dz)         the reference's CPU build (g++ -O2 without FMA)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FUSED>
+__device__ __forceinline__ float sqdist3(float dx, float dy, float dz) {
+    if (FUSED) return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Packed FP32x2 version (Blackwell FADD2/FMUL2/FFMA2): two distances per instruction, each lane IEEE-rn, so the results
+// are bit-identical to sqdist3 on the two halves.
+// NOTE (ptxas 12.9): a packed mul.rn.f32x2 feeding a packed add.rn.f32x2 -- or even fma.rn.f32x2(x, 1, y) -- IS contracted
+// into FFMA2 despite the .rn qualifiers (checked in SASS, and caught by the unfused parity test).  The unfused variant
+// therefore does its two additions with scalar __fadd_rn, which ptxas never contracts.
+template <bool FUSED>
+__device__ __forceinline__ float2 sqdist3x2(float2 dx, float2 dy, float2 dz) {
+    if (FUSED) return __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+    const float2 px = __fmul2_rn(dx, dx), py = __fmul2_rn(dy, dy), pz = __fmul2_rn(dz, dz);
+    return make_float2(__fadd_rn(__fadd_rn(px.x, py.x), pz.x), __fadd_rn(__fadd_rn(px.y, py.y), pz.y));
+}
+
+// 3-input min (FMNMX3 on sm_100).
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP): contiguous global -> shared, completion on an mbarrier.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Packed (distance, index) key: for d >= +0 the float bit pattern is monotone as an unsigned integer, so an integer min
+// over keys yields "smallest distance, then smallest index" -- the reference's first-minimum rule -- exactly.
+__device__ __forceinline__ unsigned long long pack_key(float d, int idx) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace rfnet

@@ -1,0 +1,184 @@
+// query_ball_point, group_point and its gradient for sm_100a.
+//
+// Replaces query_ball_point_gpu / group_point_gpu / group_point_grad_gpu (tf_ops/grouping/tf_grouping_g.cu:3-78).
+//
+// Ball query design: the reference gives each query to one thread which streams the whole dataset from global memory
+// (uncoalesced, one block per cloud).  Here a WARP owns a query: the dataset is staged tile by tile in shared memory, each
+// lane tests one point of a 32-point group, and a ballot + popcount appends the hits IN INDEX ORDER, so "the first
+// nsample points inside the ball" (tf_grouping_g.cu:17-31) is reproduced exactly, with early exit once the row is full.
+//
+// The predicate max(sqrtf(d2), 1e-20f) < r is evaluated without a square root: sqrt_rn is monotone, so it equals
+// d2 < T with T = min{t : sqrt_rn(t) >= r}; T is found once per thread by stepping nextafter around r*r.
+#include "common.cuh"
+#include "rfnet_ops.h"
+
+namespace rfnet {
+
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_QPW = 4;      // queries per warp
+constexpr int BQ_TILE = 2048;  // dataset points per shared-memory tile (24 KiB)
+
+__device__ __forceinline__ float ball_threshold(float r) {
+    if (!(r > 1e-20f)) return 0.0f;                          // max(.,1e-20f) < r can never hold (also r = NaN)
+    if (r == __int_as_float(0x7f800000)) return r;           // every finite distance is inside
+    float t = __fmul_rn(r, r);
+    while (t > 0.0f && __fsqrt_rn(t) >= r) t = __uint_as_float(__float_as_uint(t) - 1u);  // down to sqrt(t) < r
+    while (__fsqrt_rn(t) < r) t = __uint_as_float(__float_as_uint(t) + 1u);               // up to the first t with sqrt(t) >= r
+    return t;
+}
+
+__global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m, const float* __restrict__ radius, int nsample,
+                                                                   const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                                   int* __restrict__ idx, int* __restrict__ pts_cnt) {
+    __shared__ float tile[BQ_TILE * 3];
+    const int cloud = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* __restrict__ data = xyz1 + (size_t)cloud * n * 3;
+    const float T = ball_threshold(radius[0]);
+
+    const int qbase = (blockIdx.x * BQ_WARPS + warp) * BQ_QPW;
+    float qx[BQ_QPW], qy[BQ_QPW], qz[BQ_QPW];
+    int cnt[BQ_QPW], first[BQ_QPW];
+#pragma unroll
+    for (int u = 0; u < BQ_QPW; ++u) {
+        const int j = qbase + u;
+        const bool v = j < m;
+        const float* q = xyz2 + ((size_t)cloud * m + (v ? j : 0)) * 3;
+        qx[u] = q[0]; qy[u] = q[1]; qz[u] = q[2];
+        cnt[u] = v ? 0 : nsample;  // out-of-range queries count as already full
+        first[u] = 0;
+    }
+
+    for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
+        const int len = min(BQ_TILE, n - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < len * 3; i += BQ_WARPS * 32) tile[i] = data[(size_t)t0 * 3 + i];
+        __syncthreads();
+        bool all_full = true;
+#pragma unroll
+        for (int u = 0; u < BQ_QPW; ++u) {
+            if (cnt[u] >= nsample) continue;  // warp-uniform
+            int* __restrict__ row = idx + ((size_t)cloud * m + qbase + u) * nsample;
+            for (int k0 = 0; k0 < len && cnt[u] < nsample; k0 += 32) {
+                const int k = k0 + lane;
+                bool hit = false;
+                if (k < len) {
+                    // (query - dataset), the operand order of tf_grouping_g.cu:24
+                    const float d2 = sqdist3<true>(qx[u] - tile[k * 3 + 0], qy[u] - tile[k * 3 + 1], qz[u] - tile[k * 3 + 2]);
+                    hit = d2 < T;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (mask) {
+                    if (cnt[u] == 0) first[u] = t0 + k0 + __ffs(mask) - 1;
+                    const int pos = cnt[u] + __popc(mask & ((1u << lane) - 1u));
+                    if (hit && pos < nsample) row[pos] = t0 + k;
+                    cnt[u] += __popc(mask);
+                }
+            }
+            all_full = all_full && cnt[u] >= nsample;
+        }
+        if (__syncthreads_and(all_full)) break;
+    }
+
+#pragma unroll
+    for (int u = 0; u < BQ_QPW; ++u) {
+        const int j = qbase + u;
+        if (j >= m) continue;
+        const int c = min(cnt[u], nsample);
+        int* __restrict__ row = idx + ((size_t)cloud * m + j) * nsample;
+        // remaining slots repeat the first hit (tf_grouping_g.cu:26-29); rows without any hit are defined as 0 here
+        for (int s = c + lane; s < nsample; s += 32) row[s] = first[u];
+        if (lane == 0) pts_cnt[(size_t)cloud * m + j] = c;
+    }
+}
+
+// out[i,j,k,:] = points[i, idx[i,j,k], :]                                         (tf_grouping_g.cu:40-57)
+template <typename VEC>
+__global__ void group_point_kernel(int n, int cv, size_t rows_per_cloud, size_t total_vec, const VEC* __restrict__ points,
+                                   const int* __restrict__ idx, VEC* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output vector
+    if (t >= total_vec) return;
+    const size_t row = t / cv;
+    const int l = (int)(t - row * cv);
+    const size_t cloud = row / rows_per_cloud;
+    out[t] = __ldg(points + (cloud * n + (size_t)idx[row]) * cv + l);
+}
+
+// grad_points[i, idx[i,j,k], :] += grad_out[i,j,k,:]  after zero-fill                (tf_grouping_g.cu:61-78, tf_grouping.cpp:208)
+__global__ void group_point_grad_kernel(int n, int c, size_t rows_per_cloud, size_t total, const float* __restrict__ grad_out,
+                                        const int* __restrict__ idx, float* __restrict__ grad_points) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const size_t row = t / c;
+    const int l = (int)(t - row * c);
+    const size_t cloud = row / rows_per_cloud;
+    atomicAdd(grad_points + (cloud * n + (size_t)idx[row]) * c + l, grad_out[t]);
+}
+// c % 4 == 0 and 16-byte aligned rows: one 128-bit reduction (REDG.ADD.F32x4) per four channels
+__global__ void group_point_grad_v4_kernel(int n, int cv, size_t rows_per_cloud, size_t total_vec, const float4* __restrict__ grad_out,
+                                           const int* __restrict__ idx, float4* __restrict__ grad_points) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_vec) return;
+    const size_t row = t / cv;
+    const int l = (int)(t - row * cv);
+    const size_t cloud = row / rows_per_cloud;
+    const float4 g = grad_out[t];
+    float4* dst = grad_points + (cloud * n + (size_t)idx[row]) * cv + l;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+}
+
+}  // namespace rfnet
+
+using namespace rfnet;
+
+extern "C" int rfnet_query_ball_point(int b, int n, int m, const float* radius, int nsample, const float* xyz1, const float* xyz2,
+                                      int* idx, int* pts_cnt, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && nsample > 0);  // tf_grouping.cpp:75
+    if (b == 0 || m == 0) return 0;
+    RFNET_CHECK_ARG(radius && xyz2 && idx && pts_cnt && (n == 0 || xyz1));
+    RFNET_CHECK_ARG(b <= 65535);
+    const int per_block = BQ_WARPS * BQ_QPW;
+    dim3 grid((unsigned)((m + per_block - 1) / per_block), (unsigned)b);
+    ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt);
+    return launch_status();
+}
+
+extern "C" int rfnet_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx, float* out,
+                                 rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0);
+    const size_t rows = (size_t)b * m * nsample;
+    if (rows == 0 || c == 0) return 0;
+    RFNET_CHECK_ARG(n > 0 && points && idx && out);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t rpc = (size_t)m * nsample;
+    if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
+        const size_t tv = rows * (c / 4);
+        group_point_kernel<float4><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, rpc, tv, (const float4*)points, idx, (float4*)out);
+    } else {
+        const size_t tv = rows * c;
+        group_point_kernel<float><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, rpc, tv, points, idx, out);
+    }
+    return launch_status();
+}
+
+extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx, float* grad_points,
+                                      rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((size_t)b * n * c) {
+        RFNET_CHECK_ARG(grad_points);
+        RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, s));
+    }
+    const size_t rows = (size_t)b * m * nsample;
+    if (rows == 0 || c == 0) return 0;
+    RFNET_CHECK_ARG(n > 0 && grad_out && idx);
+    const size_t rpc = (size_t)m * nsample;
+    if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
+        const size_t tv = rows * (c / 4);
+        group_point_grad_v4_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, rpc, tv, (const float4*)grad_out, idx, (float4*)grad_points);
+    } else {
+        const size_t tv = rows * c;
+        group_point_grad_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, rpc, tv, grad_out, idx, grad_points);
+    }
+    return launch_status();
+}

@@ -1,0 +1,209 @@
+// three_nn, three_interpolate and its gradient for sm_100a.
+//
+// The reference has NO GPU code for these ops (tf_ops/interpolation/tf_interpolate.cpp registers DEVICE_CPU only,
+// :187,222,262); these are the first GPU kernels for them and follow threenn_cpu / threeinterpolate_cpu /
+// threeinterpolate_grad_cpu (tf_interpolate.cpp:60-153) bit for bit where order matters:
+//   * three_nn evaluates d2 UNFUSED ((dx*dx + dy*dy) + dz*dz), as the reference's CPU build does, and keeps the three
+//     smallest with the same strict-'<' insertion, so earlier indices win ties;
+//   * three_interpolate evaluates (p1*w1 + p2*w2) + p3*w3 unfused.
+// three_nn uses the same machinery as nn_distance: queries in registers as packed pairs (FADD2/FMUL2), candidates
+// broadcast from shared memory, a 3-input-min filter so the insertion code only runs when a candidate can enter the top 3.
+#include "common.cuh"
+#include "rfnet_ops.h"
+
+namespace rfnet {
+
+constexpr int TN_THREADS = 128;
+constexpr int TN_Q = 4;        // queries per thread (two packed pairs)
+constexpr int TN_TILE = 2048;  // candidates per shared-memory tile
+
+struct Top3 {
+    float d1, d2, d3;
+    int i1, i2, i3;
+};
+__device__ __forceinline__ void top3_insert(Top3& t, float d, int k) {  // tf_interpolate.cpp:76-92
+    if (d < t.d1) {
+        t.d3 = t.d2; t.i3 = t.i2; t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = k;
+    } else if (d < t.d2) {
+        t.d3 = t.d2; t.i3 = t.i2; t.d2 = d; t.i2 = k;
+    } else if (d < t.d3) {
+        t.d3 = d; t.i3 = k;
+    }
+}
+
+__global__ void __launch_bounds__(TN_THREADS) three_nn_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                              float* __restrict__ dist, int* __restrict__ idx) {
+    __shared__ __align__(16) float tile[TN_TILE * 3];
+    const int cloud = blockIdx.y;
+    const int tid = threadIdx.x;
+    const float* __restrict__ qbase = xyz1 + (size_t)cloud * n * 3;
+    const float* __restrict__ cbase = xyz2 + (size_t)cloud * m * 3;
+    const int q0 = blockIdx.x * (TN_THREADS * TN_Q) + tid;
+
+    float2 qx[TN_Q / 2], qy[TN_Q / 2], qz[TN_Q / 2];
+    Top3 top[TN_Q];
+#pragma unroll
+    for (int h = 0; h < TN_Q / 2; ++h) {
+        const int ia = q0 + (2 * h) * TN_THREADS, ib = ia + TN_THREADS;
+        const bool va = ia < n, vb = ib < n;
+        qx[h].x = va ? qbase[(size_t)ia * 3 + 0] : 0.f; qy[h].x = va ? qbase[(size_t)ia * 3 + 1] : 0.f; qz[h].x = va ? qbase[(size_t)ia * 3 + 2] : 0.f;
+        qx[h].y = vb ? qbase[(size_t)ib * 3 + 0] : 0.f; qy[h].y = vb ? qbase[(size_t)ib * 3 + 1] : 0.f; qz[h].y = vb ? qbase[(size_t)ib * 3 + 2] : 0.f;
+    }
+    const float inf = __int_as_float(0x7f800000);  // (float)1e40 of the reference
+#pragma unroll
+    for (int i = 0; i < TN_Q; ++i) { top[i].d1 = top[i].d2 = top[i].d3 = inf; top[i].i1 = top[i].i2 = top[i].i3 = 0; }
+
+    for (int t0 = 0; t0 < m; t0 += TN_TILE) {
+        const int len = min(TN_TILE, m - t0);
+        const int len4 = (len + 3) & ~3;
+        __syncthreads();
+        for (int i = tid; i < len * 3; i += TN_THREADS) tile[i] = cbase[(size_t)t0 * 3 + i];
+        for (int i = len * 3 + tid; i < len4 * 3; i += TN_THREADS) tile[i] = inf;  // padded candidates: d2 = inf, never inserted
+        __syncthreads();
+        const float4* __restrict__ c4 = reinterpret_cast<const float4*>(tile);
+#pragma unroll 1
+        for (int k = 0; k < len4; k += 4) {
+            const float4 v0 = c4[(k >> 2) * 3 + 0], v1 = c4[(k >> 2) * 3 + 1], v2 = c4[(k >> 2) * 3 + 2];
+            const float cx[4] = {v0.x, v0.w, v1.z, v2.y};
+            const float cy[4] = {v0.y, v1.x, v1.w, v2.z};
+            const float cz[4] = {v0.z, v1.y, v2.x, v2.w};
+#pragma unroll
+            for (int h = 0; h < TN_Q / 2; ++h) {
+                float2 d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 dx = __fadd2_rn(qx[h], make_float2(-cx[j], -cx[j]));
+                    const float2 dy = __fadd2_rn(qy[h], make_float2(-cy[j], -cy[j]));
+                    const float2 dz = __fadd2_rn(qz[h], make_float2(-cz[j], -cz[j]));
+                    d[j] = sqdist3x2<false>(dx, dy, dz);
+                }
+                if (fmin3(fminf(d[0].x, d[1].x), d[2].x, d[3].x) < top[2 * h].d3) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) top3_insert(top[2 * h], d[j].x, t0 + k + j);
+                }
+                if (fmin3(fminf(d[0].y, d[1].y), d[2].y, d[3].y) < top[2 * h + 1].d3) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) top3_insert(top[2 * h + 1], d[j].y, t0 + k + j);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TN_Q; ++i) {
+        const int qi = q0 + i * TN_THREADS;
+        if (qi < n) {
+            const size_t o = ((size_t)cloud * n + qi) * 3;
+            dist[o] = top[i].d1; dist[o + 1] = top[i].d2; dist[o + 2] = top[i].d3;
+            idx[o] = top[i].i1; idx[o + 1] = top[i].i2; idx[o + 2] = top[i].i3;
+        }
+    }
+}
+
+// out[i,j,l] = (p[i1,l]*w1 + p[i2,l]*w2) + p[i3,l]*w3        (tf_interpolate.cpp:107-127).  One thread per output vector.
+template <typename VEC>
+__device__ __forceinline__ VEC blend3(VEC a, VEC b, VEC c, float w1, float w2, float w3);
+template <>
+__device__ __forceinline__ float blend3<float>(float a, float b, float c, float w1, float w2, float w3) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, w1), __fmul_rn(b, w2)), __fmul_rn(c, w3));
+}
+template <>
+__device__ __forceinline__ float4 blend3<float4>(float4 a, float4 b, float4 c, float w1, float w2, float w3) {
+    return make_float4(blend3<float>(a.x, b.x, c.x, w1, w2, w3), blend3<float>(a.y, b.y, c.y, w1, w2, w3),
+                       blend3<float>(a.z, b.z, c.z, w1, w2, w3), blend3<float>(a.w, b.w, c.w, w1, w2, w3));
+}
+template <typename VEC>
+__global__ void three_interpolate_kernel(int m, int cv, int n, size_t total_vec, const VEC* __restrict__ points, const int* __restrict__ idx,
+                                         const float* __restrict__ weight, VEC* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_vec) return;
+    const size_t row = t / cv;  // = cloud*n + j
+    const int l = (int)(t - row * cv);
+    const size_t cloud = row / n;
+    const int* id = idx + row * 3;
+    const float* w = weight + row * 3;
+    const VEC* P = points + cloud * (size_t)m * cv + l;
+    out[t] = blend3<VEC>(__ldg(P + (size_t)id[0] * cv), __ldg(P + (size_t)id[1] * cv), __ldg(P + (size_t)id[2] * cv), w[0], w[1], w[2]);
+}
+
+// grad_points[i, i_t, l] += grad_out[i,j,l] * w_t  after zero-fill             (tf_interpolate.cpp:131-153, :258)
+__global__ void three_interpolate_grad_kernel(int n, int c, int m, size_t total, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                                              const float* __restrict__ weight, float* __restrict__ grad_points) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const size_t row = t / c;
+    const int l = (int)(t - row * c);
+    const size_t cloud = row / n;
+    const float g = grad_out[t];
+    float* G = grad_points + cloud * (size_t)m * c + l;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) atomicAdd(G + (size_t)idx[row * 3 + u] * c, __fmul_rn(g, weight[row * 3 + u]));
+}
+__global__ void three_interpolate_grad_v4_kernel(int n, int cv, int m, size_t total_vec, const float4* __restrict__ grad_out,
+                                                 const int* __restrict__ idx, const float* __restrict__ weight, float4* __restrict__ grad_points) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_vec) return;
+    const size_t row = t / cv;
+    const int l = (int)(t - row * cv);
+    const size_t cloud = row / n;
+    const float4 g = grad_out[t];
+    float4* G = grad_points + cloud * (size_t)m * cv + l;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const float w = weight[row * 3 + u];
+        float4* dst = G + (size_t)idx[row * 3 + u] * cv;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__fmul_rn(g.x, w)), "f"(__fmul_rn(g.y, w)),
+                     "f"(__fmul_rn(g.z, w)), "f"(__fmul_rn(g.w, w))
+                     : "memory");
+    }
+}
+
+}  // namespace rfnet
+
+using namespace rfnet;
+
+extern "C" int rfnet_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0 || n == 0) return 0;
+    RFNET_CHECK_ARG(xyz1 && dist && idx && (m == 0 || xyz2) && b <= 65535);
+    dim3 grid((unsigned)((n + TN_THREADS * TN_Q - 1) / (TN_THREADS * TN_Q)), (unsigned)b);
+    three_nn_kernel<<<grid, TN_THREADS, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, dist, idx);
+    return launch_status();
+}
+
+extern "C" int rfnet_three_interpolate(int b, int m, int c, int n, const float* points, const int* idx, const float* weight, float* out,
+                                       rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0);
+    const size_t rows = (size_t)b * n;
+    if (rows == 0 || c == 0) return 0;
+    RFNET_CHECK_ARG(m > 0 && points && idx && weight && out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
+        const size_t tv = rows * (c / 4);
+        three_interpolate_kernel<float4><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(m, c / 4, n, tv, (const float4*)points, idx, weight, (float4*)out);
+    } else {
+        const size_t tv = rows * c;
+        three_interpolate_kernel<float><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(m, c, n, tv, points, idx, weight, out);
+    }
+    return launch_status();
+}
+
+extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
+                                            float* grad_points, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((size_t)b * m * c) {
+        RFNET_CHECK_ARG(grad_points);
+        RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, s));
+    }
+    const size_t rows = (size_t)b * n;
+    if (rows == 0 || c == 0) return 0;
+    RFNET_CHECK_ARG(m > 0 && grad_out && idx && weight);
+    if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
+        const size_t tv = rows * (c / 4);
+        three_interpolate_grad_v4_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, m, tv, (const float4*)grad_out, idx, weight, (float4*)grad_points);
+    } else {
+        const size_t tv = rows * c;
+        three_interpolate_grad_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, m, tv, grad_out, idx, weight, grad_points);
+    }
+    return launch_status();
+}

@@ -1,0 +1,435 @@
+"""PyTorch custom ops (namespace ``rfnet::``) over the C ABI of librfnet_ops.so.
+
+One op per TensorFlow op the reference registers (REGISTER_OP in pc_distance/tf_nndistance.cpp:3-18,
+pc_distance/tf_approxmatch.cpp:7-21, tf_ops/sampling/tf_sampling.cpp:14-63, tf_ops/grouping/tf_grouping.cpp:14-64,
+tf_ops/interpolation/tf_interpolate.cpp:12-46): same inputs, attrs, output tuples, dtypes and shape checks; the checks
+raise ``ValueError`` with the reference's InvalidArgument message.  Autograd mirrors each ``RegisterGradient`` /
+``NoGradient`` of the reference's Python wrappers.  torch is plumbing here (device memory, streams, autograd graph); all
+compute is in the CUDA library and there is no other path: CPU tensors are rejected.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None and t.numel() > 0 else _vp(0)
+
+
+def _stream(t):
+    return _vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _cuda_f32(name, t):
+    _require(isinstance(t, torch.Tensor) and t.is_cuda, "%s must be a CUDA tensor (rfnet_b200 has no CPU path)" % name)
+    _require(t.dtype == torch.float32, "%s must be float32" % name)
+    return t.contiguous()
+
+
+def _cuda_i32(name, t):
+    _require(isinstance(t, torch.Tensor) and t.is_cuda, "%s must be a CUDA tensor (rfnet_b200 has no CPU path)" % name)
+    _require(t.dtype == torch.int32, "%s must be int32" % name)
+    return t.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------------------ nn_distance
+@torch.library.custom_op("rfnet::nn_distance", mutates_args=(), device_types="cuda")
+def nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, unfused: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    # shape checks of NnDistanceGpuOp::Compute, pc_distance/tf_nndistance.cpp:175-182
+    _require(xyz1.dim() == 3, "NnDistance requires xyz1 be of shape (batch,#points,3)")
+    _require(xyz1.shape[2] == 3, "NnDistance only accepts 3d point set xyz1")
+    _require(xyz2.dim() == 3, "NnDistance requires xyz2 be of shape (batch,#points,3)")
+    _require(xyz2.shape[2] == 3, "NnDistance only accepts 3d point set xyz2")
+    _require(xyz2.shape[0] == xyz1.shape[0], "NnDistance expects xyz1 and xyz2 have same batch size")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    dev = xyz1.device
+    dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+    idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+    dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+    idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    wsb = lib.rfnet_nn_distance_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rfnet_nn_distance(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(dist1), _ptr(idx1), _ptr(dist2), _ptr(idx2), _ptr(ws), wsb,
+                                         1 if unfused else 0, _stream(xyz1)), "rfnet_nn_distance")
+    return dist1, idx1, dist2, idx2
+
+
+@nn_distance_op.register_fake
+def _(xyz1, xyz2, unfused=False):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    return (xyz1.new_empty((b, n)), xyz1.new_empty((b, n), dtype=torch.int32), xyz1.new_empty((b, m)), xyz1.new_empty((b, m), dtype=torch.int32))
+
+
+@torch.library.custom_op("rfnet::nn_distance_grad", mutates_args=(), device_types="cuda")
+def nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torch.Tensor, idx1: torch.Tensor, grad_dist2: torch.Tensor,
+                        idx2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    # NnDistanceGradGpuOp::Compute, pc_distance/tf_nndistance.cpp:209-253
+    _require(xyz1.dim() == 3, "NnDistanceGrad requires xyz1 be of shape (batch,#points,3)")
+    _require(xyz1.shape[2] == 3, "NnDistanceGrad only accepts 3d point set xyz1")
+    _require(xyz2.dim() == 3, "NnDistanceGrad requires xyz2 be of shape (batch,#points,3)")
+    _require(xyz2.shape[2] == 3, "NnDistanceGrad only accepts 3d point set xyz2")
+    _require(xyz2.shape[0] == xyz1.shape[0], "NnDistanceGrad expects xyz1 and xyz2 have same batch size")
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    _require(tuple(grad_dist1.shape) == (b, n), "NnDistanceGrad requires grad_dist1 be of shape(batch,#points)")
+    _require(tuple(idx1.shape) == (b, n), "NnDistanceGrad requires idx1 be of shape(batch,#points)")
+    _require(tuple(grad_dist2.shape) == (b, m), "NnDistanceGrad requires grad_dist2 be of shape(batch,#points)")
+    _require(tuple(idx2.shape) == (b, m), "NnDistanceGrad requires idx2 be of shape(batch,#points)")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    grad_dist1, grad_dist2 = _cuda_f32("grad_dist1", grad_dist1), _cuda_f32("grad_dist2", grad_dist2)
+    idx1, idx2 = _cuda_i32("idx1", idx1), _cuda_i32("idx2", idx2)
+    g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(_lib.load().rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
+                                                      _ptr(g1), _ptr(g2), _stream(xyz1)), "rfnet_nn_distance_grad")
+    return g1, g2
+
+
+@nn_distance_grad_op.register_fake
+def _(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
+    return torch.empty_like(xyz1), torch.empty_like(xyz2)
+
+
+def _nn_distance_setup(ctx, inputs, output):
+    xyz1, xyz2, _unfused = inputs
+    ctx.save_for_backward(xyz1, xyz2, output[1], output[3])
+
+
+def _nn_distance_backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
+    # tf_ops/CD/tf_nndistance.py:26-32: idx grads are ignored; a missing upstream grad is zero
+    xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+    if grad_dist1 is None:
+        grad_dist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=xyz1.device)
+    if grad_dist2 is None:
+        grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=xyz1.device)
+    g1, g2 = nn_distance_grad_op(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)
+    return g1, g2, None
+
+
+nn_distance_op.register_autograd(_nn_distance_backward, setup_context=_nn_distance_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------ approx_match
+@torch.library.custom_op("rfnet::approx_match", mutates_args=(), device_types="cuda")
+def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> torch.Tensor:
+    # ApproxMatchGpuOp::Compute, pc_distance/tf_approxmatch.cpp:145-173
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ApproxMatch expects (batch_size,num_points,3) xyz2 shape, and batch_size must match")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    match = torch.empty((b, m, n), dtype=torch.float32, device=xyz1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_approxmatch_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(lib.rfnet_approxmatch(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match), _ptr(ws), wsb, _stream(xyz1)), "rfnet_approxmatch")
+    return match
+
+
+@approx_match_op.register_fake
+def _(xyz1, xyz2):
+    return xyz1.new_empty((xyz1.shape[0], xyz2.shape[1], xyz1.shape[1]))
+
+
+def _check_match_args(op, xyz1, xyz2, match):
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "%s expects (batch_size,num_points,3) xyz1 shape" % op)
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "%s expects (batch_size,num_points,3) xyz2 shape, and batch_size must match" % op)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    _require(match.dim() == 3 and tuple(match.shape) == (b, m, n), "%s expects (batch_size,#query,#dataset) match shape" % op)
+    return b, n, m
+
+
+@torch.library.custom_op("rfnet::match_cost", mutates_args=(), device_types="cuda")
+def match_cost_op(xyz1: torch.Tensor, xyz2: torch.Tensor, match: torch.Tensor) -> torch.Tensor:
+    # MatchCostGpuOp::Compute, pc_distance/tf_approxmatch.cpp:201-229
+    b, n, m = _check_match_args("MatchCost", xyz1, xyz2, match)
+    xyz1, xyz2, match = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2), _cuda_f32("match", match)
+    cost = torch.empty((b,), dtype=torch.float32, device=xyz1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_matchcost_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(lib.rfnet_matchcost(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match), _ptr(cost), _ptr(ws), wsb, _stream(xyz1)), "rfnet_matchcost")
+    return cost
+
+
+@match_cost_op.register_fake
+def _(xyz1, xyz2, match):
+    return xyz1.new_empty((xyz1.shape[0],))
+
+
+@torch.library.custom_op("rfnet::match_cost_grad", mutates_args=(), device_types="cuda")
+def match_cost_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, match: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    # MatchCostGradGpuOp::Compute, pc_distance/tf_approxmatch.cpp:262-294
+    b, n, m = _check_match_args("MatchCostGrad", xyz1, xyz2, match)
+    xyz1, xyz2, match = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2), _cuda_f32("match", match)
+    g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    lib = _lib.load()
+    wsb = lib.rfnet_matchcostgrad_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(lib.rfnet_matchcostgrad(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match), _ptr(g1), _ptr(g2), _ptr(ws), wsb, _stream(xyz1)),
+                   "rfnet_matchcostgrad")
+    return g1, g2
+
+
+@match_cost_grad_op.register_fake
+def _(xyz1, xyz2, match):
+    return torch.empty_like(xyz1), torch.empty_like(xyz2)
+
+
+def _match_cost_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _match_cost_backward(ctx, grad_cost):
+    # pc_distance/tf_approxmatch.py:44-50: grads scaled by grad_cost[:,None,None]; no gradient to match
+    xyz1, xyz2, match = ctx.saved_tensors
+    g1, g2 = match_cost_grad_op(xyz1, xyz2, match)
+    s = grad_cost[:, None, None]
+    return g1 * s, g2 * s, None
+
+
+match_cost_op.register_autograd(_match_cost_backward, setup_context=_match_cost_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------ sampling
+@torch.library.custom_op("rfnet::farthest_point_sample", mutates_args=(), device_types="cuda")
+def farthest_point_sample_op(inp: torch.Tensor, npoint: int) -> torch.Tensor:
+    # FarthestPointSampleGpuOp, tf_ops/sampling/tf_sampling.cpp:95-123
+    _require(npoint > 0, "FarthestPointSample expects positive npoint")
+    _require(inp.dim() == 3 and inp.shape[2] == 3, "FarthestPointSample expects (batch_size,num_points,3) inp shape")
+    inp = _cuda_f32("inp", inp)
+    b, n = inp.shape[0], inp.shape[1]
+    out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_farthestpointsampling_workspace_bytes(b, n, npoint)
+    ws = _workspace(wsb, inp.device)
+    with torch.cuda.device(inp.device):
+        _lib.check(lib.rfnet_farthestpointsampling(b, n, npoint, _ptr(inp), _ptr(ws), wsb, _ptr(out), _stream(inp)), "rfnet_farthestpointsampling")
+    return out
+
+
+@farthest_point_sample_op.register_fake
+def _(inp, npoint):
+    return inp.new_empty((inp.shape[0], npoint), dtype=torch.int32)
+
+
+@torch.library.custom_op("rfnet::gather_point", mutates_args=(), device_types="cuda")
+def gather_point_op(inp: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    # GatherPointGpuOp, tf_ops/sampling/tf_sampling.cpp:126-148
+    _require(inp.dim() == 3 and inp.shape[2] == 3, "GatherPoint expects (batch_size,num_points,3) inp shape")
+    _require(idx.dim() == 2 and idx.shape[0] == inp.shape[0], "GatherPoint expects (batch_size,num_result) idx shape")
+    inp, idx = _cuda_f32("inp", inp), _cuda_i32("idx", idx)
+    b, n, m = inp.shape[0], inp.shape[1], idx.shape[1]
+    out = torch.empty((b, m, 3), dtype=torch.float32, device=inp.device)
+    with torch.cuda.device(inp.device):
+        _lib.check(_lib.load().rfnet_gatherpoint(b, n, m, _ptr(inp), _ptr(idx), _ptr(out), _stream(inp)), "rfnet_gatherpoint")
+    return out
+
+
+@gather_point_op.register_fake
+def _(inp, idx):
+    return inp.new_empty((inp.shape[0], idx.shape[1], 3))
+
+
+@torch.library.custom_op("rfnet::gather_point_grad", mutates_args=(), device_types="cuda")
+def gather_point_grad_op(inp: torch.Tensor, idx: torch.Tensor, out_g: torch.Tensor) -> torch.Tensor:
+    # GatherPointGradGpuOp, tf_ops/sampling/tf_sampling.cpp:151-178
+    _require(inp.dim() == 3 and inp.shape[2] == 3, "GatherPointGradGpuOp expects (batch_size,num_points,3) inp")
+    _require(idx.dim() == 2 and idx.shape[0] == inp.shape[0], "GatherPointGradGpuOp expects (batch_size,num_result) idx shape")
+    b, n, m = inp.shape[0], inp.shape[1], idx.shape[1]
+    _require(out_g.dim() == 3 and tuple(out_g.shape) == (b, m, 3), "GatherPointGradGpuOp expects (batch_size,num_result,3) out_g shape")
+    idx, out_g = _cuda_i32("idx", idx), _cuda_f32("out_g", out_g)
+    inp_g = torch.empty((b, n, 3), dtype=torch.float32, device=out_g.device)
+    with torch.cuda.device(out_g.device):
+        _lib.check(_lib.load().rfnet_scatteraddpoint(b, n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _stream(out_g)), "rfnet_scatteraddpoint")
+    return inp_g
+
+
+@gather_point_grad_op.register_fake
+def _(inp, idx, out_g):
+    return torch.empty_like(inp)
+
+
+def _gather_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _gather_backward(ctx, out_g):
+    inp, idx = ctx.saved_tensors  # tf_ops/sampling/tf_sampling.py:43-47
+    return gather_point_grad_op(inp, idx, out_g), None
+
+
+gather_point_op.register_autograd(_gather_backward, setup_context=_gather_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------ grouping
+@torch.library.custom_op("rfnet::query_ball_point", mutates_args=(), device_types="cuda")
+def query_ball_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, radius: torch.Tensor, nsample: int) -> tuple[torch.Tensor, torch.Tensor]:
+    # QueryBallPointGpuOp, tf_ops/grouping/tf_grouping.cpp:68-110 -- radius is a tensor input there too (:93-95)
+    _require(nsample > 0, "QueryBallPoint expects positive nsample")
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3, "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
+    _require(xyz2.shape[0] == xyz1.shape[0], "QueryBallPoint expects xyz1 and xyz2 have same batch size")
+    xyz1, xyz2, radius = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2), _cuda_f32("radius", radius)
+    _require(radius.numel() >= 1, "QueryBallPoint expects a radius")
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(_lib.load().rfnet_query_ball_point(b, n, m, _ptr(radius), nsample, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt), _stream(xyz1)),
+                   "rfnet_query_ball_point")
+    return idx, cnt
+
+
+@query_ball_point_op.register_fake
+def _(xyz1, xyz2, radius, nsample):
+    b, m = xyz2.shape[0], xyz2.shape[1]
+    return xyz1.new_empty((b, m, nsample), dtype=torch.int32), xyz1.new_empty((b, m), dtype=torch.int32)
+
+
+@torch.library.custom_op("rfnet::group_point", mutates_args=(), device_types="cuda")
+def group_point_op(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    # GroupPointGpuOp, tf_ops/grouping/tf_grouping.cpp:147-175
+    _require(points.dim() == 3, "GroupPoint expects (batch_size, num_points, channel) points shape")
+    _require(idx.dim() == 3 and idx.shape[0] == points.shape[0], "GroupPoint expects (batch_size, npoints, nsample) idx shape")
+    points, idx = _cuda_f32("points", points), _cuda_i32("idx", idx)
+    b, n, c = points.shape
+    m, ns = idx.shape[1], idx.shape[2]
+    out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.load().rfnet_group_point(b, n, c, m, ns, _ptr(points), _ptr(idx), _ptr(out), _stream(points)), "rfnet_group_point")
+    return out
+
+
+@group_point_op.register_fake
+def _(points, idx):
+    return points.new_empty((points.shape[0], idx.shape[1], idx.shape[2], points.shape[2]))
+
+
+@torch.library.custom_op("rfnet::group_point_grad", mutates_args=(), device_types="cuda")
+def group_point_grad_op(points: torch.Tensor, idx: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    # GroupPointGradGpuOp, tf_ops/grouping/tf_grouping.cpp:178-212
+    _require(points.dim() == 3, "GroupPointGrad expects (batch_size, num_points, channel) points shape")
+    _require(idx.dim() == 3 and idx.shape[0] == points.shape[0], "GroupPointGrad expects (batch_size, npoints, nsample) idx shape")
+    b, n, c = points.shape
+    m, ns = idx.shape[1], idx.shape[2]
+    _require(grad_out.dim() == 4 and tuple(grad_out.shape) == (b, m, ns, c), "GroupPointGrad expects (batch_size, npoints, nsample, channel) grad_out shape")
+    idx, grad_out = _cuda_i32("idx", idx), _cuda_f32("grad_out", grad_out)
+    g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(_lib.load().rfnet_group_point_grad(b, n, c, m, ns, _ptr(grad_out), _ptr(idx), _ptr(g), _stream(grad_out)), "rfnet_group_point_grad")
+    return g
+
+
+@group_point_grad_op.register_fake
+def _(points, idx, grad_out):
+    return torch.empty_like(points)
+
+
+def _group_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _group_backward(ctx, grad_out):
+    points, idx = ctx.saved_tensors  # tf_ops/grouping/tf_grouping.py:42-46
+    return group_point_grad_op(points, idx, grad_out), None
+
+
+group_point_op.register_autograd(_group_backward, setup_context=_group_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------ interpolation
+@torch.library.custom_op("rfnet::three_nn", mutates_args=(), device_types="cuda")
+def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    # ThreeNNOp, tf_ops/interpolation/tf_interpolate.cpp:157-187
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ThreeNN expects (b,n,3) xyz1 shape")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3, "ThreeNN expects (b,m,3) xyz2 shape")
+    _require(xyz2.shape[0] == xyz1.shape[0], "ThreeNN expects xyz1 and xyz2 have same batch size")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(_lib.load().rfnet_three_nn(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _stream(xyz1)), "rfnet_three_nn")
+    return dist, idx
+
+
+@three_nn_op.register_fake
+def _(xyz1, xyz2):
+    b, n = xyz1.shape[0], xyz1.shape[1]
+    return xyz1.new_empty((b, n, 3)), xyz1.new_empty((b, n, 3), dtype=torch.int32)
+
+
+def _check_interp(op, points, idx, weight):
+    _require(points.dim() == 3, "%s expects (b,m,c) points shape" % op)
+    b = points.shape[0]
+    _require(idx.dim() == 3 and idx.shape[0] == b and idx.shape[2] == 3, "%s expects (b,n,3) idx shape" % op)
+    _require(weight.dim() == 3 and tuple(weight.shape) == tuple(idx.shape), "%s expects (b,n,3) weight shape" % op)
+
+
+@torch.library.custom_op("rfnet::three_interpolate", mutates_args=(), device_types="cuda")
+def three_interpolate_op(points: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    # ThreeInterpolateOp, tf_ops/interpolation/tf_interpolate.cpp:191-222
+    _check_interp("ThreeInterpolate", points, idx, weight)
+    points, idx, weight = _cuda_f32("points", points), _cuda_i32("idx", idx), _cuda_f32("weight", weight)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    out = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.load().rfnet_three_interpolate(b, m, c, n, _ptr(points), _ptr(idx), _ptr(weight), _ptr(out), _stream(points)),
+                   "rfnet_three_interpolate")
+    return out
+
+
+@three_interpolate_op.register_fake
+def _(points, idx, weight):
+    return points.new_empty((points.shape[0], idx.shape[1], points.shape[2]))
+
+
+@torch.library.custom_op("rfnet::three_interpolate_grad", mutates_args=(), device_types="cuda")
+def three_interpolate_grad_op(points: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    # ThreeInterpolateGradOp, tf_ops/interpolation/tf_interpolate.cpp:226-262
+    _check_interp("ThreeInterpolateGrad", points, idx, weight)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    _require(grad_out.dim() == 3 and tuple(grad_out.shape) == (b, n, c), "ThreeInterpolateGrad expects (b,n,c) grad_out shape")
+    idx, weight, grad_out = _cuda_i32("idx", idx), _cuda_f32("weight", weight), _cuda_f32("grad_out", grad_out)
+    g = torch.empty((b, m, c), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(_lib.load().rfnet_three_interpolate_grad(b, n, c, m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g), _stream(grad_out)),
+                   "rfnet_three_interpolate_grad")
+    return g
+
+
+@three_interpolate_grad_op.register_fake
+def _(points, idx, weight, grad_out):
+    return torch.empty_like(points)
+
+
+def _interp_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _interp_backward(ctx, grad_out):
+    points, idx, weight = ctx.saved_tensors  # tf_ops/interpolation/tf_interpolate.py:29-34
+    return three_interpolate_grad_op(points, idx, weight, grad_out), None, None
+
+
+three_interpolate_op.register_autograd(_interp_backward, setup_context=_interp_setup)

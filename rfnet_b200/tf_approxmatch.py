@@ -1,0 +1,29 @@
+"""Drop-in for the reference's pc_distance/tf_approxmatch.py."""
+from . import ops
+
+
+def approx_match(xyz1, xyz2):
+    '''
+input:
+	xyz1 : batch_size * #dataset_points * 3
+	xyz2 : batch_size * #query_points * 3
+returns:
+	match : batch_size * #query_points * #dataset_points
+
+No gradient flows through approx_match (ops.NoGradient('ApproxMatch'), tf_approxmatch.py:19).
+    '''
+    return ops.approx_match_op(xyz1.detach(), xyz2.detach())
+
+
+def match_cost(xyz1, xyz2, match):
+    '''
+input:
+	xyz1 : batch_size * #dataset_points * 3
+	xyz2 : batch_size * #query_points * 3
+	match : batch_size * #query_points * #dataset_points
+returns:
+	cost : batch_size
+
+Differentiable w.r.t. xyz1 and xyz2 (not match), as RegisterGradient('MatchCost') (tf_approxmatch.py:44-50).
+    '''
+    return ops.match_cost_op(xyz1, xyz2, match.detach())

@@ -1,0 +1,51 @@
+"""Drop-in for the reference's tf_ops/grouping/tf_grouping.py."""
+import torch
+
+from . import ops
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    '''
+    Input:
+        radius: float32, ball search radius (python float or 1-element tensor)
+        nsample: int32, number of points selected in each ball region
+        xyz1: (batch_size, ndataset, 3) float32 array, input points
+        xyz2: (batch_size, npoint, 3) float32 array, query points
+    Output:
+        idx: (batch_size, npoint, nsample) int32 array, indices to input points
+        pts_cnt: (batch_size, npoint) int32 array, number of unique points in each local region
+
+    Rows with no point inside the ball hold 0 (the reference leaves them uninitialised) and pts_cnt 0.
+    '''
+    if not isinstance(radius, torch.Tensor):
+        radius = torch.tensor([float(radius)], dtype=torch.float32, device=xyz1.device)
+    return ops.query_ball_point_op(xyz1.detach(), xyz2.detach(), radius.detach().reshape(-1), int(nsample))
+
+
+def group_point(points, idx):
+    '''
+    Input:
+        points: (batch_size, ndataset, channel) float32 array, points to sample from
+        idx: (batch_size, npoint, nsample) int32 array, indices to points
+    Output:
+        out: (batch_size, npoint, nsample, channel) float32 array, values sampled from points
+    '''
+    return ops.group_point_op(points, idx)
+
+
+def knn_point(k, xyz1, xyz2):
+    '''
+    Input:
+        k: int32, number of k in k-nn search
+        xyz1: (batch_size, ndataset, c) float32 array, input points
+        xyz2: (batch_size, npoint, c) float32 array, query points
+    Output:
+        val: (batch_size, npoint, k) float32 array, NEGATED squared L2 distances (the reference returns top_k(-dist))
+        idx: (batch_size, npoint, k) int32 array, indices to input points
+
+    The reference implements this with framework ops only (tf.nn.top_k on a materialised (b,m,n) matrix,
+    tf_grouping.py:64-73); so does this function -- it is outside the custom-kernel path.
+    '''
+    dist = ((xyz1[:, None, :, :] - xyz2[:, :, None, :]) ** 2).sum(-1)
+    val, idx = torch.topk(-dist, k=int(k), dim=-1)
+    return val, idx.to(torch.int32)

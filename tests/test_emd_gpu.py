@@ -1,0 +1,120 @@
+"""GPU parity of approx_match / match_cost / match_cost_grad against the CPU oracle and the reference CUDA kernels.
+Tolerance: 1e-4 relative (BASELINE.json north_star), measured against the largest entry of the compared tensor."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cloud
+from oracle import port, ref
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def close(got, want, rtol=RTOL):
+    scale = max(float(np.abs(want).max()), 1e-30)
+    err = float(np.abs(got - want).max())
+    assert err <= rtol * scale, "max abs err %.3e vs scale %.3e (rel %.3e)" % (err, scale, err / scale)
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# n = dataset points (xyz1), m = query points (xyz2); includes n != m (integer-division multipliers) and ragged tiles
+SHAPES = [(1, 1, 1), (2, 16, 16), (2, 100, 100), (1, 257, 130), (1, 64, 200), (2, 512, 512), (1, 1030, 1030)]
+
+
+@pytest.mark.parametrize("b,n,m", SHAPES)
+def test_approx_match_vs_oracle(cuda, rng, b, n, m):
+    from rfnet_b200 import tf_approxmatch
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    want = port.approx_match(x1, x2)
+    got = tf_approxmatch.approx_match(t(x1, cuda), t(x2, cuda)).cpu().numpy()
+    assert got.shape == (b, m, n)
+    close(got, want)
+    # transport-plan properties: non-negative, row/column mass bounded by the multipliers (tf_approxmatch.cu:4-10)
+    assert (got >= 0).all()
+    multiL, multiR = (1, n // m) if n >= m else (m // n, 1)
+    assert (got.sum(axis=1) <= multiL * (1 + 1e-3)).all() and (got.sum(axis=2) <= multiR * (1 + 1e-3)).all()
+
+
+def test_approx_match_noisy_copy(cuda, rng):
+    # second input distribution of SURVEY.md 8(d): GT + N(0, 0.01^2) noise (stresses the high levels)
+    from rfnet_b200 import tf_approxmatch
+    x1 = cloud(rng, 2, 400)
+    x2 = (x1 + rng.normal(0, 0.01, x1.shape)).astype(np.float32)
+    want = port.approx_match(x1, x2)
+    got = tf_approxmatch.approx_match(t(x1, cuda), t(x2, cuda)).cpu().numpy()
+    close(got, want)
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 100, 100), (1, 257, 130), (2, 512, 512)])
+def test_match_cost_and_grad_vs_oracle(cuda, rng, b, n, m):
+    from rfnet_b200 import ops, tf_approxmatch
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    match = port.approx_match(x1, x2)
+    want_cost = port.match_cost(x1, x2, match)
+    got_cost = tf_approxmatch.match_cost(t(x1, cuda), t(x2, cuda), t(match, cuda)).cpu().numpy()
+    assert np.allclose(got_cost, want_cost, rtol=RTOL, atol=0)
+    w1, w2 = port.match_cost_grad(x1, x2, match)
+    g1, g2 = ops.match_cost_grad_op(t(x1, cuda), t(x2, cuda), t(match, cuda))
+    close(g1.cpu().numpy(), w1)
+    close(g2.cpu().numpy(), w2)
+
+
+def test_earth_mover_autograd(cuda, rng):
+    """earth_mover (vv_recon.py:392-399) forward + backward: gradient = match_cost_grad scaled by 1/(B*n)."""
+    from rfnet_b200 import losses
+    b, n = 3, 256
+    x1n, x2n = cloud(rng, b, n), cloud(rng, b, n)
+    x1 = t(x1n, cuda).requires_grad_(True)
+    x2 = t(x2n, cuda).requires_grad_(True)
+    loss = losses.earth_mover(x1, x2)
+    loss.backward()
+    match = port.approx_match(x1n, x2n)
+    cost = port.match_cost(x1n, x2n, match)
+    assert abs(loss.item() - float((cost / n).mean())) <= RTOL * abs(float((cost / n).mean()))
+    w1, w2 = port.match_cost_grad(x1n, x2n, match)
+    close(x1.grad.cpu().numpy(), w1 / (b * n), rtol=2e-4)
+    close(x2.grad.cpu().numpy(), w2 / (b * n), rtol=2e-4)
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+@pytest.mark.parametrize("b,n,m", [(2, 512, 512), (1, 2048, 2048), (1, 1000, 3000)])
+def test_emd_vs_reference_cuda_kernels(cuda, rng, b, n, m):
+    """Against the reference's own CUDA kernels (tf_approxmatch.cu recompiled for sm_100a), same inputs."""
+    from rfnet_b200 import ops, tf_approxmatch
+    x1, x2 = t(cloud(rng, b, n), cuda), t(cloud(rng, b, m), cuda)
+    (want,) = ref.run_gpu("ApproxMatch", [x1, x2], [((b, m, n), torch.float32)])
+    got = tf_approxmatch.approx_match(x1, x2)
+    close(got.cpu().numpy(), want.cpu().numpy())
+    (wcost,) = ref.run_gpu("MatchCost", [x1, x2, want], [((b,), torch.float32)])
+    gcost = tf_approxmatch.match_cost(x1, x2, want)
+    assert np.allclose(gcost.cpu().numpy(), wcost.cpu().numpy(), rtol=RTOL)
+    wg1, wg2 = ref.run_gpu("MatchCostGrad", [x1, x2, want], [((b, n, 3), torch.float32), ((b, m, 3), torch.float32)])
+    g1, g2 = ops.match_cost_grad_op(x1, x2, want)
+    close(g1.cpu().numpy(), wg1.cpu().numpy())
+    close(g2.cpu().numpy(), wg2.cpu().numpy())
+
+
+def test_emd_full_size_properties(cuda):
+    """BASELINE config 3 size (n = m = 16384, one cloud): mass conservation of the plan and cost consistency.
+    Every dataset point ends up (almost) fully matched: column sums of match == 1 within 1e-3."""
+    from rfnet_b200 import tf_approxmatch
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = 16384
+    x1 = (torch.rand((1, n, 3), generator=g) - 0.5).to(cuda)
+    x2 = (torch.rand((1, n, 3), generator=g) - 0.5).to(cuda)
+    match = tf_approxmatch.approx_match(x1, x2)
+    assert match.shape == (1, n, n) and bool((match >= 0).all())
+    rows, cols = match.sum(dim=2), match.sum(dim=1)
+    assert float(rows.max()) <= 1 + 1e-3 and float(cols.max()) <= 1 + 1e-3
+    assert float(cols.mean()) > 0.99  # nearly all mass is transported after the level-0 pass
+    cost = tf_approxmatch.match_cost(x1, x2, match)
+    # cost = <match, dist> computed independently with torch in float64 on a 2048-column slab
+    sl = slice(0, 2048)
+    d = torch.cdist(x2.double(), x1[:, sl].double())          # (1, m, 2048): match[l,k] pairs xyz2[l] with xyz1[k]
+    part = (match[:, :, sl].double() * d).sum()
+    full_est = part * (n / 2048.0)
+    assert abs(cost.item() - full_est.item()) < 0.05 * abs(full_est.item())

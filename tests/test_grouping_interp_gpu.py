@@ -1,0 +1,158 @@
+"""GPU parity of query_ball_point / group_point / three_nn / three_interpolate (+grads)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cloud
+from oracle import port, ref
+
+pytestmark = pytest.mark.gpu
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("b,n,m,ns,r", [(1, 128, 8, 32, 0.3), (2, 1000, 77, 16, 0.1), (2, 5000, 300, 32, 0.1), (3, 2050, 129, 5, 0.05),
+                                        (2, 300, 40, 64, 10.0), (2, 300, 40, 8, 1e-6), (1, 4500, 33, 1, 0.2)])
+def test_query_ball_point_bit_exact(cuda, rng, b, n, m, ns, r):
+    """idx and pts_cnt bit-exact.  (1,128,8,32,0.3) is the shape of the reference's own test, tf_grouping_op_test.py:9-25.
+    r = 10 covers every point in the ball (early exit), r = 1e-6 covers empty rows (defined as 0 in both)."""
+    from rfnet_b200 import tf_grouping
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    x2[:, : min(m, 5)] = x1[:, : min(m, 5)]  # queries that coincide with dataset points (d = 0 -> max(.,1e-20) branch)
+    wi, wc = port.query_ball_point(r, ns, x1, x2, fill_empty=0)
+    gi, gc = tf_grouping.query_ball_point(r, ns, t(x1, cuda), t(x2, cuda))
+    assert np.array_equal(gc.cpu().numpy(), wc)
+    assert np.array_equal(gi.cpu().numpy(), wi)
+
+
+def test_ball_threshold_is_exact(cuda):
+    """The sqrt-free predicate: on distances straddling r the kernel must agree with max(sqrtf(d2),1e-20f) < r."""
+    from rfnet_b200 import tf_grouping
+    r = np.float32(0.1)
+    # candidates at distance r*(1+k*2^-23) along x from the query, k = -40..40: d2 values are adjacent floats around r^2
+    ks = np.arange(-40, 41)
+    xs = (r * (1 + ks * 2.0 ** -23)).astype(np.float32)
+    x1 = np.zeros((1, len(ks), 3), np.float32)
+    x1[0, :, 0] = xs
+    x2 = np.zeros((1, 1, 3), np.float32)
+    wi, wc = port.query_ball_point(float(r), 128, x1, x2)
+    gi, gc = tf_grouping.query_ball_point(float(r), 128, t(x1, cuda), t(x2, cuda))
+    assert np.array_equal(gc.cpu().numpy(), wc) and np.array_equal(gi.cpu().numpy(), wi)
+    assert 0 < wc[0, 0] < len(ks)
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+def test_query_ball_point_vs_reference_cuda_kernel(cuda, rng):
+    from rfnet_b200 import tf_grouping
+    b, n, m, ns = 4, 16384, 512, 32
+    x1, x2 = t(cloud(rng, b, n), cuda), t(cloud(rng, b, m), cuda)
+    r = torch.tensor([0.1], device=cuda)
+    wi, wc = ref.run_gpu("QueryBallPoint", [x1, x2, r], [((b, m, ns), torch.int32), ((b, m), torch.int32)], attrs={"nsample": ns}, zero_outputs=True)
+    gi, gc = tf_grouping.query_ball_point(r, ns, x1, x2)
+    assert torch.equal(gc, wc) and torch.equal(gi, wi)
+
+
+@pytest.mark.parametrize("c", [1, 3, 16, 64, 6])
+def test_group_point_and_grad(cuda, rng, c):
+    from rfnet_b200 import ops, tf_grouping
+    b, n, m, ns = 2, 300, 50, 9
+    pts = rng.standard_normal((b, n, c)).astype(np.float32)
+    idx = rng.integers(0, n, size=(b, m, ns)).astype(np.int32)
+    got = tf_grouping.group_point(t(pts, cuda), t(idx, cuda)).cpu().numpy()
+    assert np.array_equal(got, port.group_point(pts, idx))
+    go = rng.standard_normal((b, m, ns, c)).astype(np.float32)
+    want = port.group_point_grad(pts, idx, go)
+    gg = ops.group_point_grad_op(t(pts, cuda), t(idx, cuda), t(go, cuda)).cpu().numpy()
+    assert np.allclose(gg, want, rtol=1e-5, atol=1e-5)
+
+
+def test_group_point_gradient_check_like_reference(cuda):
+    """tf_grouping_op_test.py:9-25: query_ball_point(0.3, 32) on (1,128,3)/(1,8,3) + group_point on (1,128,16);
+    numeric-vs-analytic gradient error of GroupPointGrad < 1e-4."""
+    from rfnet_b200 import tf_grouping
+    r = np.random.default_rng(0)
+    pts = torch.from_numpy(r.random((1, 128, 16)).astype(np.float32)).to(cuda)
+    x1 = torch.from_numpy(r.random((1, 128, 3)).astype(np.float32)).to(cuda)
+    x2 = torch.from_numpy(r.random((1, 8, 3)).astype(np.float32)).to(cuda)
+    idx, _ = tf_grouping.query_ball_point(0.3, 32, x1, x2)
+    w = torch.from_numpy(r.standard_normal((1, 8, 32, 16)).astype(np.float32)).to(cuda)
+    p = pts.clone().requires_grad_(True)
+    (tf_grouping.group_point(p, idx) * w).sum().backward()
+    # the op is linear in points: the exact gradient is the scatter of w
+    want = torch.zeros_like(pts).double()
+    want.index_put_((torch.zeros_like(idx).long().reshape(-1), idx.long().reshape(-1)), w.double().reshape(-1, 16), accumulate=True)
+    assert float((p.grad.double() - want).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("b,n,m", [(1, 128, 8), (2, 1000, 300), (2, 4100, 2049), (1, 50, 2), (1, 10, 1)])
+def test_three_nn_bit_exact(cuda, rng, b, n, m):
+    from rfnet_b200 import tf_interpolate
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    x2[:, m // 2:] = x2[:, : m - m // 2]  # duplicates: ties resolved by insertion order
+    wd, wi = port.three_nn(x1, x2, fused=False)
+    gd, gi = tf_interpolate.three_nn(t(x1, cuda), t(x2, cuda))
+    assert np.array_equal(gi.cpu().numpy(), wi)
+    assert np.array_equal(gd.cpu().numpy(), wd)
+
+
+@pytest.mark.parametrize("c", [1, 5, 16, 64])
+def test_three_interpolate_and_grad(cuda, rng, c):
+    from rfnet_b200 import ops, tf_interpolate
+    b, n, m = 2, 700, 90
+    pts = rng.standard_normal((b, m, c)).astype(np.float32)
+    idx = rng.integers(0, m, size=(b, n, 3)).astype(np.int32)
+    w = rng.random((b, n, 3)).astype(np.float32)
+    got = tf_interpolate.three_interpolate(t(pts, cuda), t(idx, cuda), t(w, cuda)).cpu().numpy()
+    assert np.array_equal(got, port.three_interpolate(pts, idx, w))  # same unfused operation order -> bit-exact
+    go = rng.standard_normal((b, n, c)).astype(np.float32)
+    want = port.three_interpolate_grad(pts, idx, w, go)
+    gg = ops.three_interpolate_grad_op(t(pts, cuda), t(idx, cuda), t(w, cuda), t(go, cuda)).cpu().numpy()
+    assert np.allclose(gg, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+def test_three_interpolate_gradient_check_like_reference(cuda):
+    """tf_interpolate_op_test.py:9-21: points (1,8,16), xyz1 (1,128,3), xyz2 (1,8,3), weights 1/3; gradient error < 1e-4."""
+    from rfnet_b200 import tf_interpolate
+    r = np.random.default_rng(1)
+    pts = torch.from_numpy(r.random((1, 8, 16)).astype(np.float32)).to(cuda)
+    x1 = torch.from_numpy(r.random((1, 128, 3)).astype(np.float32)).to(cuda)
+    x2 = torch.from_numpy(r.random((1, 8, 3)).astype(np.float32)).to(cuda)
+    _, idx = tf_interpolate.three_nn(x1, x2)
+    w = torch.full((1, 128, 3), 1.0 / 3.0, device=cuda)
+    up = torch.from_numpy(r.standard_normal((1, 128, 16)).astype(np.float32)).to(cuda)
+    p = pts.clone().requires_grad_(True)
+    (tf_interpolate.three_interpolate(p, idx, w) * up).sum().backward()
+    want = torch.zeros((1, 8, 16), device=cuda, dtype=torch.float64)
+    for u in range(3):
+        want.index_put_((torch.zeros(128, dtype=torch.long, device=cuda), idx[0, :, u].long()), (up[0].double() / 3.0), accumulate=True)
+    assert float((p.grad.double() - want).abs().max()) < 1e-4
+
+
+def test_config4_pipeline_properties(cuda):
+    """BASELINE config 4 at full size: FPS 16384->2048, ball query r=0.1 k=32, group (c=3), three_nn + interpolate (c=64).
+    Checked through size-independent properties (the small-shape tests above are the bit-exact ones)."""
+    from rfnet_b200 import tf_grouping, tf_interpolate, tf_sampling
+    g = torch.Generator(device="cpu").manual_seed(11)
+    b, n, m, ns = 32, 16384, 2048, 32
+    x = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    q = tf_sampling.gather_point(x, tf_sampling.farthest_point_sample(m, x))
+    idx, cnt = tf_grouping.query_ball_point(0.1, ns, x, q)
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= ns           # every query is itself a dataset point
+    grouped = tf_grouping.group_point(x, idx)                      # (b, m, ns, 3)
+    d = (grouped - q[:, :, None, :]).norm(dim=-1)
+    assert float(d.max()) < 0.1 + 1e-6                             # everything returned lies inside the ball
+    asc = idx[:, :, 1:] >= idx[:, :, :-1]
+    valid = torch.arange(1, ns, device=cuda)[None, None, :] < cnt[:, :, None]
+    assert bool((asc | ~valid).all())                              # hits are in ascending dataset order
+    dist, i3 = tf_interpolate.three_nn(x, q)
+    assert bool((dist[..., 0] <= dist[..., 1]).all() and (dist[..., 1] <= dist[..., 2]).all())
+    w = 1.0 / torch.clamp(dist, min=1e-10)
+    w = w / w.sum(-1, keepdim=True)
+    feats = torch.randn((b, m, 64), generator=torch.Generator(device="cpu").manual_seed(1)).to(cuda)
+    out = tf_interpolate.three_interpolate(feats, i3, w)
+    ref_out = (torch.gather(feats, 1, i3[..., 0].long()[..., None].expand(-1, -1, 64)) * w[..., 0:1]
+               + torch.gather(feats, 1, i3[..., 1].long()[..., None].expand(-1, -1, 64)) * w[..., 1:2]
+               + torch.gather(feats, 1, i3[..., 2].long()[..., None].expand(-1, -1, 64)) * w[..., 2:3])
+    assert torch.allclose(out, ref_out, rtol=1e-5, atol=1e-6)

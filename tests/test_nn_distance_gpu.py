@@ -1,0 +1,122 @@
+"""GPU parity of nn_distance / its gradient against the CPU oracle (bit-exact indices AND distances)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cloud
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, x1, x2, unfused=False):
+    from rfnet_b200 import tf_nndistance
+    out = tf_nndistance.nn_distance(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), unfused=unfused)
+    return [o.cpu().numpy() for o in out]
+
+
+# (b, n, m): ragged sizes, tiles that do not divide, TMA-aligned (m % 4 == 0) and unaligned rows, n or m tiny
+SHAPES = [(1, 1, 1), (2, 5, 3), (3, 64, 1024), (2, 300, 257), (2, 1000, 1029), (1, 2048, 2048), (2, 2049, 4100), (4, 515, 8192), (1, 4096, 37)]
+
+
+@pytest.mark.parametrize("b,n,m", SHAPES)
+@pytest.mark.parametrize("unfused", [False, True])
+def test_nn_distance_bit_exact(cuda, rng, b, n, m, unfused):
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    want = port.nn_distance(x1, x2, fused=not unfused)
+    got = _run(cuda, x1, x2, unfused)
+    for name, g, w in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+        assert g.dtype == w.dtype and g.shape == w.shape
+        assert np.array_equal(g, w), "%s differs at %d positions" % (name, (g != w).sum())
+
+
+def test_nn_distance_ties_pick_lowest_index(cuda, rng):
+    # duplicated candidates (data_util.resample_pcd duplicates points): ties must go to the first index
+    base = cloud(rng, 2, 200)
+    x2 = np.concatenate([base, base, base[:, :37]], axis=1)  # every point appears 2-3 times
+    x1 = cloud(rng, 2, 333)
+    x1[:, :50] = base[:, :50]  # exact hits, distance 0
+    want = port.nn_distance(x1, x2, fused=True)
+    got = _run(cuda, x1, x2)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert (got[1][:, :50] == np.arange(50)).all()
+
+
+def test_nn_distance_integer_grid_many_ties(cuda):
+    # points on a coarse integer grid: many exactly equal distances
+    r = np.random.default_rng(7)
+    x1 = r.integers(-3, 4, size=(3, 700, 3)).astype(np.float32)
+    x2 = r.integers(-3, 4, size=(3, 1500, 3)).astype(np.float32)
+    want = port.nn_distance(x1, x2, fused=True)
+    got = _run(cuda, x1, x2)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_nn_distance_large_property(cuda):
+    """BASELINE config 2 shape (B=32, 2048 vs 16384): too big for the scalar oracle in seconds, so check properties:
+    the reported distance is exactly d2(query, candidate[idx]) and no candidate of a random sample is closer or ties with
+    a lower index; a sampled subset of queries is checked against the oracle in full."""
+    g = torch.Generator(device="cpu").manual_seed(2)
+    b, n, m = 32, 2048, 16384
+    x1 = (torch.rand((b, n, 3), generator=g) - 0.5)
+    x2 = (torch.rand((b, m, 3), generator=g) - 0.5)
+    d1, i1, d2, i2 = _run(cuda, x1.numpy(), x2.numpy())
+    assert i1.min() >= 0 and i1.max() < m and i2.min() >= 0 and i2.max() < n
+    # oracle on a slice: clouds 0 and 31, first 64 queries of each direction
+    for c in (0, 31):
+        w = port.nn_distance(x1[c:c + 1, :64].numpy(), x2[c:c + 1].numpy(), fused=True)
+        assert np.array_equal(d1[c, :64], w[0][0]) and np.array_equal(i1[c, :64], w[1][0])
+        w = port.nn_distance(x2[c:c + 1, :64].numpy(), x1[c:c + 1].numpy(), fused=True)
+        assert np.array_equal(d2[c, :64], w[0][0]) and np.array_equal(i2[c, :64], w[1][0])
+    # min property over everything, in float64 with a tolerance far below the gaps (exactness is covered above)
+    x1d, x2d = x1.double().to(cuda), x2.double().to(cuda)
+    full = torch.cdist(x1d, x2d) ** 2
+    assert np.allclose(full.min(dim=2).values.cpu().numpy(), d1, rtol=1e-5, atol=1e-9)
+    assert np.allclose(full.min(dim=1).values.cpu().numpy(), d2, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 5, 3), (2, 300, 257), (3, 1024, 2050)])
+def test_nn_distance_grad(cuda, rng, b, n, m):
+    from rfnet_b200 import ops
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    _, i1, _, i2 = port.nn_distance(x1, x2)
+    g1 = rng.standard_normal((b, n)).astype(np.float32)
+    g2 = rng.standard_normal((b, m)).astype(np.float32)
+    want = port.nn_distance_grad(x1, x2, g1, i1, g2, i2)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    got = ops.nn_distance_grad_op(t(x1), t(x2), t(g1), t(i1), t(g2), t(i2))
+    for g, w in zip(got, want):
+        # accumulation order differs (atomics vs sequential): 1e-5 relative to the largest gradient component
+        assert np.allclose(g.cpu().numpy(), w, rtol=1e-5, atol=1e-5 * np.abs(w).max())
+
+
+def test_nn_distance_autograd_matches_reference_formula(cuda, rng):
+    from rfnet_b200 import losses
+    x1 = torch.from_numpy(cloud(rng, 2, 400)).to(cuda).requires_grad_(True)
+    x2 = torch.from_numpy(cloud(rng, 2, 300)).to(cuda).requires_grad_(True)
+    loss, _ = losses.chamfer_big(x1, x2)
+    loss.backward()
+    # same loss built from oracle indices with plain torch ops
+    a, c = x1.detach().cpu().double().requires_grad_(True), x2.detach().cpu().double().requires_grad_(True)
+    _, i1, _, i2 = port.nn_distance(a.detach().float().numpy(), c.detach().float().numpy())
+    i1, i2 = torch.from_numpy(i1).long(), torch.from_numpy(i2).long()
+    d1 = ((a - torch.gather(c, 1, i1[..., None].expand(-1, -1, 3))) ** 2).sum(-1)
+    d2 = ((c - torch.gather(a, 1, i2[..., None].expand(-1, -1, 3))) ** 2).sum(-1)
+    ref = (d1.sqrt().mean() + d2.sqrt().mean()) / 2
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert np.allclose(x1.grad.cpu().numpy(), a.grad.numpy(), rtol=1e-4, atol=1e-7)
+    assert np.allclose(x2.grad.cpu().numpy(), c.grad.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_nn_distance_empty_and_errors(cuda):
+    from rfnet_b200 import tf_nndistance
+    z = torch.zeros((0, 5, 3), device=cuda)
+    out = tf_nndistance.nn_distance(z, torch.zeros((0, 7, 3), device=cuda))
+    assert [tuple(o.shape) for o in out] == [(0, 5), (0, 5), (0, 7), (0, 7)]
+    with pytest.raises(ValueError, match="3d point set xyz1"):
+        tf_nndistance.nn_distance(torch.zeros((1, 5, 2), device=cuda), torch.zeros((1, 7, 3), device=cuda))
+    with pytest.raises(ValueError, match="same batch size"):
+        tf_nndistance.nn_distance(torch.zeros((1, 5, 3), device=cuda), torch.zeros((2, 7, 3), device=cuda))
