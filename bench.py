@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): Chamfer nearest-neighbour search, forward + gradient.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- nn_distance forward + NnDistanceGrad, B=32 clouds per GPU, partial
+2048 points vs dense 16384 points, synthetic uniform [-0.5,0.5]^3 clouds.  One step = one pass over one
+batch.  Unit of work = point pair (2*B*N*M per step, two directed searches).  Batches are sharded over ranks with no
+data-path collective; the only exchange is the 16-byte all-reduce of the loss partial sums (weak scaling: B per GPU fixed).
+
+One JSON line on stdout (rank 0).  Besides the contract's keys it carries
+  roofline      the dominant kernel (nn_search_kernel) against the FP32 pipe: 6 lane-ops per pair (3 sub, 1 mul, 2 fma --
+                the reference's operand order admits no fewer), peak = 148 SMs x 128 lanes x sm clock
+  cpu_baseline  the reference's own CPU kernel (oracle/_ref: /root/reference/pc_distance/tf_nndistance.cpp compiled
+                unmodified) timed on this host's cores on a bounded sample of the same workload
+  e2e           the same metric through the public API from pinned HOST buffers, copies inside the timed region
+  extra         north-star shape (B=32, 16384^2) and EMD clouds/s, measured after the timed region (not part of `value`)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, N, M = 32, 2048, 16384          # BASELINE.json configs[1], per GPU
+WORKLOAD = "chamfer_nn_fwd+grad B=32/gpu N=2048(partial) M=16384(dense) fp32 xyz"
+METRIC = "chamfer_nn_point_pairs_per_s"
+UNIT = "Gpairs/s"
+L2_BYTES = 126 * 1024 * 1024
+LANE_OPS_PER_PAIR = 6.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the post-run extra measurements")
+    return ap.parse_args()
+
+
+def host_clouds(nclouds, npts, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return (rng.random((nclouds, npts, 3), dtype=np.float32) - 0.5)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU NnDistance + NnDistanceGrad kernels on all host threads
+# ------------------------------------------------------------------------------------------------------------------
+_CPU_INPUTS = {}
+
+
+def cpu_reference_rate(nclouds, repeats=1):
+    """Gpairs/s of the reference CPU kernels over `nclouds` clouds of the workload shape, one cloud per task, all cores."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    from oracle import port, ref
+    kind = "reference" if ref.available("cpu") else "port"
+    cores = os.cpu_count() or 1
+    if nclouds not in _CPU_INPUTS:
+        _CPU_INPUTS[nclouds] = (host_clouds(nclouds, N, 1), host_clouds(nclouds, M, 2))
+    x1, x2 = _CPU_INPUTS[nclouds]
+    g1, g2 = np.ones((1, N), np.float32), np.ones((1, M), np.float32)
+
+    def one(i):
+        a, c = x1[i:i + 1], x2[i:i + 1]
+        if kind == "reference":
+            d1, i1, d2, i2 = ref.nn_distance(a, c)             # ctypes releases the GIL: tasks run in parallel
+            ref.nn_distance_grad(a, c, g1, i1, g2, i2)
+        else:
+            d1, i1, d2, i2 = port.nn_distance(a, c, fused=False)
+            port.nn_distance_grad(a, c, g1, i1, g2, i2)
+        return float(d1[0, 0])
+
+    best = None
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(one, range(min(cores, nclouds))))          # warm-up (page in, spin up threads)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(nclouds)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    pairs = 2.0 * nclouds * N * M
+    return pairs / best / 1e9, best, cores, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    nclouds = max(cores, 8)                                    # bounded sample per step: ~0.15 core-seconds per cloud
+    rates, times = [], []
+    for s in range(args.warmup + args.steps):
+        rate, dt, cores, kind = cpu_reference_rate(nclouds)
+        if s >= args.warmup:
+            rates.append(rate)
+            times.append(dt)
+    value = 2.0 * nclouds * N * M * len(times) / sum(times) / 1e9
+    sample = "%d clouds of the workload shape per step (of %d per GPU batch), one cloud per task on %d host threads" % (nclouds, B, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs during the timed region
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag, self.ok = index, [], set(), None, threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            self.sample()
+            time.sleep(0.005)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- rfnet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    from rfnet_b200 import _lib, losses, ops, tf_approxmatch, tf_nndistance
+    lib = _lib.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs: enough distinct batches that consecutive steps never find their inputs in L2 (rotating sets > L2)
+    set_bytes = B * (N + M) * 12
+    nsets = max(2, -(-int(1.5 * L2_BYTES) // set_bytes))
+    h1 = torch.from_numpy(host_clouds(nsets * B, N, 1000 * 2 + rank)).reshape(nsets, B, N, 3).pin_memory()
+    h2 = torch.from_numpy(host_clouds(nsets * B, M, 7000 * 2 + rank)).reshape(nsets, B, M, 3).pin_memory()
+    d1s, d2s = h1.to(dev), h2.to(dev)
+    gd1 = torch.full((B, N), 0.5 / (B * N * world), device=dev)   # upstream grads of a mean-type loss
+    gd2 = torch.full((B, M), 0.5 / (B * M * world), device=dev)
+    sums = torch.zeros(4, device=dev)
+
+    def step(i):
+        x1, x2 = d1s[i % nsets], d2s[i % nsets]
+        dist1, idx1, dist2, idx2 = ops.nn_distance_op(x1, x2)
+        g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
+        part = losses.chamfer_partial_sums(dist1, dist2)            # the loss-level reduction of chamfer_big
+        losses.all_reduce_scalars(part)                             # the path's only collective: 16 bytes
+        sums.copy_(part)
+        return g1, g2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- count OUR kernels in one step (CUPTI activity records, outside the timed region)
+    launches_per_step = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(0)
+            torch.cuda.synchronize()
+        launches_per_step = sum(1 for e in prof.events() if "rfnet" in e.name)
+    except Exception:
+        launches_per_step = None
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.sample()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    sampler.sample()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    pairs_per_step = 2.0 * B * N * M * world
+    value = pairs_per_step * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- dominant kernel against its roofline: the forward search alone, CUDA events on its stream
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record()
+    for i in range(args.steps):
+        ops.nn_distance_op(d1s[i % nsets], d2s[i % nsets])
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / args.steps
+    clocks = sampler.result()
+    sm_max = (clocks["sm_max_mhz"] or 1965) * 1e6
+    peak = 148 * 128 * sm_max / 1e12                               # T lane-ops/s at max clock
+    achieved = 2.0 * B * N * M * LANE_OPS_PER_PAIR / (fwd_ms * 1e-3) / 1e12
+    # measured FP32 pipe peak: a dependency-free FFMA2 stream on every SM (rfnet_probe_fp32)
+    import ctypes
+    sink = torch.zeros(4, device=dev)
+    lane_ops = ctypes.c_ulonglong(0)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.rfnet_probe_fp32(2000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(lane_ops), stream)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    lib.rfnet_probe_fp32(20000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(lane_ops), stream)
+    p1.record()
+    torch.cuda.synchronize()
+    peak_measured = lane_ops.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    roofline = {"bound": "fp32_fma_pipe", "kernel": "rfnet::nn_search_kernel (timed as the forward call: + 2 key-unpack kernels, ~1%)",
+                "achieved": achieved, "peak": peak, "unit": "Tlaneop/s", "frac": achieved / peak,
+                "peak_source": "148 SMs x 128 FP32 lanes x %.0f MHz (architectural; MEASURED_PEAKS.json has no FP32-pipe figure)" % (sm_max / 1e6),
+                "peak_measured_ffma2_stream": peak_measured, "frac_of_measured": achieved / peak_measured,
+                "algorithmic_laneops_per_pair": LANE_OPS_PER_PAIR, "fwd_ms": fwd_ms, "traffic": None}
+
+    # ---- e2e: the same step through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+    out_d1 = torch.empty((B, N), dtype=torch.float32).pin_memory()
+    out_d2 = torch.empty((B, M), dtype=torch.float32).pin_memory()
+    out_g1 = torch.empty((B, N, 3), dtype=torch.float32).pin_memory()
+    out_g2 = torch.empty((B, M, 3), dtype=torch.float32).pin_memory()
+    out_loss = torch.empty(4, dtype=torch.float32).pin_memory()
+    k_e2e = max(3, min(args.steps, 50))
+
+    def e2e_step(i):
+        x1 = h1[i % nsets].to(dev, non_blocking=True)
+        x2 = h2[i % nsets].to(dev, non_blocking=True)
+        dist1, idx1, dist2, idx2 = tf_nndistance.nn_distance(x1, x2)
+        g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
+        part = losses.all_reduce_scalars(losses.chamfer_partial_sums(dist1, dist2))
+        out_d1.copy_(dist1, non_blocking=True)
+        out_d2.copy_(dist2, non_blocking=True)
+        out_g1.copy_(g1, non_blocking=True)
+        out_g2.copy_(g2, non_blocking=True)
+        out_loss.copy_(part, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(k_e2e):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step * k_e2e / (float(t.item()) * 1e-3) / 1e9
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": B * (N + M) * 4 + B * (N + M) * 12 + 16,
+           "steps": k_e2e, "api": "rfnet_b200.tf_nndistance.nn_distance + rfnet::nn_distance_grad on pinned host tensors"}
+
+    # ---- extras (rank 0, not part of `value`): north-star shape and EMD
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        def timed(fn, iters):
+            fn()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / iters
+        g = torch.Generator(device="cpu").manual_seed(5)
+        y1 = (torch.rand((B, M, 3), generator=g) - 0.5).to(dev)
+        y2 = (torch.rand((B, M, 3), generator=g) - 0.5).to(dev)
+        ms_ns = timed(lambda: ops.nn_distance_op(y1, y2), 10)
+        pr = 2.0 * B * M * M
+        extra["chamfer_nn_fwd_B32_16384x16384"] = {"ms": ms_ns, "Gpairs_per_s": pr / ms_ns / 1e6, "frac_fp32_peak": pr * LANE_OPS_PER_PAIR / (ms_ns * 1e-3) / 1e12 / peak}
+        for (eb, en) in ((32, 2048), (4, 16384)):
+            z1, z2 = y1[:eb, :en].contiguous(), y2[:eb, :en].contiguous()
+            ms_e = timed(lambda: tf_approxmatch.match_cost(z1, z2, tf_approxmatch.approx_match(z1, z2)), 3)
+            extra["emd_approx_match+match_cost_B%d_n%d" % (eb, en)] = {"ms": ms_e, "clouds_per_s": eb / ms_e * 1e3,
+                                                                      "frac_mufu_peak": eb / (ms_e * 1e-3) * 30.0 * en * en / (148 * 16 * sm_max)}
+        del y1, y2
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": pairs_per_step, "clouds_per_gpu": B, "parallelism": "batch-sharded x%d, 16-byte loss all-reduce" % world,
+                       "l2": "rotating %d input batches (%.0f MB > 126 MB L2), one per step" % (nsets, nsets * set_bytes / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step or 0) * args.steps, "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "extra": extra}
+
+    if rank == 0 and world == 1:
+        try:
+            cores = os.cpu_count() or 1
+            rate, dt, cores, kind = cpu_reference_rate(max(2 * cores, 16), repeats=2)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%d clouds of the workload shape (N=%d, M=%d), fwd+grad, one cloud per task on %d threads, best of 2 (%.1f s)" % (max(2 * cores, 16), N, M, cores, dt)}
+        except Exception as ex:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

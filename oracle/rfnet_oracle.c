@@ -108,16 +108,18 @@ RFO_API void rfo_approxmatch(int b, int n, int m, const float *xyz1, const float
         for (int j = start_level; j >= -2; j--) {
             float level = -powf(4.0f, (float)j);
             if (j == -2) level = 0;
+            /* The multiply-adds below are fused exactly where nvcc fuses them in the reference binary (sm_100a PTX of
+             * tf_approxmatch.cu: fma(e, remainR, suml); fma(e, ratioL, sumr); t = ratioL*e, fma(t, ratioR, match), fma(t, ratioR, suml)). */
             /* pass 1 (.cu:26-59): ratioL[k] = remainL[k] / (1e-9 + sum_l e(k,l) * remainR[l]) */
             for (int k = 0; k < n; k++) {
                 float suml = 1e-9f;
-                for (int l = 0; l < m; l++) suml += expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * remainR[l];
+                for (int l = 0; l < m; l++) suml = fmaf(expf(level * sqdist(B + 3 * l, A + 3 * k, 1)), remainR[l], suml);
                 ratioL[k] = remainL[k] / suml;
             }
             /* pass 2 (.cu:75-108): column sums with ratioL, consumption clamp, remainR update */
             for (int l = 0; l < m; l++) {
                 float sumr = 0;
-                for (int k = 0; k < n; k++) sumr += expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * ratioL[k];
+                for (int k = 0; k < n; k++) sumr = fmaf(expf(level * sqdist(B + 3 * l, A + 3 * k, 1)), ratioL[k], sumr);
                 sumr *= remainR[l];
                 float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
                 ratioR[l] = consumption * remainR[l];
@@ -127,9 +129,9 @@ RFO_API void rfo_approxmatch(int b, int n, int m, const float *xyz1, const float
             for (int k = 0; k < n; k++) {
                 float suml = 0;
                 for (int l = 0; l < m; l++) {
-                    float w = expf(level * sqdist(B + 3 * l, A + 3 * k, 1)) * ratioL[k] * ratioR[l];
-                    M[(size_t)l * n + k] += w;
-                    suml += w;
+                    float t = ratioL[k] * expf(level * sqdist(B + 3 * l, A + 3 * k, 1));
+                    M[(size_t)l * n + k] = fmaf(t, ratioR[l], M[(size_t)l * n + k]);
+                    suml = fmaf(t, ratioR[l], suml);
                 }
                 remainL[k] = fmaxf(0.0f, remainL[k] - suml);
             }

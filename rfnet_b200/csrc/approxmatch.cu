@@ -66,12 +66,18 @@ static EmdWs emd_carve(float* w, int b, int n, int m) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Weighted exp-sum sweep:  partial[cloud][split][row] = sum_{c in split} ex2(lvl2 * d2(row, c)) * w[c]
-//   rows: (b, nr, 3), cands: (b, nc, 3), w: (b, nc).  grid.x = b * nrt * nsplit.
+// Weighted exp-sum sweep:  partial[cloud][split][row] = init + sum_{c in split, ascending} ex2(lvl2 * d2(row, c)) * w[c]
+//   rows: (b, nr, 3), cands: (b, nc, 3), w: (b, nc).  grid.x = b * nrt * nsplit.  Q rows per thread (Q/2 packed pairs).
+// The accumulation is the reference binary's, term by term and in candidate order:
+//   passes 1 and 2:  acc = fma(e, w[c], acc)                       (acc starts at 1e-9 in pass 1: tf_approxmatch.cu:36)
+//   pass 3 (PASS3):  acc = fma(rowfac[row] * e, w[c], acc)         (t = ratioL*e; suml = fma(t, ratioR, suml))
+// so with nsplit == 1 every row sum is bit-identical to what the reference's thread computes.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2,
+template <int Q, bool PASS3>
+__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2, float init0,
                                                                const float* __restrict__ rows, const float* __restrict__ cands,
-                                                               const float* __restrict__ w, float* __restrict__ partial) {
+                                                               const float* __restrict__ w, const float* __restrict__ rowfac,
+                                                               float* __restrict__ partial) {
     __shared__ __align__(16) float4 sC[EMD_TC];
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -82,16 +88,22 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
     const float* __restrict__ cbase = cands + (size_t)cloud * nc * 3;
     const float* __restrict__ wbase = w + (size_t)cloud * nc;
 
-    const int r0 = tile * (EMD_THREADS * EMD_Q) + tid;
-    float2 rx[EMD_Q / 2], ry[EMD_Q / 2], rz[EMD_Q / 2], acc[EMD_Q / 2];
+    const int r0 = tile * (EMD_THREADS * Q) + tid;
+    float2 rx[Q / 2], ry[Q / 2], rz[Q / 2], rf[Q / 2], acc[Q / 2];
+    const float a0 = split == 0 ? init0 : 0.0f;
 #pragma unroll
-    for (int h = 0; h < EMD_Q / 2; ++h) {
+    for (int h = 0; h < Q / 2; ++h) {
         const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
         const bool va = ia < nr, vb = ib < nr;
         // rows are kept NEGATED so that (cand - row) is one FADD2 with a broadcast scalar: c + (-r) == c - r exactly
         rx[h].x = va ? -rbase[(size_t)ia * 3 + 0] : 0.f; ry[h].x = va ? -rbase[(size_t)ia * 3 + 1] : 0.f; rz[h].x = va ? -rbase[(size_t)ia * 3 + 2] : 0.f;
         rx[h].y = vb ? -rbase[(size_t)ib * 3 + 0] : 0.f; ry[h].y = vb ? -rbase[(size_t)ib * 3 + 1] : 0.f; rz[h].y = vb ? -rbase[(size_t)ib * 3 + 2] : 0.f;
-        acc[h] = make_float2(0.f, 0.f);
+        rf[h] = make_float2(1.f, 1.f);
+        if (PASS3) {
+            rf[h].x = va ? rowfac[(size_t)cloud * nr + ia] : 0.f;
+            rf[h].y = vb ? rowfac[(size_t)cloud * nr + ib] : 0.f;
+        }
+        acc[h] = make_float2(a0, a0);
     }
     const float2 L2 = make_float2(lvl2, lvl2);
 
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
         const int len = min(EMD_TC, c_end - c0);
         __syncthreads();
         for (int i = tid; i < EMD_TC; i += EMD_THREADS) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padded candidates carry weight 0
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padded candidates carry weight 0: fma(e, 0, acc) == acc
             if (i < len) {
                 const float* c = cbase + (size_t)(c0 + i) * 3;
                 v = make_float4(c[0], c[1], c[2], wbase[c0 + i]);
@@ -114,19 +126,20 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
         for (int k = 0; k < len2; ++k) {
             const float4 c = sC[k];
 #pragma unroll
-            for (int h = 0; h < EMD_Q / 2; ++h) {
-                const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // cand - row, as tf_approxmatch.cu:51
+            for (int h = 0; h < Q / 2; ++h) {
+                const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // the sign of the difference is irrelevant after squaring
                 const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
                 const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
                 const float2 a = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
-                const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                if (PASS3) e = __fmul2_rn(rf[h], e);
                 acc[h] = __ffma2_rn(e, make_float2(c.w, c.w), acc[h]);
             }
         }
     }
     float* __restrict__ out = partial + ((size_t)cloud * nsplit + split) * nr;
 #pragma unroll
-    for (int h = 0; h < EMD_Q / 2; ++h) {
+    for (int h = 0; h < Q / 2; ++h) {
         const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
         if (ia < nr) out[ia] = acc[h].x;
         if (ib < nr) out[ib] = acc[h].y;
@@ -135,8 +148,8 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
 
 // ---- epilogues: one thread per row; sum the split partials in fixed order, then the pass's update rule -----------
 __device__ __forceinline__ float emd_sum_partials(const float* __restrict__ partial, size_t cloud, int nsplit, int nr, int r) {
-    float s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) s += partial[(cloud * nsplit + sp) * nr + r];
+    float s = partial[(cloud * nsplit) * nr + r];
+    for (int sp = 1; sp < nsplit; ++sp) s += partial[(cloud * nsplit + sp) * nr + r];
     return s;
 }
 __global__ void emd_init_kernel(size_t bn, size_t bm, float multiL, float multiR, float* __restrict__ remainL, float* __restrict__ remainR) {
@@ -149,7 +162,7 @@ __global__ void emd_epi1_kernel(int n, int nsplit, size_t bn, const float* __res
                                 float* __restrict__ ratioL, float* __restrict__ facL) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bn) return;
-    const float suml = 1e-9f + emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));
+    const float suml = emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));  // the 1e-9 seed is inside split 0
     const float r = remainL[t] / suml;
     ratioL[t] = r;
     facL[t] = r;
@@ -168,11 +181,10 @@ __global__ void emd_epi2_kernel(int m, int nsplit, size_t bm, const float* __res
     remainR[t] = fmaxf(0.0f, rem - sumr);
 }
 // pass 3 (tf_approxmatch.cu:127-160), without the match write: remainL[k] = max(0, remainL[k] - ratioL[k] * sum_l e*ratioR[l])
-__global__ void emd_epi3_kernel(int n, int nsplit, size_t bn, const float* __restrict__ partial, const float* __restrict__ ratioL,
-                                float* __restrict__ remainL) {
+__global__ void emd_epi3_kernel(int n, int nsplit, size_t bn, const float* __restrict__ partial, float* __restrict__ remainL) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= bn) return;
-    const float suml = ratioL[t] * emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));
+    const float suml = emd_sum_partials(partial, t / n, nsplit, n, (int)(t % n));  // ratioL is applied per term in the sweep
     remainL[t] = fmaxf(0.0f, remainL[t] - suml);
 }
 
@@ -333,19 +345,40 @@ __global__ void __launch_bounds__(G2_WARPS * 32) matchcostgrad2_kernel(int n, in
     }
 }
 
-static void emd_sweep(int b, int nr, int nc, float lvl2, const float* rows, const float* cands, const float* w, float* partial, int& nsplit_out,
-                      cudaStream_t s) {
-    const int nrt = (nr + EMD_THREADS * EMD_Q - 1) / (EMD_THREADS * EMD_Q);
+// Sweep launch policy.  Prefer NO candidate split -- row sums then follow the reference's order bit for bit -- whenever the
+// batch alone fills the chip: rows-per-thread Q = 8, 4 or 2 with at least 8, 4 or 4 CTAs per SM respectively.  Otherwise
+// (few or small clouds) the candidate range is split across CTAs and the partials are summed in split order: still
+// deterministic, but a different rounding order than the reference's single sequential chain.
+struct SweepPlan { int Q, nrt, nsplit, cps; };
+static SweepPlan emd_plan(int b, int nr, int nc) {
+    SweepPlan p;
     const int chunks = (nc + EMD_TC - 1) / EMD_TC;
-    // aim for >= 32 CTAs per SM (several waves, small tail); never more splits than emd_max_split() reserved room for
-    long want = ((long)kNumSMs * 32 + (long)b * nrt - 1) / ((long)b * nrt);
+    const int qs[3] = {8, 4, 2};
+    const long need[3] = {8L * kNumSMs, 4L * kNumSMs, 4L * kNumSMs};
+    for (int i = 0; i < 3; ++i) {
+        p.Q = qs[i];
+        p.nrt = (nr + EMD_THREADS * p.Q - 1) / (EMD_THREADS * p.Q);
+        if ((long)b * p.nrt >= need[i]) { p.nsplit = 1; p.cps = chunks; return p; }
+    }
+    p.Q = nr >= EMD_THREADS * 4 ? 4 : 2;
+    p.nrt = (nr + EMD_THREADS * p.Q - 1) / (EMD_THREADS * p.Q);
+    long want = ((long)kNumSMs * 8 + (long)b * p.nrt - 1) / ((long)b * p.nrt);
     int nsplit = (int)(want < 1 ? 1 : want);
     if (nsplit > chunks) nsplit = chunks;
     if (nsplit > 32) nsplit = 32;
-    const int cps = (chunks + nsplit - 1) / nsplit;
-    nsplit = (chunks + cps - 1) / cps;
-    nsplit_out = nsplit;
-    emd_sweep_kernel<<<(unsigned)(b * nrt * nsplit), EMD_THREADS, 0, s>>>(nr, nc, nrt, nsplit, cps, lvl2, rows, cands, w, partial);
+    p.cps = (chunks + nsplit - 1) / nsplit;
+    p.nsplit = (chunks + p.cps - 1) / p.cps;
+    return p;
+}
+template <bool PASS3>
+static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands, const float* w, const float* rowfac,
+                      float* partial, int& nsplit_out, cudaStream_t s) {
+    const SweepPlan p = emd_plan(b, nr, nc);
+    nsplit_out = p.nsplit;
+    const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
+    if (p.Q == 8) emd_sweep_kernel<8, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+    else if (p.Q == 4) emd_sweep_kernel<4, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+    else emd_sweep_kernel<2, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
 }
 
 }  // namespace rfnet
@@ -374,14 +407,14 @@ extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const f
         lv.lvl2[li] = lvl2;
         int ns;
         // pass 1: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR
-        emd_sweep(b, n, m, lvl2, xyz1, xyz2, ws.remainR, ws.partial, ns, s);
+        emd_sweep<false>(b, n, m, lvl2, 1e-9f, xyz1, xyz2, ws.remainR, nullptr, ws.partial, ns, s);
         emd_epi1_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn);
         // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL
-        emd_sweep(b, m, n, lvl2, xyz2, xyz1, ws.ratioL, ws.partial, ns, s);
+        emd_sweep<false>(b, m, n, lvl2, 0.0f, xyz2, xyz1, ws.ratioL, nullptr, ws.partial, ns, s);
         emd_epi2_kernel<<<(unsigned)((bm + 255) / 256), 256, 0, s>>>(m, ns, bm, ws.partial, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm);
         // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR
-        emd_sweep(b, n, m, lvl2, xyz1, xyz2, ws.ratioR, ws.partial, ns, s);
-        emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.ratioL, ws.remainL);
+        emd_sweep<true>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, ns, s);
+        emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL);
     }
     dim3 grid((unsigned)((n + MT_THREADS - 1) / MT_THREADS), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
     RFNET_CHECK_ARG(grid.y <= 65535);

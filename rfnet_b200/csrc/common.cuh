@@ -54,9 +54,14 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// 2^x on the MUFU pipe.  The reference's __expf compiles to ex2.approx.f32 WITHOUT .ftz, which ptxas expands to
+// FSETP + FMUL + MUFU.EX2 + FMUL (halve the argument / square the result below 2^-126 so that denormal results survive).
+// The .ftz form is the bare MUFU.EX2: identical bits whenever the result is a normal number, and 0 instead of a denormal
+// (< 1.2e-38) otherwise -- a difference that cannot reach any output of approx_match (every sum it enters carries a 1e-9
+// regulariser or is compared against one), and buys ~25 % of the sweep's FMA-pipe time.
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
-    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 

@@ -1,0 +1,123 @@
+"""CPU tier: the oracle (oracle/rfnet_oracle.c) against the reference.
+
+* against tests/golden/ref_cpu.npz -- outputs of the reference's CPU OpKernels (always available);
+* against tests/golden/ref_gpu.npz -- outputs of the reference's CUDA kernels captured on a B200 (when committed);
+* live against oracle/_ref/libref_cpu.so where that library exists (build container, and the GPU box via the snapshot);
+* against the numpy formula the reference documents as its intended check (tf_ops/CD/tf_nndistance.py:72-80).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import cloud
+from oracle import port, ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip(name + " not generated yet")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden_cpu_nn_distance(tag):
+    g = gold("ref_cpu.npz")
+    x1, x2 = g["nn_%s_xyz1" % tag], g["nn_%s_xyz2" % tag]
+    d1, i1, d2, i2 = port.nn_distance(x1, x2, fused=False)   # the reference CPU build does not contract
+    for k, v in dict(dist1=d1, idx1=i1, dist2=d2, idx2=i2).items():
+        assert np.array_equal(v, g["nn_%s_%s" % (tag, k)]), k
+    gx1, gx2 = port.nn_distance_grad(x1, x2, g["nn_%s_gd1" % tag], i1, g["nn_%s_gd2" % tag], i2)
+    assert np.array_equal(gx1, g["nn_%s_gxyz1" % tag]) and np.array_equal(gx2, g["nn_%s_gxyz2" % tag])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden_cpu_emd(tag):
+    g = gold("ref_cpu.npz")
+    x1, x2 = g["emd_%s_xyz1" % tag], g["emd_%s_xyz2" % tag]
+    twin = port.approx_match_cpu_twin(x1, x2)
+    assert np.array_equal(twin, g["emd_%s_match_nm" % tag])           # restatement of the CPU kernel: bit-exact
+    # GPU-contract oracle with 11 levels vs the CPU kernel (transposed): same algorithm up to update-order details
+    gpu_like = port.approx_match(x1, x2, start_level=8).transpose(0, 2, 1)
+    assert np.abs(gpu_like - twin).max() < 5e-3
+    m_mn = np.ascontiguousarray(twin.transpose(0, 2, 1))
+    assert np.allclose(port.match_cost(x1, x2, m_mn), g["emd_%s_cost" % tag], rtol=1e-5)
+    g1, g2 = port.match_cost_grad(x1, x2, m_mn)
+    assert np.allclose(g1, g["emd_%s_grad1" % tag], rtol=1e-4, atol=1e-5)
+    assert np.allclose(g2, g["emd_%s_grad2" % tag], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden_cpu_interpolation(tag):
+    g = gold("ref_cpu.npz")
+    p = lambda k: g["interp_%s_%s" % (tag, k)]
+    dist, idx = port.three_nn(p("xyz1"), p("xyz2"), fused=False)
+    assert np.array_equal(dist, p("dist")) and np.array_equal(idx, p("idx"))
+    assert np.array_equal(port.three_interpolate(p("points"), idx, p("weight")), p("out"))
+    assert np.array_equal(port.three_interpolate_grad(p("points"), idx, p("weight"), p("grad_out")), p("grad_points"))
+
+
+def test_golden_gpu_reference_kernels():
+    """Oracle vs what the reference's CUDA kernels produced on a B200 (indices bit-exact, EMD within 1e-4)."""
+    g = gold("ref_gpu.npz")
+    for tag in ("a", "b"):
+        d1, i1, d2, i2 = port.nn_distance(g["nn_%s_xyz1" % tag], g["nn_%s_xyz2" % tag], fused=True)
+        for k, v in dict(dist1=d1, idx1=i1, dist2=d2, idx2=i2).items():
+            assert np.array_equal(v, g["nn_%s_%s" % (tag, k)]), (tag, k)
+    for tag in ("a", "b", "c"):
+        inp, want = g["fps_%s_inp" % tag], g["fps_%s_idx" % tag]
+        assert np.array_equal(port.farthest_point_sample(want.shape[1], inp), want), tag
+    for tag in ("a", "b", "c"):
+        idx, cnt = port.query_ball_point(float(g["ball_%s_radius" % tag][0]), g["ball_%s_idx" % tag].shape[2], g["ball_%s_xyz1" % tag], g["ball_%s_xyz2" % tag], fill_empty=0)
+        assert np.array_equal(cnt, g["ball_%s_cnt" % tag]) and np.array_equal(idx, g["ball_%s_idx" % tag]), tag
+    for tag in ("a", "b"):
+        x1, x2, want = g["emd_%s_xyz1" % tag], g["emd_%s_xyz2" % tag], g["emd_%s_match" % tag]
+        got = port.approx_match(x1, x2)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+        assert np.allclose(port.match_cost(x1, x2, want), g["emd_%s_cost" % tag], rtol=1e-4)
+        g1, g2 = port.match_cost_grad(x1, x2, want)
+        assert np.abs(g1 - g["emd_%s_grad1" % tag]).max() <= 1e-4 * np.abs(g1).max()
+        assert np.abs(g2 - g["emd_%s_grad2" % tag]).max() <= 1e-4 * np.abs(g2).max()
+
+
+@pytest.mark.skipif(not ref.available("cpu"), reason="oracle/_ref/libref_cpu.so not built (needs /root/reference)")
+def test_live_against_reference_cpu_kernels(rng):
+    x1, x2 = cloud(rng, 3, 211), cloud(rng, 3, 97)
+    want = ref.nn_distance(x1, x2)
+    got = port.nn_distance(x1, x2, fused=False)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    g1, g2 = rng.standard_normal((3, 211)).astype(np.float32), rng.standard_normal((3, 97)).astype(np.float32)
+    assert all(np.array_equal(a, b) for a, b in zip(port.nn_distance_grad(x1, x2, g1, want[1], g2, want[3]), ref.nn_distance_grad(x1, x2, g1, want[1], g2, want[3])))
+    assert np.array_equal(port.approx_match_cpu_twin(x1, x2), ref.approx_match(x1, x2).reshape(3, 211, 97))
+    d, i = ref.three_nn(x1, x2)
+    pd, pi = port.three_nn(x1, x2, fused=False)
+    assert np.array_equal(d, pd) and np.array_equal(i, pi)
+    with pytest.raises(ValueError, match="3d point set xyz1"):       # OP_REQUIRES of the reference, tf_nndistance.cpp:67
+        ref.nn_distance(np.zeros((1, 4, 2), np.float32), np.zeros((1, 4, 3), np.float32))
+
+
+def test_nn_distance_against_documented_numpy_check(rng):
+    """tf_ops/CD/tf_nndistance.py:72-80: ((xyz1[:,s,None,:]-xyz2[:,None,:,:])**2).sum(-1).min/argmin(-1)."""
+    x1, x2 = cloud(rng, 2, 150), cloud(rng, 2, 220)
+    d1, i1, d2, i2 = port.nn_distance(x1, x2, fused=True)
+    full = ((x1[:, :, None, :].astype(np.float64) - x2[:, None, :, :]) ** 2).sum(-1)
+    assert np.array_equal(i1, full.argmin(-1)) and np.allclose(d1, full.min(-1), rtol=1e-5)
+    assert np.array_equal(i2, full.argmin(1)) and np.allclose(d2, full.min(1), rtol=1e-5)
+
+
+def test_oracle_edge_cases(rng):
+    # ties -> lowest index; FPS on duplicated points; ball query empty rows and full rows; three_nn with < 3 candidates
+    x = np.zeros((1, 4, 3), np.float32)
+    d1, i1, _, _ = port.nn_distance(x, x)
+    assert (i1 == 0).all() and (d1 == 0).all()
+    assert port.farthest_point_sample(3, x).tolist() == [[0, 0, 0]]
+    idx, cnt = port.query_ball_point(1e-6, 4, cloud(rng, 1, 20) + 5, cloud(rng, 1, 3))
+    assert (cnt == 0).all() and (idx == 0).all()
+    idx, cnt = port.query_ball_point(100.0, 4, cloud(rng, 1, 20), cloud(rng, 1, 3))
+    assert (cnt == 4).all() and (idx == np.arange(4)).all()
+    dist, idx = port.three_nn(cloud(rng, 1, 5), cloud(rng, 1, 2))
+    assert np.isinf(dist[..., 2]).all() and (idx[..., 2] == 0).all()
+    assert port.ball_threshold(0.1) <= np.float32(0.1) * np.float32(0.1)
