@@ -191,7 +191,7 @@ def main():
         x1, x2 = d1s[i % nsets], d2s[i % nsets]
         dist1, idx1, dist2, idx2 = ops.nn_distance_op(x1, x2)
         g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
-        part = losses.chamfer_partial_sums(dist1, dist2)            # the loss-level reduction of chamfer_big
+        part = ops.chamfer_partial_sums_op(dist1, dist2)            # the loss-level reduction of chamfer_big (vv_recon.py:381-385)
         losses.all_reduce_scalars(part)                             # the path's only collective: 16 bytes
         sums.copy_(part)
         return g1, g2
@@ -283,7 +283,7 @@ def main():
         x2 = h2[i % nsets].to(dev, non_blocking=True)
         dist1, idx1, dist2, idx2 = tf_nndistance.nn_distance(x1, x2)
         g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
-        part = losses.all_reduce_scalars(losses.chamfer_partial_sums(dist1, dist2))
+        part = losses.all_reduce_scalars(ops.chamfer_partial_sums_op(dist1, dist2))
         out_d1.copy_(dist1, non_blocking=True)
         out_d2.copy_(dist2, non_blocking=True)
         out_g1.copy_(g1, non_blocking=True)

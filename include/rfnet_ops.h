@@ -49,6 +49,13 @@ int rfnet_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *
                            const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
                            float *grad_xyz2, rfnet_stream_t stream);
 
+/* Loss-level epilogue of the reference's chamfer_big / fidelity_loss (vv_recon.py:381-390), which the reference leaves to
+ * framework ops: sums4 = { sum sqrt(dist1), b*n, sum sqrt(dist2), b*m } in a fixed summation order.  chamfer_big is then
+ * (sums4[0]/sums4[1] + sums4[2]/sums4[3]) / 2, and across GPUs the four numbers are what gets all-reduced. */
+size_t rfnet_chamfer_partial_sums_workspace_bytes(void);
+int rfnet_chamfer_partial_sums(int b, int n, int m, const float *dist1, const float *dist2, float *sums4,
+                               void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * approx_match / match_cost (EMD).  Replace approxmatchLauncher, matchcostLauncher, matchcostgradLauncher,
  * pc_distance/tf_approxmatch.cpp:141-143 (defined pc_distance/tf_approxmatch.cu:180-182,226-228,292-295).

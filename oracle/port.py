@@ -85,6 +85,31 @@ def approx_match(xyz1, xyz2, start_level=7):
     return match
 
 
+def approx_match_f64(xyz1, xyz2, start_level=7):
+    """Same algorithm in double precision: the yardstick for the float32 noise band of approx_match on these inputs."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    match = np.empty((b, m, n), np.float32)
+    lib().rfo_approxmatch_f64(b, n, m, p1, p2, match.ctypes.data_as(_f32p), int(start_level))
+    return match
+
+
+def approx_match_noise_band(xyz1, xyz2, match_f32=None):
+    """max |float32 oracle - float64 oracle| relative to the largest entry: how far two correct float32 evaluations of
+    approx_match may be expected to drift apart on these inputs."""
+    m32 = approx_match(xyz1, xyz2) if match_f32 is None else match_f32
+    m64 = approx_match_f64(xyz1, xyz2)
+    return float(np.abs(m32 - m64).max() / max(float(np.abs(m64).max()), 1e-30))
+
+
+def approx_match_tolerance(xyz1, xyz2, match_f32=None, floor=1e-4, factor=8.0, cap=5e-2):
+    """Tolerance (relative to the largest entry) for comparing two float32 evaluations of approx_match on these inputs:
+    `factor` x the measured float32 noise band, never tighter than `floor` (BASELINE.json's 1e-4) nor looser than `cap`."""
+    return min(cap, max(floor, factor * approx_match_noise_band(xyz1, xyz2, match_f32)))
+
+
 def approx_match_cpu_twin(xyz1, xyz2):
     """The reference's CPU variant: 11 levels, double accumulation, returned in its native (b, n, m) element order."""
     xyz1, p1 = _f(xyz1)

@@ -140,6 +140,53 @@ RFO_API void rfo_approxmatch(int b, int n, int m, const float *xyz1, const float
     free(remainL);
 }
 
+/* approx_match in DOUBLE precision (same algorithm and level schedule as rfo_approxmatch, exp() in double, no 1-ulp noise).
+ * Not a contract of the reference -- a yardstick: |rfo_approxmatch - rfo_approxmatch_f64| is the float32 rounding noise
+ * band of this ill-conditioned iteration on a given input, against which the parity tests scale their tolerance. */
+RFO_API void rfo_approxmatch_f64(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, int start_level) {
+    double *remainL = malloc(sizeof(double) * (size_t)(n + m) * 2);
+    double *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+    double *M = malloc(sizeof(double) * (size_t)n * m);
+    double multiL, multiR;
+    if (n >= m) { multiL = 1; multiR = (double)(n / m); } else { multiL = (double)(m / n); multiR = 1; }
+    for (int i = 0; i < b; i++) {
+        const float *A = xyz1 + (size_t)i * n * 3, *B = xyz2 + (size_t)i * m * 3;
+        for (size_t t = 0; t < (size_t)n * m; t++) M[t] = 0;
+        for (int k = 0; k < n; k++) remainL[k] = multiL;
+        for (int l = 0; l < m; l++) remainR[l] = multiR;
+        for (int j = start_level; j >= -2; j--) {
+            double level = j == -2 ? 0.0 : -pow(4.0, (double)j);
+#define D2(k, l) (((double)B[3*(l)]-A[3*(k)])*((double)B[3*(l)]-A[3*(k)]) + ((double)B[3*(l)+1]-A[3*(k)+1])*((double)B[3*(l)+1]-A[3*(k)+1]) + ((double)B[3*(l)+2]-A[3*(k)+2])*((double)B[3*(l)+2]-A[3*(k)+2]))
+            for (int k = 0; k < n; k++) {
+                double suml = 1e-9;
+                for (int l = 0; l < m; l++) suml += exp(level * D2(k, l)) * remainR[l];
+                ratioL[k] = remainL[k] / suml;
+            }
+            for (int l = 0; l < m; l++) {
+                double sumr = 0;
+                for (int k = 0; k < n; k++) sumr += exp(level * D2(k, l)) * ratioL[k];
+                sumr *= remainR[l];
+                double consumption = fmin(remainR[l] / (sumr + 1e-9), 1.0);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmax(0.0, remainR[l] - sumr);
+            }
+            for (int k = 0; k < n; k++) {
+                double suml = 0;
+                for (int l = 0; l < m; l++) {
+                    double w = exp(level * D2(k, l)) * ratioL[k] * ratioR[l];
+                    M[(size_t)l * n + k] += w;
+                    suml += w;
+                }
+                remainL[k] = fmax(0.0, remainL[k] - suml);
+            }
+#undef D2
+        }
+        for (size_t t = 0; t < (size_t)n * m; t++) match[(size_t)i * n * m + t] = (float)M[t];
+    }
+    free(M);
+    free(remainL);
+}
+
 /* approx_match, CPU twin.  pc_distance/tf_approxmatch.cpp:23-84: double accumulation, 11 levels (j = 8..-2),
  * match laid out (n, m): match[k*m + l] (.cpp:44,75).  Keeps the reference's n*m double weight matrix.          */
 RFO_API void rfo_approxmatch_cpu_twin(int b, int n, int m, const float *xyz1, const float *xyz2, float *match) {

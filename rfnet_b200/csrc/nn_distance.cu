@@ -10,8 +10,11 @@
 //     (cp.async.bulk + mbarrier, double buffered) -- plain loads when rows are not 16-byte aligned;
 //   * each thread keeps Q queries in registers as Q/2 packed pairs and evaluates two distances per instruction with
 //     Blackwell's packed FP32 pipe (FADD2 / FMUL2 / FFMA2); candidates are warp-broadcast LDS.128;
-//   * min tracking costs < 1 instruction per pair: eight distances and the running best are folded with four 3-input
-//     FMNMX3, one compare decides whether the rare slow path (find the FIRST index attaining the new minimum) runs;
+//   * min tracking is branch-free and costs 0.75 instruction per pair: eight distances and the running best are folded
+//     with four 3-input FMNMX3, one compare + one predicated move remember the 8-GROUP where the best strictly decreased;
+//     the index inside that group is recovered once per work item by re-evaluating its eight distances (same bits).
+//     (A first version branched to an index-selection slow path; ncu showed it taken in nearly every group, because 32
+//     lanes x 8 candidates almost always contain a new running minimum near the start of an item.)
 //   * splits are merged with a 64-bit atomicMin on (distance bits, index) keys, which is exactly the reference's
 //     "smallest distance, lowest index" rule.
 // The distance is evaluated in the reference's operand order (common.cuh: sqdist3x2), so indices are bit-exact.
@@ -42,7 +45,7 @@ struct NNParams {
 };
 
 template <int Q, bool FUSED>
-__global__ void __launch_bounds__(NN_THREADS) nn_search_kernel(const NNParams p) {
+__global__ void __launch_bounds__(NN_THREADS, 5) nn_search_kernel(const NNParams p) {
     static_assert(Q % 2 == 0, "queries are processed as packed pairs");
     __shared__ __align__(128) float sC[2][NN_TC * 3];
     __shared__ __align__(8) uint64_t bar[2];
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_search_kernel(const NNParams p)
     const int q0 = tile * (NN_THREADS * Q) + tid;
     float2 qx[Q / 2], qy[Q / 2], qz[Q / 2];
     float best[Q];
-    int besti[Q];
+    int bestk[Q];  // first candidate index of the 8-group in which `best` was attained
 #pragma unroll
     for (int h = 0; h < Q / 2; ++h) {
         const int ia = q0 + (2 * h) * NN_THREADS, ib = ia + NN_THREADS;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_search_kernel(const NNParams p)
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         best[i] = __int_as_float(0x7f800000);  // +inf: the first candidate always wins unless its distance is +inf too,
-        besti[i] = 0;                           // in which case index 0 stands -- same as the reference's k==0 seed
+        bestk[i] = 0;                           // in which case index 0 stands -- same as the reference's k==0 seed
     }
 
     const int nchunks_total = (nc + chunk - 1) / chunk;
@@ -145,43 +148,58 @@ __global__ void __launch_bounds__(NN_THREADS) nn_search_kernel(const NNParams p)
                     const float2 dz = __fadd2_rn(qz[h], make_float2(-cz[j], -cz[j]));
                     d[j] = sqdist3x2<FUSED>(dx, dy, dz);
                 }
+                // Branch-free min tracking: fold the eight distances and the running best with four FMNMX3; remember only
+                // the GROUP in which the best strictly decreased (one predicated move).  The index inside the group is
+                // recovered once per work item (resolve_group below).  Strict '<' keeps the FIRST group attaining the minimum.
                 {
                     const float g = fmin3(fmin3(d[0].x, d[1].x, d[2].x), fmin3(d[3].x, d[4].x, d[5].x), fmin3(d[6].x, d[7].x, best[2 * h]));
-                    if (g < best[2 * h]) {  // rare: a strictly smaller distance appeared; take the FIRST index attaining it
-                        best[2 * h] = g;
-                        int j = 7;
-#pragma unroll
-                        for (int t = 6; t >= 0; --t) j = (d[t].x == g) ? t : j;
-                        besti[2 * h] = kbase + j;
-                    }
+                    bestk[2 * h] = (g < best[2 * h]) ? kbase : bestk[2 * h];
+                    best[2 * h] = g;
                 }
                 {
                     const float g = fmin3(fmin3(d[0].y, d[1].y, d[2].y), fmin3(d[3].y, d[4].y, d[5].y), fmin3(d[6].y, d[7].y, best[2 * h + 1]));
-                    if (g < best[2 * h + 1]) {
-                        best[2 * h + 1] = g;
-                        int j = 7;
-#pragma unroll
-                        for (int t = 6; t >= 0; --t) j = (d[t].y == g) ? t : j;
-                        besti[2 * h + 1] = kbase + j;
-                    }
+                    bestk[2 * h + 1] = (g < best[2 * h + 1]) ? kbase : bestk[2 * h + 1];
+                    best[2 * h + 1] = g;
                 }
             }
         }
         __syncthreads();  // everyone is done with sbuf before the copy engine may overwrite it
     }
 
-    // ---- results
+    // ---- results: recover the index inside the winning group by re-evaluating its (up to) eight distances -- the same
+    // operations on the same operands as in the loop, hence the same bits -- and taking the first that equals `best`.
+    // (best, bestk) go through shared memory (the candidate buffers are free now: the loop ended with a barrier) so that
+    // this epilogue is a rolled loop and does not inflate the register budget of the main loop.
+    float* sBest = sC[0];
+    int* sBk = reinterpret_cast<int*>(sC[0]) + Q * NN_THREADS;
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
+        sBest[i * NN_THREADS + tid] = best[i];
+        sBk[i * NN_THREADS + tid] = bestk[i];
+    }
+#pragma unroll 1
+    for (int i = 0; i < Q; ++i) {
         const int qi = q0 + i * NN_THREADS;
-        if (qi < nq) {
-            const size_t o = (size_t)cloud * nq + qi;
-            if (D.nsplit == 1) {
-                D.dist[o] = best[i];
-                D.idx[o] = besti[i];
-            } else {
-                atomicMin(&D.keys[o], pack_key(best[i], besti[i]));
+        if (qi >= nq) break;
+        const float bd = sBest[i * NN_THREADS + tid];
+        const int k0 = sBk[i * NN_THREADS + tid];
+        const float qxs = qbase[(size_t)qi * 3 + 0], qys = qbase[(size_t)qi * 3 + 1], qzs = qbase[(size_t)qi * 3 + 2];
+        const int lim = min(8, nc - k0);
+        int j = 0;
+#pragma unroll
+        for (int t = 7; t >= 0; --t) {
+            if (t < lim) {
+                const float* __restrict__ c = cbase + (size_t)(k0 + t) * 3;
+                const float dd = sqdist3<FUSED>(qxs - c[0], qys - c[1], qzs - c[2]);  // (query - candidate), as in the loop
+                j = (dd == bd) ? t : j;
             }
+        }
+        const size_t o = (size_t)cloud * nq + qi;
+        if (D.nsplit == 1) {
+            D.dist[o] = bd;
+            D.idx[o] = k0 + j;
+        } else {
+            atomicMin(&D.keys[o], pack_key(bd, k0 + j));
         }
     }
 }
@@ -253,22 +271,69 @@ __global__ void nn_grad_scatter_kernel(int n, int m, const float* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Loss-level epilogue of chamfer_big / fidelity_loss (vv_recon.py:381-390): sums[0] = sum sqrt(dist1), sums[1] = #dist1,
+// sums[2] = sum sqrt(dist2), sums[3] = #dist2.  Two tiny launches, fixed summation order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CS_BLOCKS = 74;  // per direction
+__global__ void __launch_bounds__(256) chamfer_sums_kernel(size_t n1, size_t n2, const float* __restrict__ dist1, const float* __restrict__ dist2,
+                                                           float* __restrict__ partial) {
+    __shared__ float sW[8];
+    const int dir = blockIdx.x >= CS_BLOCKS;
+    const int blk = blockIdx.x - dir * CS_BLOCKS;
+    const float* __restrict__ d = dir ? dist2 : dist1;
+    const size_t n = dir ? n2 : n1;
+    float s = 0.f;
+    for (size_t i = (size_t)blk * 256 + threadIdx.x; i < n; i += (size_t)CS_BLOCKS * 256) s += __fsqrt_rn(d[i]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sW[i];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void chamfer_sums_final_kernel(size_t n1, size_t n2, const float* __restrict__ partial, float* __restrict__ sums) {
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int i = 0; i < CS_BLOCKS; ++i) t += partial[threadIdx.x * CS_BLOCKS + i];
+        sums[threadIdx.x * 2] = t;
+        sums[threadIdx.x * 2 + 1] = (float)(threadIdx.x ? n2 : n1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, long target_items) {
+constexpr int NN_CTAS_PER_SM = 5;  // __launch_bounds__(128, 5): 96 registers
+
+// One work item = one chunk of candidates for one query tile.  Every item pays a fixed price (query loads, pipeline fill,
+// index resolution, key merge) worth roughly 48 candidates of scanning, and the grid runs in ceil(items / resident CTAs)
+// rounds; pick the chunk length that minimises rounds x (chunk + 48).
+static int pick_chunk(int b, int n, int m, int Q) {
+    const int TQ = NN_THREADS * Q;
+    const long slots = (long)kNumSMs * NN_CTAS_PER_SM;
+    int best_chunk = NN_TC;
+    long best_cost = -1;
+    for (int chunk = NN_TC; chunk >= 256; chunk >>= 1) {
+        const long items = (long)b * ((n + TQ - 1) / TQ) * ((m + chunk - 1) / chunk) + (long)b * ((m + TQ - 1) / TQ) * ((n + chunk - 1) / chunk);
+        const long rounds = (items + slots - 1) / slots;
+        const int longest = (n > m ? n : m) < chunk ? (n > m ? n : m) : chunk;
+        const long cost = rounds * (longest + 48);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunk = chunk; }
+    }
+    return best_chunk;
+}
+
+static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, bool split) {
     D.nq = nq;
     D.nc = nc;
     const int TQ = NN_THREADS * Q;
     D.nqt = (nq + TQ - 1) / TQ;
-    int chunk = NN_TC;
-    while (chunk > 256 && (long)b * D.nqt * ((nc + chunk - 1) / chunk) < target_items) chunk >>= 1;
     D.chunk = chunk;
     const int nchunks = (nc + chunk - 1) / chunk;
-    long cps = ((long)b * D.nqt * nchunks) / target_items;
-    if (cps < 1) cps = 1;
-    if (cps > nchunks) cps = nchunks;
-    D.cps = (int)cps;
-    D.nsplit = (nchunks + D.cps - 1) / D.cps;
+    D.cps = split ? 1 : nchunks;
+    D.nsplit = split ? nchunks : 1;
     D.items = b * D.nqt * D.nsplit;
     D.tma = (nc % 4 == 0) && (((uintptr_t)D.c & 15u) == 0);
 }
@@ -308,9 +373,12 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     NNParams p;
     p.d[0].q = xyz1; p.d[0].c = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1;
     p.d[1].q = xyz2; p.d[1].c = xyz1; p.d[1].dist = dist2; p.d[1].idx = idx2;
-    const long target = (long)kNumSMs * 16;  // per direction
-    plan_direction(p.d[0], b, n, m, Q, target);
-    plan_direction(p.d[1], b, m, n, Q, target);
+    // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
+    // written directly, no key merge and no extra launches
+    const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
+    const int chunk = split ? pick_chunk(b, n, m, Q) : NN_TC;
+    plan_direction(p.d[0], b, n, m, Q, chunk, split);
+    plan_direction(p.d[1], b, m, n, Q, chunk, split);
     unsigned long long* keys = (unsigned long long*)workspace;
     p.d[0].keys = keys;
     p.d[1].keys = keys ? keys + (size_t)b * n : nullptr;
@@ -352,5 +420,17 @@ extern "C" int rfnet_nn_distance_grad(int b, int n, const float* xyz1, int m, co
     const unsigned grid = (unsigned)((t1 + t2 + 255) / 256);
     nn_grad_own_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, t1, t2);
     nn_grad_scatter_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, t1, t2);
+    return launch_status();
+}
+
+extern "C" size_t rfnet_chamfer_partial_sums_workspace_bytes(void) { return sizeof(float) * 2 * CS_BLOCKS; }
+
+extern "C" int rfnet_chamfer_partial_sums(int b, int n, int m, const float* dist1, const float* dist2, float* sums4, void* workspace,
+                                          size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && sums4 && workspace && workspace_bytes >= rfnet_chamfer_partial_sums_workspace_bytes());
+    RFNET_CHECK_ARG(((size_t)b * n == 0 || dist1) && ((size_t)b * m == 0 || dist2));
+    cudaStream_t s = (cudaStream_t)stream;
+    chamfer_sums_kernel<<<2 * CS_BLOCKS, 256, 0, s>>>((size_t)b * n, (size_t)b * m, dist1, dist2, (float*)workspace);
+    chamfer_sums_final_kernel<<<1, 32, 0, s>>>((size_t)b * n, (size_t)b * m, (const float*)workspace, sums4);
     return launch_status();
 }

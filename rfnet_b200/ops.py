@@ -124,6 +124,27 @@ def _nn_distance_backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
 nn_distance_op.register_autograd(_nn_distance_backward, setup_context=_nn_distance_setup)
 
 
+@torch.library.custom_op("rfnet::chamfer_partial_sums", mutates_args=(), device_types="cuda")
+def chamfer_partial_sums_op(dist1: torch.Tensor, dist2: torch.Tensor) -> torch.Tensor:
+    """[sum sqrt(dist1), numel(dist1), sum sqrt(dist2), numel(dist2)]: the reductions chamfer_big (vv_recon.py:381-385)
+    performs with framework ops, in one deterministic pass.  Not differentiable (use rfnet_b200.losses for training)."""
+    _require(dist1.dim() == 2 and dist2.dim() == 2 and dist1.shape[0] == dist2.shape[0], "chamfer_partial_sums expects (batch,#points) distances")
+    dist1, dist2 = _cuda_f32("dist1", dist1), _cuda_f32("dist2", dist2)
+    out = torch.empty((4,), dtype=torch.float32, device=dist1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_chamfer_partial_sums_workspace_bytes()
+    ws = _workspace(wsb, dist1.device)
+    with torch.cuda.device(dist1.device):
+        _lib.check(lib.rfnet_chamfer_partial_sums(dist1.shape[0], dist1.shape[1], dist2.shape[1], _ptr(dist1), _ptr(dist2), _ptr(out), _ptr(ws), wsb,
+                                                  _stream(dist1)), "rfnet_chamfer_partial_sums")
+    return out
+
+
+@chamfer_partial_sums_op.register_fake
+def _(dist1, dist2):
+    return dist1.new_empty((4,))
+
+
 # ------------------------------------------------------------------------------------------------------------ approx_match
 @torch.library.custom_op("rfnet::approx_match", mutates_args=(), device_types="cuda")
 def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> torch.Tensor:

@@ -120,3 +120,16 @@ def test_nn_distance_empty_and_errors(cuda):
         tf_nndistance.nn_distance(torch.zeros((1, 5, 2), device=cuda), torch.zeros((1, 7, 3), device=cuda))
     with pytest.raises(ValueError, match="same batch size"):
         tf_nndistance.nn_distance(torch.zeros((1, 5, 3), device=cuda), torch.zeros((2, 7, 3), device=cuda))
+
+
+def test_chamfer_partial_sums(cuda, rng):
+    from rfnet_b200 import losses, ops
+    d1 = torch.from_numpy(rng.random((7, 333), dtype=np.float32)).to(cuda)
+    d2 = torch.from_numpy(rng.random((7, 1999), dtype=np.float32)).to(cuda)
+    got = ops.chamfer_partial_sums_op(d1, d2).cpu().numpy()
+    want = losses.chamfer_partial_sums(d1, d2).cpu().numpy()
+    assert got[1] == 7 * 333 and got[3] == 7 * 1999
+    assert np.allclose(got, want, rtol=1e-5)
+    assert np.allclose(got[0], np.sqrt(d1.cpu().numpy().astype(np.float64)).sum(), rtol=1e-5)
+    # deterministic: fixed summation order
+    assert np.array_equal(got, ops.chamfer_partial_sums_op(d1, d2).cpu().numpy())
