@@ -22,8 +22,16 @@ namespace rfnet {
 constexpr int EMD_LEVELS = 10;   // j = 7 .. -2   (tf_approxmatch.cu:21)
 constexpr int EMD_THREADS = 128;
 constexpr int EMD_Q = 8;         // rows per thread in the sweep (4 packed pairs)
-constexpr int EMD_TC = 512;      // candidates per shared-memory chunk (float4 each: 8 KiB)
+#ifndef EMD_TC_VALUE
+#define EMD_TC_VALUE 512
+#endif
+constexpr int EMD_TC = EMD_TC_VALUE;  // candidates per shared-memory chunk (float4 each: 8 KiB)
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef EMD_UNROLL
+#define EMD_UNROLL 2  // candidates per unrolled step of the sweep (tools/emd_tune.cu sweeps this)
+#endif
+#define EMD_PRAGMA_(x) _Pragma(#x)
+#define EMD_PRAGMA_UNROLL(n) EMD_PRAGMA_(unroll n)
 
 __host__ __device__ inline float emd_level(int li) {  // li = 0..9  ->  j = 7..-2 ; level = -4^j, 0 at j = -2
     const int j = 7 - li;
@@ -72,8 +80,10 @@ static EmdWs emd_carve(float* w, int b, int n, int m) {
 //   passes 1 and 2:  acc = fma(e, w[c], acc)                       (acc starts at 1e-9 in pass 1: tf_approxmatch.cu:36)
 //   pass 3 (PASS3):  acc = fma(rowfac[row] * e, w[c], acc)         (t = ratioL*e; suml = fma(t, ratioR, suml))
 // so with nsplit == 1 every row sum is bit-identical to what the reference's thread computes.
+// UNIT_E: the last level (j = -2) has level = 0, i.e. e = ex2(0 * d2) = 1 for every pair; the same accumulation chain is run
+// without evaluating distances or exponentials (1 lane-op per pair instead of 8 + a MUFU).
 // ---------------------------------------------------------------------------------------------------------------
-template <int Q, bool PASS3>
+template <int Q, bool PASS3, bool UNIT_E>
 __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2, float init0,
                                                                const float* __restrict__ rows, const float* __restrict__ cands,
                                                                const float* __restrict__ w, const float* __restrict__ rowfac,
@@ -121,19 +131,24 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
             sC[i] = v;
         }
         __syncthreads();
-        const int len2 = (len + 1) & ~1;
-#pragma unroll 2
+        const int len2 = (len + EMD_UNROLL - 1) / EMD_UNROLL * EMD_UNROLL;  // padded entries carry weight 0 (EMD_TC % EMD_UNROLL == 0)
+        EMD_PRAGMA_UNROLL(EMD_UNROLL)
         for (int k = 0; k < len2; ++k) {
             const float4 c = sC[k];
 #pragma unroll
             for (int h = 0; h < Q / 2; ++h) {
-                const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // the sign of the difference is irrelevant after squaring
-                const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
-                const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
-                const float2 a = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
-                float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-                if (PASS3) e = __fmul2_rn(rf[h], e);
-                acc[h] = __ffma2_rn(e, make_float2(c.w, c.w), acc[h]);
+                if (UNIT_E) {
+                    // e == 1: fma(1, w, acc) == acc + w and fma(rf * 1, w, acc) == fma(rf, w, acc), bit for bit
+                    acc[h] = PASS3 ? __ffma2_rn(rf[h], make_float2(c.w, c.w), acc[h]) : __fadd2_rn(acc[h], make_float2(c.w, c.w));
+                } else {
+                    const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // the sign of the difference is irrelevant after squaring
+                    const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
+                    const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
+                    const float2 a = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
+                    float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                    if (PASS3) e = __fmul2_rn(rf[h], e);
+                    acc[h] = __ffma2_rn(e, make_float2(c.w, c.w), acc[h]);
+                }
             }
         }
     }
@@ -370,15 +385,23 @@ static SweepPlan emd_plan(int b, int nr, int nc) {
     p.nsplit = (chunks + p.cps - 1) / p.cps;
     return p;
 }
+template <int Q, bool PASS3>
+static void emd_sweep_q(const SweepPlan& p, unsigned grid, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands,
+                        const float* w, const float* rowfac, float* partial, cudaStream_t s) {
+    if (lvl2 == 0.0f)
+        emd_sweep_kernel<Q, PASS3, true><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+    else
+        emd_sweep_kernel<Q, PASS3, false><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+}
 template <bool PASS3>
 static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands, const float* w, const float* rowfac,
                       float* partial, int& nsplit_out, cudaStream_t s) {
     const SweepPlan p = emd_plan(b, nr, nc);
     nsplit_out = p.nsplit;
     const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
-    if (p.Q == 8) emd_sweep_kernel<8, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
-    else if (p.Q == 4) emd_sweep_kernel<4, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
-    else emd_sweep_kernel<2, PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+    if (p.Q == 8) emd_sweep_q<8, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
+    else if (p.Q == 4) emd_sweep_q<4, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
+    else emd_sweep_q<2, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
 }
 
 }  // namespace rfnet

@@ -10,15 +10,19 @@ from oracle import ref
 dev = torch.device("cuda:0")
 
 
-def timeit(fn, warm=3, iters=10):
+def timeit(fn, warm=3, iters=10, reps=3):
+    """ms per call, `iters` calls back to back between two events (host launch overhead overlaps GPU work); min over reps."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []
-    for _ in range(iters):
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+    for _ in range(reps):
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / iters)
     return float(np.median(ts)), float(np.min(ts))
 
 
