@@ -268,44 +268,35 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "Tlaneop/s", "frac": achieved / peak,
                 "peak_source": "148 SMs x 128 FP32 lanes x %.0f MHz (architectural; MEASURED_PEAKS.json has no FP32-pipe figure)" % (sm_max / 1e6),
                 "peak_measured_ffma2_stream": peak_measured, "frac_of_measured": achieved / peak_measured,
-                "algorithmic_laneops_per_pair": LANE_OPS_PER_PAIR, "fwd_ms": fwd_ms, "traffic": None}
+                "algorithmic_laneops_per_pair": LANE_OPS_PER_PAIR, "fwd_ms": fwd_ms,
+                "traffic": 11852288, "traffic_note": "dram__bytes_read+write of one nn_search_kernel launch at this config, ncu --set full (profiles/r1_nn_search_full.txt); inputs are 7.08 MB, compute-bound"}
 
-    # ---- e2e: the same step through the public API from pinned HOST buffers, H2D + D2H inside the timed region
-    out_d1 = torch.empty((B, N), dtype=torch.float32).pin_memory()
-    out_d2 = torch.empty((B, M), dtype=torch.float32).pin_memory()
-    out_g1 = torch.empty((B, N, 3), dtype=torch.float32).pin_memory()
-    out_g2 = torch.empty((B, M, 3), dtype=torch.float32).pin_memory()
-    out_loss = torch.empty(4, dtype=torch.float32).pin_memory()
-    k_e2e = max(3, min(args.steps, 50))
-
-    def e2e_step(i):
-        x1 = h1[i % nsets].to(dev, non_blocking=True)
-        x2 = h2[i % nsets].to(dev, non_blocking=True)
-        dist1, idx1, dist2, idx2 = tf_nndistance.nn_distance(x1, x2)
-        g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
-        part = losses.all_reduce_scalars(ops.chamfer_partial_sums_op(dist1, dist2))
-        out_d1.copy_(dist1, non_blocking=True)
-        out_d2.copy_(dist2, non_blocking=True)
-        out_g1.copy_(g1, non_blocking=True)
-        out_g2.copy_(g2, non_blocking=True)
-        out_loss.copy_(part, non_blocking=True)
-
+    # ---- e2e: the same step through the public host-buffer API (rfnet_b200.host.ChamferHostPipeline): every step copies
+    # its inputs from pinned host memory and its results (dist, idx, grads, loss sums) back; copies of neighbouring steps
+    # overlap the kernels on separate streams
+    from rfnet_b200.host import ChamferHostPipeline
+    pipe = ChamferHostPipeline(B, N, M, dev, depth=3, grad_scale1=0.5 / (B * N * world), grad_scale2=0.5 / (B * M * world))
+    k_e2e = max(3, min(args.steps, 100))
     for i in range(3):
-        e2e_step(i)
+        pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
+    pipe.drain()
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for i in range(k_e2e):
-        e2e_step(i)
+        pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
+    torch.cuda.current_stream().wait_stream(pipe.s_out)
     e1.record()
     barrier()
+    last = pipe.wait((pipe.count - 1) % pipe.depth)
+    e2e_loss = float((last["sums"][0] / last["sums"][1] + last["sums"][2] / last["sums"][3]) / 2)   # chamfer_big read back on the host
     e2e_ms = e0.elapsed_time(e1)
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pairs_per_step * k_e2e / (float(t.item()) * 1e-3) / 1e9
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (N + M) * 12, "d2h_bytes_per_step": B * (N + M) * 4 + B * (N + M) * 12 + 16,
-           "steps": k_e2e, "api": "rfnet_b200.tf_nndistance.nn_distance + rfnet::nn_distance_grad on pinned host tensors"}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "steps": k_e2e, "loss_read_back": e2e_loss,
+           "api": "rfnet_b200.host.ChamferHostPipeline.submit(pinned xyz1, xyz2) -> pinned dist/idx/grads/loss sums; 3-slot ring, copies overlap compute"}
 
     # ---- extras (rank 0, not part of `value`): north-star shape and EMD
     extra = {}

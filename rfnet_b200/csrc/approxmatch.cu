@@ -23,9 +23,9 @@ constexpr int EMD_LEVELS = 10;   // j = 7 .. -2   (tf_approxmatch.cu:21)
 constexpr int EMD_THREADS = 128;
 constexpr int EMD_Q = 8;         // rows per thread in the sweep (4 packed pairs)
 #ifndef EMD_TC_VALUE
-#define EMD_TC_VALUE 512
+#define EMD_TC_VALUE 256
 #endif
-constexpr int EMD_TC = EMD_TC_VALUE;  // candidates per shared-memory chunk (float4 each: 8 KiB)
+constexpr int EMD_TC = EMD_TC_VALUE;  // candidates per shared-memory chunk (float4 each: 4 KiB)
 constexpr float LOG2E = 1.4426950408889634f;
 #ifndef EMD_UNROLL
 #define EMD_UNROLL 2  // candidates per unrolled step of the sweep (tools/emd_tune.cu sweeps this)
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int 
         const int l = i / EMD_LEVELS, j = i % EMD_LEVELS;
         sF[l][j] = facR[(size_t)j * bm + (size_t)cloud * m + l0 + l];
     }
-    float x1 = 0.f, y1 = 0.f, z1 = 0.f, fl[EMD_LEVELS];
+    float x1 = __int_as_float(0x7f800000), y1 = 0.f, z1 = 0.f, fl[EMD_LEVELS];  // lanes past n sit at infinity: they never block a level skip
     const bool valid = k < n;
     if (valid) {
         const float* p = xyz1 + ((size_t)cloud * n + k) * 3;
@@ -234,15 +234,20 @@ __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int 
 #pragma unroll
     for (int j = 0; j < EMD_LEVELS; ++j) fl[j] = valid ? facL[(size_t)j * bn + (size_t)cloud * n + k] : 0.f;
     __syncthreads();
-    if (!valid) return;
     float* __restrict__ out = match + ((size_t)cloud * m + l0) * n + k;
     for (int l = 0; l < nl; ++l) {
         const float d2 = sqdist3<true>(sP[l][0] - x1, sP[l][1] - y1, sP[l][2] - z1);
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < EMD_LEVELS - 1; ++j) acc = __fmaf_rn(__fmul_rn(ex2_approx(__fmul_rn(d2, lv.lvl2[j])), fl[j]), sF[l][j], acc);
+        for (int j = 0; j < EMD_LEVELS - 1; ++j) {
+            // ex2.approx.ftz returns exactly 0 below 2^-126: when that holds for the whole warp the level contributes
+            // fma(0, ., acc) == acc and its MUFU can be skipped (top levels: most pairs are farther than 0.07 / 0.15 apart)
+            const float a = __fmul_rn(d2, lv.lvl2[j]);
+            if (j < 3 && !__any_sync(0xffffffffu, a >= -126.0f)) continue;
+            acc = __fmaf_rn(__fmul_rn(ex2_approx(a), fl[j]), sF[l][j], acc);
+        }
         acc = __fmaf_rn(fl[EMD_LEVELS - 1], sF[l][EMD_LEVELS - 1], acc);  // j = -2: level 0, e = 1
-        out[(size_t)l * n] = acc;
+        if (valid) out[(size_t)l * n] = acc;
     }
 }
 
@@ -360,24 +365,20 @@ __global__ void __launch_bounds__(G2_WARPS * 32) matchcostgrad2_kernel(int n, in
     }
 }
 
-// Sweep launch policy.  Prefer NO candidate split -- row sums then follow the reference's order bit for bit -- whenever the
-// batch alone fills the chip: rows-per-thread Q = 8, 4 or 2 with at least 8, 4 or 4 CTAs per SM respectively.  Otherwise
-// (few or small clouds) the candidate range is split across CTAs and the partials are summed in split order: still
-// deterministic, but a different rounding order than the reference's single sequential chain.
+// Sweep launch policy (numbers from tools/emd_tune.cu on B200, profiles/r1_emd_tune_*.txt).  The sweep is MUFU-bound and
+// needs ~40 resident warps per SM to hide the ex2 latency; Q = 4 rows per thread is the sweet spot.
+//   * No candidate split when the batch alone provides >= 6.5 CTAs per SM (e.g. B=32 x 16384 rows): every row sum then
+//     follows the reference's order bit for bit; costs ~9 % against the split grid (77 % vs 84 % of MUFU peak).
+//   * Otherwise (few or small clouds) the candidate range is split across up to 32 CTAs per row tile, ~20 CTAs per SM, and
+//     the partials are summed in split order: deterministic, but a different rounding order than the reference's chain.
 struct SweepPlan { int Q, nrt, nsplit, cps; };
 static SweepPlan emd_plan(int b, int nr, int nc) {
     SweepPlan p;
     const int chunks = (nc + EMD_TC - 1) / EMD_TC;
-    const int qs[3] = {8, 4, 2};
-    const long need[3] = {8L * kNumSMs, 4L * kNumSMs, 4L * kNumSMs};
-    for (int i = 0; i < 3; ++i) {
-        p.Q = qs[i];
-        p.nrt = (nr + EMD_THREADS * p.Q - 1) / (EMD_THREADS * p.Q);
-        if ((long)b * p.nrt >= need[i]) { p.nsplit = 1; p.cps = chunks; return p; }
-    }
     p.Q = nr >= EMD_THREADS * 4 ? 4 : 2;
     p.nrt = (nr + EMD_THREADS * p.Q - 1) / (EMD_THREADS * p.Q);
-    long want = ((long)kNumSMs * 8 + (long)b * p.nrt - 1) / ((long)b * p.nrt);
+    if ((long)b * p.nrt * 2 >= 13L * kNumSMs) { p.nsplit = 1; p.cps = chunks; return p; }
+    long want = ((long)kNumSMs * 20 + (long)b * p.nrt - 1) / ((long)b * p.nrt);
     int nsplit = (int)(want < 1 ? 1 : want);
     if (nsplit > chunks) nsplit = chunks;
     if (nsplit > 32) nsplit = 32;
@@ -399,8 +400,7 @@ static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const floa
     const SweepPlan p = emd_plan(b, nr, nc);
     nsplit_out = p.nsplit;
     const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
-    if (p.Q == 8) emd_sweep_q<8, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
-    else if (p.Q == 4) emd_sweep_q<4, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
+    if (p.Q == 4) emd_sweep_q<4, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
     else emd_sweep_q<2, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
 }
 

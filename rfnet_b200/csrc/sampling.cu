@@ -4,9 +4,10 @@
 //
 // FPS design: the reference runs one 512-thread block per cloud, keeps the running min-distance in global memory and does
 // a 9-level shared-memory tree per pick.  Here a thread-block CLUSTER owns a cloud: every CTA keeps its slice of the
-// points AND their running distances in registers, a pick is a warp-shuffle arg-max, one DSMEM store per warp into every
-// CTA of the cluster, one cluster barrier, and a second shuffle arg-max -- no global traffic inside the loop (the
-// coordinates of the winner come from a shared-memory copy of the cloud).
+// points AND their running distances in registers, a pick is a warp-shuffle arg-max, one DSMEM store + one remote
+// mbarrier arrive per warp into every CTA of the cluster, a local mbarrier wait, and a second shuffle arg-max -- no
+// global traffic and no hardware cluster barrier inside the loop (the coordinates of the winner come from a
+// shared-memory copy of the cloud).
 //
 // Exactness: d2 is the reference's fused expression (common.cuh sqdist3<true>); the arg-max reproduces the reference's
 // tie rule (tf_sampling_g.cu:146-163): among equal maxima the lowest (k mod 512) wins, then the lowest k.  This is encoded
@@ -43,12 +44,48 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// ---- cluster-scope mbarrier helpers (one arrival per remote warp, waited on locally): cheaper than the hardware cluster
+// barrier, which has to collect every thread of every CTA
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t remote_addr, unsigned long long v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // One cluster per cloud.  P = points per thread (register resident).  SMEM_CLOUD: a copy of the whole cloud lives in
 // dynamic shared memory (n*12 bytes) so the winner's coordinates are one LDS away; otherwise they are read from global.
+//
+// One pick = (1) update the P running distances and keep the thread's own maximum -- all points of a thread share
+// k mod 512 and are visited in increasing k, so a strict '>' reproduces the reference's per-thread scan
+// (tf_sampling_g.cu:146-149) -- (2) warp arg-max of the 64-bit keys, (3) lanes 0..C-1 store the warp's key into slot
+// [rank][warp] of CTA `lane` and arrive (release, cluster scope) on that CTA's mbarrier, (4) everybody waits (acquire) on
+// the local mbarrier, which expects C*16 arrivals, reads the C*16 keys and reduces them again.  Slots and barriers are
+// double buffered by pick parity: a warp can only publish pick j+2 after every warp of the cluster has published j+1,
+// i.e. after everyone has finished reading pick j.
 template <int P, bool SMEM_CLOUD>
 __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int m, const float* __restrict__ inp, int* __restrict__ out) {
     extern __shared__ __align__(16) float s_cloud[];
-    __shared__ unsigned long long slots[2][FPS_MAX_CLUSTER * FPS_WARPS];
+    __shared__ __align__(8) unsigned long long slots[2][FPS_MAX_CLUSTER * FPS_WARPS];
+    __shared__ __align__(8) uint64_t bars[2];
 
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
@@ -58,6 +95,11 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
     const float* __restrict__ pts = inp + (size_t)cloud * n * 3;
     int* __restrict__ idxs = out + (size_t)cloud * m;
 
+    if (tid == 0) {
+        mbar_init(&bars[0], (unsigned)(C * FPS_WARPS));
+        mbar_init(&bars[1], (unsigned)(C * FPS_WARPS));
+        mbar_fence_init();
+    }
     if (SMEM_CLOUD) {
         for (int i = tid; i < n * 3; i += FPS_THREADS) s_cloud[i] = pts[i];
     }
@@ -73,10 +115,16 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
         px[i] = v ? pts[(size_t)k * 3 + 0] : 0.f;
         py[i] = v ? pts[(size_t)k * 3 + 1] : 0.f;
         pz[i] = v ? pts[(size_t)k * 3 + 2] : 0.f;
-        td[i] = 1e38f;  // tf_sampling_g.cu:119
+        td[i] = v ? 1e38f : -1.0f;  // tf_sampling_g.cu:119; slots past the slice can never win (every real distance is >= 0)
     }
     if (rank == 0 && tid == 0) idxs[0] = 0;
-    if (SMEM_CLOUD) __syncthreads();
+    // remote addresses this lane publishes to (lane r < C -> CTA r)
+    const int dst = lane < C ? lane : 0;
+    const uint32_t r_slot0 = map_to_rank(smem_u32(&slots[0][rank * FPS_WARPS + warp]), dst);
+    const uint32_t r_slot1 = map_to_rank(smem_u32(&slots[1][rank * FPS_WARPS + warp]), dst);
+    const uint32_t r_bar0 = map_to_rank(smem_u32(&bars[0]), dst);
+    const uint32_t r_bar1 = map_to_rank(smem_u32(&bars[1]), dst);
+    cluster.sync();  // barriers initialised and cloud copies complete in every CTA before anyone publishes
 
     int old = 0;
     for (int j = 1; j < m; ++j) {
@@ -86,26 +134,22 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
         } else {
             lx = __ldg(pts + (size_t)old * 3 + 0); ly = __ldg(pts + (size_t)old * 3 + 1); lz = __ldg(pts + (size_t)old * 3 + 2);
         }
-        unsigned long long key = 0;  // below every real key (real keys have a non-zero low word)
+        float bestv = -1.0f;
+        int bi = 0;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            const int k = k0 + tid + i * FPS_THREADS;
             const float d = sqdist3<true>(px[i] - lx, py[i] - ly, pz[i] - lz);
             td[i] = fminf(d, td[i]);
-            if (k < kend) {
-                const unsigned long long kk = fps_key(td[i], k);
-                key = kk > key ? kk : key;
-            }
+            if (td[i] > bestv) { bestv = td[i]; bi = i; }
         }
+        unsigned long long key = bestv >= 0.0f ? fps_key(bestv, k0 + tid + bi * FPS_THREADS) : 0ull;  // 0 < every real key
         key = warp_max_u64(key);
         const int par = j & 1;
-        if (lane == 0) {
-            for (int r = 0; r < C; ++r) {
-                unsigned long long* remote = cluster.map_shared_rank(&slots[par][0], r);
-                remote[rank * FPS_WARPS + warp] = key;
-            }
+        if (lane < C) {
+            st_cluster_u64(par ? r_slot1 : r_slot0, key);
+            mbar_arrive_remote_release(par ? r_bar1 : r_bar0);
         }
-        cluster.sync();  // release/acquire: every warp's key is visible in every CTA
+        mbar_wait_cluster_acquire(&bars[par], (unsigned)((j >> 1) & 1));
         unsigned long long best = 0;
         for (int s = lane; s < C * FPS_WARPS; s += 32) {
             const unsigned long long kk = slots[par][s];

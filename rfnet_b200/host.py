@@ -1,0 +1,69 @@
+"""Host-buffer front-end of the Chamfer path: what a caller that owns HOST memory uses (the reference's CPU-side callers
+feed numpy batches through feed_dict, vv_recon.py:424-428, and read losses back).
+
+``ChamferHostPipeline`` takes pinned host clouds, runs nn_distance forward + gradient + the loss partial sums on the
+GPU, and returns the results in pinned host buffers.  Host->device copies, compute and device->host copies of
+consecutive batches overlap on three CUDA streams (a ring of `depth` device/host slots); every batch still pays its own
+copies -- they are just hidden behind the neighbouring batches' kernels, which is how a PCIe-attached B200 is fed.
+"""
+import torch
+
+from . import ops
+
+
+class ChamferHostPipeline:
+    def __init__(self, b, n, m, device, depth=3, grad_scale1=None, grad_scale2=None):
+        self.b, self.n, self.m, self.dev, self.depth = b, n, m, torch.device(device), depth
+        dev = self.dev
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.x1 = [torch.empty((b, n, 3), device=dev) for _ in range(depth)]
+        self.x2 = [torch.empty((b, m, 3), device=dev) for _ in range(depth)]
+        pin = lambda *s, dtype=torch.float32: torch.empty(s, dtype=dtype).pin_memory()
+        self.out = [dict(dist1=pin(b, n), dist2=pin(b, m), idx1=pin(b, n, dtype=torch.int32), idx2=pin(b, m, dtype=torch.int32),
+                         grad1=pin(b, n, 3), grad2=pin(b, m, 3), sums=pin(4)) for _ in range(depth)]
+        self.gd1 = torch.full((b, n), 0.5 / (b * n) if grad_scale1 is None else grad_scale1, device=dev)
+        self.gd2 = torch.full((b, m), 0.5 / (b * m) if grad_scale2 is None else grad_scale2, device=dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_compute = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.count = 0
+        self.h2d_bytes = b * (n + m) * 12
+        self.d2h_bytes = b * (n + m) * (4 + 4 + 12) + 16
+
+    def submit(self, h_xyz1, h_xyz2, reduce_fn=None):
+        """Enqueue one batch (pinned host tensors).  Returns the slot whose `out` buffers will hold the results once
+        `wait(slot)` returns.  `reduce_fn` (optional) is applied to the 4 loss partial sums on the compute stream (e.g. an
+        all-reduce across ranks)."""
+        k = self.count % self.depth
+        self.count += 1
+        compute = torch.cuda.current_stream(self.dev)
+        # the slot's device inputs are free once the compute that last read them has finished; its host outputs once
+        # the previous copy-out has finished
+        self.s_in.wait_event(self.ev_compute[k])
+        with torch.cuda.stream(self.s_in):
+            self.x1[k].copy_(h_xyz1, non_blocking=True)
+            self.x2[k].copy_(h_xyz2, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        compute.wait_event(self.ev_in[k])
+        dist1, idx1, dist2, idx2 = ops.nn_distance_op(self.x1[k], self.x2[k])
+        g1, g2 = ops.nn_distance_grad_op(self.x1[k], self.x2[k], self.gd1, idx1, self.gd2, idx2)
+        sums = ops.chamfer_partial_sums_op(dist1, dist2)
+        if reduce_fn is not None:
+            sums = reduce_fn(sums)
+        self.ev_compute[k].record(compute)
+        self.s_out.wait_event(self.ev_compute[k])
+        with torch.cuda.stream(self.s_out):
+            o = self.out[k]
+            for name, t in (("dist1", dist1), ("idx1", idx1), ("dist2", dist2), ("idx2", idx2), ("grad1", g1), ("grad2", g2), ("sums", sums)):
+                o[name].copy_(t, non_blocking=True)
+                t.record_stream(self.s_out)
+            self.ev_out[k].record(self.s_out)
+        return k
+
+    def wait(self, slot):
+        self.ev_out[slot].synchronize()
+        return self.out[slot]
+
+    def drain(self):
+        self.s_out.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

@@ -133,3 +133,22 @@ def test_chamfer_partial_sums(cuda, rng):
     assert np.allclose(got[0], np.sqrt(d1.cpu().numpy().astype(np.float64)).sum(), rtol=1e-5)
     # deterministic: fixed summation order
     assert np.array_equal(got, ops.chamfer_partial_sums_op(d1, d2).cpu().numpy())
+
+
+def test_host_pipeline_matches_direct_ops(cuda, rng):
+    """rfnet_b200.host.ChamferHostPipeline: pinned host buffers in, pinned host buffers out, overlapped copies."""
+    from rfnet_b200.host import ChamferHostPipeline
+    b, n, m = 3, 700, 1500
+    pipe = ChamferHostPipeline(b, n, m, cuda, depth=2)
+    batches = [(torch.from_numpy(cloud(rng, b, n)).pin_memory(), torch.from_numpy(cloud(rng, b, m)).pin_memory()) for _ in range(5)]
+    for h1, h2 in batches:
+        slot = pipe.submit(h1, h2)
+        out = pipe.wait(slot)
+        want = port.nn_distance(h1.numpy(), h2.numpy())
+        assert np.array_equal(out["dist1"].numpy(), want[0]) and np.array_equal(out["idx1"].numpy(), want[1])
+        assert np.array_equal(out["dist2"].numpy(), want[2]) and np.array_equal(out["idx2"].numpy(), want[3])
+        g1, g2 = port.nn_distance_grad(h1.numpy(), h2.numpy(), np.full((b, n), 0.5 / (b * n), np.float32), want[1],
+                                       np.full((b, m), 0.5 / (b * m), np.float32), want[3])
+        assert np.allclose(out["grad1"].numpy(), g1, rtol=1e-5, atol=1e-9) and np.allclose(out["grad2"].numpy(), g2, rtol=1e-5, atol=1e-9)
+        assert np.allclose(out["sums"].numpy()[0], np.sqrt(want[0].astype(np.float64)).sum(), rtol=1e-5)
+    pipe.drain()
