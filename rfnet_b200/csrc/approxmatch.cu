@@ -365,6 +365,147 @@ __global__ void __launch_bounds__(G2_WARPS * 32) matchcostgrad2_kernel(int n, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Vector variants of match_cost / match_cost_grad for n % 4 == 0 (rows of `match` 16-byte aligned): each thread owns four
+// consecutive k, reads `match` as float4, does the distance algebra on packed pairs and uses one MUFU per element
+// (sqrt.approx / rsqrt.approx; the reductions are float sums in a different order than the reference anyway, and the
+// results are held to 1e-4).  These are single streaming passes over `match`: 4 algorithmic bytes per pair, HBM-bound.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+struct Pts4 {  // four consecutive points, negated, as packed pairs (01) and (23)
+    float2 nx01, nx23, ny01, ny23, nz01, nz23;
+};
+__device__ __forceinline__ Pts4 load_pts4_neg(const float* __restrict__ p) {  // p 16-byte aligned, 12 floats
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1), c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+    Pts4 r;
+    r.nx01 = make_float2(-a.x, -a.w); r.nx23 = make_float2(-b.z, -c.y);
+    r.ny01 = make_float2(-a.y, -b.x); r.ny23 = make_float2(-b.w, -c.z);
+    r.nz01 = make_float2(-a.z, -b.y); r.nz23 = make_float2(-c.x, -c.w);
+    return r;
+}
+constexpr int MV_THREADS = 128;
+__global__ void __launch_bounds__(MV_THREADS) matchcost_v4_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                                  const float* __restrict__ match, float* __restrict__ partial) {
+    __shared__ float sP[MC_L * 3];
+    __shared__ float sW[MV_THREADS / 32];
+    const int cloud = blockIdx.z;
+    const int k4 = (blockIdx.x * MV_THREADS + threadIdx.x) * 4;
+    const int l0 = blockIdx.y * MC_L;
+    const int nl = min(MC_L, m - l0);
+    for (int i = threadIdx.x; i < nl * 3; i += MV_THREADS) sP[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    __syncthreads();
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+    if (k4 < n) {
+        const Pts4 q = load_pts4_neg(xyz1 + ((size_t)cloud * n + k4) * 3);
+        const float4* __restrict__ mp = reinterpret_cast<const float4*>(match + ((size_t)cloud * m + l0) * n + k4);
+        const size_t stride = (size_t)(n >> 2);
+#pragma unroll 8
+        for (int l = 0; l < nl; ++l) {
+            const float4 mv = __ldg(mp + (size_t)l * stride);
+            const float px = sP[l * 3], py = sP[l * 3 + 1], pz = sP[l * 3 + 2];
+            const float2 d01 = sqdist3x2<true>(__fadd2_rn(q.nx01, make_float2(px, px)), __fadd2_rn(q.ny01, make_float2(py, py)), __fadd2_rn(q.nz01, make_float2(pz, pz)));
+            const float2 d23 = sqdist3x2<true>(__fadd2_rn(q.nx23, make_float2(px, px)), __fadd2_rn(q.ny23, make_float2(py, py)), __fadd2_rn(q.nz23, make_float2(pz, pz)));
+            s01 = __ffma2_rn(make_float2(sqrt_approx(d01.x), sqrt_approx(d01.y)), make_float2(mv.x, mv.y), s01);
+            s23 = __ffma2_rn(make_float2(sqrt_approx(d23.x), sqrt_approx(d23.y)), make_float2(mv.z, mv.w), s23);
+        }
+    }
+    float sum = warp_sum((s01.x + s01.y) + (s23.x + s23.y));
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < MV_THREADS / 32; ++i) t += sW[i];
+        partial[((size_t)cloud * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+// grad1 partials over an l-range: thread owns 4 k (12 accumulators), same partial layout as matchcostgrad1_kernel
+__global__ void __launch_bounds__(MV_THREADS) matchcostgrad1_v4_kernel(int n, int m, int nlt, const float* __restrict__ xyz1,
+                                                                       const float* __restrict__ xyz2, const float* __restrict__ match,
+                                                                       float* __restrict__ partial) {
+    __shared__ float sP[G1_L * 3];
+    const int cloud = blockIdx.z;
+    const int k4 = (blockIdx.x * MV_THREADS + threadIdx.x) * 4;
+    const int l0 = blockIdx.y * G1_L;
+    const int nl = min(G1_L, m - l0);
+    for (int i = threadIdx.x; i < nl * 3; i += MV_THREADS) sP[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    __syncthreads();
+    if (k4 >= n) return;
+    const Pts4 q = load_pts4_neg(xyz1 + ((size_t)cloud * n + k4) * 3);
+    const float4* __restrict__ mp = reinterpret_cast<const float4*>(match + ((size_t)cloud * m + l0) * n + k4);
+    const size_t stride = (size_t)(n >> 2);
+    float2 gx01 = make_float2(0.f, 0.f), gx23 = gx01, gy01 = gx01, gy23 = gx01, gz01 = gx01, gz23 = gx01;
+#pragma unroll 4
+    for (int l = 0; l < nl; ++l) {
+        const float4 mv = __ldg(mp + (size_t)l * stride);
+        const float px = sP[l * 3], py = sP[l * 3 + 1], pz = sP[l * 3 + 2];
+        // e = p2 - p1 (packed); grad1 accumulates (p1 - p2) * s = e * (-s)
+        const float2 ex01 = __fadd2_rn(q.nx01, make_float2(px, px)), ey01 = __fadd2_rn(q.ny01, make_float2(py, py)), ez01 = __fadd2_rn(q.nz01, make_float2(pz, pz));
+        const float2 ex23 = __fadd2_rn(q.nx23, make_float2(px, px)), ey23 = __fadd2_rn(q.ny23, make_float2(py, py)), ez23 = __fadd2_rn(q.nz23, make_float2(pz, pz));
+        const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
+        const float2 ns01 = make_float2(-mv.x * rsqrtf(fmaxf(d01.x, 1e-20f)), -mv.y * rsqrtf(fmaxf(d01.y, 1e-20f)));
+        const float2 ns23 = make_float2(-mv.z * rsqrtf(fmaxf(d23.x, 1e-20f)), -mv.w * rsqrtf(fmaxf(d23.y, 1e-20f)));
+        gx01 = __ffma2_rn(ex01, ns01, gx01); gy01 = __ffma2_rn(ey01, ns01, gy01); gz01 = __ffma2_rn(ez01, ns01, gz01);
+        gx23 = __ffma2_rn(ex23, ns23, gx23); gy23 = __ffma2_rn(ey23, ns23, gy23); gz23 = __ffma2_rn(ez23, ns23, gz23);
+    }
+    float* o = partial + (((size_t)cloud * nlt + blockIdx.y) * n + k4) * 3;  // 12 consecutive floats, 16-byte aligned
+    reinterpret_cast<float4*>(o)[0] = make_float4(gx01.x, gy01.x, gz01.x, gx01.y);
+    reinterpret_cast<float4*>(o)[1] = make_float4(gy01.y, gz01.y, gx23.x, gy23.x);
+    reinterpret_cast<float4*>(o)[2] = make_float4(gz23.x, gx23.y, gy23.y, gz23.y);
+}
+
+// grad2: one warp per l, 16 rows per CTA sharing shared-memory tiles of xyz1; lanes stride k in float4 chunks
+constexpr int G2V_WARPS = 16;
+constexpr int G2V_TILE = 1024;  // points of xyz1 per tile (12 KiB)
+__global__ void __launch_bounds__(G2V_WARPS * 32) matchcostgrad2_v4_kernel(int n, int m, const float* __restrict__ xyz1,
+                                                                           const float* __restrict__ xyz2, const float* __restrict__ match,
+                                                                           float* __restrict__ grad2) {
+    __shared__ __align__(16) float tile[G2V_TILE * 3];
+    const int cloud = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.x * G2V_WARPS + warp;
+    const bool live = l < m;
+    float x2 = 0.f, y2 = 0.f, z2 = 0.f;
+    if (live) {
+        const float* q = xyz2 + ((size_t)cloud * m + l) * 3;
+        x2 = q[0]; y2 = q[1]; z2 = q[2];
+    }
+    const float* __restrict__ a = xyz1 + (size_t)cloud * n * 3;
+    const float* __restrict__ mrow = match + ((size_t)cloud * m + (live ? l : 0)) * n;
+    float2 gx = make_float2(0.f, 0.f), gy = gx, gz = gx;
+    for (int t0 = 0; t0 < n; t0 += G2V_TILE) {
+        const int len = min(G2V_TILE, n - t0);  // multiple of 4
+        __syncthreads();
+        for (int i = threadIdx.x; i < (len * 3) >> 2; i += G2V_WARPS * 32) reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(a + (size_t)t0 * 3) + i);
+        __syncthreads();
+        if (live) {
+#pragma unroll 2
+            for (int k4 = lane * 4; k4 < len; k4 += 128) {
+                const float4 mv = __ldg(reinterpret_cast<const float4*>(mrow + t0 + k4));
+                const float4 A = reinterpret_cast<const float4*>(tile + k4 * 3)[0], B = reinterpret_cast<const float4*>(tile + k4 * 3)[1], C = reinterpret_cast<const float4*>(tile + k4 * 3)[2];
+                // e = p2 - p1 for the four points (packed pairs 01, 23)
+                const float2 ex01 = make_float2(x2 - A.x, x2 - A.w), ex23 = make_float2(x2 - B.z, x2 - C.y);
+                const float2 ey01 = make_float2(y2 - A.y, y2 - B.x), ey23 = make_float2(y2 - B.w, y2 - C.z);
+                const float2 ez01 = make_float2(z2 - A.z, z2 - B.y), ez23 = make_float2(z2 - C.x, z2 - C.w);
+                const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
+                const float2 s01 = make_float2(mv.x * rsqrtf(fmaxf(d01.x, 1e-20f)), mv.y * rsqrtf(fmaxf(d01.y, 1e-20f)));
+                const float2 s23 = make_float2(mv.z * rsqrtf(fmaxf(d23.x, 1e-20f)), mv.w * rsqrtf(fmaxf(d23.y, 1e-20f)));
+                gx = __ffma2_rn(ex01, s01, gx); gy = __ffma2_rn(ey01, s01, gy); gz = __ffma2_rn(ez01, s01, gz);
+                gx = __ffma2_rn(ex23, s23, gx); gy = __ffma2_rn(ey23, s23, gy); gz = __ffma2_rn(ez23, s23, gz);
+            }
+        }
+    }
+    const float sx = warp_sum(gx.x + gx.y), sy = warp_sum(gy.x + gy.y), sz = warp_sum(gz.x + gz.y);
+    if (live && lane == 0) {
+        float* o = grad2 + ((size_t)cloud * m + l) * 3;
+        o[0] = sx; o[1] = sy; o[2] = sz;
+    }
+}
+
 // Sweep launch policy (numbers from tools/emd_tune.cu on B200, profiles/r1_emd_tune_*.txt).  The sweep is MUFU-bound and
 // needs ~40 resident warps per SM to hide the ex2 latency; Q = 4 rows per thread is the sweet spot.
 //   * No candidate split when the batch alone provides >= 6.5 CTAs per SM (e.g. B=32 x 16384 rows): every row sum then
@@ -463,7 +604,13 @@ extern "C" int rfnet_matchcost(int b, int n, int m, const float* xyz1, const flo
     RFNET_CHECK_ARG(xyz1 && xyz2 && match && workspace && workspace_bytes >= rfnet_matchcost_workspace_bytes(b, n, m) && b <= 65535);
     dim3 grid((unsigned)((n + MC_THREADS - 1) / MC_THREADS), (unsigned)((m + MC_L - 1) / MC_L), (unsigned)b);
     RFNET_CHECK_ARG(grid.y <= 65535);
-    matchcost_kernel<<<grid, MC_THREADS, 0, s>>>(n, m, xyz1, xyz2, match, (float*)workspace);
+    const bool vec = (n % 4 == 0) && ((((uintptr_t)match | (uintptr_t)xyz1) & 15u) == 0);
+    if (vec) {
+        grid.x = (unsigned)((n + MV_THREADS * 4 - 1) / (MV_THREADS * 4));
+        matchcost_v4_kernel<<<grid, MV_THREADS, 0, s>>>(n, m, xyz1, xyz2, match, (float*)workspace);
+    } else {
+        matchcost_kernel<<<grid, MC_THREADS, 0, s>>>(n, m, xyz1, xyz2, match, (float*)workspace);
+    }
     reduce_partials_kernel<<<b, 256, 0, s>>>((int)(grid.x * grid.y), (const float*)workspace, out);
     return launch_status();
 }
@@ -487,10 +634,21 @@ extern "C" int rfnet_matchcostgrad(int b, int n, int m, const float* xyz1, const
     const int nlt = (m + G1_L - 1) / G1_L;
     RFNET_CHECK_ARG(nlt <= 65535);
     const size_t bn = (size_t)b * n;
-    dim3 g1((unsigned)((n + G1_THREADS - 1) / G1_THREADS), (unsigned)nlt, (unsigned)b);
-    matchcostgrad1_kernel<<<g1, G1_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
+    const bool vec = (n % 4 == 0) && ((((uintptr_t)match | (uintptr_t)xyz1 | (uintptr_t)workspace) & 15u) == 0);
+    if (vec) {
+        dim3 g1((unsigned)((n + MV_THREADS * 4 - 1) / (MV_THREADS * 4)), (unsigned)nlt, (unsigned)b);
+        matchcostgrad1_v4_kernel<<<g1, MV_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
+    } else {
+        dim3 g1((unsigned)((n + G1_THREADS - 1) / G1_THREADS), (unsigned)nlt, (unsigned)b);
+        matchcostgrad1_kernel<<<g1, G1_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
+    }
     matchcostgrad1_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, nlt, bn, (const float*)workspace, grad1);
-    dim3 g2((unsigned)((m + G2_WARPS - 1) / G2_WARPS), (unsigned)b);
-    matchcostgrad2_kernel<<<g2, G2_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
+    if (vec) {
+        dim3 g2((unsigned)((m + G2V_WARPS - 1) / G2V_WARPS), (unsigned)b);
+        matchcostgrad2_v4_kernel<<<g2, G2V_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
+    } else {
+        dim3 g2((unsigned)((m + G2_WARPS - 1) / G2_WARPS), (unsigned)b);
+        matchcostgrad2_kernel<<<g2, G2_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
+    }
     return launch_status();
 }

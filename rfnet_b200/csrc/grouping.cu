@@ -93,37 +93,41 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m,
 }
 
 // out[i,j,k,:] = points[i, idx[i,j,k], :]                                         (tf_grouping_g.cu:40-57)
+// grid.y = cloud, so all index arithmetic inside a cloud is 32-bit (64-bit divisions dominated the first version)
 template <typename VEC>
-__global__ void group_point_kernel(int n, int cv, size_t rows_per_cloud, size_t total_vec, const VEC* __restrict__ points,
-                                   const int* __restrict__ idx, VEC* __restrict__ out) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output vector
-    if (t >= total_vec) return;
-    const size_t row = t / cv;
-    const int l = (int)(t - row * cv);
-    const size_t cloud = row / rows_per_cloud;
-    out[t] = __ldg(points + (cloud * n + (size_t)idx[row]) * cv + l);
+__global__ void group_point_kernel(int n, int cv, unsigned rows_per_cloud, const VEC* __restrict__ points, const int* __restrict__ idx,
+                                   VEC* __restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output vector of this cloud
+    const unsigned row = t / (unsigned)cv;
+    if (row >= rows_per_cloud) return;
+    const unsigned l = t - row * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const size_t grow = cloud * rows_per_cloud + row;
+    out[grow * cv + l] = __ldg(points + (cloud * n + (size_t)idx[grow]) * cv + l);
 }
 
 // grad_points[i, idx[i,j,k], :] += grad_out[i,j,k,:]  after zero-fill                (tf_grouping_g.cu:61-78, tf_grouping.cpp:208)
-__global__ void group_point_grad_kernel(int n, int c, size_t rows_per_cloud, size_t total, const float* __restrict__ grad_out,
-                                        const int* __restrict__ idx, float* __restrict__ grad_points) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const size_t row = t / c;
-    const int l = (int)(t - row * c);
-    const size_t cloud = row / rows_per_cloud;
-    atomicAdd(grad_points + (cloud * n + (size_t)idx[row]) * c + l, grad_out[t]);
+__global__ void group_point_grad_kernel(int n, int c, unsigned rows_per_cloud, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                                        float* __restrict__ grad_points) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned row = t / (unsigned)c;
+    if (row >= rows_per_cloud) return;
+    const unsigned l = t - row * (unsigned)c;
+    const size_t cloud = blockIdx.y;
+    const size_t grow = cloud * rows_per_cloud + row;
+    atomicAdd(grad_points + (cloud * n + (size_t)idx[grow]) * c + l, grad_out[grow * c + l]);
 }
 // c % 4 == 0 and 16-byte aligned rows: one 128-bit reduction (REDG.ADD.F32x4) per four channels
-__global__ void group_point_grad_v4_kernel(int n, int cv, size_t rows_per_cloud, size_t total_vec, const float4* __restrict__ grad_out,
-                                           const int* __restrict__ idx, float4* __restrict__ grad_points) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_vec) return;
-    const size_t row = t / cv;
-    const int l = (int)(t - row * cv);
-    const size_t cloud = row / rows_per_cloud;
-    const float4 g = grad_out[t];
-    float4* dst = grad_points + (cloud * n + (size_t)idx[row]) * cv + l;
+__global__ void group_point_grad_v4_kernel(int n, int cv, unsigned rows_per_cloud, const float4* __restrict__ grad_out, const int* __restrict__ idx,
+                                           float4* __restrict__ grad_points) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned row = t / (unsigned)cv;
+    if (row >= rows_per_cloud) return;
+    const unsigned l = t - row * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const size_t grow = cloud * rows_per_cloud + row;
+    const float4 g = grad_out[grow * cv + l];
+    float4* dst = grad_points + (cloud * n + (size_t)idx[grow]) * cv + l;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
 }
 
@@ -151,12 +155,13 @@ extern "C" int rfnet_group_point(int b, int n, int c, int m, int nsample, const 
     RFNET_CHECK_ARG(n > 0 && points && idx && out);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t rpc = (size_t)m * nsample;
+    RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
-        const size_t tv = rows * (c / 4);
-        group_point_kernel<float4><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, rpc, tv, (const float4*)points, idx, (float4*)out);
+        dim3 grid((unsigned)((rpc * (c / 4) + 255) / 256), (unsigned)b);
+        group_point_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
     } else {
-        const size_t tv = rows * c;
-        group_point_kernel<float><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, rpc, tv, points, idx, out);
+        dim3 grid((unsigned)((rpc * c + 255) / 256), (unsigned)b);
+        group_point_kernel<float><<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, points, idx, out);
     }
     return launch_status();
 }
@@ -173,12 +178,13 @@ extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, c
     if (rows == 0 || c == 0) return 0;
     RFNET_CHECK_ARG(n > 0 && grad_out && idx);
     const size_t rpc = (size_t)m * nsample;
+    RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
-        const size_t tv = rows * (c / 4);
-        group_point_grad_v4_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, rpc, tv, (const float4*)grad_out, idx, (float4*)grad_points);
+        dim3 grid((unsigned)((rpc * (c / 4) + 255) / 256), (unsigned)b);
+        group_point_grad_v4_kernel<<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)grad_out, idx, (float4*)grad_points);
     } else {
-        const size_t tv = rows * c;
-        group_point_grad_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, rpc, tv, grad_out, idx, grad_points);
+        dim3 grid((unsigned)((rpc * c + 255) / 256), (unsigned)b);
+        group_point_grad_kernel<<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, idx, grad_points);
     }
     return launch_status();
 }

@@ -111,41 +111,45 @@ __device__ __forceinline__ float4 blend3<float4>(float4 a, float4 b, float4 c, f
     return make_float4(blend3<float>(a.x, b.x, c.x, w1, w2, w3), blend3<float>(a.y, b.y, c.y, w1, w2, w3),
                        blend3<float>(a.z, b.z, c.z, w1, w2, w3), blend3<float>(a.w, b.w, c.w, w1, w2, w3));
 }
+// grid.y = cloud: 32-bit index arithmetic inside a cloud
 template <typename VEC>
-__global__ void three_interpolate_kernel(int m, int cv, int n, size_t total_vec, const VEC* __restrict__ points, const int* __restrict__ idx,
+__global__ void three_interpolate_kernel(int m, int cv, int n, const VEC* __restrict__ points, const int* __restrict__ idx,
                                          const float* __restrict__ weight, VEC* __restrict__ out) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_vec) return;
-    const size_t row = t / cv;  // = cloud*n + j
-    const int l = (int)(t - row * cv);
-    const size_t cloud = row / n;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned j = t / (unsigned)cv;
+    if (j >= (unsigned)n) return;
+    const unsigned l = t - j * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const size_t row = cloud * n + j;
     const int* id = idx + row * 3;
     const float* w = weight + row * 3;
     const VEC* P = points + cloud * (size_t)m * cv + l;
-    out[t] = blend3<VEC>(__ldg(P + (size_t)id[0] * cv), __ldg(P + (size_t)id[1] * cv), __ldg(P + (size_t)id[2] * cv), w[0], w[1], w[2]);
+    out[row * cv + l] = blend3<VEC>(__ldg(P + (size_t)id[0] * cv), __ldg(P + (size_t)id[1] * cv), __ldg(P + (size_t)id[2] * cv), w[0], w[1], w[2]);
 }
 
 // grad_points[i, i_t, l] += grad_out[i,j,l] * w_t  after zero-fill             (tf_interpolate.cpp:131-153, :258)
-__global__ void three_interpolate_grad_kernel(int n, int c, int m, size_t total, const float* __restrict__ grad_out, const int* __restrict__ idx,
+__global__ void three_interpolate_grad_kernel(int n, int c, int m, const float* __restrict__ grad_out, const int* __restrict__ idx,
                                               const float* __restrict__ weight, float* __restrict__ grad_points) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const size_t row = t / c;
-    const int l = (int)(t - row * c);
-    const size_t cloud = row / n;
-    const float g = grad_out[t];
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned j = t / (unsigned)c;
+    if (j >= (unsigned)n) return;
+    const unsigned l = t - j * (unsigned)c;
+    const size_t cloud = blockIdx.y;
+    const size_t row = cloud * n + j;
+    const float g = grad_out[row * c + l];
     float* G = grad_points + cloud * (size_t)m * c + l;
 #pragma unroll
     for (int u = 0; u < 3; ++u) atomicAdd(G + (size_t)idx[row * 3 + u] * c, __fmul_rn(g, weight[row * 3 + u]));
 }
-__global__ void three_interpolate_grad_v4_kernel(int n, int cv, int m, size_t total_vec, const float4* __restrict__ grad_out,
-                                                 const int* __restrict__ idx, const float* __restrict__ weight, float4* __restrict__ grad_points) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_vec) return;
-    const size_t row = t / cv;
-    const int l = (int)(t - row * cv);
-    const size_t cloud = row / n;
-    const float4 g = grad_out[t];
+__global__ void three_interpolate_grad_v4_kernel(int n, int cv, int m, const float4* __restrict__ grad_out, const int* __restrict__ idx,
+                                                 const float* __restrict__ weight, float4* __restrict__ grad_points) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned j = t / (unsigned)cv;
+    if (j >= (unsigned)n) return;
+    const unsigned l = t - j * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const size_t row = cloud * n + j;
+    const float4 g = grad_out[row * cv + l];
     float4* G = grad_points + cloud * (size_t)m * cv + l;
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
@@ -177,12 +181,13 @@ extern "C" int rfnet_three_interpolate(int b, int m, int c, int n, const float* 
     if (rows == 0 || c == 0) return 0;
     RFNET_CHECK_ARG(m > 0 && points && idx && weight && out);
     cudaStream_t s = (cudaStream_t)stream;
+    RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
-        const size_t tv = rows * (c / 4);
-        three_interpolate_kernel<float4><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(m, c / 4, n, tv, (const float4*)points, idx, weight, (float4*)out);
+        dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
+        three_interpolate_kernel<float4><<<grid, 256, 0, s>>>(m, c / 4, n, (const float4*)points, idx, weight, (float4*)out);
     } else {
-        const size_t tv = rows * c;
-        three_interpolate_kernel<float><<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(m, c, n, tv, points, idx, weight, out);
+        dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
+        three_interpolate_kernel<float><<<grid, 256, 0, s>>>(m, c, n, points, idx, weight, out);
     }
     return launch_status();
 }
@@ -198,12 +203,13 @@ extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const fl
     const size_t rows = (size_t)b * n;
     if (rows == 0 || c == 0) return 0;
     RFNET_CHECK_ARG(m > 0 && grad_out && idx && weight);
+    RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
-        const size_t tv = rows * (c / 4);
-        three_interpolate_grad_v4_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c / 4, m, tv, (const float4*)grad_out, idx, weight, (float4*)grad_points);
+        dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
+        three_interpolate_grad_v4_kernel<<<grid, 256, 0, s>>>(n, c / 4, m, (const float4*)grad_out, idx, weight, (float4*)grad_points);
     } else {
-        const size_t tv = rows * c;
-        three_interpolate_grad_kernel<<<(unsigned)((tv + 255) / 256), 256, 0, s>>>(n, c, m, tv, grad_out, idx, weight, grad_points);
+        dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
+        three_interpolate_grad_kernel<<<grid, 256, 0, s>>>(n, c, m, grad_out, idx, weight, grad_points);
     }
     return launch_status();
 }

@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
             st_cluster_u64(par ? r_slot1 : r_slot0, key);
             mbar_arrive_remote_release(par ? r_bar1 : r_bar0);
         }
-        mbar_wait_cluster_acquire(&bars[par], (unsigned)((j >> 1) & 1));
+        // bars[par] is used by picks par, par+2, ... (bars[1] first at j=1, bars[0] first at j=2): use number (j-1)/2, phase parity its low bit
+        mbar_wait_cluster_acquire(&bars[par], (unsigned)(((j - 1) >> 1) & 1));
         unsigned long long best = 0;
         for (int s = lane; s < C * FPS_WARPS; s += 32) {
             const unsigned long long kk = slots[par][s];

@@ -12,8 +12,13 @@ from . import ops
 
 
 class ChamferHostPipeline:
-    def __init__(self, b, n, m, device, depth=3, grad_scale1=None, grad_scale2=None):
+    ALL_OUTPUTS = ("dist1", "idx1", "dist2", "idx2", "grad1", "grad2", "sums")
+
+    def __init__(self, b, n, m, device, depth=3, grad_scale1=None, grad_scale2=None, outputs=ALL_OUTPUTS):
+        """outputs: which results are copied back to the host each step.  A training loop reads back only the loss
+        ("sums": sum sqrt(dist1), count1, sum sqrt(dist2), count2 -> chamfer_big); gradients normally stay on the device."""
         self.b, self.n, self.m, self.dev, self.depth = b, n, m, torch.device(device), depth
+        self.outputs = tuple(outputs)
         dev = self.dev
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.x1 = [torch.empty((b, n, 3), device=dev) for _ in range(depth)]
@@ -28,7 +33,8 @@ class ChamferHostPipeline:
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         self.count = 0
         self.h2d_bytes = b * (n + m) * 12
-        self.d2h_bytes = b * (n + m) * (4 + 4 + 12) + 16
+        per = {"dist1": b * n * 4, "idx1": b * n * 4, "dist2": b * m * 4, "idx2": b * m * 4, "grad1": b * n * 12, "grad2": b * m * 12, "sums": 16}
+        self.d2h_bytes = sum(per[k] for k in self.outputs)
 
     def submit(self, h_xyz1, h_xyz2, reduce_fn=None):
         """Enqueue one batch (pinned host tensors).  Returns the slot whose `out` buffers will hold the results once
@@ -55,9 +61,11 @@ class ChamferHostPipeline:
         with torch.cuda.stream(self.s_out):
             o = self.out[k]
             for name, t in (("dist1", dist1), ("idx1", idx1), ("dist2", dist2), ("idx2", idx2), ("grad1", g1), ("grad2", g2), ("sums", sums)):
-                o[name].copy_(t, non_blocking=True)
-                t.record_stream(self.s_out)
+                if name in self.outputs:
+                    o[name].copy_(t, non_blocking=True)
+                    t.record_stream(self.s_out)
             self.ev_out[k].record(self.s_out)
+        self.last = dict(dist1=dist1, idx1=idx1, dist2=dist2, idx2=idx2, grad1=g1, grad2=g2, sums=sums)  # device-side results of the last batch
         return k
 
     def wait(self, slot):
