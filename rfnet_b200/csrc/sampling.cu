@@ -35,13 +35,13 @@ __device__ __forceinline__ int fps_key_index(unsigned long long key) {
     const unsigned tie = 0xffffffffu - (unsigned)(key & 0xffffffffull);
     return (int)((tie & 0x7fffffu) * FPS_REF_BLOCK + (tie >> 23));
 }
+// 64-bit warp max with two REDUX.MAX (32-bit hardware warp reductions) instead of a 5-step shuffle tree: first the high
+// words, then the low words of the lanes that hold the winning high word.
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w > v ? w : v;
-    }
-    return v;
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
 }
 
 // ---- cluster-scope mbarrier helpers (one arrival per remote warp, waited on locally): cheaper than the hardware cluster
