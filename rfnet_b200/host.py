@@ -23,6 +23,13 @@ class ChamferHostPipeline:
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.x1 = [torch.empty((b, n, 3), device=dev) for _ in range(depth)]
         self.x2 = [torch.empty((b, m, 3), device=dev) for _ in range(depth)]
+        # device-side results and scratch, one set per slot: the steady-state loop allocates nothing and calls the C ABI directly
+        f32, i32 = torch.float32, torch.int32
+        self.dres = [dict(dist1=torch.empty((b, n), dtype=f32, device=dev), idx1=torch.empty((b, n), dtype=i32, device=dev),
+                          dist2=torch.empty((b, m), dtype=f32, device=dev), idx2=torch.empty((b, m), dtype=i32, device=dev),
+                          grad1=torch.empty((b, n, 3), dtype=f32, device=dev), grad2=torch.empty((b, m, 3), dtype=f32, device=dev),
+                          sums=torch.empty((4,), dtype=f32, device=dev),
+                          ws=torch.empty((ops.nn_distance_workspace_bytes(b, n, m),), dtype=torch.uint8, device=dev)) for _ in range(depth)]
         pin = lambda *s, dtype=torch.float32: torch.empty(s, dtype=dtype).pin_memory()
         self.out = [dict(dist1=pin(b, n), dist2=pin(b, m), idx1=pin(b, n, dtype=torch.int32), idx2=pin(b, m, dtype=torch.int32),
                          grad1=pin(b, n, 3), grad2=pin(b, m, 3), sums=pin(4)) for _ in range(depth)]
@@ -51,21 +58,21 @@ class ChamferHostPipeline:
             self.x2[k].copy_(h_xyz2, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         compute.wait_event(self.ev_in[k])
-        dist1, idx1, dist2, idx2 = ops.nn_distance_op(self.x1[k], self.x2[k])
-        g1, g2 = ops.nn_distance_grad_op(self.x1[k], self.x2[k], self.gd1, idx1, self.gd2, idx2)
-        sums = ops.chamfer_partial_sums_op(dist1, dist2)
+        compute.wait_event(self.ev_out[k])   # the slot's device results were last read by the copy-out of batch count - depth
+        r = self.dres[k]
+        ops.raw_nn_distance(self.x1[k], self.x2[k], r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["ws"])
+        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"])
+        ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
         if reduce_fn is not None:
-            sums = reduce_fn(sums)
+            reduce_fn(r["sums"])              # in place (e.g. an all-reduce across ranks)
         self.ev_compute[k].record(compute)
         self.s_out.wait_event(self.ev_compute[k])
         with torch.cuda.stream(self.s_out):
             o = self.out[k]
-            for name, t in (("dist1", dist1), ("idx1", idx1), ("dist2", dist2), ("idx2", idx2), ("grad1", g1), ("grad2", g2), ("sums", sums)):
-                if name in self.outputs:
-                    o[name].copy_(t, non_blocking=True)
-                    t.record_stream(self.s_out)
+            for name in self.outputs:
+                o[name].copy_(r[name], non_blocking=True)
             self.ev_out[k].record(self.s_out)
-        self.last = dict(dist1=dist1, idx1=idx1, dist2=dist2, idx2=idx2, grad1=g1, grad2=g2, sums=sums)  # device-side results of the last batch
+        self.last = r                         # device-side results of the last batch
         return k
 
     def wait(self, slot):

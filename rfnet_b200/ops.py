@@ -45,6 +45,31 @@ def _workspace(nbytes, device):
     return torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device)
 
 
+# ------------------------------------------------------------------------------------------------------------ raw calls
+# Allocation-free entry points over caller-owned CUDA tensors (contiguous, right dtype, all on the current device): what
+# rfnet_b200.host uses in its steady-state loop, where the torch dispatcher and per-call allocations would dominate.
+def raw_nn_distance(xyz1, xyz2, dist1, idx1, dist2, idx2, workspace, unfused=False):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    _lib.check(_lib.load().rfnet_nn_distance(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(dist1), _ptr(idx1), _ptr(dist2), _ptr(idx2), _ptr(workspace),
+                                             workspace.numel(), 1 if unfused else 0, _stream(xyz1)), "rfnet_nn_distance")
+
+
+def raw_nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    _lib.check(_lib.load().rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
+                                                  _ptr(grad_xyz1), _ptr(grad_xyz2), _stream(xyz1)), "rfnet_nn_distance_grad")
+
+
+def raw_chamfer_partial_sums(dist1, dist2, sums4, workspace):
+    _lib.check(_lib.load().rfnet_chamfer_partial_sums(dist1.shape[0], dist1.shape[1], dist2.shape[1], _ptr(dist1), _ptr(dist2), _ptr(sums4),
+                                                      _ptr(workspace), workspace.numel(), _stream(dist1)), "rfnet_chamfer_partial_sums")
+
+
+def nn_distance_workspace_bytes(b, n, m):
+    lib = _lib.load()
+    return max(int(lib.rfnet_nn_distance_workspace_bytes(b, n, m)), int(lib.rfnet_chamfer_partial_sums_workspace_bytes()), 16)
+
+
 # ------------------------------------------------------------------------------------------------------------ nn_distance
 @torch.library.custom_op("rfnet::nn_distance", mutates_args=(), device_types="cuda")
 def nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, unfused: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
