@@ -76,15 +76,16 @@ __device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, unsigne
 //
 // One pick = (1) update the P running distances and keep the thread's own maximum -- all points of a thread share
 // k mod 512 and are visited in increasing k, so a strict '>' reproduces the reference's per-thread scan
-// (tf_sampling_g.cu:146-149) -- (2) warp arg-max of the 64-bit keys, (3) lanes 0..C-1 store the warp's key into slot
-// [rank][warp] of CTA `lane` and arrive (release, cluster scope) on that CTA's mbarrier, (4) everybody waits (acquire) on
-// the local mbarrier, which expects C*16 arrivals, reads the C*16 keys and reduces them again.  Slots and barriers are
-// double buffered by pick parity: a warp can only publish pick j+2 after every warp of the cluster has published j+1,
-// i.e. after everyone has finished reading pick j.
+// (tf_sampling_g.cu:146-149) -- (2) warp arg-max of the 64-bit keys (two REDUX), per-warp maxima to shared memory, CTA
+// barrier, (3) warp 0 reduces them and its lanes 0..C-1 store the CTA's key into slot [rank] of CTA `lane` and arrive
+// (release, cluster scope) on that CTA's mbarrier, (4) everybody waits (acquire) on the local mbarrier, which expects C
+// arrivals, and takes the maximum of the C keys.  Slots, per-warp keys and barriers are double buffered by pick parity: a
+// CTA can only publish pick j+2 after every CTA of the cluster has published j+1, i.e. after everyone has read pick j.
 template <int P, bool SMEM_CLOUD>
 __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int m, const float* __restrict__ inp, int* __restrict__ out) {
     extern __shared__ __align__(16) float s_cloud[];
-    __shared__ __align__(8) unsigned long long slots[2][FPS_MAX_CLUSTER * FPS_WARPS];
+    __shared__ __align__(8) unsigned long long wkeys[2][FPS_WARPS];          // per-warp maxima of this CTA
+    __shared__ __align__(8) unsigned long long slots[2][FPS_MAX_CLUSTER];    // per-CTA maxima of the whole cluster
     __shared__ __align__(8) uint64_t bars[2];
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
     int* __restrict__ idxs = out + (size_t)cloud * m;
 
     if (tid == 0) {
-        mbar_init(&bars[0], (unsigned)(C * FPS_WARPS));
-        mbar_init(&bars[1], (unsigned)(C * FPS_WARPS));
+        mbar_init(&bars[0], (unsigned)C);   // one arrival per CTA of the cluster and pick
+        mbar_init(&bars[1], (unsigned)C);
         mbar_fence_init();
     }
     if (SMEM_CLOUD) {
@@ -118,10 +119,10 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
         td[i] = v ? 1e38f : -1.0f;  // tf_sampling_g.cu:119; slots past the slice can never win (every real distance is >= 0)
     }
     if (rank == 0 && tid == 0) idxs[0] = 0;
-    // remote addresses this lane publishes to (lane r < C -> CTA r)
+    // remote addresses that lane r < C of warp 0 publishes to (CTA r)
     const int dst = lane < C ? lane : 0;
-    const uint32_t r_slot0 = map_to_rank(smem_u32(&slots[0][rank * FPS_WARPS + warp]), dst);
-    const uint32_t r_slot1 = map_to_rank(smem_u32(&slots[1][rank * FPS_WARPS + warp]), dst);
+    const uint32_t r_slot0 = map_to_rank(smem_u32(&slots[0][rank]), dst);
+    const uint32_t r_slot1 = map_to_rank(smem_u32(&slots[1][rank]), dst);
     const uint32_t r_bar0 = map_to_rank(smem_u32(&bars[0]), dst);
     const uint32_t r_bar1 = map_to_rank(smem_u32(&bars[1]), dst);
     cluster.sync();  // barriers initialised and cloud copies complete in every CTA before anyone publishes
@@ -145,18 +146,25 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
         unsigned long long key = bestv >= 0.0f ? fps_key(bestv, k0 + tid + bi * FPS_THREADS) : 0ull;  // 0 < every real key
         key = warp_max_u64(key);
         const int par = j & 1;
-        if (lane < C) {
-            st_cluster_u64(par ? r_slot1 : r_slot0, key);
-            mbar_arrive_remote_release(par ? r_bar1 : r_bar0);
+        if (lane == 0) wkeys[par][warp] = key;
+        __syncthreads();
+        if (warp == 0) {
+            // CTA maximum, then ONE store + ONE remote arrive per destination CTA (a first version let all 16 warps publish:
+            // 64 remote arrivals per barrier and pick serialised on the barrier word)
+            unsigned long long ck = lane < FPS_WARPS ? wkeys[par][lane] : 0ull;
+            ck = warp_max_u64(ck);
+            if (lane < C) {
+                st_cluster_u64(par ? r_slot1 : r_slot0, ck);
+                mbar_arrive_remote_release(par ? r_bar1 : r_bar0);
+            }
         }
         // bars[par] is used by picks par, par+2, ... (bars[1] first at j=1, bars[0] first at j=2): use number (j-1)/2, phase parity its low bit
         mbar_wait_cluster_acquire(&bars[par], (unsigned)(((j - 1) >> 1) & 1));
-        unsigned long long best = 0;
-        for (int s = lane; s < C * FPS_WARPS; s += 32) {
-            const unsigned long long kk = slots[par][s];
+        unsigned long long best = slots[par][0];
+        for (int r = 1; r < C; ++r) {
+            const unsigned long long kk = slots[par][r];
             best = kk > best ? kk : best;
         }
-        best = warp_max_u64(best);
         old = fps_key_index(best);
         if (rank == 0 && tid == 0) idxs[j] = old;
     }
