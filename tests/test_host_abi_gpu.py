@@ -84,3 +84,45 @@ def test_sharded_losses_single_rank_equal_plain_losses(cuda, rng):
     e1.backward(); e2.backward()
     assert abs(e1.item() - e2.item()) <= 1e-6 * abs(e1.item())
     assert torch.allclose(a3.grad, a4.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_ops_are_cuda_graph_capturable(cuda, rng):
+    """calls are stream-ordered with no host sync and no allocation inside the library, so a whole
+    forward+backward step can be captured in a CUDA graph and replayed on new data."""
+    import torch
+    from rfnet_b200 import ops
+    b, n, m = 4, 1024, 4096          # large enough to take the split/atomic-merge path of nn_distance
+    x1 = torch.from_numpy(cloud(rng, b, n)).to(cuda)
+    x2 = torch.from_numpy(cloud(rng, b, m)).to(cuda)
+    f32, i32 = torch.float32, torch.int32
+    d1, i1 = torch.empty((b, n), dtype=f32, device=cuda), torch.empty((b, n), dtype=i32, device=cuda)
+    d2, i2 = torch.empty((b, m), dtype=f32, device=cuda), torch.empty((b, m), dtype=i32, device=cuda)
+    g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
+    gd1, gd2 = torch.ones((b, n), device=cuda), torch.ones((b, m), device=cuda)
+    sums = torch.empty(4, device=cuda)
+    ws = torch.empty(ops.nn_distance_workspace_bytes(b, n, m), dtype=torch.uint8, device=cuda)
+    fps_idx = torch.empty((b, 64), dtype=i32, device=cuda)
+
+    def body():
+        ops.raw_nn_distance(x1, x2, d1, i1, d2, i2, ws)
+        ops.raw_nn_distance_grad(x1, x2, gd1, i1, gd2, i2, g1, g2)
+        ops.raw_chamfer_partial_sums(d1, d2, sums, ws)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()                        # warm-up outside capture (lazy module loading)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        body()
+    # replay on NEW data written into the captured input buffers
+    y1, y2 = cloud(rng, b, n), cloud(rng, b, m)
+    x1.copy_(torch.from_numpy(y1)); x2.copy_(torch.from_numpy(y2))
+    graph.replay()
+    torch.cuda.synchronize()
+    want = port.nn_distance(y1, y2)
+    assert np.array_equal(d1.cpu().numpy(), want[0]) and np.array_equal(i1.cpu().numpy(), want[1])
+    assert np.array_equal(d2.cpu().numpy(), want[2]) and np.array_equal(i2.cpu().numpy(), want[3])
+    w1, w2 = port.nn_distance_grad(y1, y2, np.ones((b, n), np.float32), want[1], np.ones((b, m), np.float32), want[3])
+    assert np.allclose(g1.cpu().numpy(), w1, rtol=1e-5, atol=1e-6) and np.allclose(g2.cpu().numpy(), w2, rtol=1e-5, atol=1e-6)
