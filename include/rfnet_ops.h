@@ -44,10 +44,18 @@ int rfnet_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2,
                       int *idx2, void *workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream);
 
 /* Replaces NmDistanceGradKernelLauncher, pc_distance/tf_nndistance.cpp:208 (tf_nndistance_g.cu:151-156).
- * grad_xyz1 / grad_xyz2 are fully overwritten (the launcher zero-fills them itself, as the reference does). */
+ * grad_xyz1 / grad_xyz2 are fully overwritten (the launcher zero-fills them itself, as the reference does).
+ *
+ * GRADIENT SCATTERS (this function, rfnet_scatteraddpoint, rfnet_group_point_grad, rfnet_three_interpolate_grad):
+ * with a workspace of rfnet_<op>_workspace_bytes() the scatter is ATOMIC-FREE and DETERMINISTIC -- the index list is
+ * inverted with integer atomics only and every point's contributions are summed in ascending source order, which is the
+ * summation order of the reference's sequential CPU kernels, so the result is bit-exact with them and reproducible run to
+ * run.  With workspace == NULL the reference GPU formulation is used (float reductions after a zero-fill), whose last
+ * bits depend on thread timing. */
+size_t rfnet_nn_distance_grad_workspace_bytes(int b, int n, int m);
 int rfnet_nn_distance_grad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
                            const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
-                           float *grad_xyz2, rfnet_stream_t stream);
+                           float *grad_xyz2, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
 /* Loss-level epilogue of the reference's chamfer_big / fidelity_loss (vv_recon.py:381-390), which the reference leaves to
  * framework ops: sums4 = { sum sqrt(dist1), b*n, sum sqrt(dist2), b*m } in a fixed summation order.  chamfer_big is then
@@ -82,7 +90,9 @@ size_t rfnet_farthestpointsampling_workspace_bytes(int b, int n, int m);
 int rfnet_farthestpointsampling(int b, int n, int m, const float *inp, void *workspace, size_t workspace_bytes,
                                 int *out, rfnet_stream_t stream);
 int rfnet_gatherpoint(int b, int n, int m, const float *inp, const int *idx, float *out, rfnet_stream_t stream);
-int rfnet_scatteraddpoint(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, rfnet_stream_t stream);
+size_t rfnet_scatteraddpoint_workspace_bytes(int b, int n, int m);
+int rfnet_scatteraddpoint(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, void *workspace,
+                          size_t workspace_bytes, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * grouping.  Replace queryBallPointLauncher, groupPointLauncher, groupPointGradLauncher,
@@ -95,8 +105,9 @@ int rfnet_query_ball_point(int b, int n, int m, const float *radius, int nsample
                            const float *xyz2, int *idx, int *pts_cnt, rfnet_stream_t stream);
 int rfnet_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
                       rfnet_stream_t stream);
+size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, int m, int nsample);
 int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
-                           float *grad_points, rfnet_stream_t stream);
+                           float *grad_points, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * interpolation.  The reference has CPU code only: threenn_cpu, threeinterpolate_cpu, threeinterpolate_grad_cpu,
@@ -108,8 +119,10 @@ int rfnet_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, fl
                    rfnet_stream_t stream);
 int rfnet_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
                             float *out, rfnet_stream_t stream);
+size_t rfnet_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m);
 int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
-                                 const float *weight, float *grad_points, rfnet_stream_t stream);
+                                 const float *weight, float *grad_points, void *workspace, size_t workspace_bytes,
+                                 rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points: what a CPU-side caller (e.g. the reference's DEVICE_CPU OpKernels,

@@ -16,7 +16,8 @@ SIGNATURES = {
     "rfnet_error_string": (ctypes.c_char_p, [_i]),
     "rfnet_nn_distance_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_nn_distance": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
-    "rfnet_nn_distance_grad": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rfnet_nn_distance_grad_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_nn_distance_grad": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_chamfer_partial_sums_workspace_bytes": (_z, []),
     "rfnet_chamfer_partial_sums": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "rfnet_approxmatch_workspace_bytes": (_z, [_i, _i, _i]),
@@ -28,13 +29,16 @@ SIGNATURES = {
     "rfnet_farthestpointsampling_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_farthestpointsampling": (_i, [_i, _i, _i, _p, _p, _z, _p, _p]),
     "rfnet_gatherpoint": (_i, [_i, _i, _i, _p, _p, _p, _p]),
-    "rfnet_scatteraddpoint": (_i, [_i, _i, _i, _p, _p, _p, _p]),
+    "rfnet_scatteraddpoint_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_scatteraddpoint": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "rfnet_query_ball_point": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "rfnet_group_point": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "rfnet_group_point_grad_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
+    "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "rfnet_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "rfnet_three_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "rfnet_three_interpolate_grad_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "rfnet_three_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_nn_distance_host": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i]),
     "rfnet_emd_host": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_probe_fp32": (_i, [_i, _p, _p, _p]),

@@ -11,6 +11,7 @@
 // d2 < T with T = min{t : sqrt_rn(t) >= r}; T is found once per thread by stepping nextafter around r*r.
 #include "common.cuh"
 #include "rfnet_ops.h"
+#include "segscatter.cuh"
 
 namespace rfnet {
 
@@ -131,6 +132,39 @@ __global__ void group_point_grad_v4_kernel(int n, int cv, unsigned rows_per_clou
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
 }
 
+// Atomic-free gradient: grad_points[i, t, :] = sum of grad_out rows whose idx is t, in ascending row order (the order of
+// the reference's CPU prototype, tf_ops/grouping/query_ball_point.cpp:69-84) -> deterministic, bit-exact with it.
+template <typename VEC>
+__device__ __forceinline__ VEC vec_add(VEC a, VEC b);
+template <>
+__device__ __forceinline__ float vec_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <>
+__device__ __forceinline__ float4 vec_add<float4>(float4 a, float4 b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+template <typename VEC>
+__device__ __forceinline__ VEC vec_zero();
+template <>
+__device__ __forceinline__ float vec_zero<float>() { return 0.f; }
+template <>
+__device__ __forceinline__ float4 vec_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <typename VEC>
+__global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC* __restrict__ grad_out, const int* __restrict__ offset,
+                                            const int* __restrict__ list, VEC* __restrict__ grad_points) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (target point, channel vector) of this cloud
+    const unsigned i = t / (unsigned)cv;
+    if (i >= (unsigned)n) return;
+    const unsigned l = t - i * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const int beg = offset[cloud * (n + 1) + i], end = offset[cloud * (n + 1) + i + 1];
+    const int* __restrict__ seg = list + cloud * R;
+    const VEC* __restrict__ G = grad_out + cloud * (size_t)R * cv + l;
+    VEC acc = vec_zero<VEC>();
+    for (int e = beg; e < end; ++e) acc = vec_add<VEC>(acc, __ldg(G + (size_t)seg[e] * cv));
+    grad_points[(cloud * n + i) * cv + l] = acc;
+}
+
 }  // namespace rfnet
 
 using namespace rfnet;
@@ -166,20 +200,41 @@ extern "C" int rfnet_group_point(int b, int n, int c, int m, int nsample, const 
     return launch_status();
 }
 
+extern "C" size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, int m, int nsample) {
+    (void)c;
+    if (b <= 0 || n <= 0) return 0;
+    return seg::csr_bytes(b, n, (size_t)(m > 0 ? m : 0) * (nsample > 0 ? nsample : 0));
+}
+
 extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx, float* grad_points,
-                                      rfnet_stream_t stream) {
+                                      void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0);
     cudaStream_t s = (cudaStream_t)stream;
-    if ((size_t)b * n * c) {
-        RFNET_CHECK_ARG(grad_points);
-        RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, s));
-    }
     const size_t rows = (size_t)b * m * nsample;
-    if (rows == 0 || c == 0) return 0;
-    RFNET_CHECK_ARG(n > 0 && grad_out && idx);
     const size_t rpc = (size_t)m * nsample;
-    RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull);
-    if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
+    if ((size_t)b * n * c == 0) return 0;
+    RFNET_CHECK_ARG(grad_points && (rows == 0 || (grad_out && idx)));
+    RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull && (size_t)n * c < 0x7fffffffull);
+    const bool vec = c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0;
+    if (workspace) {
+        // atomic-free, deterministic path
+        RFNET_CHECK_ARG(workspace_bytes >= rfnet_group_point_grad_workspace_bytes(b, n, c, m, nsample));
+        seg::Csr csr = seg::csr_carve(workspace, b, n, rpc);
+        const int rc = seg::csr_build(csr, b, n, rpc, idx, s);
+        if (rc) return rc;
+        if (vec) {
+            dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
+            group_point_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)grad_out, csr.offset, csr.list, (float4*)grad_points);
+        } else {
+            dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
+            group_point_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, csr.offset, csr.list, grad_points);
+        }
+        return launch_status();
+    }
+    // no workspace: the reference's formulation (zero-fill + float reductions), order-dependent in the last bits
+    RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, s));
+    if (rows == 0) return 0;
+    if (vec) {
         dim3 grid((unsigned)((rpc * (c / 4) + 255) / 256), (unsigned)b);
         group_point_grad_v4_kernel<<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)grad_out, idx, (float4*)grad_points);
     } else {

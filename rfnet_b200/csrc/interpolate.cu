@@ -10,6 +10,7 @@
 // broadcast from shared memory, a 3-input-min filter so the insertion code only runs when a candidate can enter the top 3.
 #include "common.cuh"
 #include "rfnet_ops.h"
+#include "segscatter.cuh"
 
 namespace rfnet {
 
@@ -161,6 +162,46 @@ __global__ void three_interpolate_grad_v4_kernel(int n, int cv, int m, const flo
     }
 }
 
+// Atomic-free gradient.  Source entries are the 3n (j, u) pairs in row-major order; grad_points[t, :] accumulates
+// grad_out[j, :] * w[j, u] over the entries that point at t in ascending (j, u) -- exactly the order of
+// threeinterpolate_grad_cpu (tf_interpolate.cpp:131-153), unfused, so the result is bit-exact with the reference.
+template <typename VEC>
+__device__ __forceinline__ VEC vec_madd_unfused(VEC acc, VEC g, float w);
+template <>
+__device__ __forceinline__ float vec_madd_unfused<float>(float acc, float g, float w) { return __fadd_rn(acc, __fmul_rn(g, w)); }
+template <>
+__device__ __forceinline__ float4 vec_madd_unfused<float4>(float4 acc, float4 g, float w) {
+    return make_float4(__fadd_rn(acc.x, __fmul_rn(g.x, w)), __fadd_rn(acc.y, __fmul_rn(g.y, w)), __fadd_rn(acc.z, __fmul_rn(g.z, w)),
+                       __fadd_rn(acc.w, __fmul_rn(g.w, w)));
+}
+template <typename VEC>
+__device__ __forceinline__ VEC vec_zero3();
+template <>
+__device__ __forceinline__ float vec_zero3<float>() { return 0.f; }
+template <>
+__device__ __forceinline__ float4 vec_zero3<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <typename VEC>
+__global__ void three_interpolate_grad_seg_kernel(int n, int cv, int m, const VEC* __restrict__ grad_out, const float* __restrict__ weight,
+                                                  const int* __restrict__ offset, const int* __restrict__ list, VEC* __restrict__ grad_points) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (known point, channel vector) of this cloud
+    const unsigned i = t / (unsigned)cv;
+    if (i >= (unsigned)m) return;
+    const unsigned l = t - i * (unsigned)cv;
+    const size_t cloud = blockIdx.y;
+    const size_t R = (size_t)n * 3;
+    const int beg = offset[cloud * (m + 1) + i], end = offset[cloud * (m + 1) + i + 1];
+    const int* __restrict__ seg = list + cloud * R;
+    const VEC* __restrict__ G = grad_out + cloud * (size_t)n * cv + l;
+    const float* __restrict__ W = weight + cloud * R;
+    VEC acc = vec_zero3<VEC>();
+    for (int e = beg; e < end; ++e) {
+        const int src = seg[e];  // = 3*j + u
+        acc = vec_madd_unfused<VEC>(acc, __ldg(G + (size_t)(src / 3) * cv), __ldg(W + src));
+    }
+    grad_points[(cloud * m + i) * cv + l] = acc;
+}
+
 }  // namespace rfnet
 
 using namespace rfnet;
@@ -192,19 +233,38 @@ extern "C" int rfnet_three_interpolate(int b, int m, int c, int n, const float* 
     return launch_status();
 }
 
+extern "C" size_t rfnet_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m) {
+    (void)c;
+    if (b <= 0 || m <= 0) return 0;
+    return seg::csr_bytes(b, m, (size_t)(n > 0 ? n : 0) * 3);
+}
+
 extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
-                                            float* grad_points, rfnet_stream_t stream) {
+                                            float* grad_points, void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0);
     cudaStream_t s = (cudaStream_t)stream;
-    if ((size_t)b * m * c) {
-        RFNET_CHECK_ARG(grad_points);
-        RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, s));
-    }
+    if ((size_t)b * m * c == 0) return 0;
     const size_t rows = (size_t)b * n;
-    if (rows == 0 || c == 0) return 0;
-    RFNET_CHECK_ARG(m > 0 && grad_out && idx && weight);
-    RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull);
-    if (c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0) {
+    RFNET_CHECK_ARG(grad_points && (rows == 0 || (grad_out && idx && weight)));
+    RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull && (size_t)m * c < 0x7fffffffull && (size_t)n * 3 < 0x7fffffffull);
+    const bool vec = c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0;
+    if (workspace) {
+        RFNET_CHECK_ARG(workspace_bytes >= rfnet_three_interpolate_grad_workspace_bytes(b, n, c, m));
+        seg::Csr csr = seg::csr_carve(workspace, b, m, (size_t)n * 3);
+        const int rc = seg::csr_build(csr, b, m, (size_t)n * 3, idx, s);   // idx (b, n, 3) read as (b, 3n) source entries
+        if (rc) return rc;
+        if (vec) {
+            dim3 grid((unsigned)(((size_t)m * (c / 4) + 255) / 256), (unsigned)b);
+            three_interpolate_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, m, (const float4*)grad_out, weight, csr.offset, csr.list, (float4*)grad_points);
+        } else {
+            dim3 grid((unsigned)(((size_t)m * c + 255) / 256), (unsigned)b);
+            three_interpolate_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, m, grad_out, weight, csr.offset, csr.list, grad_points);
+        }
+        return launch_status();
+    }
+    RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, s));
+    if (rows == 0) return 0;
+    if (vec) {
         dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
         three_interpolate_grad_v4_kernel<<<grid, 256, 0, s>>>(n, c / 4, m, (const float4*)grad_out, idx, weight, (float4*)grad_points);
     } else {

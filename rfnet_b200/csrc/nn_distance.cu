@@ -20,6 +20,7 @@
 // The distance is evaluated in the reference's operand order (common.cuh: sqdist3x2), so indices are bit-exact.
 #include "common.cuh"
 #include "rfnet_ops.h"
+#include "segscatter.cuh"
 
 namespace rfnet {
 
@@ -270,6 +271,59 @@ __global__ void nn_grad_scatter_kernel(int n, int m, const float* __restrict__ x
     }
 }
 
+// Atomic-free gradient (used when the caller provides a workspace): one thread per point of either cloud assembles that
+// point's whole gradient in the reference's own summation order (NnDistanceGradOp::Compute, tf_nndistance.cpp:126-163):
+//   point p of xyz1:  own term first, then  -= g2[k] * (xyz2[k] - xyz1[p])  for the k with idx2[k] == p, ascending k;
+//   point q of xyz2:  -= g1[j] * (xyz1[j] - xyz2[q])  for the j with idx1[j] == q, ascending j, THEN += its own term
+// with every product and sum rounded separately, so the result is bit-exact with the reference's CPU kernel and
+// independent of thread timing.  The two index lists are inverted by seg::csr_build (integer atomics only).
+__global__ void nn_grad_seg_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2, const float* __restrict__ gd1,
+                                   const int* __restrict__ idx1, const float* __restrict__ gd2, const int* __restrict__ idx2,
+                                   const int* __restrict__ off_to1, const int* __restrict__ list_to1,   // sources k of xyz2 grouped by target p of xyz1
+                                   const int* __restrict__ off_to2, const int* __restrict__ list_to2,   // sources j of xyz1 grouped by target q of xyz2
+                                   float* __restrict__ g1, float* __restrict__ g2) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cloud = blockIdx.y;
+    const float* __restrict__ A = xyz1 + cloud * (size_t)n * 3;
+    const float* __restrict__ B = xyz2 + cloud * (size_t)m * 3;
+    if (t < (unsigned)n) {
+        const unsigned p = t;
+        const float px = A[p * 3], py = A[p * 3 + 1], pz = A[p * 3 + 2];
+        const int j2 = idx1[cloud * n + p];
+        const float g = __fmul_rn(gd1[cloud * n + p], 2.0f);
+        float ax = __fmul_rn(g, __fsub_rn(px, B[j2 * 3])), ay = __fmul_rn(g, __fsub_rn(py, B[j2 * 3 + 1])), az = __fmul_rn(g, __fsub_rn(pz, B[j2 * 3 + 2]));
+        const int beg = off_to1[cloud * (n + 1) + p], end = off_to1[cloud * (n + 1) + p + 1];
+        for (int e = beg; e < end; ++e) {
+            const int k = list_to1[cloud * m + e];
+            const float gk = __fmul_rn(gd2[cloud * m + k], 2.0f);
+            ax = __fsub_rn(ax, __fmul_rn(gk, __fsub_rn(B[k * 3], px)));
+            ay = __fsub_rn(ay, __fmul_rn(gk, __fsub_rn(B[k * 3 + 1], py)));
+            az = __fsub_rn(az, __fmul_rn(gk, __fsub_rn(B[k * 3 + 2], pz)));
+        }
+        float* o = g1 + (cloud * n + p) * 3;
+        o[0] = ax; o[1] = ay; o[2] = az;
+    } else if (t < (unsigned)(n + m)) {
+        const unsigned q = t - n;
+        const float qx = B[q * 3], qy = B[q * 3 + 1], qz = B[q * 3 + 2];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const int beg = off_to2[cloud * (m + 1) + q], end = off_to2[cloud * (m + 1) + q + 1];
+        for (int e = beg; e < end; ++e) {
+            const int j = list_to2[cloud * n + e];
+            const float gj = __fmul_rn(gd1[cloud * n + j], 2.0f);
+            ax = __fsub_rn(ax, __fmul_rn(gj, __fsub_rn(A[j * 3], qx)));
+            ay = __fsub_rn(ay, __fmul_rn(gj, __fsub_rn(A[j * 3 + 1], qy)));
+            az = __fsub_rn(az, __fmul_rn(gj, __fsub_rn(A[j * 3 + 2], qz)));
+        }
+        const int j2 = idx2[cloud * m + q];
+        const float g = __fmul_rn(gd2[cloud * m + q], 2.0f);
+        ax = __fadd_rn(ax, __fmul_rn(g, __fsub_rn(qx, A[j2 * 3])));
+        ay = __fadd_rn(ay, __fmul_rn(g, __fsub_rn(qy, A[j2 * 3 + 1])));
+        az = __fadd_rn(az, __fmul_rn(g, __fsub_rn(qz, A[j2 * 3 + 2])));
+        float* o = g2 + (cloud * m + q) * 3;
+        o[0] = ax; o[1] = ay; o[2] = az;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Loss-level epilogue of chamfer_big / fidelity_loss (vv_recon.py:381-390): sums[0] = sum sqrt(dist1), sums[1] = #dist1,
 // sums[2] = sum sqrt(dist2), sums[3] = #dist2.  Two tiny launches, fixed summation order (deterministic).
@@ -404,9 +458,14 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     return launch_status();
 }
 
+extern "C" size_t rfnet_nn_distance_grad_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return seg::csr_bytes(b, n, (size_t)m) + seg::csr_bytes(b, m, (size_t)n);
+}
+
 extern "C" int rfnet_nn_distance_grad(int b, int n, const float* xyz1, int m, const float* xyz2, const float* grad_dist1,
                                       const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1, float* grad_xyz2,
-                                      rfnet_stream_t stream) {
+                                      void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
     if (b == 0 || (n == 0 && m == 0)) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -416,6 +475,20 @@ extern "C" int rfnet_nn_distance_grad(int b, int n, const float* xyz1, int m, co
         return 0;
     }
     RFNET_CHECK_ARG(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2);
+    if (workspace) {
+        RFNET_CHECK_ARG(workspace_bytes >= rfnet_nn_distance_grad_workspace_bytes(b, n, m) && b <= 65535);
+        seg::Csr to1 = seg::csr_carve(workspace, b, n, (size_t)m);                                   // idx2: xyz2 rows -> xyz1 points
+        seg::Csr to2 = seg::csr_carve((char*)workspace + seg::csr_bytes(b, n, (size_t)m), b, m, (size_t)n);  // idx1: xyz1 rows -> xyz2 points
+        int rc = seg::csr_build(to1, b, n, (size_t)m, idx2, s);
+        if (rc) return rc;
+        rc = seg::csr_build(to2, b, m, (size_t)n, idx1, s);
+        if (rc) return rc;
+        dim3 grid((unsigned)(((size_t)n + m + 255) / 256), (unsigned)b);
+        nn_grad_seg_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, to1.offset, to1.list, to2.offset, to2.list,
+                                                grad_xyz1, grad_xyz2);
+        return launch_status();
+    }
+    // no workspace: own terms by plain stores, scattered terms by float reductions (order-dependent in the last bits)
     const size_t t1 = (size_t)b * n, t2 = (size_t)b * m;
     const unsigned grid = (unsigned)((t1 + t2 + 255) / 256);
     nn_grad_own_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, t1, t2);

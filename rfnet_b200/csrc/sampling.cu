@@ -293,16 +293,11 @@ extern "C" int rfnet_gatherpoint(int b, int n, int m, const float* inp, const in
     return launch_status();
 }
 
-extern "C" int rfnet_scatteraddpoint(int b, int n, int m, const float* out_g, const int* idx, float* inp_g, rfnet_stream_t stream) {
-    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
-    cudaStream_t s = (cudaStream_t)stream;
-    if ((size_t)b * n) {
-        RFNET_CHECK_ARG(inp_g);
-        RFNET_CUDA(cudaMemsetAsync(inp_g, 0, sizeof(float) * 3 * (size_t)b * n, s));
-    }
-    const size_t total = (size_t)b * m;
-    if (total == 0) return 0;
-    RFNET_CHECK_ARG(n > 0 && out_g && idx);
-    scatteradd_point_kernel<<<(unsigned)((total * 3 + 255) / 256), 256, 0, s>>>(n, m, total, out_g, idx, inp_g);
-    return launch_status();
+extern "C" size_t rfnet_scatteraddpoint_workspace_bytes(int b, int n, int m) { return rfnet_group_point_grad_workspace_bytes(b, n, 3, m, 1); }
+
+// gather_point's gradient is group_point's with c = 3 and one sample per row: same atomic-free segmented sum when a
+// workspace is given, the reference's zero-fill + float reductions otherwise.
+extern "C" int rfnet_scatteraddpoint(int b, int n, int m, const float* out_g, const int* idx, float* inp_g, void* workspace, size_t workspace_bytes,
+                                     rfnet_stream_t stream) {
+    return rfnet_group_point_grad(b, n, 3, m, 1, out_g, idx, inp_g, workspace, workspace_bytes, stream);
 }

@@ -61,7 +61,7 @@ class ChamferHostPipeline:
         compute.wait_event(self.ev_out[k])   # the slot's device results were last read by the copy-out of batch count - depth
         r = self.dres[k]
         ops.raw_nn_distance(self.x1[k], self.x2[k], r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["ws"])
-        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"])
+        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"], r["ws"])
         ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
         if reduce_fn is not None:
             reduce_fn(r["sums"])              # in place (e.g. an all-reduce across ranks)

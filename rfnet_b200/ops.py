@@ -54,10 +54,12 @@ def raw_nn_distance(xyz1, xyz2, dist1, idx1, dist2, idx2, workspace, unfused=Fal
                                              workspace.numel(), 1 if unfused else 0, _stream(xyz1)), "rfnet_nn_distance")
 
 
-def raw_nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2):
+def raw_nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, workspace=None):
+    """workspace (uint8 tensor of rfnet_nn_distance_grad_workspace_bytes) selects the atomic-free deterministic scatter."""
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     _lib.check(_lib.load().rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
-                                                  _ptr(grad_xyz1), _ptr(grad_xyz2), _stream(xyz1)), "rfnet_nn_distance_grad")
+                                                  _ptr(grad_xyz1), _ptr(grad_xyz2), _ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                                  _stream(xyz1)), "rfnet_nn_distance_grad")
 
 
 def raw_chamfer_partial_sums(dist1, dist2, sums4, workspace):
@@ -67,7 +69,8 @@ def raw_chamfer_partial_sums(dist1, dist2, sums4, workspace):
 
 def nn_distance_workspace_bytes(b, n, m):
     lib = _lib.load()
-    return max(int(lib.rfnet_nn_distance_workspace_bytes(b, n, m)), int(lib.rfnet_chamfer_partial_sums_workspace_bytes()), 16)
+    return max(int(lib.rfnet_nn_distance_workspace_bytes(b, n, m)), int(lib.rfnet_chamfer_partial_sums_workspace_bytes()),
+               int(lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m)), 16)
 
 
 # ------------------------------------------------------------------------------------------------------------ nn_distance
@@ -119,9 +122,12 @@ def nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torc
     grad_dist1, grad_dist2 = _cuda_f32("grad_dist1", grad_dist1), _cuda_f32("grad_dist2", grad_dist2)
     idx1, idx2 = _cuda_i32("idx1", idx1), _cuda_i32("idx2", idx2)
     g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    lib = _lib.load()
+    wsb = lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m)   # workspace => atomic-free deterministic scatter
+    ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(_lib.load().rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
-                                                      _ptr(g1), _ptr(g2), _stream(xyz1)), "rfnet_nn_distance_grad")
+        _lib.check(lib.rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
+                                              _ptr(g1), _ptr(g2), _ptr(ws) if wsb else _vp(0), wsb, _stream(xyz1)), "rfnet_nn_distance_grad")
     return g1, g2
 
 
@@ -303,8 +309,12 @@ def gather_point_grad_op(inp: torch.Tensor, idx: torch.Tensor, out_g: torch.Tens
     _require(out_g.dim() == 3 and tuple(out_g.shape) == (b, m, 3), "GatherPointGradGpuOp expects (batch_size,num_result,3) out_g shape")
     idx, out_g = _cuda_i32("idx", idx), _cuda_f32("out_g", out_g)
     inp_g = torch.empty((b, n, 3), dtype=torch.float32, device=out_g.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_scatteraddpoint_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, out_g.device)
     with torch.cuda.device(out_g.device):
-        _lib.check(_lib.load().rfnet_scatteraddpoint(b, n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _stream(out_g)), "rfnet_scatteraddpoint")
+        _lib.check(lib.rfnet_scatteraddpoint(b, n, m, _ptr(out_g), _ptr(idx), _ptr(inp_g), _ptr(ws) if wsb else _vp(0), wsb, _stream(out_g)),
+                   "rfnet_scatteraddpoint")
     return inp_g
 
 
@@ -379,8 +389,12 @@ def group_point_grad_op(points: torch.Tensor, idx: torch.Tensor, grad_out: torch
     _require(grad_out.dim() == 4 and tuple(grad_out.shape) == (b, m, ns, c), "GroupPointGrad expects (batch_size, npoints, nsample, channel) grad_out shape")
     idx, grad_out = _cuda_i32("idx", idx), _cuda_f32("grad_out", grad_out)
     g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_group_point_grad_workspace_bytes(b, n, c, m, ns)
+    ws = _workspace(wsb, grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.check(_lib.load().rfnet_group_point_grad(b, n, c, m, ns, _ptr(grad_out), _ptr(idx), _ptr(g), _stream(grad_out)), "rfnet_group_point_grad")
+        _lib.check(lib.rfnet_group_point_grad(b, n, c, m, ns, _ptr(grad_out), _ptr(idx), _ptr(g), _ptr(ws) if wsb else _vp(0), wsb, _stream(grad_out)),
+                   "rfnet_group_point_grad")
     return g
 
 
@@ -458,9 +472,12 @@ def three_interpolate_grad_op(points: torch.Tensor, idx: torch.Tensor, weight: t
     _require(grad_out.dim() == 3 and tuple(grad_out.shape) == (b, n, c), "ThreeInterpolateGrad expects (b,n,c) grad_out shape")
     idx, weight, grad_out = _cuda_i32("idx", idx), _cuda_f32("weight", weight), _cuda_f32("grad_out", grad_out)
     g = torch.empty((b, m, c), dtype=torch.float32, device=grad_out.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_three_interpolate_grad_workspace_bytes(b, n, c, m)
+    ws = _workspace(wsb, grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.check(_lib.load().rfnet_three_interpolate_grad(b, n, c, m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g), _stream(grad_out)),
-                   "rfnet_three_interpolate_grad")
+        _lib.check(lib.rfnet_three_interpolate_grad(b, n, c, m, _ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(g), _ptr(ws) if wsb else _vp(0), wsb,
+                                                    _stream(grad_out)), "rfnet_three_interpolate_grad")
     return g
 
 

@@ -65,7 +65,7 @@ def test_group_point_and_grad(cuda, rng, c):
     go = rng.standard_normal((b, m, ns, c)).astype(np.float32)
     want = port.group_point_grad(pts, idx, go)
     gg = ops.group_point_grad_op(t(pts, cuda), t(idx, cuda), t(go, cuda)).cpu().numpy()
-    assert np.allclose(gg, want, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(gg, want)    # atomic-free scatter in the CPU prototype's order (query_ball_point.cpp:69-84): bit-exact
 
 
 def test_group_point_gradient_check_like_reference(cuda):
@@ -109,7 +109,7 @@ def test_three_interpolate_and_grad(cuda, rng, c):
     go = rng.standard_normal((b, n, c)).astype(np.float32)
     want = port.three_interpolate_grad(pts, idx, w, go)
     gg = ops.three_interpolate_grad_op(t(pts, cuda), t(idx, cuda), t(w, cuda), t(go, cuda)).cpu().numpy()
-    assert np.allclose(gg, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    assert np.array_equal(gg, want)    # same (j, u) order and unfused arithmetic as threeinterpolate_grad_cpu: bit-exact
 
 
 def test_three_interpolate_gradient_check_like_reference(cuda):
@@ -156,3 +156,25 @@ def test_config4_pipeline_properties(cuda):
                + torch.gather(feats, 1, i3[..., 1].long()[..., None].expand(-1, -1, 64)) * w[..., 1:2]
                + torch.gather(feats, 1, i3[..., 2].long()[..., None].expand(-1, -1, 64)) * w[..., 2:3])
     assert torch.allclose(out, ref_out, rtol=1e-5, atol=1e-6)
+
+
+def test_group_point_grad_heavy_collisions_and_atomic_path(cuda, rng):
+    """All rows gather the same few points (segment lengths in every class of the CSR sort); then the workspace-free
+    (float-reduction) path of the C ABI on the same data, equal within rounding."""
+    import ctypes
+    from rfnet_b200 import _lib, ops
+    b, n, m, ns, c = 2, 50, 300, 20, 8
+    pts = rng.standard_normal((b, n, c)).astype(np.float32)
+    idx = (rng.integers(0, 3, size=(b, m, ns)) * 7).astype(np.int32)          # only points 0, 7, 14 are ever gathered
+    go = rng.standard_normal((b, m, ns, c)).astype(np.float32)
+    want = port.group_point_grad(pts, idx, go)
+    got = ops.group_point_grad_op(t(pts, cuda), t(idx, cuda), t(go, cuda))
+    assert np.array_equal(got.cpu().numpy(), want)
+    out = torch.empty((b, n, c), device=cuda)
+    lib = _lib.load()
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    gi, gg = t(idx, cuda), t(go, cuda)
+    rc = lib.rfnet_group_point_grad(b, n, c, m, ns, p(gg), p(gi), p(out), ctypes.c_void_p(0), 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.allclose(out.cpu().numpy(), want, rtol=1e-4, atol=1e-3)
