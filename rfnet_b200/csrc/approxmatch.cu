@@ -210,44 +210,60 @@ __global__ void emd_epi3_kernel(int n, int nsplit, size_t bn, const float* __res
 constexpr int MT_THREADS = 128;
 constexpr int MT_L = 64;
 struct EmdLevels { float lvl2[EMD_LEVELS]; };
+// CTA = 256 k's (two per thread, a packed pair) x MT_L l's.  Per l the thread reads the point and its 10 factors with four
+// LDS.128 (shared by both k's) and runs the level loop on packed pairs: FMUL2 (argument), 2 MUFU.EX2, FMUL2 (x facL pair),
+// FFMA2 (x facR broadcast, accumulate).  The accumulation is the reference's: acc = fma(facL * e, facR, acc), level by level.
 __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int m, size_t bn, size_t bm, EmdLevels lv,
                                                                      const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                                      const float* __restrict__ facL, const float* __restrict__ facR,
                                                                      float* __restrict__ match) {
-    __shared__ float sP[MT_L][4];
-    __shared__ float sF[MT_L][EMD_LEVELS];
+    __shared__ __align__(16) float4 sP[MT_L];       // x, y, z of xyz2[l]
+    __shared__ __align__(16) float sF[MT_L][12];    // facR_j[l], j = 0..9 (+2 pad)
     const int cloud = blockIdx.z;
-    const int k = blockIdx.x * MT_THREADS + threadIdx.x;
+    const int ka = blockIdx.x * (2 * MT_THREADS) + threadIdx.x, kb = ka + MT_THREADS;
     const int l0 = blockIdx.y * MT_L;
     const int nl = min(MT_L, m - l0);
-    for (int i = threadIdx.x; i < nl * 3; i += MT_THREADS) sP[i / 3][i % 3] = xyz2[((size_t)cloud * m + l0) * 3 + i];
+    for (int i = threadIdx.x; i < nl; i += MT_THREADS) {
+        const float* q = xyz2 + ((size_t)cloud * m + l0 + i) * 3;
+        sP[i] = make_float4(q[0], q[1], q[2], 0.f);
+    }
     for (int i = threadIdx.x; i < nl * EMD_LEVELS; i += MT_THREADS) {
         const int l = i / EMD_LEVELS, j = i % EMD_LEVELS;
         sF[l][j] = facR[(size_t)j * bm + (size_t)cloud * m + l0 + l];
     }
-    float x1 = __int_as_float(0x7f800000), y1 = 0.f, z1 = 0.f, fl[EMD_LEVELS];  // lanes past n sit at infinity: they never block a level skip
-    const bool valid = k < n;
-    if (valid) {
-        const float* p = xyz1 + ((size_t)cloud * n + k) * 3;
-        x1 = p[0]; y1 = p[1]; z1 = p[2];
-    }
+    const bool va = ka < n, vb = kb < n;
+    // rows negated (cand + (-row) == cand - row exactly); lanes past n sit at infinity so they never block a level skip
+    const float inf = __int_as_float(0x7f800000);
+    float2 nx = make_float2(-inf, -inf), ny = make_float2(0.f, 0.f), nz = make_float2(0.f, 0.f);
+    float2 fl[EMD_LEVELS];
+    if (va) { const float* p = xyz1 + ((size_t)cloud * n + ka) * 3; nx.x = -p[0]; ny.x = -p[1]; nz.x = -p[2]; }
+    if (vb) { const float* p = xyz1 + ((size_t)cloud * n + kb) * 3; nx.y = -p[0]; ny.y = -p[1]; nz.y = -p[2]; }
 #pragma unroll
-    for (int j = 0; j < EMD_LEVELS; ++j) fl[j] = valid ? facL[(size_t)j * bn + (size_t)cloud * n + k] : 0.f;
+    for (int j = 0; j < EMD_LEVELS; ++j) {
+        fl[j].x = va ? facL[(size_t)j * bn + (size_t)cloud * n + ka] : 0.f;
+        fl[j].y = vb ? facL[(size_t)j * bn + (size_t)cloud * n + kb] : 0.f;
+    }
     __syncthreads();
-    float* __restrict__ out = match + ((size_t)cloud * m + l0) * n + k;
+    float* __restrict__ out = match + ((size_t)cloud * m + l0) * n;
+#pragma unroll 2
     for (int l = 0; l < nl; ++l) {
-        const float d2 = sqdist3<true>(sP[l][0] - x1, sP[l][1] - y1, sP[l][2] - z1);
-        float acc = 0.f;
+        const float4 q = sP[l];
+        const float4 f0 = *reinterpret_cast<const float4*>(&sF[l][0]), f1 = *reinterpret_cast<const float4*>(&sF[l][4]), f2 = *reinterpret_cast<const float4*>(&sF[l][8]);
+        const float fr[EMD_LEVELS] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y};
+        const float2 d2 = sqdist3x2<true>(__fadd2_rn(nx, make_float2(q.x, q.x)), __fadd2_rn(ny, make_float2(q.y, q.y)), __fadd2_rn(nz, make_float2(q.z, q.z)));
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < EMD_LEVELS - 1; ++j) {
             // ex2.approx.ftz returns exactly 0 below 2^-126: when that holds for the whole warp the level contributes
-            // fma(0, ., acc) == acc and its MUFU can be skipped (top levels: most pairs are farther than 0.07 / 0.15 apart)
-            const float a = __fmul_rn(d2, lv.lvl2[j]);
-            if (j < 3 && !__any_sync(0xffffffffu, a >= -126.0f)) continue;
-            acc = __fmaf_rn(__fmul_rn(ex2_approx(a), fl[j]), sF[l][j], acc);
+            // fma(0, ., acc) == acc and its MUFUs can be skipped (top levels: most pairs are farther than 0.07 / 0.15 apart)
+            const float2 a = __fmul2_rn(d2, make_float2(lv.lvl2[j], lv.lvl2[j]));
+            if (j < 3 && !__any_sync(0xffffffffu, a.x >= -126.0f || a.y >= -126.0f)) continue;
+            const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            acc = __ffma2_rn(__fmul2_rn(fl[j], e), make_float2(fr[j], fr[j]), acc);
         }
-        acc = __fmaf_rn(fl[EMD_LEVELS - 1], sF[l][EMD_LEVELS - 1], acc);  // j = -2: level 0, e = 1
-        if (valid) out[(size_t)l * n] = acc;
+        acc = __ffma2_rn(fl[EMD_LEVELS - 1], make_float2(fr[EMD_LEVELS - 1], fr[EMD_LEVELS - 1]), acc);  // j = -2: level 0, e = 1
+        if (va) out[(size_t)l * n + ka] = acc.x;
+        if (vb) out[(size_t)l * n + kb] = acc.y;
     }
 }
 
@@ -580,7 +596,7 @@ extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const f
         emd_sweep<true>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, ns, s);
         emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL);
     }
-    dim3 grid((unsigned)((n + MT_THREADS - 1) / MT_THREADS), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
+    dim3 grid((unsigned)((n + 2 * MT_THREADS - 1) / (2 * MT_THREADS)), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
     RFNET_CHECK_ARG(grid.y <= 65535);
     emd_materialise_kernel<<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, match);
     return launch_status();

@@ -276,25 +276,33 @@ __global__ void nn_grad_scatter_kernel(int n, int m, const float* __restrict__ x
 //   point p of xyz1:  own term first, then  -= g2[k] * (xyz2[k] - xyz1[p])  for the k with idx2[k] == p, ascending k;
 //   point q of xyz2:  -= g1[j] * (xyz1[j] - xyz2[q])  for the j with idx1[j] == q, ascending j, THEN += its own term
 // with every product and sum rounded separately, so the result is bit-exact with the reference's CPU kernel and
-// independent of thread timing.  The two index lists are inverted by seg::csr_build (integer atomics only).
+// independent of thread timing.  Both index lists are inverted in ONE CSR over the n+m points of a cloud pair
+// (seg::csr_build, integer atomics only): source r < m is row r of xyz2 and targets point idx2[r] of xyz1; source
+// r >= m is row r-m of xyz1 and targets point n + idx1[r-m], i.e. a point of xyz2.
+__global__ void nn_grad_combine_idx_kernel(int n, int m, const int* __restrict__ idx1, const int* __restrict__ idx2, int* __restrict__ comb) {
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (unsigned)(n + m)) return;
+    const size_t cloud = blockIdx.y;
+    comb[cloud * (n + m) + r] = r < (unsigned)m ? idx2[cloud * m + r] : n + idx1[cloud * n + (r - m)];
+}
 __global__ void nn_grad_seg_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2, const float* __restrict__ gd1,
                                    const int* __restrict__ idx1, const float* __restrict__ gd2, const int* __restrict__ idx2,
-                                   const int* __restrict__ off_to1, const int* __restrict__ list_to1,   // sources k of xyz2 grouped by target p of xyz1
-                                   const int* __restrict__ off_to2, const int* __restrict__ list_to2,   // sources j of xyz1 grouped by target q of xyz2
-                                   float* __restrict__ g1, float* __restrict__ g2) {
+                                   const int* __restrict__ offset, const int* __restrict__ list, float* __restrict__ g1, float* __restrict__ g2) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)(n + m)) return;
     const size_t cloud = blockIdx.y;
     const float* __restrict__ A = xyz1 + cloud * (size_t)n * 3;
     const float* __restrict__ B = xyz2 + cloud * (size_t)m * 3;
+    const int beg = offset[cloud * (n + m + 1) + t], end = offset[cloud * (n + m + 1) + t + 1];
+    const int* __restrict__ seg = list + cloud * (size_t)(n + m);
     if (t < (unsigned)n) {
         const unsigned p = t;
         const float px = A[p * 3], py = A[p * 3 + 1], pz = A[p * 3 + 2];
         const int j2 = idx1[cloud * n + p];
         const float g = __fmul_rn(gd1[cloud * n + p], 2.0f);
         float ax = __fmul_rn(g, __fsub_rn(px, B[j2 * 3])), ay = __fmul_rn(g, __fsub_rn(py, B[j2 * 3 + 1])), az = __fmul_rn(g, __fsub_rn(pz, B[j2 * 3 + 2]));
-        const int beg = off_to1[cloud * (n + 1) + p], end = off_to1[cloud * (n + 1) + p + 1];
         for (int e = beg; e < end; ++e) {
-            const int k = list_to1[cloud * m + e];
+            const int k = seg[e];  // row of xyz2
             const float gk = __fmul_rn(gd2[cloud * m + k], 2.0f);
             ax = __fsub_rn(ax, __fmul_rn(gk, __fsub_rn(B[k * 3], px)));
             ay = __fsub_rn(ay, __fmul_rn(gk, __fsub_rn(B[k * 3 + 1], py)));
@@ -302,13 +310,12 @@ __global__ void nn_grad_seg_kernel(int n, int m, const float* __restrict__ xyz1,
         }
         float* o = g1 + (cloud * n + p) * 3;
         o[0] = ax; o[1] = ay; o[2] = az;
-    } else if (t < (unsigned)(n + m)) {
+    } else {
         const unsigned q = t - n;
         const float qx = B[q * 3], qy = B[q * 3 + 1], qz = B[q * 3 + 2];
         float ax = 0.f, ay = 0.f, az = 0.f;
-        const int beg = off_to2[cloud * (m + 1) + q], end = off_to2[cloud * (m + 1) + q + 1];
         for (int e = beg; e < end; ++e) {
-            const int j = list_to2[cloud * n + e];
+            const int j = seg[e] - m;  // row of xyz1
             const float gj = __fmul_rn(gd1[cloud * n + j], 2.0f);
             ax = __fsub_rn(ax, __fmul_rn(gj, __fsub_rn(A[j * 3], qx)));
             ay = __fsub_rn(ay, __fmul_rn(gj, __fsub_rn(A[j * 3 + 1], qy)));
@@ -460,7 +467,7 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
 
 extern "C" size_t rfnet_nn_distance_grad_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return seg::csr_bytes(b, n, (size_t)m) + seg::csr_bytes(b, m, (size_t)n);
+    return sizeof(int) * (size_t)b * ((size_t)n + m) + 64 + seg::csr_bytes(b, n + m, (size_t)n + m);
 }
 
 extern "C" int rfnet_nn_distance_grad(int b, int n, const float* xyz1, int m, const float* xyz2, const float* grad_dist1,
@@ -477,15 +484,14 @@ extern "C" int rfnet_nn_distance_grad(int b, int n, const float* xyz1, int m, co
     RFNET_CHECK_ARG(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2);
     if (workspace) {
         RFNET_CHECK_ARG(workspace_bytes >= rfnet_nn_distance_grad_workspace_bytes(b, n, m) && b <= 65535);
-        seg::Csr to1 = seg::csr_carve(workspace, b, n, (size_t)m);                                   // idx2: xyz2 rows -> xyz1 points
-        seg::Csr to2 = seg::csr_carve((char*)workspace + seg::csr_bytes(b, n, (size_t)m), b, m, (size_t)n);  // idx1: xyz1 rows -> xyz2 points
-        int rc = seg::csr_build(to1, b, n, (size_t)m, idx2, s);
-        if (rc) return rc;
-        rc = seg::csr_build(to2, b, m, (size_t)n, idx1, s);
-        if (rc) return rc;
+        int* comb = reinterpret_cast<int*>(workspace);
+        const size_t comb_bytes = (sizeof(int) * (size_t)b * ((size_t)n + m) + 63) & ~(size_t)63;
+        seg::Csr csr = seg::csr_carve((char*)workspace + comb_bytes, b, n + m, (size_t)n + m);
         dim3 grid((unsigned)(((size_t)n + m + 255) / 256), (unsigned)b);
-        nn_grad_seg_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, to1.offset, to1.list, to2.offset, to2.list,
-                                                grad_xyz1, grad_xyz2);
+        nn_grad_combine_idx_kernel<<<grid, 256, 0, s>>>(n, m, idx1, idx2, comb);
+        const int rc = seg::csr_build(csr, b, n + m, (size_t)n + m, comb, s);
+        if (rc) return rc;
+        nn_grad_seg_kernel<<<grid, 256, 0, s>>>(n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, csr.offset, csr.list, grad_xyz1, grad_xyz2);
         return launch_status();
     }
     // no workspace: own terms by plain stores, scattered terms by float reductions (order-dependent in the last bits)

@@ -18,18 +18,23 @@ constexpr int kSegSortMax = 8192;
 constexpr int kSegSmem = 1024;  // segments up to this length are rank-sorted through shared memory (8 warps x 4 KiB per CTA)
 
 struct Csr {
-    int* offset;  // (b, n+1)  exclusive prefix of the per-target counts
-    int* cursor;  // (b, n)    counts, then fill cursors
-    int* list;    // (b, R)    source rows grouped by target, ascending inside a segment
+    int* offset;      // (b, n+1)  exclusive prefix of the per-target counts
+    int* cursor;      // (b, n)    counts, then fill cursors
+    int* list;        // (b, R)    source rows grouped by target, ascending inside a segment
+    int* long_count;  // (1)       number of queued long segments   (directly before cursor: one memset clears both)
+    int2* long_list;  // (b * n)   (cloud, target) of segments longer than kSegThread
 };
 static inline size_t csr_bytes(int b, int n, size_t R) {
-    return sizeof(int) * ((size_t)b * (n + 1) + (size_t)b * n + (size_t)b * R) + 64;
+    return sizeof(int) * ((size_t)b * (n + 1) + 4 + (size_t)b * n + (size_t)b * R + 2 * (size_t)b * n) + 64;
 }
 static inline Csr csr_carve(void* ws, int b, int n, size_t R) {
     Csr c;
-    c.offset = reinterpret_cast<int*>(ws);
-    c.cursor = c.offset + (size_t)b * (n + 1);
-    c.list = c.cursor + (size_t)b * n;
+    int* p = reinterpret_cast<int*>(ws);
+    c.long_list = reinterpret_cast<int2*>(p);  p += 2 * (size_t)b * n;      // 8-byte aligned: first
+    c.offset = p;                              p += (size_t)b * (n + 1);
+    c.long_count = p;                          p += 1;
+    c.cursor = p;                              p += (size_t)b * n;
+    c.list = p;
     (void)R;
     return c;
 }
@@ -42,48 +47,44 @@ static __global__ void csr_count_kernel(int n, unsigned R, const int* __restrict
     atomicAdd(cursor + cloud * n + idx[cloud * R + r], 1);
 }
 
-// one CTA of 1024 threads per cloud: exclusive scan of the counts (n arbitrary), cursor := offset
+// one CTA of 1024 threads per cloud: exclusive scan of the counts (n arbitrary), cursor := offset.  Each thread owns a
+// run of consecutive targets, so there is a single block-wide scan of 1024 partial sums whatever n is.
 static __global__ void __launch_bounds__(1024) csr_scan_kernel(int n, int* __restrict__ cursor, int* __restrict__ offset) {
     __shared__ int warp_tot[32];
-    __shared__ int carry_s;
     const size_t cloud = blockIdx.x;
     int* cnt = cursor + cloud * n;
     int* off = offset + cloud * (n + 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const int per = (n + 1023) / 1024;
+    const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+    int local = 0;
+    for (int i = beg; i < end; ++i) local += cnt[i];
+    int x = local;  // inclusive scan of the thread sums inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < n ? cnt[i] : 0;
-        int x = v;  // inclusive scan inside the warp
+    if (warp == 0) {
+        int t = warp_tot[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            const int y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
         }
-        if (lane == 31) warp_tot[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int t = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += y;
-            }
-            warp_tot[lane] = t;  // inclusive totals of the warps
-        }
-        __syncthreads();
-        const int carry = carry_s;
-        const int excl = carry + (warp ? warp_tot[warp - 1] : 0) + x - v;
-        if (i < n) {
-            off[i] = excl;
-            cnt[i] = excl;  // becomes the fill cursor
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
-        __syncthreads();
+        warp_tot[lane] = t;  // inclusive totals of the warps
     }
-    if (threadIdx.x == 0) off[n] = carry_s;
+    __syncthreads();
+    int run = (warp ? warp_tot[warp - 1] : 0) + x - local;  // exclusive prefix of this thread's run
+    for (int i = beg; i < end; ++i) {
+        const int v = cnt[i];
+        off[i] = run;
+        cnt[i] = run;  // becomes the fill cursor
+        run += v;
+    }
+    if (threadIdx.x == 1023) off[n] = warp_tot[31];
 }
 
 static __global__ void csr_fill_kernel(int n, unsigned R, const int* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ list) {
@@ -94,54 +95,72 @@ static __global__ void csr_fill_kernel(int n, unsigned R, const int* __restrict_
     list[cloud * R + pos] = (int)r;
 }
 
-// one warp per target: sort its segment ascending.  Entries are distinct, so the rank of an entry is the number of
-// smaller entries.  grid (ceil(n/8), b), 256 threads; dynamic smem = 8 warps * kSegSmem ints
-static __global__ void __launch_bounds__(256) csr_sort_kernel(int n, unsigned R, const int* __restrict__ offset, int* __restrict__ list) {
-    extern __shared__ int seg_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + warp;
-    if (t >= n) return;
+// Sort every segment ascending (entries are distinct source rows).  Short segments -- the overwhelming majority: a point is
+// typically referenced a handful of times -- are insertion-sorted by ONE THREAD per target; longer ones are queued
+// (integer atomic on a counter) for the warp-per-segment kernel below.  grid (ceil(n/256), b)
+constexpr int kSegThread = 16;
+static __global__ void csr_sort_short_kernel(int n, unsigned R, const int* __restrict__ offset, int* __restrict__ list, int* __restrict__ long_count,
+                                             int2* __restrict__ long_list) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)n) return;
     const size_t cloud = blockIdx.y;
     const int beg = offset[cloud * (n + 1) + t], end = offset[cloud * (n + 1) + t + 1];
     const int L = end - beg;
-    if (L <= 1 || L > kSegSortMax) return;
+    if (L <= 1) return;
     int* seg = list + cloud * R + beg;
-    if (L <= 32) {
-        const int v = lane < L ? seg[lane] : 0x7fffffff;
-        int rank = 0;
-#pragma unroll 8
-        for (int o = 0; o < 32; ++o) rank += (__shfl_sync(0xffffffffu, v, o) < v) ? 1 : 0;
-        __syncwarp();
-        if (lane < L) seg[rank] = v;
-        return;
-    }
-    if (L <= kSegSmem) {
-        int* s = seg_smem + warp * kSegSmem;
-        for (int i = lane; i < L; i += 32) s[i] = seg[i];
-        __syncwarp();
-        for (int i = lane; i < L; i += 32) {
-            const int v = s[i];
-            int rank = 0;
-            for (int o = 0; o < L; ++o) rank += (s[o] < v) ? 1 : 0;
-            seg[rank] = v;
+    if (L <= kSegThread) {
+        for (int i = 1; i < L; ++i) {
+            const int v = seg[i];
+            int j = i - 1;
+            while (j >= 0 && seg[j] > v) { seg[j + 1] = seg[j]; --j; }
+            seg[j + 1] = v;
         }
         return;
     }
-    // long segment (kSegSmem < L <= kSegSortMax): in-place odd-even transposition sort over global memory, cooperative
-    // across the warp -- O(L^2 / 64) steps per lane, only reached when one point collects thousands of contributions
-    for (int pass = 0; pass < L; ++pass) {
-        for (int i = (pass & 1) + 2 * lane; i + 1 < L; i += 64) {
-            const int a = seg[i], b2 = seg[i + 1];
-            if (a > b2) { seg[i] = b2; seg[i + 1] = a; }
+    if (L <= kSegSortMax) long_list[atomicAdd(long_count, 1)] = make_int2((int)cloud, (int)t);
+}
+
+// persistent warps over the queue of long segments.  The rank of an entry is the number of smaller entries.
+static __global__ void __launch_bounds__(256) csr_sort_long_kernel(int n, unsigned R, const int* __restrict__ offset, int* __restrict__ list,
+                                                                   const int* __restrict__ long_count, const int2* __restrict__ long_list) {
+    __shared__ int seg_smem[8 * kSegSmem];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = *long_count;
+    for (int w = blockIdx.x * 8 + warp; w < total; w += gridDim.x * 8) {
+        const int2 ct = long_list[w];
+        const size_t cloud = (size_t)ct.x;
+        const int beg = offset[cloud * (n + 1) + ct.y], end = offset[cloud * (n + 1) + ct.y + 1];
+        const int L = end - beg;
+        int* seg = list + cloud * R + beg;
+        if (L <= kSegSmem) {
+            int* s = seg_smem + warp * kSegSmem;
+            for (int i = lane; i < L; i += 32) s[i] = seg[i];
+            __syncwarp();
+            for (int i = lane; i < L; i += 32) {
+                const int v = s[i];
+                int rank = 0;
+                for (int o = 0; o < L; ++o) rank += (s[o] < v) ? 1 : 0;
+                seg[rank] = v;
+            }
+            __syncwarp();
+        } else {
+            // kSegSmem < L <= kSegSortMax: in-place odd-even transposition sort over global memory, cooperative across the
+            // warp -- O(L^2 / 64) steps per lane, only reached when one point collects thousands of contributions
+            for (int pass = 0; pass < L; ++pass) {
+                for (int i = (pass & 1) + 2 * lane; i + 1 < L; i += 64) {
+                    const int a = seg[i], b2 = seg[i + 1];
+                    if (a > b2) { seg[i] = b2; seg[i + 1] = a; }
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
     }
 }
 
 // Builds the CSR for idx (b, R) -> targets [0, n).  All work is stream-ordered; `ws` must hold csr_bytes(b, n, R).
 static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaStream_t s) {
     if (b == 0 || n == 0) return 0;
-    RFNET_CUDA(cudaMemsetAsync(c.cursor, 0, sizeof(int) * (size_t)b * n, s));
+    RFNET_CUDA(cudaMemsetAsync(c.long_count, 0, sizeof(int) * ((size_t)b * n + 1), s));  // long_count and cursor are adjacent
     if (R) {
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
         csr_count_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor);
@@ -150,8 +169,9 @@ static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaS
     if (R) {
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
         csr_fill_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor, c.list);
-        dim3 gs((unsigned)((n + 7) / 8), (unsigned)b);
-        csr_sort_kernel<<<gs, 256, 8 * kSegSmem * sizeof(int), s>>>(n, (unsigned)R, c.offset, c.list);
+        dim3 gs((unsigned)((n + 255) / 256), (unsigned)b);
+        csr_sort_short_kernel<<<gs, 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
+        csr_sort_long_kernel<<<kNumSMs, 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
     }
     return launch_status();
 }
