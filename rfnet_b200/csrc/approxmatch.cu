@@ -474,13 +474,14 @@ __global__ void __launch_bounds__(MV_THREADS) matchcostgrad1_v4_kernel(int n, in
     reinterpret_cast<float4*>(o)[2] = make_float4(gz23.x, gx23.y, gy23.y, gz23.y);
 }
 
-// grad2: one warp per l, 16 rows per CTA sharing shared-memory tiles of xyz1; lanes stride k in float4 chunks
+// grad2: one warp per l, 16 rows per CTA sharing shared-memory tiles of xyz1 (stored negated, structure-of-arrays, so the
+// differences p2 - p1 are FADD2 with a broadcast scalar on packed pairs); lanes stride k in float4 chunks of `match`
 constexpr int G2V_WARPS = 16;
 constexpr int G2V_TILE = 1024;  // points of xyz1 per tile (12 KiB)
 __global__ void __launch_bounds__(G2V_WARPS * 32) matchcostgrad2_v4_kernel(int n, int m, const float* __restrict__ xyz1,
                                                                            const float* __restrict__ xyz2, const float* __restrict__ match,
                                                                            float* __restrict__ grad2) {
-    __shared__ __align__(16) float tile[G2V_TILE * 3];
+    __shared__ __align__(16) float sx[G2V_TILE], sy[G2V_TILE], sz[G2V_TILE];
     const int cloud = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int l = blockIdx.x * G2V_WARPS + warp;
@@ -490,35 +491,42 @@ __global__ void __launch_bounds__(G2V_WARPS * 32) matchcostgrad2_v4_kernel(int n
         const float* q = xyz2 + ((size_t)cloud * m + l) * 3;
         x2 = q[0]; y2 = q[1]; z2 = q[2];
     }
+    const float2 X2 = make_float2(x2, x2), Y2 = make_float2(y2, y2), Z2 = make_float2(z2, z2);
     const float* __restrict__ a = xyz1 + (size_t)cloud * n * 3;
     const float* __restrict__ mrow = match + ((size_t)cloud * m + (live ? l : 0)) * n;
     float2 gx = make_float2(0.f, 0.f), gy = gx, gz = gx;
     for (int t0 = 0; t0 < n; t0 += G2V_TILE) {
         const int len = min(G2V_TILE, n - t0);  // multiple of 4
         __syncthreads();
-        for (int i = threadIdx.x; i < (len * 3) >> 2; i += G2V_WARPS * 32) reinterpret_cast<float4*>(tile)[i] = __ldg(reinterpret_cast<const float4*>(a + (size_t)t0 * 3) + i);
+        for (int i4 = threadIdx.x * 4; i4 < len; i4 += G2V_WARPS * 32 * 4) {  // four points per thread: 3 float4 in, 3 float4 out
+            const float4* src = reinterpret_cast<const float4*>(a + (size_t)(t0 + i4) * 3);
+            const float4 A = __ldg(src), B = __ldg(src + 1), C = __ldg(src + 2);
+            *reinterpret_cast<float4*>(&sx[i4]) = make_float4(-A.x, -A.w, -B.z, -C.y);
+            *reinterpret_cast<float4*>(&sy[i4]) = make_float4(-A.y, -B.x, -B.w, -C.z);
+            *reinterpret_cast<float4*>(&sz[i4]) = make_float4(-A.z, -B.y, -C.x, -C.w);
+        }
         __syncthreads();
         if (live) {
 #pragma unroll 2
             for (int k4 = lane * 4; k4 < len; k4 += 128) {
                 const float4 mv = __ldg(reinterpret_cast<const float4*>(mrow + t0 + k4));
-                const float4 A = reinterpret_cast<const float4*>(tile + k4 * 3)[0], B = reinterpret_cast<const float4*>(tile + k4 * 3)[1], C = reinterpret_cast<const float4*>(tile + k4 * 3)[2];
+                const float4 NX = *reinterpret_cast<const float4*>(&sx[k4]), NY = *reinterpret_cast<const float4*>(&sy[k4]), NZ = *reinterpret_cast<const float4*>(&sz[k4]);
                 // e = p2 - p1 for the four points (packed pairs 01, 23)
-                const float2 ex01 = make_float2(x2 - A.x, x2 - A.w), ex23 = make_float2(x2 - B.z, x2 - C.y);
-                const float2 ey01 = make_float2(y2 - A.y, y2 - B.x), ey23 = make_float2(y2 - B.w, y2 - C.z);
-                const float2 ez01 = make_float2(z2 - A.z, z2 - B.y), ez23 = make_float2(z2 - C.x, z2 - C.w);
+                const float2 ex01 = __fadd2_rn(make_float2(NX.x, NX.y), X2), ex23 = __fadd2_rn(make_float2(NX.z, NX.w), X2);
+                const float2 ey01 = __fadd2_rn(make_float2(NY.x, NY.y), Y2), ey23 = __fadd2_rn(make_float2(NY.z, NY.w), Y2);
+                const float2 ez01 = __fadd2_rn(make_float2(NZ.x, NZ.y), Z2), ez23 = __fadd2_rn(make_float2(NZ.z, NZ.w), Z2);
                 const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
-                const float2 s01 = make_float2(mv.x * rsqrtf(fmaxf(d01.x, 1e-20f)), mv.y * rsqrtf(fmaxf(d01.y, 1e-20f)));
-                const float2 s23 = make_float2(mv.z * rsqrtf(fmaxf(d23.x, 1e-20f)), mv.w * rsqrtf(fmaxf(d23.y, 1e-20f)));
+                const float2 s01 = __fmul2_rn(make_float2(mv.x, mv.y), make_float2(rsqrtf(fmaxf(d01.x, 1e-20f)), rsqrtf(fmaxf(d01.y, 1e-20f))));
+                const float2 s23 = __fmul2_rn(make_float2(mv.z, mv.w), make_float2(rsqrtf(fmaxf(d23.x, 1e-20f)), rsqrtf(fmaxf(d23.y, 1e-20f))));
                 gx = __ffma2_rn(ex01, s01, gx); gy = __ffma2_rn(ey01, s01, gy); gz = __ffma2_rn(ez01, s01, gz);
                 gx = __ffma2_rn(ex23, s23, gx); gy = __ffma2_rn(ey23, s23, gy); gz = __ffma2_rn(ez23, s23, gz);
             }
         }
     }
-    const float sx = warp_sum(gx.x + gx.y), sy = warp_sum(gy.x + gy.y), sz = warp_sum(gz.x + gz.y);
+    const float sx_ = warp_sum(gx.x + gx.y), sy_ = warp_sum(gy.x + gy.y), sz_ = warp_sum(gz.x + gz.y);
     if (live && lane == 0) {
         float* o = grad2 + ((size_t)cloud * m + l) * 3;
-        o[0] = sx; o[1] = sy; o[2] = sz;
+        o[0] = sx_; o[1] = sy_; o[2] = sz_;
     }
 }
 

@@ -335,7 +335,7 @@ __global__ void nn_grad_seg_kernel(int n, int m, const float* __restrict__ xyz1,
 // Loss-level epilogue of chamfer_big / fidelity_loss (vv_recon.py:381-390): sums[0] = sum sqrt(dist1), sums[1] = #dist1,
 // sums[2] = sum sqrt(dist2), sums[3] = #dist2.  Two tiny launches, fixed summation order (deterministic).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int CS_BLOCKS = 74;  // per direction
+constexpr int CS_BLOCKS = 148;  // per direction
 __global__ void __launch_bounds__(256) chamfer_sums_kernel(size_t n1, size_t n2, const float* __restrict__ dist1, const float* __restrict__ dist2,
                                                            float* __restrict__ partial) {
     __shared__ float sW[8];
@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(256) chamfer_sums_kernel(size_t n1, size_t n2,
     const float* __restrict__ d = dir ? dist2 : dist1;
     const size_t n = dir ? n2 : n1;
     float s = 0.f;
-    for (size_t i = (size_t)blk * 256 + threadIdx.x; i < n; i += (size_t)CS_BLOCKS * 256) s += __fsqrt_rn(d[i]);
+#pragma unroll 4
+    for (size_t i = (size_t)blk * 256 + threadIdx.x; i < n; i += (size_t)CS_BLOCKS * 256) s += __fsqrt_rn(__ldg(d + i));
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -355,11 +356,14 @@ __global__ void __launch_bounds__(256) chamfer_sums_kernel(size_t n1, size_t n2,
     }
 }
 __global__ void chamfer_sums_final_kernel(size_t n1, size_t n2, const float* __restrict__ partial, float* __restrict__ sums) {
-    if (threadIdx.x < 2) {
-        float t = 0.f;
-        for (int i = 0; i < CS_BLOCKS; ++i) t += partial[threadIdx.x * CS_BLOCKS + i];
-        sums[threadIdx.x * 2] = t;
-        sums[threadIdx.x * 2 + 1] = (float)(threadIdx.x ? n2 : n1);
+    // two warps, one per direction; fixed lane-strided order followed by a fixed shuffle tree: deterministic
+    const int dir = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float t = 0.f;
+    for (int i = lane; i < CS_BLOCKS; i += 32) t += partial[dir * CS_BLOCKS + i];
+    t = warp_sum(t);
+    if (lane == 0) {
+        sums[dir * 2] = t;
+        sums[dir * 2 + 1] = (float)(dir ? n2 : n1);
     }
 }
 
@@ -510,6 +514,6 @@ extern "C" int rfnet_chamfer_partial_sums(int b, int n, int m, const float* dist
     RFNET_CHECK_ARG(((size_t)b * n == 0 || dist1) && ((size_t)b * m == 0 || dist2));
     cudaStream_t s = (cudaStream_t)stream;
     chamfer_sums_kernel<<<2 * CS_BLOCKS, 256, 0, s>>>((size_t)b * n, (size_t)b * m, dist1, dist2, (float*)workspace);
-    chamfer_sums_final_kernel<<<1, 32, 0, s>>>((size_t)b * n, (size_t)b * m, (const float*)workspace, sums4);
+    chamfer_sums_final_kernel<<<1, 64, 0, s>>>((size_t)b * n, (size_t)b * m, (const float*)workspace, sums4);
     return launch_status();
 }

@@ -14,11 +14,12 @@ from . import ops
 class ChamferHostPipeline:
     ALL_OUTPUTS = ("dist1", "idx1", "dist2", "idx2", "grad1", "grad2", "sums")
 
-    def __init__(self, b, n, m, device, depth=3, grad_scale1=None, grad_scale2=None, outputs=ALL_OUTPUTS):
+    def __init__(self, b, n, m, device, depth=3, grad_scale1=None, grad_scale2=None, outputs=ALL_OUTPUTS, deterministic=False):
         """outputs: which results are copied back to the host each step.  A training loop reads back only the loss
         ("sums": sum sqrt(dist1), count1, sum sqrt(dist2), count2 -> chamfer_big); gradients normally stay on the device."""
         self.b, self.n, self.m, self.dev, self.depth = b, n, m, torch.device(device), depth
         self.outputs = tuple(outputs)
+        self.deterministic = bool(deterministic)   # atomic-free CSR scatter for the gradient (bit-reproducible, slower)
         dev = self.dev
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.x1 = [torch.empty((b, n, 3), device=dev) for _ in range(depth)]
@@ -61,7 +62,8 @@ class ChamferHostPipeline:
         compute.wait_event(self.ev_out[k])   # the slot's device results were last read by the copy-out of batch count - depth
         r = self.dres[k]
         ops.raw_nn_distance(self.x1[k], self.x2[k], r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["ws"])
-        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"], r["ws"])
+        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"],
+                                 r["ws"] if self.deterministic else None)
         ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
         if reduce_fn is not None:
             reduce_fn(r["sums"])              # in place (e.g. an all-reduce across ranks)

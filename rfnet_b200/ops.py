@@ -106,8 +106,11 @@ def _(xyz1, xyz2, unfused=False):
 
 @torch.library.custom_op("rfnet::nn_distance_grad", mutates_args=(), device_types="cuda")
 def nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torch.Tensor, idx1: torch.Tensor, grad_dist2: torch.Tensor,
-                        idx2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-    # NnDistanceGradGpuOp::Compute, pc_distance/tf_nndistance.cpp:209-253
+                        idx2: torch.Tensor, deterministic: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    # NnDistanceGradGpuOp::Compute, pc_distance/tf_nndistance.cpp:209-253.
+    # deterministic=False: the reference GPU formulation (float reductions, tf_nndistance_g.cu:131-150), fastest.
+    # deterministic=True : atomic-free CSR scatter, bit-exact with the reference CPU kernel's summation order (~4x the
+    #                      cost of this small op; set RFNET_DETERMINISTIC=1 to make it the default for autograd too).
     _require(xyz1.dim() == 3, "NnDistanceGrad requires xyz1 be of shape (batch,#points,3)")
     _require(xyz1.shape[2] == 3, "NnDistanceGrad only accepts 3d point set xyz1")
     _require(xyz2.dim() == 3, "NnDistanceGrad requires xyz2 be of shape (batch,#points,3)")
@@ -123,7 +126,7 @@ def nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torc
     idx1, idx2 = _cuda_i32("idx1", idx1), _cuda_i32("idx2", idx2)
     g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
     lib = _lib.load()
-    wsb = lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m)   # workspace => atomic-free deterministic scatter
+    wsb = lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m) if deterministic else 0   # workspace => atomic-free deterministic scatter
     ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
         _lib.check(lib.rfnet_nn_distance_grad(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(idx1), _ptr(grad_dist2), _ptr(idx2),
@@ -132,8 +135,12 @@ def nn_distance_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grad_dist1: torc
 
 
 @nn_distance_grad_op.register_fake
-def _(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
+def _(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, deterministic=False):
     return torch.empty_like(xyz1), torch.empty_like(xyz2)
+
+
+import os as _os
+DETERMINISTIC_DEFAULT = _os.environ.get("RFNET_DETERMINISTIC", "0") not in ("", "0", "false", "False")
 
 
 def _nn_distance_setup(ctx, inputs, output):
@@ -148,7 +155,7 @@ def _nn_distance_backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
         grad_dist1 = torch.zeros(idx1.shape, dtype=torch.float32, device=xyz1.device)
     if grad_dist2 is None:
         grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=xyz1.device)
-    g1, g2 = nn_distance_grad_op(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2)
+    g1, g2 = nn_distance_grad_op(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, DETERMINISTIC_DEFAULT)
     return g1, g2, None
 
 
