@@ -9,7 +9,7 @@ NCCL over NVLink on GPUs, gloo in the CPU tests).  Gradients need no collective:
 import torch
 import torch.distributed as dist
 
-from . import tf_approxmatch, tf_nndistance
+from . import tf_approxmatch, tf_grouping, tf_nndistance, tf_sampling
 
 
 def chamfer_big(pcd1, pcd2):
@@ -33,6 +33,44 @@ def earth_mover(pcd1, pcd2):
     match = tf_approxmatch.approx_match(pcd1, pcd2)
     cost = tf_approxmatch.match_cost(pcd1, pcd2, match)
     return torch.mean(cost / num_points)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The other callers of the operators in the reference's model/loss code, as thin torch functions
+# over the drop-in ops -- same arithmetic, same argument meaning.
+# ----------------------------------------------------------------------------------------------------------------------
+def sampling(npoint, xyz):
+    """vv_recon.py:67-70 (use_type='f'): farthest point sampling followed by the gather of the picked points."""
+    idx = tf_sampling.farthest_point_sample(npoint, xyz)
+    return tf_sampling.gather_point(xyz, idx)
+
+
+def merge_layer(rawpts, newpts, decfactor):
+    """vv_recon.py:132-139: pull every new point towards its nearest raw point with weight exp(-d2 / (1e-8 + decfactor^2))."""
+    _, _, _, idx2 = tf_nndistance.nn_distance(rawpts, newpts)
+    grouped_xyz = tf_grouping.group_point(rawpts, idx2.unsqueeze(-1))            # (b, npoint_new, 1, 3)
+    diff = grouped_xyz - newpts.unsqueeze(2)
+    dismat = (diff * diff).sum(-1, keepdim=True)
+    ratio = torch.exp(-dismat / (1e-8 + decfactor * decfactor))
+    return newpts + (ratio * diff).sum(2)
+
+
+def re_chamfer(gt, pred, part=8):
+    """vv_recon.py:171-193: mean of chamfer_big over `part` equal slices of the point axis (pred slice vs gt slice)."""
+    interval = gt.shape[1] // 8                                                     # the reference divides by 8, not by `part`
+    total = 0.0
+    for i in range(part):
+        sl = slice(i * interval, (i + 1) * interval)
+        total = total + chamfer_big(pred[:, sl].contiguous(), gt[:, sl].contiguous())[0]
+    return total / part
+
+
+def zero_groupnear(ptcens, rawpts, outmat):
+    """vv_recon.py:414-419: relu(mean |outmat|^2 - 0.4 * mean nn-dist2(rawpts -> ptcens))."""
+    _, _, dist, _ = tf_nndistance.nn_distance(ptcens, rawpts)
+    inval = dist.mean()
+    outval = (outmat * outmat).sum(-1).mean(-1).mean(-1).mean()
+    return torch.relu(outval - 0.4 * inval)
 
 
 def shard_bounds(global_batch, rank, world_size):

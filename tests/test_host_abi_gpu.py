@@ -126,3 +126,59 @@ def test_ops_are_cuda_graph_capturable(cuda, rng):
     assert np.array_equal(d2.cpu().numpy(), want[2]) and np.array_equal(i2.cpu().numpy(), want[3])
     w1, w2 = port.nn_distance_grad(y1, y2, np.ones((b, n), np.float32), want[1], np.ones((b, m), np.float32), want[3])
     assert np.array_equal(g1.cpu().numpy(), w1) and np.array_equal(g2.cpu().numpy(), w2)
+
+
+def test_model_level_callers(cuda, rng):
+    """sampling / merge_layer / re_chamfer / zero_groupnear (vv_recon.py:67-70,132-139,171-193,414-419) over the drop-in ops,
+    against the same formulas evaluated with the CPU oracle's indices."""
+    import torch
+    from rfnet_b200 import losses
+    b, n_raw, n_new = 2, 300, 512
+    raw, new = cloud(rng, b, n_raw), cloud(rng, b, n_new)
+    traw, tnew = torch.from_numpy(raw).to(cuda), torch.from_numpy(new).to(cuda)
+    # sampling == FPS + gather
+    got = losses.sampling(32, traw).cpu().numpy()
+    assert np.array_equal(got, port.gather_point(raw, port.farthest_point_sample(32, raw)))
+    # merge_layer
+    _, _, _, i2 = port.nn_distance(raw, new)
+    nearest = np.take_along_axis(raw, i2[..., None].astype(np.int64), axis=1)
+    diff = nearest - new
+    want = new + np.exp(-(diff ** 2).sum(-1, keepdims=True) / (1e-8 + 0.05 ** 2)) * diff
+    assert np.allclose(losses.merge_layer(traw, tnew, 0.05).cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    # re_chamfer: 8 slices of 64 points
+    gt, pred = cloud(rng, b, 512), cloud(rng, b, 512)
+    vals = []
+    for i in range(8):
+        d1, _, d2, _ = port.nn_distance(pred[:, i * 64:(i + 1) * 64], gt[:, i * 64:(i + 1) * 64])
+        vals.append((np.sqrt(d1).mean() + np.sqrt(d2).mean()) / 2)
+    got = losses.re_chamfer(torch.from_numpy(gt).to(cuda), torch.from_numpy(pred).to(cuda)).item()
+    assert abs(got - np.mean(vals)) <= 1e-5 * abs(np.mean(vals))
+    # zero_groupnear
+    cens = cloud(rng, b, 16)
+    outmat = rng.standard_normal((b, 16, 8, 3)).astype(np.float32) * 0.01
+    _, _, dist, _ = port.nn_distance(cens, raw)
+    want = max(0.0, float((outmat ** 2).sum(-1).mean() - 0.4 * dist.mean()))
+    got = losses.zero_groupnear(torch.from_numpy(cens).to(cuda), traw, torch.from_numpy(outmat).to(cuda)).item()
+    assert abs(got - want) <= 1e-5 * max(abs(want), 1e-6)
+
+
+def test_64bit_offsets_beyond_int32(cuda):
+    """b*n*m = 9 * 16384^2 = 2.4e9 > 2^31: the reference's approxmatch indexes with int and cannot run this
+    (tf_approxmatch.cu:15); every cloud of the batched call must equal the same cloud run alone."""
+    import torch
+    from rfnet_b200 import tf_approxmatch
+    g = torch.Generator(device="cpu").manual_seed(17)
+    b, n = 9, 16384
+    x1 = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    x2 = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    match = tf_approxmatch.approx_match(x1, x2)
+    assert match.numel() > 2 ** 31
+    cost = tf_approxmatch.match_cost(x1, x2, match)
+    for c in (0, 8):
+        alone = tf_approxmatch.approx_match(x1[c:c + 1].contiguous(), x2[c:c + 1].contiguous())
+        # batch of 9 and batch of 1 take different sweep plans (split counts), so compare within the float32 noise of a 16384-term sum
+        assert float((match[c] - alone[0]).abs().max()) <= 5e-3
+        assert abs(float(match[c].sum()) - float(alone.sum())) <= 1e-3 * float(alone.sum())
+        c_alone = tf_approxmatch.match_cost(x1[c:c + 1].contiguous(), x2[c:c + 1].contiguous(), alone)
+        assert abs(cost[c].item() - c_alone.item()) <= 1e-3 * c_alone.item()
+    del match

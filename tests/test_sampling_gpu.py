@@ -14,7 +14,8 @@ def t(a, dev):
 
 
 # (b, n, m): cluster sizes 1/2/4/8, points-per-thread 1/2/4/8, m > n (repeats), n < 512, tiny
-SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 3000, 32), (4, 4097, 128), (2, 16384, 256), (1, 20000, 64), (40, 1024, 64)]
+SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 3000, 32), (4, 4097, 128), (2, 16384, 256), (1, 20000, 64), (40, 1024, 64),
+          (1, 40000, 24)]   # the last one exceeds 8 CTAs x 512 threads x 8 points: generic one-CTA kernel with global scratch
 
 
 @pytest.mark.parametrize("b,n,m", SHAPES)
