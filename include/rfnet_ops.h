@@ -109,6 +109,12 @@ size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, int m, int ns
 int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
+/* knn_point for 3-d points, k <= 32.  The reference has no kernel for it: tf_ops/grouping/tf_grouping.py:48-73 materialises
+ * the (b, m, n) distance matrix with framework ops and calls tf.nn.top_k(-dist) on the CPU.  xyz1 = dataset (b,n,3),
+ * xyz2 = queries (b,m,3); val (b,m,k) = NEGATED squared distances in descending order (i.e. nearest first), idx (b,m,k). */
+int rfnet_knn_point(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *val, int *idx,
+                    rfnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * interpolation.  The reference has CPU code only: threenn_cpu, threeinterpolate_cpu, threeinterpolate_grad_cpu,
  * tf_ops/interpolation/tf_interpolate.cpp:60,107,131.  Same argument orders.  three_nn evaluates d2 UNFUSED, as the

@@ -212,6 +212,18 @@ def group_point_grad(points, idx, grad_out):
     return g
 
 
+def knn_point(k, xyz1, xyz2):
+    """xyz1 dataset (b,n,3), xyz2 queries (b,m,3) -> val (b,m,k) negated squared distances, idx (b,m,k).  tf_grouping.py:48-73."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    val = np.empty((b, m, k), np.float32)
+    idx = np.empty((b, m, k), np.int32)
+    lib().rfo_knn_point(b, n, m, int(k), p1, p2, val.ctypes.data_as(_f32p), idx.ctypes.data_as(_i32p))
+    return val, idx
+
+
 def three_nn(xyz1, xyz2, fused=False):
     """xyz1 unknown (b,n,3), xyz2 known (b,m,3) -> dist (b,n,3), idx (b,n,3).  tf_interpolate.py:8-18."""
     xyz1, p1 = _f(xyz1)

@@ -434,6 +434,29 @@ RFO_API void rfo_three_interpolate_grad(int b, int n, int c, int m, const float 
         }
 }
 
+/* knn_point for 3-d points.  tf_ops/grouping/tf_grouping.py:48-73: dist = reduce_sum((xyz1 - xyz2)^2, -1) over the (b, m, n)
+ * broadcast, then tf.nn.top_k(-dist, k): values are the negated distances, largest first; equal values keep the lower index
+ * first.  xyz1 = dataset (b,n,3), xyz2 = queries (b,m,3). */
+RFO_API void rfo_knn_point(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *val, int *idx) {
+    float *d = malloc(sizeof(float) * (size_t)n);
+    char *used = malloc((size_t)n);
+    for (int i = 0; i < b; i++)
+        for (int j = 0; j < m; j++) {
+            const float *Q = xyz2 + ((size_t)i * m + j) * 3;
+            for (int t = 0; t < n; t++) { d[t] = sqdist(xyz1 + ((size_t)i * n + t) * 3, Q, 0); used[t] = 0; }
+            for (int s = 0; s < k; s++) {
+                int best = -1;
+                for (int t = 0; t < n; t++)
+                    if (!used[t] && (best < 0 || d[t] < d[best])) best = t;
+                used[best] = 1;
+                val[((size_t)i * m + j) * k + s] = -d[best];
+                idx[((size_t)i * m + j) * k + s] = best;
+            }
+        }
+    free(used);
+    free(d);
+}
+
 /* Smallest float T such that sqrtf(T) >= r, i.e. (max(sqrtf(d2),1e-20f) < r)  <=>  (d2 < T) for r > 1e-20f.
  * Used by tests to check the sqrt-free ball-query predicate of the CUDA kernel. */
 RFO_API float rfo_ball_threshold(float r) {

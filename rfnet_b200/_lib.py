@@ -35,6 +35,7 @@ SIGNATURES = {
     "rfnet_group_point": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_group_point_grad_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
     "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "rfnet_knn_point": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate_grad_workspace_bytes": (_z, [_i, _i, _i, _i]),

@@ -100,6 +100,64 @@ __global__ void __launch_bounds__(TN_THREADS) three_nn_kernel(int n, int m, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// knn_point for 3-d points.  The reference builds the full (b, m, n) distance matrix with framework
+// ops and calls tf.nn.top_k(-dist) "ONLY SUPPORT CPU" (tf_ops/grouping/tf_grouping.py:48-73); this kernel never
+// materialises the matrix: one thread per query keeps its K best (distance, index) sorted in registers, candidates are
+// broadcast from shared memory, and the insertion code runs only when a candidate beats the current K-th best.
+// dist = ((dx*dx + dy*dy) + dz*dz) unfused; equal distances keep the lower index first, as top_k does.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 2048;
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                          float* __restrict__ val, int* __restrict__ idx) {
+    __shared__ __align__(16) float tile[KNN_TILE * 3];
+    const int cloud = blockIdx.y;
+    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const float* __restrict__ data = xyz1 + (size_t)cloud * n * 3;
+    const bool valid = q < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) {
+        const float* p = xyz2 + ((size_t)cloud * m + q) * 3;
+        qx = p[0]; qy = p[1]; qz = p[2];
+    }
+    const float inf = __int_as_float(0x7f800000);
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) { bd[t] = inf; bi[t] = 0; }
+    for (int t0 = 0; t0 < n; t0 += KNN_TILE) {
+        const int len = min(KNN_TILE, n - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < len * 3; i += KNN_THREADS) tile[i] = data[(size_t)t0 * 3 + i];
+        __syncthreads();
+        if (!valid) continue;
+        for (int c = 0; c < len; ++c) {
+            const float d = sqdist3<false>(tile[c * 3] - qx, tile[c * 3 + 1] - qy, tile[c * 3 + 2] - qz);
+            if (d < bd[K - 1]) {
+                // insert after every entry <= d (stable: earlier index first on ties), shifting the tail down
+                float cd = d;
+                int ci = t0 + c;
+#pragma unroll
+                for (int t = 0; t < K; ++t) {
+                    if (cd < bd[t]) {
+                        const float td = bd[t]; const int ti = bi[t];
+                        bd[t] = cd; bi[t] = ci;
+                        cd = td; ci = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    float* v = val + ((size_t)cloud * m + q) * k;
+    int* o = idx + ((size_t)cloud * m + q) * k;
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+        if (t < k) { v[t] = -bd[t]; o[t] = bi[t]; }   // top_k(-dist): values are the NEGATED squared distances (tf_grouping.py:72)
+}
+
 // out[i,j,l] = (p[i1,l]*w1 + p[i2,l]*w2) + p[i3,l]*w3        (tf_interpolate.cpp:107-127).  One thread per output vector.
 template <typename VEC>
 __device__ __forceinline__ VEC blend3(VEC a, VEC b, VEC c, float w1, float w2, float w3);
@@ -271,5 +329,20 @@ extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const fl
         dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
         three_interpolate_grad_kernel<<<grid, 256, 0, s>>>(n, c, m, grad_out, idx, weight, grad_points);
     }
+    return launch_status();
+}
+
+extern "C" int rfnet_knn_point(int b, int n, int m, int k, const float* xyz1, const float* xyz2, float* val, int* idx, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && k > 0 && k <= 32 && k <= (n > 0 ? n : 1));
+    if (b == 0 || m == 0) return 0;
+    RFNET_CHECK_ARG(xyz1 && xyz2 && val && idx && n > 0 && b <= 65535);
+    dim3 grid((unsigned)((m + KNN_THREADS - 1) / KNN_THREADS), (unsigned)b);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k <= 1) knn_kernel<1><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
+    else if (k <= 2) knn_kernel<2><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
+    else if (k <= 4) knn_kernel<4><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
+    else if (k <= 8) knn_kernel<8><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
+    else if (k <= 16) knn_kernel<16><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
+    else knn_kernel<32><<<grid, KNN_THREADS, 0, s>>>(n, m, k, xyz1, xyz2, val, idx);
     return launch_status();
 }

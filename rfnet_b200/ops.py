@@ -422,6 +422,27 @@ def _group_backward(ctx, grad_out):
 group_point_op.register_autograd(_group_backward, setup_context=_group_setup)
 
 
+@torch.library.custom_op("rfnet::knn_point", mutates_args=(), device_types="cuda")
+def knn_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """3-d k-nearest neighbours without materialising the (b,m,n) matrix; outputs as tf.nn.top_k(-dist) (tf_grouping.py:48-73)."""
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3 and xyz2.dim() == 3 and xyz2.shape[2] == 3, "knn_point kernel expects (b,n,3) and (b,m,3)")
+    _require(xyz2.shape[0] == xyz1.shape[0], "knn_point expects xyz1 and xyz2 have same batch size")
+    _require(0 < k <= 32 and k <= xyz1.shape[1], "knn_point kernel expects 0 < k <= min(32, ndataset)")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    val = torch.empty((b, m, k), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, m, k), dtype=torch.int32, device=xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(_lib.load().rfnet_knn_point(b, n, m, k, _ptr(xyz1), _ptr(xyz2), _ptr(val), _ptr(idx), _stream(xyz1)), "rfnet_knn_point")
+    return val, idx
+
+
+@knn_point_op.register_fake
+def _(xyz1, xyz2, k):
+    b, m = xyz2.shape[0], xyz2.shape[1]
+    return xyz1.new_empty((b, m, k)), xyz1.new_empty((b, m, k), dtype=torch.int32)
+
+
 # ------------------------------------------------------------------------------------------------------------ interpolation
 @torch.library.custom_op("rfnet::three_nn", mutates_args=(), device_types="cuda")
 def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:

@@ -43,9 +43,12 @@ def knn_point(k, xyz1, xyz2):
         val: (batch_size, npoint, k) float32 array, NEGATED squared L2 distances (the reference returns top_k(-dist))
         idx: (batch_size, npoint, k) int32 array, indices to input points
 
-    The reference implements this with framework ops only (tf.nn.top_k on a materialised (b,m,n) matrix,
-    tf_grouping.py:64-73); so does this function -- it is outside the custom-kernel path.
+    The reference implements this with framework ops only (tf.nn.top_k on a materialised (b,m,n) matrix, "ONLY SUPPORT
+    CPU", tf_grouping.py:64-73).  For 3-d CUDA points and k <= 32 this uses the rfnet::knn_point kernel, which never builds
+    the matrix; any other input (feature vectors, large k) takes the reference's framework formulation.
     '''
+    if xyz1.is_cuda and xyz1.shape[-1] == 3 and xyz2.shape[-1] == 3 and 0 < int(k) <= min(32, xyz1.shape[1]) and xyz1.dtype == torch.float32:
+        return ops.knn_point_op(xyz1.detach(), xyz2.detach(), int(k))
     dist = ((xyz1[:, None, :, :] - xyz2[:, :, None, :]) ** 2).sum(-1)
     val, idx = torch.topk(-dist, k=int(k), dim=-1)
     return val, idx.to(torch.int32)

@@ -178,3 +178,20 @@ def test_group_point_grad_heavy_collisions_and_atomic_path(cuda, rng):
     assert rc == 0
     torch.cuda.synchronize()
     assert np.allclose(out.cpu().numpy(), want, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("b,n,m,k", [(2, 100, 33, 1), (2, 500, 200, 3), (1, 3000, 257, 16), (2, 2100, 130, 32), (1, 40, 5, 7)])
+def test_knn_point_kernel_bit_exact(cuda, rng, b, n, m, k):
+    """3-d knn_point without the (b,m,n) matrix: values (negated squared distances) and indices equal the oracle's
+    top_k(-dist), including the lower-index-first tie rule on duplicated points."""
+    from rfnet_b200 import tf_grouping
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
+    x1[:, n // 2:] = x1[:, : n - n // 2]          # duplicates -> ties
+    wv, wi = port.knn_point(k, x1, x2)
+    gv, gi = tf_grouping.knn_point(k, t(x1, cuda), t(x2, cuda))
+    assert gi.dtype == torch.int32 and np.array_equal(gi.cpu().numpy(), wi)
+    assert np.array_equal(gv.cpu().numpy(), wv)
+    # agrees with the reference's framework formulation as well
+    d = ((t(x1, cuda)[:, None] - t(x2, cuda)[:, :, None]) ** 2).sum(-1)
+    tv, _ = torch.topk(-d, k=k, dim=-1)
+    assert torch.allclose(gv, tv, rtol=1e-5, atol=1e-7)
