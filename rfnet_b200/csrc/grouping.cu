@@ -4,7 +4,7 @@
 //
 // Ball query design: the reference gives each query to one thread which streams the whole dataset from global memory
 // (uncoalesced, one block per cloud).  Here a WARP owns a query: the dataset is staged tile by tile in shared memory, each
-// lane tests one point of a 32-point group, and a ballot + popcount appends the hits IN INDEX ORDER, so "the first
+// lane tests two consecutive points of a 64-point group (packed FP32x2), and ballots + popcounts append the hits IN INDEX ORDER, so "the first
 // nsample points inside the ball" (tf_grouping_g.cu:17-31) is reproduced exactly, with early exit once the row is full.
 //
 // The predicate max(sqrtf(d2), 1e-20f) < r is evaluated without a square root: sqrt_rn is monotone, so it equals
@@ -17,7 +17,7 @@ namespace rfnet {
 
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_QPW = 4;      // queries per warp
-constexpr int BQ_TILE = 2048;  // dataset points per shared-memory tile (24 KiB)
+constexpr int BQ_TILE = 2048;  // dataset points per shared-memory tile (24 KiB, multiple of 64)
 
 __device__ __forceinline__ float ball_threshold(float r) {
     if (!(r > 1e-20f)) return 0.0f;                          // max(.,1e-20f) < r can never hold (also r = NaN)
@@ -31,11 +31,14 @@ __device__ __forceinline__ float ball_threshold(float r) {
 __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m, const float* __restrict__ radius, int nsample,
                                                                    const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                                    int* __restrict__ idx, int* __restrict__ pts_cnt) {
-    __shared__ float tile[BQ_TILE * 3];
+    // dataset tile, structure-of-arrays and NEGATED: query + (-point) == query - point exactly (the operand order of
+    // tf_grouping_g.cu:24), and each lane reads two consecutive points per LDS.64 for the packed distance
+    __shared__ __align__(16) float sx[BQ_TILE], sy[BQ_TILE], sz[BQ_TILE];
     const int cloud = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* __restrict__ data = xyz1 + (size_t)cloud * n * 3;
     const float T = ball_threshold(radius[0]);
+    const unsigned lt = (1u << lane) - 1u;
 
     const int qbase = (blockIdx.x * BQ_WARPS + warp) * BQ_QPW;
     float qx[BQ_QPW], qy[BQ_QPW], qz[BQ_QPW];
@@ -52,28 +55,40 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m,
 
     for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
         const int len = min(BQ_TILE, n - t0);
+        const int len64 = (len + 63) & ~63;
         __syncthreads();
-        for (int i = threadIdx.x; i < len * 3; i += BQ_WARPS * 32) tile[i] = data[(size_t)t0 * 3 + i];
+        for (int i = threadIdx.x; i < len64; i += BQ_WARPS * 32) {
+            const bool v = i < len;
+            const float* p = data + (size_t)(t0 + (v ? i : 0)) * 3;
+            sx[i] = v ? -p[0] : __int_as_float(0x7f800000);  // padding sits at infinity: d2 = inf is never inside a ball
+            sy[i] = v ? -p[1] : 0.f;
+            sz[i] = v ? -p[2] : 0.f;
+        }
         __syncthreads();
         bool all_full = true;
 #pragma unroll
         for (int u = 0; u < BQ_QPW; ++u) {
             if (cnt[u] >= nsample) continue;  // warp-uniform
             int* __restrict__ row = idx + ((size_t)cloud * m + qbase + u) * nsample;
-            for (int k0 = 0; k0 < len && cnt[u] < nsample; k0 += 32) {
-                const int k = k0 + lane;
-                bool hit = false;
-                if (k < len) {
-                    // (query - dataset), the operand order of tf_grouping_g.cu:24
-                    const float d2 = sqdist3<true>(qx[u] - tile[k * 3 + 0], qy[u] - tile[k * 3 + 1], qz[u] - tile[k * 3 + 2]);
-                    hit = d2 < T;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (mask) {
-                    if (cnt[u] == 0) first[u] = t0 + k0 + __ffs(mask) - 1;
-                    const int pos = cnt[u] + __popc(mask & ((1u << lane) - 1u));
-                    if (hit && pos < nsample) row[pos] = t0 + k;
-                    cnt[u] += __popc(mask);
+            const float2 QX = make_float2(qx[u], qx[u]), QY = make_float2(qy[u], qy[u]), QZ = make_float2(qz[u], qz[u]);
+            for (int k0 = 0; k0 < len && cnt[u] < nsample; k0 += 64) {
+                const int k = k0 + 2 * lane;  // this lane tests dataset points k and k+1
+                const float2 d2 = sqdist3x2<true>(__fadd2_rn(*reinterpret_cast<const float2*>(&sx[k]), QX),
+                                                  __fadd2_rn(*reinterpret_cast<const float2*>(&sy[k]), QY),
+                                                  __fadd2_rn(*reinterpret_cast<const float2*>(&sz[k]), QZ));
+                const bool hit0 = d2.x < T, hit1 = d2.y < T;
+                const unsigned m0 = __ballot_sync(0xffffffffu, hit0), m1 = __ballot_sync(0xffffffffu, hit1);
+                if (m0 | m1) {
+                    if (cnt[u] == 0) {
+                        const int f0 = m0 ? 2 * (__ffs(m0) - 1) : 64, f1 = m1 ? 2 * (__ffs(m1) - 1) + 1 : 64;
+                        first[u] = t0 + k0 + min(f0, f1);
+                    }
+                    // position in index order: every hit of a lower lane (both of its points) comes first, then this lane's even point
+                    const int pos0 = cnt[u] + __popc(m0 & lt) + __popc(m1 & lt);
+                    const int pos1 = pos0 + (hit0 ? 1 : 0);
+                    if (hit0 && pos0 < nsample) row[pos0] = t0 + k;
+                    if (hit1 && pos1 < nsample) row[pos1] = t0 + k + 1;
+                    cnt[u] += __popc(m0) + __popc(m1);
                 }
             }
             all_full = all_full && cnt[u] >= nsample;

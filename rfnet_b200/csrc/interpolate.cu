@@ -139,12 +139,14 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(int n, int m, int k, c
                 // insert after every entry <= d (stable: earlier index first on ties), shifting the tail down
                 float cd = d;
                 int ci = t0 + c;
+                bool shifting = false;  // once the new entry is placed, everything behind it moves down one slot unconditionally
 #pragma unroll
                 for (int t = 0; t < K; ++t) {
-                    if (cd < bd[t]) {
+                    if (shifting || cd < bd[t]) {
                         const float td = bd[t]; const int ti = bi[t];
                         bd[t] = cd; bi[t] = ci;
                         cd = td; ci = ti;
+                        shifting = true;
                     }
                 }
             }
