@@ -21,7 +21,6 @@ namespace rfnet {
 
 constexpr int EMD_LEVELS = 10;   // j = 7 .. -2   (tf_approxmatch.cu:21)
 constexpr int EMD_THREADS = 128;
-constexpr int EMD_Q = 8;         // rows per thread in the sweep (4 packed pairs)
 #ifndef EMD_TC_VALUE
 #define EMD_TC_VALUE 256
 #endif
