@@ -24,7 +24,13 @@
 
 namespace rfnet {
 
-constexpr int NN_THREADS = 128;
+#ifndef NN_THREADS_VALUE
+#define NN_THREADS_VALUE 128
+#endif
+#ifndef NN_MIN_CTAS
+#define NN_MIN_CTAS 5   // 96 registers per thread at 128 threads (tools/nn_tune.cu sweeps both)
+#endif
+constexpr int NN_THREADS = NN_THREADS_VALUE;
 constexpr int NN_TC = 1024;  // max candidates per staged chunk (12 KiB per buffer)
 
 struct NNDir {
@@ -46,7 +52,7 @@ struct NNParams {
 };
 
 template <int Q, bool FUSED>
-__global__ void __launch_bounds__(NN_THREADS, 5) nn_search_kernel(const NNParams p) {
+__global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(const NNParams p) {
     static_assert(Q % 2 == 0, "queries are processed as packed pairs");
     __shared__ __align__(128) float sC[2][NN_TC * 3];
     __shared__ __align__(8) uint64_t bar[2];
@@ -370,7 +376,7 @@ __global__ void chamfer_sums_final_kernel(size_t n1, size_t n2, const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NN_CTAS_PER_SM = 5;  // __launch_bounds__(128, 5): 96 registers
+constexpr int NN_CTAS_PER_SM = NN_MIN_CTAS;  // resident CTAs per SM implied by the launch bounds
 
 // One work item = one chunk of candidates for one query tile.  Every item pays a fixed price (query loads, pipeline fill,
 // index resolution, key merge) worth roughly 48 candidates of scanning, and the grid runs in ceil(items / resident CTAs)
