@@ -447,7 +447,11 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
     // written directly, no key merge and no extra launches
     const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
+#ifdef NN_FORCE_CHUNK
+    const int chunk = split ? NN_FORCE_CHUNK : NN_TC;   // tools/nn_tune.cu
+#else
     const int chunk = split ? pick_chunk(b, n, m, Q) : NN_TC;
+#endif
     plan_direction(p.d[0], b, n, m, Q, chunk, split);
     plan_direction(p.d[1], b, m, n, Q, chunk, split);
     unsigned long long* keys = (unsigned long long*)workspace;
