@@ -79,6 +79,14 @@ int rfnet_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, c
 size_t rfnet_matchcostgrad_workspace_bytes(int b, int n, int m);
 int rfnet_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1,
                         float *grad2, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+/* Fused approx_match + match_cost for the loss-level caller earth_mover (vv_recon.py:396-399: match = approx_match,
+ * cost = match_cost, mean(cost / num_points)): the same sweeps as rfnet_approxmatch, then ONE pass that reduces
+ * cost[i] = sum sqrt(d2) * match (b floats) while the matrix entries are still in registers.  `match` may be NULL:
+ * the (b, m, n) matrix -- 1 GiB per cloud at 16384 x 16384 -- is then never written; pass a buffer to keep it for
+ * rfnet_matchcostgrad. */
+size_t rfnet_emd_cost_workspace_bytes(int b, int n, int m);
+int rfnet_emd_cost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *cost,
+                   void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * sampling.  Replace farthestpointsamplingLauncher, gatherpointLauncher, scatteraddpointLauncher,
@@ -114,6 +122,24 @@ int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float 
  * xyz2 = queries (b,m,3); val (b,m,k) = NEGATED squared distances in descending order (i.e. nearest first), idx (b,m,k). */
 int rfnet_knn_point(int b, int n, int m, int k, const float *xyz1, const float *xyz2, float *val, int *idx,
                     rfnet_stream_t stream);
+
+/* select_top_k.  Replaces selectionSortLauncher, tf_ops/grouping/tf_grouping.cpp:112 (defined tf_grouping_g.cu:129-132).
+ * dist (b,m,n) -> outi (b,m,n), out (b,m,n): per row a copy of dist / 0..n-1 after k steps of selection sort with swaps,
+ * so the first k entries are the k smallest (ascending, first index among equals) and the tail is permuted exactly as the
+ * reference leaves it.  k > n is clamped to n (the reference reads out of bounds). */
+int rfnet_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, rfnet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * auction_match.  Replaces AuctionMatchLauncher, tf_ops/emd/tf_auctionmatch.cpp:26 (defined tf_auctionmatch_g.cu:292-294).
+ * xyz1, xyz2 (b,n,3) -> matchl (b,n): index into xyz2 assigned to every xyz1 point; matchr (b,n): the inverse.
+ * Same bid sequence as the reference kernel (one bidder at a time, FIFO, tolerance 1e-4 -> 1e-2 -> 1 every 40 n bids).
+ * The reference's `cost` temp (b*n*n floats, tf_auctionmatch.cpp:54) is not needed: no workspace at all.
+ * n <= RFNET_AUCTION_MAX_POINTS (the reference stops at 4096, tf_auctionmatch.cpp:37).  Points left unassigned when
+ * the auction gives up have matchl = -1 and the corresponding matchr = -1.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RFNET_AUCTION_MAX_POINTS 8192
+int rfnet_auction_match(int b, int n, const float *xyz1, const float *xyz2, int *matchl, int *matchr,
+                        rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * interpolation.  The reference has CPU code only: threenn_cpu, threeinterpolate_cpu, threeinterpolate_grad_cpu,

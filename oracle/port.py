@@ -224,6 +224,29 @@ def knn_point(k, xyz1, xyz2):
     return val, idx
 
 
+def select_top_k(k, dist):
+    """dist (b,m,n) -> idx (b,m,n), dist_out (b,m,n): first k entries of every row are the k smallest, ascending.  tf_grouping.py:22-31."""
+    dist, pd = _f(dist)
+    b, m, n = dist.shape
+    outi = np.empty((b, m, n), np.int32)
+    out = np.empty((b, m, n), np.float32)
+    lib().rfo_selection_sort(b, n, m, int(k), pd, outi.ctypes.data_as(_i32p), out.ctypes.data_as(_f32p))
+    return outi, out
+
+
+def auction_match(xyz1, xyz2):
+    """xyz1, xyz2 (b,n,3) -> matchl (b,n): object of every xyz1 point, matchr (b,n): bidder of every xyz2 point.  tf_auctionmatch.py:11-20."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    _check_xyz(xyz1, xyz2)
+    assert xyz1.shape == xyz2.shape
+    b, n, _ = xyz1.shape
+    matchl = np.empty((b, n), np.int32)
+    matchr = np.empty((b, n), np.int32)
+    lib().rfo_auction_match(b, n, p1, p2, matchl.ctypes.data_as(_i32p), matchr.ctypes.data_as(_i32p))
+    return matchl, matchr
+
+
 def three_nn(xyz1, xyz2, fused=False):
     """xyz1 unknown (b,n,3), xyz2 known (b,m,3) -> dist (b,n,3), idx (b,n,3).  tf_interpolate.py:8-18."""
     xyz1, p1 = _f(xyz1)

@@ -465,3 +465,121 @@ RFO_API float rfo_ball_threshold(float r) {
     while (sqrtf(t) < r) t = nextafterf(t, INFINITY);
     return t;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * auction_match.   tf_ops/emd/tf_auctionmatch_g.cu:2-291 (GPU only in the reference; `n` <= 4096 there).
+ * The kernel serves ONE bidder per loop iteration (the whole 512-thread block cooperates on it), so the auction is a
+ * sequential algorithm and this is its restatement, INCLUDING the block's reduction tree, because the tree decides
+ * the bid:
+ *   cost(i,j) = sqrtf(d2(xyz1[i], xyz2[j]))   with d2 contracted as nvcc does (_g.cu:36; SASS: FMUL dy,dy; FFMA dx; FFMA dz)
+ *   queue = 0..n-1, price = 0, matchr = -1, tolerance = 1e-4                                     (_g.cu:13-22,45-48)
+ *   pop i; thread t scans its objects j = t, t+512, ... for (best, second best, bestj) of cost(i,j)+price[j], seeded
+ *   with 1e38, an equal value replacing the incumbent (_g.cu:55-214: the four unrolled variants all reduce to this);
+ *   the 512 triples are merged by a shuffle-down tree inside each warp and again across the 16 warps (_g.cu:216-256):
+ *       merge(A = lower lane, B = lane + i):  if (A.best < B.best) { A.best2 = min(B.best, A.best2) }
+ *                                             else { A.best = B.best; A.best2 = min(A.best, B.best2); A.bestj = B.bestj }
+ *   -- in the else branch A.best has ALREADY been overwritten, so best2 becomes min(B.best, B.best2) = B.best: whenever the
+ *   winning object does not belong to thread 0 the "second best" handed to the bid equals the best and
+ *   delta = best2 - best + tolerance is exactly `tolerance`.  That is what the reference computes, so it is restated as is;
+ *   price[bestj] += delta; the previous owner of bestj is pushed back; matchr[bestj] = i          (_g.cu:258-285)
+ *   every 40*n bids: stop if tolerance == 1, else tolerance = min(1, tolerance*100)               (_g.cu:275-280)
+ * The reference reads past the end of its rows when 1024 <= n < 4096 is not 1024 or 2048 (_g.cu:155-214 step by 2 or 4
+ * block widths without a bound check); for those n this restatement simply skips the objects that do not exist.
+ * Bidders left without an object when the auction gives up keep matchl = -1 (the reference writes matchl[-1] there).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define AUC_T 512
+typedef struct { float best, best2; int bestj; } auc_triple;
+static void auc_merge(auc_triple *a, const auc_triple *b) {   /* _g.cu:220-231 == :243-254, statement for statement */
+    const float b1 = b->best, b2 = b->best2;
+    const int bj = b->bestj;
+    if (a->best < b1) {
+        a->best2 = fminf(b1, a->best2);
+    } else {
+        a->best = b1;
+        a->best2 = fminf(a->best, b2);
+        a->bestj = bj;
+    }
+}
+/* shuffle-down tree over `width` lanes (width = 32 or 16): lanes whose partner is outside keep reading themselves */
+static void auc_tree(auc_triple *t, int width) {
+    auc_triple old[32];
+    for (int i = width >> 1; i > 0; i >>= 1) {
+        memcpy(old, t, sizeof(auc_triple) * (size_t)width);
+        for (int l = 0; l < width; l++) auc_merge(&t[l], &old[l + i < width ? l + i : l]);
+    }
+}
+RFO_API void rfo_auction_match(int b, int n, const float *xyz1, const float *xyz2, int *matchl, int *matchr) {
+    if (n <= 0) return;
+    int *queue = (int *)malloc(sizeof(int) * (size_t)n);
+    float *price = (float *)malloc(sizeof(float) * (size_t)n);
+    auc_triple th[AUC_T], warps[32];
+    for (int bno = 0; bno < b; bno++) {
+        const float *P = xyz1 + (size_t)bno * n * 3, *Q = xyz2 + (size_t)bno * n * 3;
+        int *ml = matchl + (size_t)bno * n, *mr = matchr + (size_t)bno * n;
+        for (int j = 0; j < n; j++) { ml[j] = -1; mr[j] = -1; queue[j] = j; price[j] = 0.0f; }
+        int qhead = 0, qlen = n, cnt = 0;
+        float tolerance = 1e-4f;
+        while (qlen) {
+            const int i = queue[qhead];
+            for (int t = 0; t < AUC_T; t++) {
+                auc_triple r = {1e38f, 1e38f, 0};
+                for (int j = t; j < n; j += AUC_T) {
+                    /* x1 - x2 with 1 = bidder (buf), 2 = object: _g.cu:30-36 */
+                    const float dx = P[i * 3] - Q[j * 3], dy = P[i * 3 + 1] - Q[j * 3 + 1], dz = P[i * 3 + 2] - Q[j * 3 + 2];
+                    const float value = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy))) + price[j];
+                    if (r.best < value) r.best2 = fminf(r.best2, value);      /* _g.cu:205-212 */
+                    else { r.best2 = r.best; r.bestj = j; r.best = value; }
+                }
+                th[t] = r;
+            }
+            for (int w = 0; w < AUC_T / 32; w++) { auc_tree(th + 32 * w, 32); warps[w] = th[32 * w]; }
+            auc_tree(warps, AUC_T / 32);
+            const float best = warps[0].best, best2 = warps[0].best2;
+            const int bestj = warps[0].bestj;
+            const float delta = best2 - best + tolerance;
+            qhead++; qlen--;
+            if (qhead >= n) qhead -= n;
+            const int old = mr[bestj];
+            price[bestj] += delta;
+            cnt++;
+            if (old != -1) {
+                int tail = qhead + qlen;
+                qlen++;
+                if (tail >= n) tail -= n;
+                queue[tail] = old;
+            }
+            if (cnt == 40 * n) {
+                if (tolerance == 1.0f) qlen = 0;
+                tolerance = fminf(1.0f, tolerance * 100);
+                cnt = 0;
+            }
+            mr[bestj] = i;
+        }
+        for (int j = 0; j < n; j++) if (mr[j] >= 0) ml[mr[j]] = j;
+    }
+    free(queue); free(price);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * selection_sort (select_top_k).   tf_ops/grouping/tf_grouping_g.cu:83-123.
+ * out = copy of dist, outi = 0..n-1 per row; then k steps of selection sort WITH SWAPS: step s finds the first minimum
+ * of out[s..n) (strict '<' from min = s) and swaps it into position s, values and indices alike.  The first k entries
+ * are the k smallest in ascending order; the tail keeps the displaced entries where the swaps left them.
+ * ---------------------------------------------------------------------------------------------------------------- */
+RFO_API void rfo_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out) {
+    if (k > n) k = n;
+    for (size_t row = 0; row < (size_t)b * m; row++) {
+        const float *src = dist + row * n;
+        float *o = out + row * n;
+        int *oi = outi + row * n;
+        for (int s = 0; s < n; s++) { o[s] = src[s]; oi[s] = s; }
+        for (int s = 0; s < k; s++) {
+            int min = s;
+            for (int t = s + 1; t < n; t++) if (o[t] < o[min]) min = t;
+            if (min != s) {
+                const float tv = o[min]; o[min] = o[s]; o[s] = tv;
+                const int ti = oi[min]; oi[min] = oi[s]; oi[s] = ti;
+            }
+        }
+    }
+}

@@ -26,6 +26,8 @@ SIGNATURES = {
     "rfnet_matchcost": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_matchcostgrad_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_matchcostgrad": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "rfnet_emd_cost_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_emd_cost": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_farthestpointsampling_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_farthestpointsampling": (_i, [_i, _i, _i, _p, _p, _z, _p, _p]),
     "rfnet_gatherpoint": (_i, [_i, _i, _i, _p, _p, _p, _p]),
@@ -36,6 +38,8 @@ SIGNATURES = {
     "rfnet_group_point_grad_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
     "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "rfnet_knn_point": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "rfnet_selection_sort": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "rfnet_auction_match": (_i, [_i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate_grad_workspace_bytes": (_z, [_i, _i, _i, _i]),

@@ -212,12 +212,22 @@ struct EmdLevels { float lvl2[EMD_LEVELS]; };
 // CTA = 256 k's (two per thread, a packed pair) x MT_L l's.  Per l the thread reads the point and its 10 factors with four
 // LDS.128 (shared by both k's) and runs the level loop on packed pairs: FMUL2 (argument), 2 MUFU.EX2, FMUL2 (x facL pair),
 // FFMA2 (x facR broadcast, accumulate).  The accumulation is the reference's: acc = fma(facL * e, facR, acc), level by level.
+// WRITE stores the matrix; COST also folds match_cost (tf_approxmatch.cu:183-225) into the same pass -- cost partial per CTA
+// = sum sqrt(d2) * match over its tile -- so a loss that only needs the cost (earth_mover, vv_recon.py:396-399) never
+// writes or re-reads the (b, m, n) matrix.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool WRITE, bool COST>
 __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int m, size_t bn, size_t bm, EmdLevels lv,
                                                                      const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                                      const float* __restrict__ facL, const float* __restrict__ facR,
-                                                                     float* __restrict__ match) {
+                                                                     float* __restrict__ match, float* __restrict__ cost_partial) {
     __shared__ __align__(16) float4 sP[MT_L];       // x, y, z of xyz2[l]
     __shared__ __align__(16) float sF[MT_L][12];    // facR_j[l], j = 0..9 (+2 pad)
+    __shared__ float sW[MT_THREADS / 32];
     const int cloud = blockIdx.z;
     const int ka = blockIdx.x * (2 * MT_THREADS) + threadIdx.x, kb = ka + MT_THREADS;
     const int l0 = blockIdx.y * MT_L;
@@ -243,7 +253,8 @@ __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int 
         fl[j].y = vb ? facL[(size_t)j * bn + (size_t)cloud * n + kb] : 0.f;
     }
     __syncthreads();
-    float* __restrict__ out = match + ((size_t)cloud * m + l0) * n;
+    float* __restrict__ out = WRITE ? match + ((size_t)cloud * m + l0) * n : nullptr;
+    float2 csum = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int l = 0; l < nl; ++l) {
         const float4 q = sP[l];
@@ -261,8 +272,22 @@ __global__ void __launch_bounds__(MT_THREADS) emd_materialise_kernel(int n, int 
             acc = __ffma2_rn(__fmul2_rn(fl[j], e), make_float2(fr[j], fr[j]), acc);
         }
         acc = __ffma2_rn(fl[EMD_LEVELS - 1], make_float2(fr[EMD_LEVELS - 1], fr[EMD_LEVELS - 1]), acc);  // j = -2: level 0, e = 1
-        if (va) out[(size_t)l * n + ka] = acc.x;
-        if (vb) out[(size_t)l * n + kb] = acc.y;
+        if (WRITE) {
+            if (va) out[(size_t)l * n + ka] = acc.x;
+            if (vb) out[(size_t)l * n + kb] = acc.y;
+        }
+        // lanes past n carry d2 = inf and acc = 0: keep inf * 0 out of the sum
+        if (COST) csum = __ffma2_rn(make_float2(va ? sqrt_approx(d2.x) : 0.f, vb ? sqrt_approx(d2.y) : 0.f), acc, csum);
+    }
+    if (COST) {
+        float sum = warp_sum(csum.x + csum.y);
+        if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < MT_THREADS / 32; ++i) t += sW[i];
+            cost_partial[((size_t)cloud * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+        }
     }
 }
 
@@ -386,11 +411,6 @@ __global__ void __launch_bounds__(G2_WARPS * 32) matchcostgrad2_kernel(int n, in
 // (sqrt.approx / rsqrt.approx; the reductions are float sums in a different order than the reference anyway, and the
 // results are held to 1e-4).  These are single streaming passes over `match`: 4 algorithmic bytes per pair, HBM-bound.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 struct Pts4 {  // four consecutive points, negated, as packed pairs (01) and (23)
     float2 nx01, nx23, ny01, ny23, nz01, nz23;
 };
@@ -568,24 +588,10 @@ static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const floa
     else emd_sweep_q<2, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
 }
 
-}  // namespace rfnet
-
-using namespace rfnet;
-
-extern "C" size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m) {
-    if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return emd_ws_floats(b, n, m) * sizeof(float);
-}
-
-extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, void* workspace,
-                                 size_t workspace_bytes, rfnet_stream_t stream) {
-    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
-    if (b == 0 || n == 0 || m == 0) return 0;
-    RFNET_CHECK_ARG(xyz1 && xyz2 && match && workspace && workspace_bytes >= rfnet_approxmatch_workspace_bytes(b, n, m));
-    RFNET_CHECK_ARG(b <= 65535);
-    cudaStream_t s = (cudaStream_t)stream;
+// sweeps (-> per-level factors in the workspace), then one pass that materialises the matrix and/or reduces the cost
+static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, float* cost, float* ws_floats, cudaStream_t s) {
     const size_t bn = (size_t)b * n, bm = (size_t)b * m;
-    EmdWs ws = emd_carve((float*)workspace, b, n, m);
+    EmdWs ws = emd_carve(ws_floats, b, n, m);
     const float multiL = n >= m ? 1.0f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.0f;  // integer division, tf_approxmatch.cu:4-10
     emd_init_kernel<<<(unsigned)((bn + bm + 255) / 256), 256, 0, s>>>(bn, bm, multiL, multiR, ws.remainL, ws.remainR);
     EmdLevels lv;
@@ -605,8 +611,53 @@ extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const f
     }
     dim3 grid((unsigned)((n + 2 * MT_THREADS - 1) / (2 * MT_THREADS)), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
     RFNET_CHECK_ARG(grid.y <= 65535);
-    emd_materialise_kernel<<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, match);
+    float* cpart = ws_floats + emd_ws_floats(b, n, m);  // only carved when a cost is requested (rfnet_emd_cost_workspace_bytes)
+    if (match && cost)
+        emd_materialise_kernel<true, true><<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, match, cpart);
+    else if (cost)
+        emd_materialise_kernel<false, true><<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, nullptr, cpart);
+    else
+        emd_materialise_kernel<true, false><<<grid, MT_THREADS, 0, s>>>(n, m, bn, bm, lv, xyz1, xyz2, ws.facL, ws.facR, match, nullptr);
+    if (cost) reduce_partials_kernel<<<b, 256, 0, s>>>((int)(grid.x * grid.y), cpart, cost);
     return launch_status();
+}
+
+}  // namespace rfnet
+
+using namespace rfnet;
+
+extern "C" size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return emd_ws_floats(b, n, m) * sizeof(float);
+}
+
+extern "C" int rfnet_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, void* workspace,
+                                 size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0 || n == 0 || m == 0) return 0;
+    RFNET_CHECK_ARG(xyz1 && xyz2 && match && workspace && workspace_bytes >= rfnet_approxmatch_workspace_bytes(b, n, m));
+    RFNET_CHECK_ARG(b <= 65535);
+    return emd_run(b, n, m, xyz1, xyz2, match, nullptr, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" size_t rfnet_emd_cost_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    const size_t tiles = (size_t)((n + 2 * MT_THREADS - 1) / (2 * MT_THREADS)) * ((m + MT_L - 1) / MT_L);
+    return (emd_ws_floats(b, n, m) + (size_t)b * tiles) * sizeof(float);
+}
+
+extern "C" int rfnet_emd_cost(int b, int n, int m, const float* xyz1, const float* xyz2, float* match, float* cost, void* workspace,
+                              size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0) return 0;
+    RFNET_CHECK_ARG(cost);
+    if (n == 0 || m == 0) {
+        RFNET_CUDA(cudaMemsetAsync(cost, 0, sizeof(float) * b, (cudaStream_t)stream));
+        return 0;
+    }
+    RFNET_CHECK_ARG(xyz1 && xyz2 && workspace && workspace_bytes >= rfnet_emd_cost_workspace_bytes(b, n, m));
+    RFNET_CHECK_ARG(b <= 65535);
+    return emd_run(b, n, m, xyz1, xyz2, match, cost, (float*)workspace, (cudaStream_t)stream);
 }
 
 extern "C" size_t rfnet_matchcost_workspace_bytes(int b, int n, int m) {

@@ -180,6 +180,63 @@ __global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC
     grad_points[(cloud * n + i) * cv + l] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// selection_sort (select_top_k, tf_grouping_g.cu:83-123): per row of dist (b*m rows of n), copy the row and run k steps
+// of selection sort WITH SWAPS, values and indices alike -- positions [0,k) end up holding the k smallest in ascending
+// order, the tail holds the displaced entries exactly where the reference's swaps leave them.
+// The reference gives a row to one thread (n*k serial global reads).  Here a WARP owns a row held in shared memory:
+// each step is a lane-strided arg-min (first minimum: lowest position among equals, as the strict '<' scan from min = s
+// gives) finished with a REDUX-free shuffle tree on (value, position), then lane 0 swaps.  Rows longer than the shared
+// budget run the same code on the output row in global memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SS_WARPS = 4;
+__global__ void __launch_bounds__(SS_WARPS * 32) selection_sort_kernel(int n, int k, size_t rows, int smem_rows, const float* __restrict__ dist,
+                                                                       int* __restrict__ outi, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t row = (size_t)blockIdx.x * SS_WARPS + warp;
+    if (row >= rows) return;
+    const float* __restrict__ src = dist + row * n;
+    float* o = out + row * n;
+    int* oi = outi + row * n;
+    float* val = smem_rows ? reinterpret_cast<float*>(ss_smem) + (size_t)warp * n : o;
+    int* pos = smem_rows ? reinterpret_cast<int*>(ss_smem) + (size_t)SS_WARPS * n + (size_t)warp * n : oi;
+    for (int i = lane; i < n; i += 32) {
+        val[i] = src[i];
+        pos[i] = i;
+    }
+    __syncwarp();
+    for (int s = 0; s < k; ++s) {
+        float bv = 0.f;
+        int bp = 0x7fffffff;   // "no element"
+        for (int t = s + lane; t < n; t += 32) {
+            const float v = val[t];
+            if (bp == 0x7fffffff || v < bv) { bv = v; bp = t; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, off);
+            // keep the smaller value; among equals the lower position; an empty lane never wins
+            const bool take = op != 0x7fffffff && (bp == 0x7fffffff || ov < bv || (ov == bv && op < bp));
+            if (take) { bv = ov; bp = op; }
+        }
+        // the reference's scan starts from min = s and only moves on a strictly smaller value: identical to the first
+        // minimum unless the row holds NaNs (a NaN at s is never displaced there; here the comparison tree may differ)
+        if (lane == 0 && bp != s) {
+            const float tv = val[bp]; val[bp] = val[s]; val[s] = tv;
+            const int tp = pos[bp]; pos[bp] = pos[s]; pos[s] = tp;
+        }
+        __syncwarp();
+    }
+    if (smem_rows) {
+        for (int i = lane; i < n; i += 32) {
+            o[i] = val[i];
+            oi[i] = pos[i];
+        }
+    }
+}
+
 }  // namespace rfnet
 
 using namespace rfnet;
@@ -256,5 +313,21 @@ extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, c
         dim3 grid((unsigned)((rpc * c + 255) / 256), (unsigned)b);
         group_point_grad_kernel<<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, idx, grad_points);
     }
+    return launch_status();
+}
+
+extern "C" int rfnet_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && k > 0);  // tf_grouping.cpp:117
+    const size_t rows = (size_t)b * m;
+    if (rows == 0 || n == 0) return 0;
+    RFNET_CHECK_ARG(dist && outi && out);
+    if (k > n) k = n;
+    const size_t blocks = (rows + SS_WARPS - 1) / SS_WARPS;
+    RFNET_CHECK_ARG(blocks <= 0x7fffffffull);
+    const size_t smem = (size_t)SS_WARPS * n * 8;   // value + position per entry, one row per warp
+    const int in_smem = smem <= 160 * 1024;
+    if (in_smem && smem > 48 * 1024)
+        RFNET_CUDA(cudaFuncSetAttribute(selection_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selection_sort_kernel<<<(unsigned)blocks, SS_WARPS * 32, in_smem ? smem : 0, (cudaStream_t)stream>>>(n, k, rows, in_smem, dist, outi, out);
     return launch_status();
 }

@@ -9,7 +9,7 @@ NCCL over NVLink on GPUs, gloo in the CPU tests).  Gradients need no collective:
 import torch
 import torch.distributed as dist
 
-from . import tf_approxmatch, tf_grouping, tf_nndistance, tf_sampling
+from . import tf_approxmatch, tf_auctionmatch, tf_grouping, tf_nndistance, tf_sampling
 
 
 def chamfer_big(pcd1, pcd2):
@@ -30,9 +30,19 @@ def earth_mover(pcd1, pcd2):
     """vv_recon.py:392-399 -> mean(cost / num_points); requires equal point counts."""
     assert pcd1.shape[1] == pcd2.shape[1]
     num_points = float(pcd1.shape[1])
-    match = tf_approxmatch.approx_match(pcd1, pcd2)
-    cost = tf_approxmatch.match_cost(pcd1, pcd2, match)
+    cost = tf_approxmatch.emd_cost(pcd1, pcd2)  # approx_match + match_cost in one call; match kept only for backward
     return torch.mean(cost / num_points)
+
+
+def emd_func(pred, gt):
+    """vv_recon.py:365-380: auction_match -> gather the matched GT points -> mean matched distance, normalised by the
+    radius of the prediction around its centroid, averaged over the batch."""
+    matchl_out, _ = tf_auctionmatch.auction_match(pred, gt)
+    matched_out = tf_sampling.gather_point(gt, matchl_out)
+    dist = torch.sqrt(((pred - matched_out) ** 2).sum(-1)).mean(-1)
+    cens = pred.mean(dim=1, keepdim=True)
+    radius = torch.sqrt(((pred - cens) ** 2).sum(-1).max(dim=-1).values)
+    return (dist / radius).mean()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -110,8 +120,7 @@ def sharded_earth_mover(pcd1_local, pcd2_local, group=None):
     """earth_mover over a sharded batch: local approx_match + match_cost, then one 8-byte all-reduce."""
     assert pcd1_local.shape[1] == pcd2_local.shape[1]
     num_points = float(pcd1_local.shape[1])
-    match = tf_approxmatch.approx_match(pcd1_local, pcd2_local)
-    cost = tf_approxmatch.match_cost(pcd1_local, pcd2_local, match)
+    cost = tf_approxmatch.emd_cost(pcd1_local, pcd2_local)
     s = (cost / num_points).sum()
     totals = all_reduce_scalars(torch.stack([s.detach(), cost.new_tensor(float(cost.numel()))]), group)
     return (totals[0] + (s - s.detach())) / totals[1]

@@ -267,6 +267,50 @@ def _match_cost_backward(ctx, grad_cost):
 match_cost_op.register_autograd(_match_cost_backward, setup_context=_match_cost_setup)
 
 
+@torch.library.custom_op("rfnet::emd_cost", mutates_args=(), device_types="cuda")
+def emd_cost_op(xyz1: torch.Tensor, xyz2: torch.Tensor, keep_match: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    # ApproxMatch followed by MatchCost (vv_recon.py:396-399) in one call: (cost (b,), match (b,m,n) or an empty tensor).
+    # Without keep_match the (b, m, n) matrix never reaches HBM.
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ApproxMatch expects (batch_size,num_points,3) xyz2 shape, and batch_size must match")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    cost = torch.empty((b,), dtype=torch.float32, device=xyz1.device)
+    match = torch.empty((b, m, n) if keep_match else (0,), dtype=torch.float32, device=xyz1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_emd_cost_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(lib.rfnet_emd_cost(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match) if keep_match else None, _ptr(cost), _ptr(ws), wsb,
+                                      _stream(xyz1)), "rfnet_emd_cost")
+    return cost, match
+
+
+@emd_cost_op.register_fake
+def _(xyz1, xyz2, keep_match):
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    return xyz1.new_empty((b,)), xyz1.new_empty((b, m, n) if keep_match else (0,))
+
+
+def _emd_cost_setup(ctx, inputs, output):
+    xyz1, xyz2, keep_match = inputs
+    ctx.keep_match = keep_match
+    ctx.save_for_backward(xyz1, xyz2, output[1])
+
+
+def _emd_cost_backward(ctx, grad_cost, grad_match):
+    # the match is a constant of the loss (NoGradient('ApproxMatch'), tf_approxmatch.py:19); d cost = MatchCostGrad
+    if not ctx.keep_match:
+        raise RuntimeError("emd_cost was called with keep_match=False: the match matrix needed by MatchCostGrad was not kept")
+    xyz1, xyz2, match = ctx.saved_tensors
+    g1, g2 = match_cost_grad_op(xyz1, xyz2, match)
+    s = grad_cost[:, None, None]
+    return g1 * s, g2 * s, None
+
+
+emd_cost_op.register_autograd(_emd_cost_backward, setup_context=_emd_cost_setup)
+
+
 # ------------------------------------------------------------------------------------------------------------ sampling
 @torch.library.custom_op("rfnet::farthest_point_sample", mutates_args=(), device_types="cuda")
 def farthest_point_sample_op(inp: torch.Tensor, npoint: int) -> torch.Tensor:
@@ -441,6 +485,51 @@ def knn_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.
 def _(xyz1, xyz2, k):
     b, m = xyz2.shape[0], xyz2.shape[1]
     return xyz1.new_empty((b, m, k)), xyz1.new_empty((b, m, k), dtype=torch.int32)
+
+
+@torch.library.custom_op("rfnet::selection_sort", mutates_args=(), device_types="cuda")
+def selection_sort_op(dist: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    # SelectionSortGpuOp, tf_ops/grouping/tf_grouping.cpp:113-143
+    _require(k > 0, "SelectionSort expects positive k")
+    _require(dist.dim() == 3, "SelectionSort expects (b,m,n) dist shape.")
+    dist = _cuda_f32("dist", dist)
+    b, m, n = dist.shape
+    outi = torch.empty((b, m, n), dtype=torch.int32, device=dist.device)
+    out = torch.empty((b, m, n), dtype=torch.float32, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.check(_lib.load().rfnet_selection_sort(b, n, m, k, _ptr(dist), _ptr(outi), _ptr(out), _stream(dist)), "rfnet_selection_sort")
+    return outi, out
+
+
+@selection_sort_op.register_fake
+def _(dist, k):
+    return dist.new_empty(dist.shape, dtype=torch.int32), dist.new_empty(dist.shape)
+
+
+# ------------------------------------------------------------------------------------------------------------ auction_match
+AUCTION_MAX_POINTS = 8192  # RFNET_AUCTION_MAX_POINTS (the reference: 4096, tf_auctionmatch.cpp:37)
+
+
+@torch.library.custom_op("rfnet::auction_match", mutates_args=(), device_types="cuda")
+def auction_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    # AuctionMatchGpuOp::Compute, tf_ops/emd/tf_auctionmatch.cpp:28-59 (its messages say "ApproxMatch"; kept)
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
+    _require(xyz1.shape[1] <= AUCTION_MAX_POINTS, "AuctionMatch handles at most %d dataset points" % AUCTION_MAX_POINTS)
+    _require(xyz2.dim() == 3 and tuple(xyz2.shape) == tuple(xyz1.shape),
+             "AuctionMatch expects (batch_size,num_points,3) xyz2 shape, and shape must match with xyz1")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n = xyz1.shape[0], xyz1.shape[1]
+    matchl = torch.empty((b, n), dtype=torch.int32, device=xyz1.device)
+    matchr = torch.empty((b, n), dtype=torch.int32, device=xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(_lib.load().rfnet_auction_match(b, n, _ptr(xyz1), _ptr(xyz2), _ptr(matchl), _ptr(matchr), _stream(xyz1)), "rfnet_auction_match")
+    return matchl, matchr
+
+
+@auction_match_op.register_fake
+def _(xyz1, xyz2):
+    b, n = xyz1.shape[0], xyz1.shape[1]
+    return xyz1.new_empty((b, n), dtype=torch.int32), xyz1.new_empty((b, n), dtype=torch.int32)
 
 
 # ------------------------------------------------------------------------------------------------------------ interpolation

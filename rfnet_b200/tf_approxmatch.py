@@ -27,3 +27,16 @@ returns:
 Differentiable w.r.t. xyz1 and xyz2 (not match), as RegisterGradient('MatchCost') (tf_approxmatch.py:44-50).
     '''
     return ops.match_cost_op(xyz1, xyz2, match.detach())
+
+
+def emd_cost(xyz1, xyz2):
+    '''
+approx_match followed by match_cost, as every caller in the reference chains them (vv_recon.py:396-399), in one call:
+	cost : batch_size
+The match matrix is kept (for the gradient of match_cost) only when a gradient can be asked for; otherwise it is never
+written to memory.  Values equal match_cost(xyz1, xyz2, approx_match(xyz1, xyz2)) up to summation order.
+    '''
+    import torch
+    keep = torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)
+    cost, _ = ops.emd_cost_op(xyz1, xyz2, keep)
+    return cost

@@ -22,6 +22,20 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return ops.query_ball_point_op(xyz1.detach(), xyz2.detach(), radius.detach().reshape(-1), int(nsample))
 
 
+def select_top_k(k, dist):
+    '''
+    Input:
+        k: int32, number of k SMALLEST elements selected
+        dist: (b,m,n) float32 array, distance matrix, m query points, n dataset points
+    Output:
+        idx: (b,m,n) int32 array, first k in n are indices to the top k
+        dist_out: (b,m,n) float32 array, first k in n are the top k
+
+    No gradient (ops.NoGradient('SelectionSort'), tf_grouping.py:32).
+    '''
+    return ops.selection_sort_op(dist.detach(), int(k))
+
+
 def group_point(points, idx):
     '''
     Input:

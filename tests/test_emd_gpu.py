@@ -151,3 +151,43 @@ def test_emd_full_size_properties(cuda):
     part_cost = tf_approxmatch.match_cost(x1[:, sl].contiguous(), x2, match[:, :, sl].contiguous())
     assert abs(part_cost.item() - part.item()) <= 1e-4 * abs(part.item())
     assert 0 < part_cost.item() < cost.item()
+
+
+@pytest.mark.parametrize("b,n,m", [(1, 1, 1), (2, 100, 100), (1, 257, 130), (1, 64, 200), (3, 512, 512), (1, 1030, 1030), (600, 256, 256)])
+def test_emd_cost_fused(cuda, rng, b, n, m):
+    """rfnet_emd_cost (approx_match + match_cost in one call, vv_recon.py:396-399): the cost equals the two-op chain at 1e-5;
+    with keep_match the matrix written is bit-identical to approx_match's; without it no matrix exists."""
+    from rfnet_b200 import ops, tf_approxmatch
+    x1n, x2n = cloud(rng, b, n), cloud(rng, b, m)
+    x1, x2 = t(x1n, cuda), t(x2n, cuda)
+    match = tf_approxmatch.approx_match(x1, x2)
+    chain = tf_approxmatch.match_cost(x1, x2, match).cpu().numpy()
+    cost0, none = ops.emd_cost_op(x1, x2, False)
+    assert none.numel() == 0 and cost0.shape == (b,)
+    assert np.allclose(cost0.cpu().numpy(), chain, rtol=1e-5, atol=1e-7)
+    cost1, kept = ops.emd_cost_op(x1, x2, True)
+    assert torch.equal(kept, match)
+    assert torch.equal(cost1, cost0)
+    assert np.allclose(tf_approxmatch.emd_cost(x1, x2).cpu().numpy(), chain, rtol=1e-5, atol=1e-7)
+    if b * n * m <= 1 << 21:
+        want = port.match_cost(x1n, x2n, port.approx_match(x1n, x2n))
+        assert np.allclose(cost0.cpu().numpy(), want, rtol=RTOL, atol=1e-7)
+
+
+def test_emd_cost_fused_edge_and_grad(cuda, rng):
+    from rfnet_b200 import ops, tf_approxmatch
+    empty = torch.zeros((2, 0, 3), device=cuda)
+    pts = t(cloud(rng, 2, 8), cuda)
+    cost, _ = ops.emd_cost_op(empty, pts, False)
+    assert cost.tolist() == [0.0, 0.0]
+    # gradient path keeps the matrix and equals the two-op chain's gradient exactly (same match, same grad kernel)
+    x1 = t(cloud(rng, 2, 300), cuda).requires_grad_(True)
+    x2 = t(cloud(rng, 2, 300), cuda).requires_grad_(True)
+    tf_approxmatch.emd_cost(x1, x2).sum().backward()
+    g1, g2 = x1.grad.clone(), x2.grad.clone()
+    x1.grad = x2.grad = None
+    tf_approxmatch.match_cost(x1, x2, tf_approxmatch.approx_match(x1, x2)).sum().backward()
+    assert torch.equal(g1, x1.grad) and torch.equal(g2, x2.grad)
+    with pytest.raises(RuntimeError, match="keep_match=False"):
+        c, _ = ops.emd_cost_op(x1, x2, False)
+        c.sum().backward()

@@ -124,3 +124,45 @@ def test_oracle_edge_cases(rng):
     dist, idx = port.three_nn(cloud(rng, 1, 5), cloud(rng, 1, 2))
     assert np.isinf(dist[..., 2]).all() and (idx[..., 2] == 0).all()
     assert port.ball_threshold(0.1) <= np.float32(0.1) * np.float32(0.1)
+
+
+def test_golden_gpu_selection_sort_and_auction():
+    """Oracle vs the reference's SelectionSort / AuctionMatch CUDA kernels on a B200 (tests/golden/make_golden_gpu2.py): bit-exact."""
+    g = gold("ref_gpu2.npz")
+    for tag in ("a", "b", "c"):
+        outi, out = port.select_top_k(int(g["sel_%s_k" % tag][0]), g["sel_%s_dist" % tag])
+        assert np.array_equal(outi, g["sel_%s_outi" % tag]) and np.array_equal(out, g["sel_%s_out" % tag]), tag
+    for tag in ("a", "b", "c", "d", "e"):
+        ml, mr = port.auction_match(g["auc_%s_xyz1" % tag], g["auc_%s_xyz2" % tag])
+        assert np.array_equal(ml, g["auc_%s_matchl" % tag]) and np.array_equal(mr, g["auc_%s_matchr" % tag]), tag
+
+
+@pytest.mark.parametrize("b,n", [(3, 1), (2, 2), (2, 50), (1, 700)])
+def test_oracle_auction_match_properties(rng, b, n):
+    """The auction ends with a perfect matching whose cost is within n * (final tolerance) of the optimum (Bertsekas).  The
+    reference's price increments are almost always the bare tolerance (see rfnet_oracle.c), so anything but a tiny problem
+    runs into the 40 n bid limit and finishes at tolerance 1e-2 or 1."""
+    from scipy.optimize import linear_sum_assignment
+    x1, x2 = cloud(rng, b, n), cloud(rng, b, n)
+    ml, mr = port.auction_match(x1, x2)
+    for i in range(b):
+        assert sorted(ml[i].tolist()) == list(range(n))
+        assert np.array_equal(mr[i][ml[i]], np.arange(n))
+        d = np.linalg.norm(x1[i][:, None, :].astype(np.float64) - x2[i][None, :, :], axis=-1)
+        r, c = linear_sum_assignment(d)
+        assert d[np.arange(n), ml[i]].sum() <= d[r, c].sum() + n * 1.0 + 1e-6
+        if n <= 2:    # finishes inside the first tolerance stage: eps-optimal with eps = 1e-4
+            assert d[np.arange(n), ml[i]].sum() <= d[r, c].sum() + n * 1e-4 + 1e-5
+
+
+def test_oracle_selection_sort(rng):
+    d = rng.random((2, 9, 33), dtype=np.float32)
+    for k in (1, 5, 33):
+        outi, out = port.select_top_k(k, d)
+        assert np.array_equal(outi[..., :k], np.argsort(d, axis=-1, kind="stable")[..., :k])
+    d[:, :, 20:25] = d[:, :, 3:8]   # equal values (selection sort by swaps is not stable: only the values are ordered)
+    for k in (1, 5, 33):
+        outi, out = port.select_top_k(k, d)
+        assert np.array_equal(out[..., :k], np.sort(d, axis=-1, kind="stable")[..., :k])
+        assert np.array_equal(np.take_along_axis(d, outi, axis=-1), out)                        # a permutation of the row
+        assert np.array_equal(np.sort(outi, axis=-1), np.broadcast_to(np.arange(33), d.shape))

@@ -102,3 +102,34 @@ if "group" in which:
     go = torch.randn((b, n, 64), device=dev)
     med, mn = timeit(lambda: ops.three_interpolate_grad_op(feats, i3, w, go))
     print("three_interpolate_grad c=64: ours %.3f ms" % mn, flush=True)
+if "emdcost" in which:
+    for (b, n) in [(32, 2048), (4, 16384), (8, 16384)]:
+        x1, x2 = rnd(b, n, 3), rnd(b, n, 4)
+        def chain():
+            match = tf_approxmatch.approx_match(x1, x2)
+            return tf_approxmatch.match_cost(x1, x2, match)
+        _, cmn = timeit(chain, warm=2, iters=5)
+        _, fmn = timeit(lambda: ops.emd_cost_op(x1, x2, False), warm=2, iters=5)
+        _, kmn = timeit(lambda: ops.emd_cost_op(x1, x2, True), warm=2, iters=5)
+        print("emd cost b=%d n=m=%d: approx_match + match_cost %.3f ms | fused, no matrix %.3f ms (%.1f clouds/s) | fused, matrix kept %.3f ms"
+              % (b, n, cmn, fmn, b / fmn * 1e3, kmn), flush=True)
+if "auction" in which:
+    from rfnet_b200 import tf_auctionmatch
+    for (b, n) in [(32, 256), (32, 1024), (148, 1024), (8, 2048), (8, 4096), (148, 4096)]:
+        x1, x2 = rnd(b, n, 5), rnd(b, n, 6)
+        _, mn = timeit(lambda: tf_auctionmatch.auction_match(x1, x2), warm=1, iters=2, reps=2)
+        line = "auction_match b=%d n=%d: ours %.2f ms (%.1f clouds/s)" % (b, n, mn, b / mn * 1e3)
+        if have_ref and n <= 4096 and b <= 32:
+            _, rmn = timeit(lambda: ref.run_gpu("AuctionMatch", [x1, x2], [((b, n), torch.int32), ((b, n), torch.int32)]), warm=1, iters=1, reps=2)
+            line += " | reference kernel %.2f ms | speedup %.1fx" % (rmn, rmn / mn)
+        print(line, flush=True)
+if "select" in which:
+    for (b, m, n, k) in [(32, 2048, 2048, 32), (8, 1024, 16384, 16)]:
+        g = torch.Generator(device="cpu").manual_seed(9)
+        d = torch.rand((b, m, n), generator=g).to(dev)
+        _, mn = timeit(lambda: tf_grouping.select_top_k(k, d), warm=1, iters=3)
+        line = "select_top_k b=%d m=%d n=%d k=%d: ours %.3f ms (%.0f GB/s over 12 B/entry)" % (b, m, n, k, mn, 12.0 * b * m * n / mn / 1e6)
+        if have_ref:
+            _, rmn = timeit(lambda: ref.run_gpu("SelectionSort", [d], [((b, m, n), torch.int32), ((b, m, n), torch.float32)], attrs={"k": k}), warm=1, iters=1, reps=2)
+            line += " | reference kernel %.2f ms | speedup %.1fx" % (rmn, rmn / mn)
+        print(line, flush=True)
