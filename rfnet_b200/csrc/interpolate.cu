@@ -6,8 +6,8 @@
 //   * three_nn evaluates d2 UNFUSED ((dx*dx + dy*dy) + dz*dz), as the reference's CPU build does, and keeps the three
 //     smallest with the same strict-'<' insertion, so earlier indices win ties;
 //   * three_interpolate evaluates (p1*w1 + p2*w2) + p3*w3 unfused.
-// three_nn uses the same machinery as nn_distance: queries in registers as packed pairs (FADD2/FMUL2), candidates
-// broadcast from shared memory, a 3-input-min filter so the insertion code only runs when a candidate can enter the top 3.
+// three_nn uses the same machinery as nn_distance: queries in registers as packed pairs, candidates broadcast from shared
+// memory, a branch-free scan that only LISTS the candidate groups able to change a top 3, and an exact pass over the list.
 #include "common.cuh"
 #include "rfnet_ops.h"
 #include "segscatter.cuh"
@@ -32,9 +32,64 @@ __device__ __forceinline__ void top3_insert(Top3& t, float d, int k) {  // tf_in
     }
 }
 
-__global__ void __launch_bounds__(TN_THREADS) three_nn_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+// the same insertion without branches (3 compares, 5 min/max, 5 selects): identical results, including which index stays
+// ahead among equal distances (strict '<' everywhere)
+__device__ __forceinline__ void top3_insert_bf(Top3& t, float d, int k) {
+    const bool p1 = d < t.d1, p2 = d < t.d2, p3 = d < t.d3;
+    t.i3 = p3 ? (p2 ? t.i2 : k) : t.i3;
+    t.i2 = p2 ? (p1 ? t.i1 : k) : t.i2;
+    t.i1 = p1 ? k : t.i1;
+    t.d3 = fminf(t.d3, fmaxf(t.d2, d));
+    t.d2 = fminf(t.d2, fmaxf(t.d1, d));
+    t.d1 = fminf(t.d1, d);
+}
+
+// Two phases per shared-memory tile, so that the hot loop has no data-dependent branch (a top-3 insertion test fires in
+// almost every 32-lane step: 128 queries per warp x ~16 insertions each over 2048 candidates):
+//   scan     per group of 8 candidates: FUSED packed distances (3 packed FP32 issues per query pair and candidate), their
+//            minimum g, and a branch-free record "g <= 3rd smallest group minimum so far (+1e-6 relative)" appended to a
+//            per-query list in shared memory.  The 3rd smallest group minimum is an upper bound of the true 3rd smallest
+//            distance, and fused / unfused evaluation differ by < 3e-7 relative, so every group holding a candidate
+//            that the reference's scan would insert is on the list (about 3 ln(groups) entries per query).
+//   resolve  the listed groups, in scan order, go through the reference's exact code: UNFUSED distance, strict-'<'
+//            insertion.  Unlisted groups cannot change the top 3, so the state after each tile is the reference's.
+// A query whose list overflows (adversarially ordered candidates) re-scans the tile with the exact code.
+constexpr int TN_MIN_CTAS = 4;
+constexpr int TN_CAP = 32;     // list entries per query and tile (u8 group numbers)
+constexpr int TN_GROUPS = TN_TILE / 8;
+static_assert(TN_GROUPS <= 256, "group numbers are stored as bytes");
+
+// exact code of the reference on one group of 8 candidates (SoA tile): unfused distance on packed candidate pairs
+// (FADD2 / FMUL2, the two additions scalar so that nothing is contracted), strict-'<' insertion in candidate order
+template <bool BRANCH_FREE>
+__device__ __forceinline__ void tn_exact_group(Top3& t, float qx, float qy, float qz, const float* __restrict__ tx, const float* __restrict__ ty,
+                                               const float* __restrict__ tz, int g, int base, bool valid) {
+    const float4 xa = *reinterpret_cast<const float4*>(tx + g * 8), xb = *reinterpret_cast<const float4*>(tx + g * 8 + 4);
+    const float4 ya = *reinterpret_cast<const float4*>(ty + g * 8), yb = *reinterpret_cast<const float4*>(ty + g * 8 + 4);
+    const float4 za = *reinterpret_cast<const float4*>(tz + g * 8), zb = *reinterpret_cast<const float4*>(tz + g * 8 + 4);
+    const float2 cx[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+    const float2 cy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+    const float2 cz[4] = {make_float2(za.x, za.y), make_float2(za.z, za.w), make_float2(zb.x, zb.y), make_float2(zb.z, zb.w)};
+    const float2 q2x = make_float2(qx, qx), q2y = make_float2(qy, qy), q2z = make_float2(qz, qz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 d = sqdist3x2<false>(__fadd2_rn(q2x, make_float2(-cx[j].x, -cx[j].y)), __fadd2_rn(q2y, make_float2(-cy[j].x, -cy[j].y)),
+                                          __fadd2_rn(q2z, make_float2(-cz[j].x, -cz[j].y)));
+        if (BRANCH_FREE) {   // an invalid entry (this query's list is shorter than its neighbours') inserts +inf: a no-op
+            top3_insert_bf(t, valid ? d.x : __int_as_float(0x7f800000), base + g * 8 + 2 * j);
+            top3_insert_bf(t, valid ? d.y : __int_as_float(0x7f800000), base + g * 8 + 2 * j + 1);
+        } else {
+            if (d.x < t.d3) top3_insert(t, d.x, base + g * 8 + 2 * j);
+            if (d.y < t.d3) top3_insert(t, d.y, base + g * 8 + 2 * j + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TN_THREADS, TN_MIN_CTAS) three_nn_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                               float* __restrict__ dist, int* __restrict__ idx) {
-    __shared__ __align__(16) float tile[TN_TILE * 3];
+    __shared__ __align__(16) float tx[TN_TILE], ty[TN_TILE], tz[TN_TILE];   // candidates, SoA
+    // [query][entry][thread]; one extra entry row per query takes the stores of an overflowing list
+    __shared__ unsigned char list[TN_Q * (TN_CAP + 1) * TN_THREADS];
     const int cloud = blockIdx.y;
     const int tid = threadIdx.x;
     const float* __restrict__ qbase = xyz1 + (size_t)cloud * n * 3;
@@ -51,41 +106,99 @@ __global__ void __launch_bounds__(TN_THREADS) three_nn_kernel(int n, int m, cons
         qx[h].y = vb ? qbase[(size_t)ib * 3 + 0] : 0.f; qy[h].y = vb ? qbase[(size_t)ib * 3 + 1] : 0.f; qz[h].y = vb ? qbase[(size_t)ib * 3 + 2] : 0.f;
     }
     const float inf = __int_as_float(0x7f800000);  // (float)1e40 of the reference
+    float ga[TN_Q], gb[TN_Q], gc[TN_Q];             // three smallest group minima so far (fused values), ascending
 #pragma unroll
-    for (int i = 0; i < TN_Q; ++i) { top[i].d1 = top[i].d2 = top[i].d3 = inf; top[i].i1 = top[i].i2 = top[i].i3 = 0; }
+    for (int i = 0; i < TN_Q; ++i) {
+        top[i].d1 = top[i].d2 = top[i].d3 = inf;
+        top[i].i1 = top[i].i2 = top[i].i3 = 0;
+        ga[i] = gb[i] = gc[i] = inf;
+    }
 
     for (int t0 = 0; t0 < m; t0 += TN_TILE) {
         const int len = min(TN_TILE, m - t0);
-        const int len4 = (len + 3) & ~3;
+        const int len8 = (len + 7) & ~7;
         __syncthreads();
-        for (int i = tid; i < len * 3; i += TN_THREADS) tile[i] = cbase[(size_t)t0 * 3 + i];
-        for (int i = len * 3 + tid; i < len4 * 3; i += TN_THREADS) tile[i] = inf;  // padded candidates: d2 = inf, never inserted
-        __syncthreads();
-        const float4* __restrict__ c4 = reinterpret_cast<const float4*>(tile);
+        // AoS -> SoA; eight independent loads in flight per thread before the first store
 #pragma unroll 1
-        for (int k = 0; k < len4; k += 4) {
-            const float4 v0 = c4[(k >> 2) * 3 + 0], v1 = c4[(k >> 2) * 3 + 1], v2 = c4[(k >> 2) * 3 + 2];
-            const float cx[4] = {v0.x, v0.w, v1.z, v2.y};
-            const float cy[4] = {v0.y, v1.x, v1.w, v2.z};
-            const float cz[4] = {v0.z, v1.y, v2.x, v2.w};
+        for (int i0 = 0; i0 < len * 3; i0 += TN_THREADS * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * TN_THREADS + tid;
+                v[u] = i < len * 3 ? __ldg(cbase + (size_t)t0 * 3 + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * TN_THREADS + tid;
+                const int c = i / 3, a = i - c * 3;
+                if (i < len * 3) (a == 0 ? tx : (a == 1 ? ty : tz))[c] = v[u];
+            }
+        }
+        for (int i = len + tid; i < len8; i += TN_THREADS) tx[i] = ty[i] = tz[i] = inf;  // padded candidates: d2 = inf, never inserted
+        __syncthreads();
+        unsigned lp[TN_Q];   // shared-memory address of the next list entry of each query (advances by TN_THREADS per record)
+        unsigned sink[TN_Q];
+        const unsigned lbase = smem_u32(list) + tid;
+#pragma unroll
+        for (int i = 0; i < TN_Q; ++i) {
+            lp[i] = lbase + i * (TN_CAP + 1) * TN_THREADS;
+            sink[i] = lp[i] + TN_CAP * TN_THREADS;
+        }
+        const int ngroups = len8 >> 3;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            const float4 xa = *reinterpret_cast<const float4*>(tx + g * 8), xb = *reinterpret_cast<const float4*>(tx + g * 8 + 4);
+            const float4 ya = *reinterpret_cast<const float4*>(ty + g * 8), yb = *reinterpret_cast<const float4*>(ty + g * 8 + 4);
+            const float4 za = *reinterpret_cast<const float4*>(tz + g * 8), zb = *reinterpret_cast<const float4*>(tz + g * 8 + 4);
+            const float cx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float cy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+            const float cz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
             for (int h = 0; h < TN_Q / 2; ++h) {
-                float2 d[4];
+                float2 d[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float2 dx = __fadd2_rn(qx[h], make_float2(-cx[j], -cx[j]));
                     const float2 dy = __fadd2_rn(qy[h], make_float2(-cy[j], -cy[j]));
                     const float2 dz = __fadd2_rn(qz[h], make_float2(-cz[j], -cz[j]));
-                    d[j] = sqdist3x2<false>(dx, dy, dz);
+                    d[j] = sqdist3x2<true>(dx, dy, dz);
                 }
-                if (fmin3(fminf(d[0].x, d[1].x), d[2].x, d[3].x) < top[2 * h].d3) {
+                const float gmin[2] = {fmin3(fmin3(d[0].x, d[1].x, d[2].x), fmin3(d[3].x, d[4].x, d[5].x), fminf(d[6].x, d[7].x)),
+                                       fmin3(fmin3(d[0].y, d[1].y, d[2].y), fmin3(d[3].y, d[4].y, d[5].y), fminf(d[6].y, d[7].y))};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) top3_insert(top[2 * h], d[j].x, t0 + k + j);
+                for (int s = 0; s < 2; ++s) {
+                    const int qi = 2 * h + s;
+                    const float gm = gmin[s];
+                    // record: predicated store + pointer bump, no branch.  Past TN_CAP entries the store lands in the spare row.
+                    const unsigned a = min(lp[qi], sink[qi]);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %2, %3;\n\t@p st.shared.u8 [%1], %4;\n\t@p add.u32 %0, %0, %5;\n\t}"
+                                 : "+r"(lp[qi]) : "r"(a), "f"(gm), "f"(gc[qi] * 1.000001f), "r"(g), "n"(TN_THREADS) : "memory");
+                    gc[qi] = fminf(gc[qi], fmaxf(gb[qi], gm));
+                    gb[qi] = fminf(gb[qi], fmaxf(ga[qi], gm));
+                    ga[qi] = fminf(ga[qi], gm);
                 }
-                if (fmin3(fminf(d[0].y, d[1].y), d[2].y, d[3].y) < top[2 * h + 1].d3) {
+            }
+        }
+        // resolve: the TN_Q lists of a thread advance together, so the four dependent insertion chains overlap
+        int cn[TN_Q], emax = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) top3_insert(top[2 * h + 1], d[j].y, t0 + k + j);
-                }
+        for (int i = 0; i < TN_Q; ++i) {
+            cn[i] = (int)((lp[i] - (lbase + i * (TN_CAP + 1) * TN_THREADS)) / TN_THREADS);
+            if (cn[i] > TN_CAP) {   // overflow: exact re-scan of the tile for this query
+                const float x = (i & 1) ? qx[i >> 1].y : qx[i >> 1].x, y = (i & 1) ? qy[i >> 1].y : qy[i >> 1].x, z = (i & 1) ? qz[i >> 1].y : qz[i >> 1].x;
+                for (int g = 0; g < ngroups; ++g) tn_exact_group<false>(top[i], x, y, z, tx, ty, tz, g, t0, true);
+                cn[i] = 0;
+            }
+            emax = max(emax, cn[i]);
+        }
+#pragma unroll 1
+        for (int e = 0; e < emax; ++e) {
+#pragma unroll
+            for (int i = 0; i < TN_Q; ++i) {
+                const float x = (i & 1) ? qx[i >> 1].y : qx[i >> 1].x, y = (i & 1) ? qy[i >> 1].y : qy[i >> 1].x, z = (i & 1) ? qz[i >> 1].y : qz[i >> 1].x;
+                const bool v = e < cn[i];
+                const int g = v ? (int)list[(i * (TN_CAP + 1) + e) * TN_THREADS + tid] : 0;
+                tn_exact_group<true>(top[i], x, y, z, tx, ty, tz, g, t0, v);
             }
         }
     }

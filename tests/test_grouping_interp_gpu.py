@@ -86,7 +86,7 @@ def test_group_point_gradient_check_like_reference(cuda):
     assert float((p.grad.double() - want).abs().max()) < 1e-4
 
 
-@pytest.mark.parametrize("b,n,m", [(1, 128, 8), (2, 1000, 300), (2, 4100, 2049), (1, 50, 2), (1, 10, 1)])
+@pytest.mark.parametrize("b,n,m", [(1, 128, 8), (2, 1000, 300), (2, 4100, 2049), (1, 50, 2), (1, 10, 1), (2, 300, 5003), (1, 700, 16384)])
 def test_three_nn_bit_exact(cuda, rng, b, n, m):
     from rfnet_b200 import tf_interpolate
     x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
@@ -95,6 +95,20 @@ def test_three_nn_bit_exact(cuda, rng, b, n, m):
     gd, gi = tf_interpolate.three_nn(t(x1, cuda), t(x2, cuda))
     assert np.array_equal(gi.cpu().numpy(), wi)
     assert np.array_equal(gd.cpu().numpy(), wd)
+
+
+def test_three_nn_adversarial_order(cuda, rng):
+    """Candidates sorted by DECREASING distance from the query cluster: every group improves the top 3, the per-query group
+    list overflows and the kernel's exact re-scan path runs.  Still bit-exact."""
+    from rfnet_b200 import tf_interpolate
+    m = 3000
+    x1 = (cloud(rng, 1, 700) * 0.01).astype(np.float32)                       # queries bunched at the origin
+    x2 = cloud(rng, 1, m)
+    order = np.argsort(-(x2[0] ** 2).sum(-1))
+    x2 = np.ascontiguousarray(x2[:, order])
+    wd, wi = port.three_nn(x1, x2, fused=False)
+    gd, gi = tf_interpolate.three_nn(t(x1, cuda), t(x2, cuda))
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gd.cpu().numpy(), wd)
 
 
 @pytest.mark.parametrize("c", [1, 5, 16, 64])
