@@ -14,6 +14,8 @@
 //     traffic instead of 80, at the price of 9 more ex2 per pair (the j = -2 level has e = 1).
 // exp(x) is ex2.approx(x * log2e) exactly as __expf in the reference; level * log2e is folded into one constant, which is
 // bit-identical because level is a power of two.  d2 is the reference's fused expression.  Offsets are 64-bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "rfnet_ops.h"
 
@@ -46,7 +48,12 @@ __host__ __device__ inline float emd_level(int li) {  // li = 0..9  ->  j = 7..-
 //   partial [b * max(n,m) * max_split]                                         sweep partial sums
 struct EmdWs {
     float *remainL, *remainR, *ratioL, *ratioR, *facL, *facR, *partial;
+    int *perm1, *perm2;          // Morton order of xyz1 / xyz2 (pruned sweeps only)
+    unsigned *maskA, *maskB;     // candidate masks: rows = xyz1 clusters vs xyz2 candidates (passes 1, 3) / the reverse (pass 2)
 };
+// pruned sweeps pay off (and their sort fits shared memory) for clouds of 4096 .. 32768 points
+static bool emd_prune_enabled(int n, int m) { return n >= 4096 && m >= 4096 && n <= 32768 && m <= 32768; }
+static size_t emd_mask_words(int b, int nr, int nc) { return (size_t)b * ((nr + 127) / 128) * 3 * ((nc + 31) / 32); }
 static int emd_max_split(int b, int n, int m) {
     // enough CTAs per sweep to give every SM ~8 at the smallest batch; bounded by the number of candidate chunks
     const int rows = n < m ? n : m, cands = n < m ? m : n;
@@ -57,7 +64,9 @@ static int emd_max_split(int b, int n, int m) {
 }
 static size_t emd_ws_floats(int b, int n, int m) {
     const size_t bn = (size_t)b * n, bm = (size_t)b * m;
-    return 2 * (bn + bm) + (size_t)EMD_LEVELS * (bn + bm) + (size_t)b * (n > m ? n : m) * emd_max_split(b, n, m);
+    size_t f = 2 * (bn + bm) + (size_t)EMD_LEVELS * (bn + bm) + (size_t)b * (n > m ? n : m) * emd_max_split(b, n, m);
+    if (emd_prune_enabled(n, m)) f += bn + bm + emd_mask_words(b, n, m) + emd_mask_words(b, m, n);
+    return f;
 }
 static EmdWs emd_carve(float* w, int b, int n, int m) {
     const size_t bn = (size_t)b * n, bm = (size_t)b * m;
@@ -68,7 +77,11 @@ static EmdWs emd_carve(float* w, int b, int n, int m) {
     s.ratioR = w; w += bm;
     s.facL = w; w += EMD_LEVELS * bn;
     s.facR = w; w += EMD_LEVELS * bm;
-    s.partial = w;
+    s.partial = w; w += (size_t)b * (n > m ? n : m) * emd_max_split(b, n, m);
+    s.perm1 = reinterpret_cast<int*>(w); w += bn;
+    s.perm2 = reinterpret_cast<int*>(w); w += bm;
+    s.maskA = reinterpret_cast<unsigned*>(w); w += emd_mask_words(b, n, m);
+    s.maskB = reinterpret_cast<unsigned*>(w);
     return s;
 }
 
@@ -157,6 +170,233 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
         const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
         if (ia < nr) out[ia] = acc[h].x;
         if (ib < nr) out[ib] = acc[h].y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact pruning of the three sharpest levels (j = 7, 6, 5: e = exp(-4^j d2) with 4^j = 16384, 4096, 1024).
+// ex2.approx.ftz returns EXACTLY 0 once its argument is below -126, i.e. for d2 > 0.0053 / 0.021 / 0.085, and a zero term
+// leaves the accumulator bit-identical (fma(0, w, acc) == acc).  At those levels almost every pair is such a no-op, so:
+//   * emd_morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, bitonic sort in shared memory);
+//     a warp of the pruned sweep then owns 128 CONSECUTIVE points of that order: a spatially tight cluster;
+//   * emd_mask_kernel marks, per cluster and level, the candidates whose distance to the cluster's bounding box still
+//     allows a non-zero term (with a safety margin of 4 in the exponent-2 argument, ~3 % in distance);
+//   * emd_sweep_pruned_kernel is the sweep above restricted to marked candidates, visited in ASCENDING candidate order:
+//     every row sum goes through the same sequence of non-trivial fma's as in the dense sweep, so the result is bit-for-bit
+//     the dense one (tests/test_emd_gpu.py::test_pruned_sweeps_are_exact) -- only the row -> thread assignment changes.
+// The masks depend on the points only: built once per call for both roles (rows = xyz1 / rows = xyz2), used by 9 sweeps.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EMD_PRUNE_LEVELS = 3;
+constexpr int EMD_CLUSTER = 128;        // rows of one warp of the pruned sweep (4 per lane)
+constexpr int EMD_SORT_MAX = 32768;     // points per cloud the in-shared-memory sort handles (15-bit index + 15-bit Morton code)
+constexpr float EMD_PRUNE_ARG = -130.0f;
+
+__device__ __forceinline__ unsigned morton_spread5(unsigned v) {  // 5 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+
+// grid = (clouds, 2): y = 0 sorts xyz1 (n points) into perm1, y = 1 sorts xyz2 (m points) into perm2.
+__global__ void __launch_bounds__(1024) emd_morton_sort_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                               int* __restrict__ perm1, int* __restrict__ perm2) {
+    extern __shared__ unsigned sort_keys[];
+    __shared__ float red[6][32];
+    const int np = blockIdx.y == 0 ? n : m;
+    const float* __restrict__ pts = (blockIdx.y == 0 ? xyz1 : xyz2) + (size_t)blockIdx.x * np * 3;
+    int* __restrict__ perm = (blockIdx.y == 0 ? perm1 : perm2) + (size_t)blockIdx.x * np;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int npad = 1;
+    while (npad < np) npad <<= 1;
+    // bounding box
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int i = tid; i < np; i += 1024)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = pts[(size_t)i * 3 + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = red[a][0], h = red[3 + a][0];
+        for (int w2 = 1; w2 < 32; ++w2) { l = fminf(l, red[a][w2]); h = fmaxf(h, red[3 + a][w2]); }
+        lo[a] = l;
+        scale[a] = h > l ? 31.999f / (h - l) : 0.f;
+    }
+    for (int i = tid; i < npad; i += 1024) {
+        unsigned key = 0xffffffffu;
+        if (i < np) {
+            unsigned c[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) c[a] = min(31u, (unsigned)fmaxf(0.f, (pts[(size_t)i * 3 + a] - lo[a]) * scale[a]));
+            key = ((morton_spread5(c[0]) | (morton_spread5(c[1]) << 1) | (morton_spread5(c[2]) << 2)) << 15) | (unsigned)i;
+        }
+        sort_keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += 1024) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                const int p2 = i | j;
+                const unsigned a = sort_keys[i], c = sort_keys[p2];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) { sort_keys[i] = c; sort_keys[p2] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < np; i += 1024) perm[i] = (int)(sort_keys[i] & 0x7fffu);
+}
+
+// grid = (clusters of rows, clouds), 256 threads.  mask[((cloud * nclusters + cluster) * 3 + lev) * nwords + word]
+__global__ void __launch_bounds__(256) emd_mask_kernel(int nr, int nc, int nwords, const float* __restrict__ rows, const int* __restrict__ perm,
+                                                       const float* __restrict__ cands, float l0, float l1, float l2, unsigned* __restrict__ mask) {
+    __shared__ float red[6][8];
+    const int cloud = blockIdx.y, cluster = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    const int s = cluster * EMD_CLUSTER + tid;
+    if (tid < EMD_CLUSTER && s < nr) {
+        const float* p = rows + ((size_t)cloud * nr + perm[(size_t)cloud * nr + s]) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) lo[a] = hi[a] = p[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = red[a][0], h = red[3 + a][0];
+        for (int w2 = 1; w2 < 8; ++w2) { l = fminf(l, red[a][w2]); h = fmaxf(h, red[3 + a][w2]); }
+        lo[a] = l;
+        hi[a] = h;
+    }
+    unsigned* __restrict__ out = mask + ((size_t)cloud * gridDim.x + cluster) * EMD_PRUNE_LEVELS * nwords;
+    const float* __restrict__ cb = cands + (size_t)cloud * nc * 3;
+    for (int c = tid; c < nwords * 32; c += 256) {
+        float d2 = inf;
+        if (c < nc) {
+            d2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = cb[(size_t)c * 3 + a];
+                const float d = fmaxf(fmaxf(lo[a] - v, v - hi[a]), 0.f);   // distance to the box along this axis
+                d2 = fmaf(d, d, d2);
+            }
+        }
+        const bool valid = c < nc;
+        const unsigned w0 = __ballot_sync(0xffffffffu, valid && l0 * d2 > EMD_PRUNE_ARG);
+        const unsigned w1 = __ballot_sync(0xffffffffu, valid && l1 * d2 > EMD_PRUNE_ARG);
+        const unsigned w2 = __ballot_sync(0xffffffffu, valid && l2 * d2 > EMD_PRUNE_ARG);
+        if (lane == 0) {
+            out[c >> 5] = w0;
+            out[nwords + (c >> 5)] = w1;
+            out[2 * nwords + (c >> 5)] = w2;
+        }
+    }
+}
+
+// The dense sweep (Q = 4) restricted to the marked candidates of the warp's cluster.  `mask` points at the level's words
+// of cluster 0 of cloud 0; clusters are EMD_PRUNE_LEVELS * nwords apart.
+template <bool PASS3>
+__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_pruned_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2, float init0,
+                                                                      const float* __restrict__ rows, const float* __restrict__ cands,
+                                                                      const float* __restrict__ w, const float* __restrict__ rowfac,
+                                                                      const int* __restrict__ perm, const unsigned* __restrict__ mask, int nwords,
+                                                                      float* __restrict__ partial) {
+    constexpr int Q = 4;
+    __shared__ __align__(16) float4 sC[EMD_TC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bid = blockIdx.x;
+    const int split = bid % nsplit;
+    const int tile = (bid / nsplit) % nrt;
+    const int cloud = bid / (nsplit * nrt);
+    const float* __restrict__ rbase = rows + (size_t)cloud * nr * 3;
+    const float* __restrict__ cbase = cands + (size_t)cloud * nc * 3;
+    const float* __restrict__ wbase = w + (size_t)cloud * nc;
+    const int* __restrict__ pbase = perm + (size_t)cloud * nr;
+    const int nclusters = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
+    const int cluster = tile * (EMD_THREADS * Q / EMD_CLUSTER) + warp;
+    const unsigned* __restrict__ mrow = mask + ((size_t)cloud * nclusters + min(cluster, nclusters - 1)) * EMD_PRUNE_LEVELS * nwords;
+
+    // sorted position of this lane's rows: the warp's cluster is 128 consecutive positions, 32 per q
+    const int s0 = cluster * EMD_CLUSTER + lane;
+    int row[Q];
+    float2 rx[Q / 2], ry[Q / 2], rz[Q / 2], rf[Q / 2], acc[Q / 2];
+    const float a0 = split == 0 ? init0 : 0.0f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) row[q] = (s0 + 32 * q) < nr ? pbase[s0 + 32 * q] : -1;
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) {
+        const int ia = row[2 * h], ib = row[2 * h + 1];
+        const bool va = ia >= 0, vb = ib >= 0;
+        rx[h].x = va ? -rbase[(size_t)ia * 3 + 0] : 0.f; ry[h].x = va ? -rbase[(size_t)ia * 3 + 1] : 0.f; rz[h].x = va ? -rbase[(size_t)ia * 3 + 2] : 0.f;
+        rx[h].y = vb ? -rbase[(size_t)ib * 3 + 0] : 0.f; ry[h].y = vb ? -rbase[(size_t)ib * 3 + 1] : 0.f; rz[h].y = vb ? -rbase[(size_t)ib * 3 + 2] : 0.f;
+        rf[h] = make_float2(1.f, 1.f);
+        if (PASS3) {
+            rf[h].x = va ? rowfac[(size_t)cloud * nr + ia] : 0.f;
+            rf[h].y = vb ? rowfac[(size_t)cloud * nr + ib] : 0.f;
+        }
+        acc[h] = make_float2(a0, a0);
+    }
+    const float2 L2 = make_float2(lvl2, lvl2);
+    const int c_begin = split * cps * EMD_TC;
+    const int c_end = min(nc, c_begin + cps * EMD_TC);
+    for (int c0 = c_begin; c0 < c_end; c0 += EMD_TC) {
+        const int len = min(EMD_TC, c_end - c0);
+        __syncthreads();
+        for (int i = tid; i < len; i += EMD_THREADS) {
+            const float* c = cbase + (size_t)(c0 + i) * 3;
+            sC[i] = make_float4(c[0], c[1], c[2], wbase[c0 + i]);
+        }
+        // this warp's mask words for the chunk (c0 is a multiple of 32): lane i holds word i
+        const int wi0 = c0 >> 5;
+        const unsigned myword = (lane < EMD_TC / 32 && wi0 + lane < nwords) ? mrow[wi0 + lane] : 0u;
+        __syncthreads();
+#pragma unroll 1
+        for (int wi = 0; wi < EMD_TC / 32; ++wi) {
+            unsigned bits = __shfl_sync(0xffffffffu, myword, wi);
+            while (bits) {
+                const int k = wi * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 c = sC[k];
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));
+                    const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
+                    const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
+                    const float2 a = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
+                    float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+                    if (PASS3) e = __fmul2_rn(rf[h], e);
+                    acc[h] = __ffma2_rn(e, make_float2(c.w, c.w), acc[h]);
+                }
+            }
+        }
+    }
+    float* __restrict__ out = partial + ((size_t)cloud * nsplit + split) * nr;
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) {
+        if (row[2 * h] >= 0) out[row[2 * h]] = acc[h].x;
+        if (row[2 * h + 1] >= 0) out[row[2 * h + 1]] = acc[h].y;
     }
 }
 
@@ -580,10 +820,15 @@ static void emd_sweep_q(const SweepPlan& p, unsigned grid, int nr, int nc, float
 }
 template <bool PASS3>
 static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands, const float* w, const float* rowfac,
-                      float* partial, int& nsplit_out, cudaStream_t s) {
+                      float* partial, int& nsplit_out, cudaStream_t s, const int* perm = nullptr, const unsigned* mask = nullptr) {
     const SweepPlan p = emd_plan(b, nr, nc);
     nsplit_out = p.nsplit;
     const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
+    if (mask && p.Q == 4) {
+        emd_sweep_pruned_kernel<PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, perm, mask,
+                                                                   (nc + 31) / 32, partial);
+        return;
+    }
     if (p.Q == 4) emd_sweep_q<4, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
     else emd_sweep_q<2, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
 }
@@ -595,18 +840,35 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
     const float multiL = n >= m ? 1.0f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.0f;  // integer division, tf_approxmatch.cu:4-10
     emd_init_kernel<<<(unsigned)((bn + bm + 255) / 256), 256, 0, s>>>(bn, bm, multiL, multiR, ws.remainL, ws.remainR);
     EmdLevels lv;
+    for (int li = 0; li < EMD_LEVELS; ++li) lv.lvl2[li] = emd_level(li) * LOG2E;
+    // exact pruning of the three sharpest levels (see emd_sweep_pruned_kernel); RFNET_EMD_NO_PRUNE=1 forces the dense sweeps
+    const char* no_prune = getenv("RFNET_EMD_NO_PRUNE");
+    const bool prune = emd_prune_enabled(n, m) && !(no_prune && no_prune[0] == '1');
+    if (prune) {
+        int np2 = 1;
+        while (np2 < (n > m ? n : m)) np2 <<= 1;
+        const size_t smem = (size_t)np2 * sizeof(unsigned);
+        if (smem > 48 * 1024) RFNET_CUDA(cudaFuncSetAttribute(emd_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emd_morton_sort_kernel<<<dim3((unsigned)b, 2), 1024, smem, s>>>(n, m, xyz1, xyz2, ws.perm1, ws.perm2);
+        emd_mask_kernel<<<dim3((unsigned)((n + EMD_CLUSTER - 1) / EMD_CLUSTER), (unsigned)b), 256, 0, s>>>(n, m, (m + 31) / 32, xyz1, ws.perm1, xyz2, lv.lvl2[0],
+                                                                                                       lv.lvl2[1], lv.lvl2[2], ws.maskA);
+        emd_mask_kernel<<<dim3((unsigned)((m + EMD_CLUSTER - 1) / EMD_CLUSTER), (unsigned)b), 256, 0, s>>>(m, n, (n + 31) / 32, xyz2, ws.perm2, xyz1, lv.lvl2[0],
+                                                                                                       lv.lvl2[1], lv.lvl2[2], ws.maskB);
+    }
     for (int li = 0; li < EMD_LEVELS; ++li) {
-        const float lvl2 = emd_level(li) * LOG2E;
-        lv.lvl2[li] = lvl2;
+        const float lvl2 = lv.lvl2[li];
         int ns;
+        const bool pl = prune && li < EMD_PRUNE_LEVELS;
+        const unsigned* mA = pl ? ws.maskA + (size_t)li * ((m + 31) / 32) : nullptr;
+        const unsigned* mB = pl ? ws.maskB + (size_t)li * ((n + 31) / 32) : nullptr;
         // pass 1: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR
-        emd_sweep<false>(b, n, m, lvl2, 1e-9f, xyz1, xyz2, ws.remainR, nullptr, ws.partial, ns, s);
+        emd_sweep<false>(b, n, m, lvl2, 1e-9f, xyz1, xyz2, ws.remainR, nullptr, ws.partial, ns, s, ws.perm1, mA);
         emd_epi1_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn);
         // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL
-        emd_sweep<false>(b, m, n, lvl2, 0.0f, xyz2, xyz1, ws.ratioL, nullptr, ws.partial, ns, s);
+        emd_sweep<false>(b, m, n, lvl2, 0.0f, xyz2, xyz1, ws.ratioL, nullptr, ws.partial, ns, s, ws.perm2, mB);
         emd_epi2_kernel<<<(unsigned)((bm + 255) / 256), 256, 0, s>>>(m, ns, bm, ws.partial, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm);
         // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR
-        emd_sweep<true>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, ns, s);
+        emd_sweep<true>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, ns, s, ws.perm1, mA);
         emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL);
     }
     dim3 grid((unsigned)((n + 2 * MT_THREADS - 1) / (2 * MT_THREADS)), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);

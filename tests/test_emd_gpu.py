@@ -191,3 +191,33 @@ def test_emd_cost_fused_edge_and_grad(cuda, rng):
     with pytest.raises(RuntimeError, match="keep_match=False"):
         c, _ = ops.emd_cost_op(x1, x2, False)
         c.sum().backward()
+
+
+@pytest.mark.parametrize("b,n,m,kind", [(2, 4096, 4096, "cube"), (1, 5000, 4100, "cube"), (1, 4096, 8192, "sphere"), (130, 4096, 4096, "cube"),
+                                        (1, 16384, 16384, "sphere")])
+def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
+    """From 4096 points per cloud the three sharpest levels run as pruned sweeps (Morton-ordered rows, per-cluster candidate
+    masks).  Skipped terms are exact zeros and the surviving ones are added in the same order, so the plan must be
+    BIT-IDENTICAL to the dense sweeps' (RFNET_EMD_NO_PRUNE=1), split or not (b = 130 runs unsplit)."""
+    import os
+    from rfnet_b200 import ops, tf_approxmatch
+    g = torch.Generator(device="cpu").manual_seed(1000 + n + m + b)
+    def pts(count):
+        x = torch.rand((b, count, 3), generator=g) - 0.5
+        if kind == "sphere":   # a surface, like real scans, with a clump of exact duplicates
+            x = 0.5 * x / x.norm(dim=-1, keepdim=True)
+            x[:, : count // 16] = x[:, count // 16: 2 * (count // 16)]
+        return x.to(cuda)
+    x1, x2 = pts(n), pts(m)
+    assert os.environ.get("RFNET_EMD_NO_PRUNE") is None
+    pruned = tf_approxmatch.approx_match(x1, x2)
+    cost_pruned, _ = ops.emd_cost_op(x1, x2, False)
+    os.environ["RFNET_EMD_NO_PRUNE"] = "1"
+    try:
+        dense = tf_approxmatch.approx_match(x1, x2)
+        cost_dense, _ = ops.emd_cost_op(x1, x2, False)
+    finally:
+        del os.environ["RFNET_EMD_NO_PRUNE"]
+    assert torch.equal(pruned, dense)
+    assert torch.equal(cost_pruned, cost_dense)
+    assert float(dense.sum()) > 0.9 * b * min(n, m)
