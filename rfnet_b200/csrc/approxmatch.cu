@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "morton.cuh"
 #include "rfnet_ops.h"
 
 namespace rfnet {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
 // Exact pruning of the three sharpest levels (j = 7, 6, 5: e = exp(-4^j d2) with 4^j = 16384, 4096, 1024).
 // ex2.approx.ftz returns EXACTLY 0 once its argument is below -126, i.e. for d2 > 0.0053 / 0.021 / 0.085, and a zero term
 // leaves the accumulator bit-identical (fma(0, w, acc) == acc).  At those levels almost every pair is such a no-op, so:
-//   * emd_morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, bitonic sort in shared memory);
+//   * morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, bitonic sort in shared memory);
 //     a warp of the pruned sweep then owns 128 CONSECUTIVE points of that order: a spatially tight cluster;
 //   * emd_mask_kernel marks, per cluster and level, the candidates whose distance to the cluster's bounding box still
 //     allows a non-zero term (with a safety margin of 4 in the exponent-2 argument, ~3 % in distance);
@@ -188,76 +189,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int EMD_PRUNE_LEVELS = 3;
 constexpr int EMD_CLUSTER = 128;        // rows of one warp of the pruned sweep (4 per lane)
-constexpr int EMD_SORT_MAX = 32768;     // points per cloud the in-shared-memory sort handles (15-bit index + 15-bit Morton code)
 constexpr float EMD_PRUNE_ARG = -130.0f;
-
-__device__ __forceinline__ unsigned morton_spread5(unsigned v) {  // 5 bits -> every third bit
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
-}
-
-// grid = (clouds, 2): y = 0 sorts xyz1 (n points) into perm1, y = 1 sorts xyz2 (m points) into perm2.
-__global__ void __launch_bounds__(1024) emd_morton_sort_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                                                               int* __restrict__ perm1, int* __restrict__ perm2) {
-    extern __shared__ unsigned sort_keys[];
-    __shared__ float red[6][32];
-    const int np = blockIdx.y == 0 ? n : m;
-    const float* __restrict__ pts = (blockIdx.y == 0 ? xyz1 : xyz2) + (size_t)blockIdx.x * np * 3;
-    int* __restrict__ perm = (blockIdx.y == 0 ? perm1 : perm2) + (size_t)blockIdx.x * np;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int npad = 1;
-    while (npad < np) npad <<= 1;
-    // bounding box
-    const float inf = __int_as_float(0x7f800000);
-    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-    for (int i = tid; i < np; i += 1024)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float v = pts[(size_t)i * 3 + a];
-            lo[a] = fminf(lo[a], v);
-            hi[a] = fmaxf(hi[a], v);
-        }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-        }
-        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
-    }
-    __syncthreads();
-    float scale[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float l = red[a][0], h = red[3 + a][0];
-        for (int w2 = 1; w2 < 32; ++w2) { l = fminf(l, red[a][w2]); h = fmaxf(h, red[3 + a][w2]); }
-        lo[a] = l;
-        scale[a] = h > l ? 31.999f / (h - l) : 0.f;
-    }
-    for (int i = tid; i < npad; i += 1024) {
-        unsigned key = 0xffffffffu;
-        if (i < np) {
-            unsigned c[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) c[a] = min(31u, (unsigned)fmaxf(0.f, (pts[(size_t)i * 3 + a] - lo[a]) * scale[a]));
-            key = ((morton_spread5(c[0]) | (morton_spread5(c[1]) << 1) | (morton_spread5(c[2]) << 2)) << 15) | (unsigned)i;
-        }
-        sort_keys[i] = key;
-    }
-    __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (npad >> 1); t += 1024) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
-                const int p2 = i | j;
-                const unsigned a = sort_keys[i], c = sort_keys[p2];
-                const bool up = (i & k) == 0;
-                if ((a > c) == up) { sort_keys[i] = c; sort_keys[p2] = a; }
-            }
-            __syncthreads();
-        }
-    for (int i = tid; i < np; i += 1024) perm[i] = (int)(sort_keys[i] & 0x7fffu);
-}
 
 // grid = (clusters of rows, clouds), 256 threads.  mask[((cloud * nclusters + cluster) * 3 + lev) * nwords + word]
 __global__ void __launch_bounds__(256) emd_mask_kernel(int nr, int nc, int nwords, const float* __restrict__ rows, const int* __restrict__ perm,
@@ -845,11 +777,7 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
     const char* no_prune = getenv("RFNET_EMD_NO_PRUNE");
     const bool prune = emd_prune_enabled(n, m) && !(no_prune && no_prune[0] == '1');
     if (prune) {
-        int np2 = 1;
-        while (np2 < (n > m ? n : m)) np2 <<= 1;
-        const size_t smem = (size_t)np2 * sizeof(unsigned);
-        if (smem > 48 * 1024) RFNET_CUDA(cudaFuncSetAttribute(emd_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emd_morton_sort_kernel<<<dim3((unsigned)b, 2), 1024, smem, s>>>(n, m, xyz1, xyz2, ws.perm1, ws.perm2);
+        { const int rc = morton_sort(b, n, m, xyz1, xyz2, ws.perm1, ws.perm2, s); if (rc) return rc; }
         emd_mask_kernel<<<dim3((unsigned)((n + EMD_CLUSTER - 1) / EMD_CLUSTER), (unsigned)b), 256, 0, s>>>(n, m, (m + 31) / 32, xyz1, ws.perm1, xyz2, lv.lvl2[0],
                                                                                                        lv.lvl2[1], lv.lvl2[2], ws.maskA);
         emd_mask_kernel<<<dim3((unsigned)((m + EMD_CLUSTER - 1) / EMD_CLUSTER), (unsigned)b), 256, 0, s>>>(m, n, (n + 31) / 32, xyz2, ws.perm2, xyz1, lv.lvl2[0],

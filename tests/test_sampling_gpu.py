@@ -13,8 +13,10 @@ def t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-# (b, n, m): cluster sizes 1/2/4/8, points-per-thread 1/2/4/8, m > n (repeats), n < 512, tiny
-SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 3000, 32), (4, 4097, 128), (2, 16384, 256), (1, 20000, 64), (40, 1024, 64),
+# (b, n, m): up to 16384 points the pruned one-CTA kernel (1/2/4/8/16/32 register slots per lane), above it the cluster
+# kernel; m > n (repeats), n < 512, tiny
+SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 513, 600), (2, 3000, 32), (2, 3000, 700), (4, 4097, 128), (2, 9000, 520), (2, 16384, 256),
+          (1, 20000, 64), (40, 1024, 64),
           (1, 40000, 24)]   # the last one exceeds 8 CTAs x 512 threads x 8 points: generic one-CTA kernel with global scratch
 
 
@@ -40,6 +42,32 @@ def test_fps_duplicated_points_tie_rule(cuda, rng):
     want = port.farthest_point_sample(200, grid)
     got = tf_sampling.farthest_point_sample(200, t(grid, cuda)).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("b,n,m,kind", [(3, 16384, 2048, "cube"), (2, 16384, 1500, "sphere"), (4, 3000, 1024, "grid"), (2, 700, 700, "dup"), (2, 100, 600, "cube")])
+def test_fps_pruned_equals_cluster_kernel(cuda, b, n, m, kind):
+    """The pruned kernel (Morton clusters whose box is out of reach of a pick are skipped) against the cluster kernel that
+    updates every point at every pick (RFNET_FPS_NO_PRUNE=1): identical indices, on volumes, surfaces, lattices (massive
+    ties) and duplicated points."""
+    import os
+    from rfnet_b200 import tf_sampling
+    g = torch.Generator(device="cpu").manual_seed(50 + n + m)
+    x = torch.rand((b, n, 3), generator=g) - 0.5
+    if kind == "sphere":
+        x = x / x.norm(dim=-1, keepdim=True)
+    elif kind == "grid":
+        x = torch.round(x * 6)
+    elif kind == "dup":
+        x[:, n // 2:] = x[:, : n - n // 2]
+    x = x.to(cuda)
+    assert os.environ.get("RFNET_FPS_NO_PRUNE") is None
+    pruned = tf_sampling.farthest_point_sample(m, x)
+    os.environ["RFNET_FPS_NO_PRUNE"] = "1"
+    try:
+        full = tf_sampling.farthest_point_sample(m, x)
+    finally:
+        del os.environ["RFNET_FPS_NO_PRUNE"]
+    assert torch.equal(pruned, full)
 
 
 @pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
