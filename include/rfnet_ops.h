@@ -69,6 +69,8 @@ int rfnet_chamfer_partial_sums(int b, int n, int m, const float *dist1, const fl
  * pc_distance/tf_approxmatch.cpp:141-143 (defined pc_distance/tf_approxmatch.cu:180-182,226-228,292-295).
  * match is (b, m, n): match[i, l, k] pairs xyz2[i,l] with xyz1[i,k] (tf_approxmatch.cu:152).  `temp` of the reference
  * ((b, 2(n+m)) floats, tf_approxmatch.cpp:168) becomes workspace.
+ * Environment switches read at call time, for A/B testing only: RFNET_EMD_NO_PRUNE=1 (dense sweeps at every level),
+ * RFNET_FPS_NO_PRUNE=1 (cluster kernel instead of the pruned one).  Results are bit-identical either way.
  * ------------------------------------------------------------------------------------------------------------- */
 size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m);
 int rfnet_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace,
@@ -91,7 +93,10 @@ int rfnet_emd_cost(int b, int n, int m, const float *xyz1, const float *xyz2, fl
 /* ---------------------------------------------------------------------------------------------------------------
  * sampling.  Replace farthestpointsamplingLauncher, gatherpointLauncher, scatteraddpointLauncher,
  * tf_ops/sampling/tf_sampling.cpp:94,125,150 (defined tf_ops/sampling/tf_sampling_g.cu:203-211).
- * FPS: out (b, m) int32, first index 0, ties broken exactly as the reference's 512-thread block does.
+ * FPS: out (b, m) int32, first index 0, ties broken exactly as the reference's 512-thread block does.  The workspace
+ * (the reference's (32, n) temp, tf_sampling.cpp:115) holds the Morton order of the clouds for the pruned kernel
+ * (n <= 16384, m >= 512) or the running distances of clouds too large for registers; with workspace == NULL clouds of up
+ * to 32768 points run on the cluster kernel, which needs none.  Every path returns the same indices.
  * scatteraddpoint zero-fills inp_g itself (the reference's OpKernel did it, tf_sampling.cpp:174).
  * ------------------------------------------------------------------------------------------------------------- */
 size_t rfnet_farthestpointsampling_workspace_bytes(int b, int n, int m);
