@@ -5,7 +5,7 @@ import inspect
 import pytest
 import torch
 
-from rfnet_b200 import losses, ops, tf_approxmatch, tf_grouping, tf_interpolate, tf_nndistance, tf_sampling
+from rfnet_b200 import losses, ops, tf_approxmatch, tf_auctionmatch, tf_grouping, tf_interpolate, tf_nndistance, tf_sampling
 
 
 def meta(*shape, dtype=torch.float32):
@@ -24,6 +24,9 @@ def test_signatures_match_reference_wrappers():
     assert list(inspect.signature(tf_grouping.knn_point).parameters) == ["k", "xyz1", "xyz2"]
     assert list(inspect.signature(tf_interpolate.three_nn).parameters) == ["xyz1", "xyz2"]
     assert list(inspect.signature(tf_interpolate.three_interpolate).parameters) == ["points", "idx", "weight"]
+    # tf_grouping.py:22 (select_top_k), tf_ops/emd/tf_auctionmatch.py:11
+    assert list(inspect.signature(tf_grouping.select_top_k).parameters) == ["k", "dist"]
+    assert list(inspect.signature(tf_auctionmatch.auction_match).parameters) == ["xyz1", "xyz2"]
 
 
 def test_output_shapes_and_dtypes_via_meta_tensors():
@@ -49,6 +52,16 @@ def test_output_shapes_and_dtypes_via_meta_tensors():
     assert dist.shape == i3.shape == (b, n, 3) and i3.dtype == torch.int32
     assert torch.ops.rfnet.three_interpolate(meta(b, m, c), meta(b, n, 3, dtype=torch.int32), meta(b, n, 3)).shape == (b, n, c)
     assert torch.ops.rfnet.three_interpolate_grad(meta(b, m, c), meta(b, n, 3, dtype=torch.int32), meta(b, n, 3), meta(b, n, c)).shape == (b, m, c)
+    outi, out = torch.ops.rfnet.selection_sort(meta(b, m, n), 5)
+    assert outi.shape == out.shape == (b, m, n) and outi.dtype == torch.int32 and out.dtype == torch.float32
+    ml, mr = torch.ops.rfnet.auction_match(meta(b, n, 3), meta(b, n, 3))
+    assert ml.shape == mr.shape == (b, n) and ml.dtype == mr.dtype == torch.int32
+    cost, kept = torch.ops.rfnet.emd_cost(meta(b, n, 3), meta(b, m, 3), True)
+    assert cost.shape == (b,) and kept.shape == (b, m, n)
+    cost, kept = torch.ops.rfnet.emd_cost(meta(b, n, 3), meta(b, m, 3), False)
+    assert cost.shape == (b,) and kept.numel() == 0
+    val, ki = torch.ops.rfnet.knn_point(meta(b, n, 3), meta(b, m, 3), 4)
+    assert val.shape == ki.shape == (b, m, 4) and ki.dtype == torch.int32
 
 
 def test_no_cpu_fallback():
@@ -56,7 +69,9 @@ def test_no_cpu_fallback():
     x, y = torch.zeros(1, 4, 3), torch.zeros(1, 5, 3)
     for call in (lambda: tf_nndistance.nn_distance(x, y), lambda: tf_approxmatch.approx_match(x, y),
                  lambda: tf_sampling.farthest_point_sample(2, x), lambda: tf_interpolate.three_nn(x, y),
-                 lambda: tf_grouping.group_point(x, torch.zeros(1, 2, 2, dtype=torch.int32))):
+                 lambda: tf_grouping.group_point(x, torch.zeros(1, 2, 2, dtype=torch.int32)),
+                 lambda: tf_auctionmatch.auction_match(x, x), lambda: tf_grouping.select_top_k(2, torch.zeros(1, 3, 4)),
+                 lambda: tf_approxmatch.emd_cost(x, y), lambda: losses.emd_func(x, x)):
         with pytest.raises((NotImplementedError, RuntimeError, ValueError)):
             call()
 
