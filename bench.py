@@ -504,6 +504,9 @@ def main():
             ms_e = timed(lambda: tf_approxmatch.match_cost(z1, z2, tf_approxmatch.approx_match(z1, z2)), 3)
             extra["emd_approx_match+match_cost_B%d_n%d" % (eb, en)] = {"ms": ms_e, "clouds_per_s": eb / ms_e * 1e3,
                                                                       "frac_mufu_peak": eb / (ms_e * 1e-3) * 30.0 * en * en / (148 * 16 * sm_max)}
+            ms_f = timed(lambda: tf_approxmatch.emd_cost(z1, z2), 3)   # the loss-level call: cost without the match matrix
+            extra["emd_cost_fused_B%d_n%d" % (eb, en)] = {"ms": ms_f, "clouds_per_s": eb / ms_f * 1e3,
+                                                         "frac_mufu_peak": eb / (ms_f * 1e-3) * 30.0 * en * en / (148 * 16 * sm_max)}
         del y1, y2
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
