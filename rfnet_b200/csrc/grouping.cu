@@ -4,7 +4,7 @@
 //
 // Ball query design: the reference gives each query to one thread which streams the whole dataset from global memory
 // (uncoalesced, one block per cloud).  Here a WARP owns a query: the dataset is staged tile by tile in shared memory, each
-// lane tests two consecutive points of a 64-point group (packed FP32x2), and ballots + popcounts append the hits IN INDEX ORDER, so "the first
+// lane tests four consecutive points of a 128-point group (two packed FP32x2 pairs), and ballots + popcounts append the hits IN INDEX ORDER, so "the first
 // nsample points inside the ball" (tf_grouping_g.cu:17-31) is reproduced exactly, with early exit once the row is full.
 //
 // The predicate max(sqrtf(d2), 1e-20f) < r is evaluated without a square root: sqrt_rn is monotone, so it equals
@@ -17,7 +17,7 @@ namespace rfnet {
 
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_QPW = 4;      // queries per warp
-constexpr int BQ_TILE = 2048;  // dataset points per shared-memory tile (24 KiB, multiple of 64)
+constexpr int BQ_TILE = 2048;  // dataset points per shared-memory tile (24 KiB, multiple of 128)
 
 __device__ __forceinline__ float ball_threshold(float r) {
     if (!(r > 1e-20f)) return 0.0f;                          // max(.,1e-20f) < r can never hold (also r = NaN)
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m,
 
     for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
         const int len = min(BQ_TILE, n - t0);
-        const int len64 = (len + 63) & ~63;
+        const int len64 = (len + 127) & ~127;   // padded to whole 128-point steps
         __syncthreads();
         for (int i = threadIdx.x; i < len64; i += BQ_WARPS * 32) {
             const bool v = i < len;
@@ -71,24 +71,29 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m,
             if (cnt[u] >= nsample) continue;  // warp-uniform
             int* __restrict__ row = idx + ((size_t)cloud * m + qbase + u) * nsample;
             const float2 QX = make_float2(qx[u], qx[u]), QY = make_float2(qy[u], qy[u]), QZ = make_float2(qz[u], qz[u]);
-            for (int k0 = 0; k0 < len && cnt[u] < nsample; k0 += 64) {
-                const int k = k0 + 2 * lane;  // this lane tests dataset points k and k+1
-                const float2 d2 = sqdist3x2<true>(__fadd2_rn(*reinterpret_cast<const float2*>(&sx[k]), QX),
-                                                  __fadd2_rn(*reinterpret_cast<const float2*>(&sy[k]), QY),
-                                                  __fadd2_rn(*reinterpret_cast<const float2*>(&sz[k]), QZ));
-                const bool hit0 = d2.x < T, hit1 = d2.y < T;
-                const unsigned m0 = __ballot_sync(0xffffffffu, hit0), m1 = __ballot_sync(0xffffffffu, hit1);
-                if (m0 | m1) {
+            for (int k0 = 0; k0 < len && cnt[u] < nsample; k0 += 128) {
+                const int k = k0 + 4 * lane;  // this lane tests dataset points k .. k+3 (two packed pairs from one LDS.128 per axis)
+                const float4 X = *reinterpret_cast<const float4*>(&sx[k]), Y = *reinterpret_cast<const float4*>(&sy[k]), Z = *reinterpret_cast<const float4*>(&sz[k]);
+                const float2 da = sqdist3x2<true>(__fadd2_rn(make_float2(X.x, X.y), QX), __fadd2_rn(make_float2(Y.x, Y.y), QY), __fadd2_rn(make_float2(Z.x, Z.y), QZ));
+                const float2 db = sqdist3x2<true>(__fadd2_rn(make_float2(X.z, X.w), QX), __fadd2_rn(make_float2(Y.z, Y.w), QY), __fadd2_rn(make_float2(Z.z, Z.w), QZ));
+                const bool h0 = da.x < T, h1 = da.y < T, h2 = db.x < T, h3 = db.y < T;
+                const unsigned any = __ballot_sync(0xffffffffu, h0 | h1 | h2 | h3);   // most steps have no hit: one vote
+                if (any) {   // warp-uniform
+                    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                    const unsigned m2 = __ballot_sync(0xffffffffu, h2), m3 = __ballot_sync(0xffffffffu, h3);
                     if (cnt[u] == 0) {
-                        const int f0 = m0 ? 2 * (__ffs(m0) - 1) : 64, f1 = m1 ? 2 * (__ffs(m1) - 1) + 1 : 64;
-                        first[u] = t0 + k0 + min(f0, f1);
+                        // first hit in index order: lowest lane with a hit, then its lowest point
+                        const int fl = __ffs(any) - 1;
+                        const int fo = ((m0 >> fl) & 1u) ? 0 : (((m1 >> fl) & 1u) ? 1 : (((m2 >> fl) & 1u) ? 2 : 3));
+                        first[u] = t0 + k0 + 4 * fl + fo;
                     }
-                    // position in index order: every hit of a lower lane (both of its points) comes first, then this lane's even point
-                    const int pos0 = cnt[u] + __popc(m0 & lt) + __popc(m1 & lt);
-                    const int pos1 = pos0 + (hit0 ? 1 : 0);
-                    if (hit0 && pos0 < nsample) row[pos0] = t0 + k;
-                    if (hit1 && pos1 < nsample) row[pos1] = t0 + k + 1;
-                    cnt[u] += __popc(m0) + __popc(m1);
+                    // position in index order: every hit of a lower lane (all four of its points) comes first, then this lane's own in order
+                    int pos = cnt[u] + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+                    if (h0) { if (pos < nsample) row[pos] = t0 + k; ++pos; }
+                    if (h1) { if (pos < nsample) row[pos] = t0 + k + 1; ++pos; }
+                    if (h2) { if (pos < nsample) row[pos] = t0 + k + 2; ++pos; }
+                    if (h3 && pos < nsample) row[pos] = t0 + k + 3;
+                    cnt[u] += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
                 }
             }
             all_full = all_full && cnt[u] >= nsample;
