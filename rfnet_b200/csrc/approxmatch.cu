@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
 // Exact pruning of the three sharpest levels (j = 7, 6, 5: e = exp(-4^j d2) with 4^j = 16384, 4096, 1024).
 // ex2.approx.ftz returns EXACTLY 0 once its argument is below -126, i.e. for d2 > 0.0053 / 0.021 / 0.085, and a zero term
 // leaves the accumulator bit-identical (fma(0, w, acc) == acc).  At those levels almost every pair is such a no-op, so:
-//   * morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, bitonic sort in shared memory);
+//   * morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, counting sort in shared memory);
 //     a warp of the pruned sweep then owns 128 CONSECUTIVE points of that order: a spatially tight cluster;
 //   * emd_mask_kernel marks, per cluster and level, the candidates whose distance to the cluster's bounding box still
 //     allows a non-zero term (with a safety margin of 4 in the exponent-2 argument, ~3 % in distance);
