@@ -95,7 +95,7 @@ int rfnet_emd_cost(int b, int n, int m, const float *xyz1, const float *xyz2, fl
  * tf_ops/sampling/tf_sampling.cpp:94,125,150 (defined tf_ops/sampling/tf_sampling_g.cu:203-211).
  * FPS: out (b, m) int32, first index 0, ties broken exactly as the reference's 512-thread block does.  The workspace
  * (the reference's (32, n) temp, tf_sampling.cpp:115) holds the Morton order of the clouds for the pruned kernel
- * (n <= 16384, m >= 512) or the running distances of clouds too large for registers; with workspace == NULL clouds of up
+ * (n <= 16384, m >= 256) or the running distances of clouds too large for registers; with workspace == NULL clouds of up
  * to 32768 points run on the cluster kernel, which needs none.  Every path returns the same indices.
  * scatteraddpoint zero-fills inp_g itself (the reference's OpKernel did it, tf_sampling.cpp:174).
  * ------------------------------------------------------------------------------------------------------------- */

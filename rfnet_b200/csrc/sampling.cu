@@ -409,7 +409,7 @@ extern "C" int rfnet_farthestpointsampling(int b, int n, int m, const float* inp
     // (RFNET_FPS_NO_PRUNE=1 forces the cluster kernel: used by the tests to compare the two)
     const char* no_prune = getenv("RFNET_FPS_NO_PRUNE");
     // (worth its prologue -- sort, gather, boxes: ~50 us -- from a few hundred picks on)
-    if (n <= FPSP_MAX_POINTS && m >= 512 && workspace && workspace_bytes >= sizeof(int) * (size_t)b * n && !(no_prune && no_prune[0] == '1')) {
+    if (n <= FPSP_MAX_POINTS && m >= 256 && workspace && workspace_bytes >= sizeof(int) * (size_t)b * n && !(no_prune && no_prune[0] == '1')) {
         int* perm = (int*)workspace;
         int rc = morton_sort(b, n, 0, inp, nullptr, perm, nullptr, s);
         if (rc) return rc;

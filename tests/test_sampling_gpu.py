@@ -15,7 +15,7 @@ def t(a, dev):
 
 # (b, n, m): up to 16384 points the pruned one-CTA kernel (1/2/4/8/16/32 register slots per lane), above it the cluster
 # kernel; m > n (repeats), n < 512, tiny
-SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 513, 600), (2, 3000, 32), (2, 3000, 700), (4, 4097, 128), (2, 9000, 520), (2, 16384, 256),
+SHAPES = [(1, 1, 1), (2, 7, 3), (3, 100, 150), (2, 512, 64), (2, 513, 600), (2, 3000, 32), (2, 3000, 700), (4, 4097, 128), (2, 9000, 520), (2, 16384, 256), (2, 16384, 255),
           (1, 20000, 64), (40, 1024, 64),
           (1, 40000, 24)]   # the last one exceeds 8 CTAs x 512 threads x 8 points: generic one-CTA kernel with global scratch
 
