@@ -61,6 +61,14 @@ def test_bad_arguments_return_error_codes(cuda):
     assert lib.rfnet_query_ball_point(1, 4, 4, z, 0, z, z, z, z, z) == 1               # nsample must be positive (tf_grouping.cpp:75)
     assert lib.rfnet_nn_distance(0, 4, z, 4, z, z, z, z, z, z, 0, 0, z) == 0           # empty batch is a no-op
     assert b"invalid" in lib.rfnet_error_string(1)
+    # entry points added for tf_ops/emd and select_top_k
+    assert lib.rfnet_auction_match(1, 9000, z, z, z, z, z) == 1                          # beyond RFNET_AUCTION_MAX_POINTS
+    assert lib.rfnet_auction_match(1, 8, z, z, z, z, z) == 1                             # null pointers
+    assert lib.rfnet_auction_match(0, 8, z, z, z, z, z) == 0 and lib.rfnet_auction_match(3, 0, z, z, z, z, z) == 0
+    assert lib.rfnet_selection_sort(1, 8, 2, 0, z, z, z, z) == 1                         # k must be positive (tf_grouping.cpp:117)
+    assert lib.rfnet_selection_sort(1, 0, 2, 3, z, z, z, z) == 0                         # empty rows: nothing to do
+    assert lib.rfnet_emd_cost(1, 8, 8, z, z, z, z, z, 0, z) == 1                         # cost pointer required
+    assert lib.rfnet_emd_cost_workspace_bytes(2, 4096, 4096) > lib.rfnet_approxmatch_workspace_bytes(2, 4096, 4096) > 0
 
 
 def test_sharded_losses_single_rank_equal_plain_losses(cuda, rng):
