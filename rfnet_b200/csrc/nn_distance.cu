@@ -211,12 +211,16 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(cons
     }
 }
 
-__global__ void nn_unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ dist, int* __restrict__ idx, size_t count) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) {
+// keys of direction 0 (count0 entries) are followed by those of direction 1: one launch unpacks whichever were merged
+__global__ void nn_unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ dist1, int* __restrict__ idx1, size_t count0,
+                                      float* __restrict__ dist2, int* __restrict__ idx2, size_t begin, size_t end) {
+    const size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) {
         const unsigned long long k = keys[i];
-        dist[i] = __uint_as_float((unsigned)(k >> 32));
-        idx[i] = (int)(unsigned)(k & 0xffffffffull);
+        const float d = __uint_as_float((unsigned)(k >> 32));
+        const int x = (int)(unsigned)(k & 0xffffffffull);
+        if (i < count0) { dist1[i] = d; idx1[i] = x; }
+        else { dist2[i - count0] = d; idx2[i - count0] = x; }
     }
 }
 
@@ -460,21 +464,20 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     const bool need0 = p.d[0].nsplit > 1, need1 = p.d[1].nsplit > 1;
     if (need0 || need1) {
         RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_nn_distance_workspace_bytes(b, n, m));
-        if (need0) RFNET_CUDA(cudaMemsetAsync(p.d[0].keys, 0xff, sizeof(unsigned long long) * (size_t)b * n, s));
-        if (need1) RFNET_CUDA(cudaMemsetAsync(p.d[1].keys, 0xff, sizeof(unsigned long long) * (size_t)b * m, s));
+        // the two key arrays are contiguous: one memset covers whichever directions are merged
+        unsigned long long* first = need0 ? p.d[0].keys : p.d[1].keys;
+        const size_t cnt = (need0 ? (size_t)b * n : 0) + (need1 ? (size_t)b * m : 0);
+        RFNET_CUDA(cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * cnt, s));
     }
     const int grid = p.d[0].items + p.d[1].items;
     const bool fused = !(flags & RFNET_NN_UNFUSED);
     if (Q == 8) launch_search<8>(p, grid, fused, s);
     else if (Q == 4) launch_search<4>(p, grid, fused, s);
     else launch_search<2>(p, grid, fused, s);
-    if (need0) {
-        const size_t cnt = (size_t)b * n;
-        nn_unpack_keys_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(p.d[0].keys, dist1, idx1, cnt);
-    }
-    if (need1) {
-        const size_t cnt = (size_t)b * m;
-        nn_unpack_keys_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(p.d[1].keys, dist2, idx2, cnt);
+    if (need0 || need1) {
+        const size_t count0 = (size_t)b * n;
+        const size_t begin = need0 ? 0 : count0, end = need1 ? count0 + (size_t)b * m : count0;
+        nn_unpack_keys_kernel<<<(unsigned)((end - begin + 255) / 256), 256, 0, s>>>(keys, dist1, idx1, count0, dist2, idx2, begin, end);
     }
     return launch_status();
 }
