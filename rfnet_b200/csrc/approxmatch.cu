@@ -96,11 +96,43 @@ static EmdWs emd_carve(float* w, int b, int n, int m) {
 // UNIT_E: the last level (j = -2) has level = 0, i.e. e = ex2(0 * d2) = 1 for every pair; the same accumulation chain is run
 // without evaluating distances or exponentials (1 lane-op per pair instead of 8 + a MUFU).
 // ---------------------------------------------------------------------------------------------------------------
-template <int Q, bool PASS3, bool UNIT_E>
+// ---- the pass's update rule ("normalise" in pass 1, "saturate" in pass 2, "consume" in pass 3) ------------------
+// EPI = 1: ratioL[k] = remainL[k] / (1e-9 + sum)                                  tf_approxmatch.cu:26-59 (the seed is in the sum)
+// EPI = 2: consumption = min(remainR / (sumr + 1e-9), 1); ratioR = consumption * remainR; remainR -= sumr   :75-108
+// EPI = 3: remainL[k] = max(0, remainL[k] - sum)                                  :127-160 (ratioL is applied per term in the sweep)
+// When the candidates are NOT split over several CTAs a sweep thread owns the complete sum of its rows and applies the rule
+// itself (fused: no partial-sum round trip, no epilogue launch); with splits the partial sums are reduced in split order by
+// the small epilogue kernels further down.  (Fusing the split case too, through a last-CTA ticket, was measured slower.)
+struct EmdEpi {
+    float* remain;   // EPI 1, 3: remainL   EPI 2: remainR
+    float* ratio;    // EPI 1: ratioL       EPI 2: ratioR
+    float* fac;      // EPI 1: facL[level]  EPI 2: facR[level]
+};
+template <int EPI>
+__device__ __forceinline__ void emd_apply(const EmdEpi& e, size_t idx, float sum) {
+    if (EPI == 1) {
+        const float r = e.remain[idx] / sum;
+        e.ratio[idx] = r;
+        e.fac[idx] = r;
+    } else if (EPI == 2) {
+        const float rem = e.remain[idx];
+        const float sumr = sum * rem;
+        const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+        const float r = consumption * rem;
+        e.ratio[idx] = r;
+        e.fac[idx] = r;
+        e.remain[idx] = fmaxf(0.0f, rem - sumr);
+    } else {
+        e.remain[idx] = fmaxf(0.0f, e.remain[idx] - sum);
+    }
+}
+
+template <int Q, int EPI, bool UNIT_E>
 __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2, float init0,
                                                                const float* __restrict__ rows, const float* __restrict__ cands,
                                                                const float* __restrict__ w, const float* __restrict__ rowfac,
-                                                               float* __restrict__ partial) {
+                                                               float* __restrict__ partial, EmdEpi epi) {
+    constexpr bool PASS3 = EPI == 3;
     __shared__ __align__(16) float4 sC[EMD_TC];
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -164,6 +196,15 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(int nr, int nc, 
                 }
             }
         }
+    }
+    if (nsplit == 1) {   // complete sums: apply the pass's rule here
+#pragma unroll
+        for (int h = 0; h < Q / 2; ++h) {
+            const int ia = r0 + (2 * h) * EMD_THREADS, ib = ia + EMD_THREADS;
+            if (ia < nr) emd_apply<EPI>(epi, (size_t)cloud * nr + ia, acc[h].x);
+            if (ib < nr) emd_apply<EPI>(epi, (size_t)cloud * nr + ib, acc[h].y);
+        }
+        return;
     }
     float* __restrict__ out = partial + ((size_t)cloud * nsplit + split) * nr;
 #pragma unroll
@@ -249,13 +290,14 @@ __global__ void __launch_bounds__(256) emd_mask_kernel(int nr, int nc, int nword
 
 // The dense sweep (Q = 4) restricted to the marked candidates of the warp's cluster.  `mask` points at the level's words
 // of cluster 0 of cloud 0; clusters are EMD_PRUNE_LEVELS * nwords apart.
-template <bool PASS3>
+template <int EPI>
 __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_pruned_kernel(int nr, int nc, int nrt, int nsplit, int cps, float lvl2, float init0,
                                                                       const float* __restrict__ rows, const float* __restrict__ cands,
                                                                       const float* __restrict__ w, const float* __restrict__ rowfac,
                                                                       const int* __restrict__ perm, const unsigned* __restrict__ mask, int nwords,
-                                                                      float* __restrict__ partial) {
+                                                                      float* __restrict__ partial, EmdEpi epi) {
     constexpr int Q = 4;
+    constexpr bool PASS3 = EPI == 3;
     __shared__ __align__(16) float4 sC[EMD_TC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int bid = blockIdx.x;
@@ -323,6 +365,14 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_sweep_pruned_kernel(int nr, i
                 }
             }
         }
+    }
+    if (nsplit == 1) {
+#pragma unroll
+        for (int h = 0; h < Q / 2; ++h) {
+            if (row[2 * h] >= 0) emd_apply<EPI>(epi, (size_t)cloud * nr + row[2 * h], acc[h].x);
+            if (row[2 * h + 1] >= 0) emd_apply<EPI>(epi, (size_t)cloud * nr + row[2 * h + 1], acc[h].y);
+        }
+        return;
     }
     float* __restrict__ out = partial + ((size_t)cloud * nsplit + split) * nr;
 #pragma unroll
@@ -742,27 +792,28 @@ static SweepPlan emd_plan(int b, int nr, int nc) {
     p.nsplit = (chunks + p.cps - 1) / p.cps;
     return p;
 }
-template <int Q, bool PASS3>
+template <int Q, int EPI>
 static void emd_sweep_q(const SweepPlan& p, unsigned grid, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands,
-                        const float* w, const float* rowfac, float* partial, cudaStream_t s) {
+                        const float* w, const float* rowfac, float* partial, const EmdEpi& epi, cudaStream_t s) {
     if (lvl2 == 0.0f)
-        emd_sweep_kernel<Q, PASS3, true><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+        emd_sweep_kernel<Q, EPI, true><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial, epi);
     else
-        emd_sweep_kernel<Q, PASS3, false><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial);
+        emd_sweep_kernel<Q, EPI, false><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, partial, epi);
 }
-template <bool PASS3>
+// nsplit_out == 1 means the sweep applied the pass's rule itself; otherwise the caller launches the epilogue kernel
+template <int EPI>
 static void emd_sweep(int b, int nr, int nc, float lvl2, float init0, const float* rows, const float* cands, const float* w, const float* rowfac,
-                      float* partial, int& nsplit_out, cudaStream_t s, const int* perm = nullptr, const unsigned* mask = nullptr) {
+                      float* partial, const EmdEpi& epi, int& nsplit_out, cudaStream_t s, const int* perm = nullptr, const unsigned* mask = nullptr) {
     const SweepPlan p = emd_plan(b, nr, nc);
     nsplit_out = p.nsplit;
     const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
     if (mask && p.Q == 4) {
-        emd_sweep_pruned_kernel<PASS3><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, perm, mask,
-                                                                   (nc + 31) / 32, partial);
+        emd_sweep_pruned_kernel<EPI><<<grid, EMD_THREADS, 0, s>>>(nr, nc, p.nrt, p.nsplit, p.cps, lvl2, init0, rows, cands, w, rowfac, perm, mask,
+                                                                 (nc + 31) / 32, partial, epi);
         return;
     }
-    if (p.Q == 4) emd_sweep_q<4, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
-    else emd_sweep_q<2, PASS3>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, s);
+    if (p.Q == 4) emd_sweep_q<4, EPI>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, epi, s);
+    else emd_sweep_q<2, EPI>(p, grid, nr, nc, lvl2, init0, rows, cands, w, rowfac, partial, epi, s);
 }
 
 // sweeps (-> per-level factors in the workspace), then one pass that materialises the matrix and/or reduces the cost
@@ -789,15 +840,17 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
         const bool pl = prune && li < EMD_PRUNE_LEVELS;
         const unsigned* mA = pl ? ws.maskA + (size_t)li * ((m + 31) / 32) : nullptr;
         const unsigned* mB = pl ? ws.maskB + (size_t)li * ((n + 31) / 32) : nullptr;
-        // pass 1: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR
-        emd_sweep<false>(b, n, m, lvl2, 1e-9f, xyz1, xyz2, ws.remainR, nullptr, ws.partial, ns, s, ws.perm1, mA);
-        emd_epi1_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn);
-        // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL
-        emd_sweep<false>(b, m, n, lvl2, 0.0f, xyz2, xyz1, ws.ratioL, nullptr, ws.partial, ns, s, ws.perm2, mB);
-        emd_epi2_kernel<<<(unsigned)((bm + 255) / 256), 256, 0, s>>>(m, ns, bm, ws.partial, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm);
-        // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR
-        emd_sweep<true>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, ns, s, ws.perm1, mA);
-        emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL);
+        // pass 1: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR            -> ratioL, facL
+        emd_sweep<1>(b, n, m, lvl2, 1e-9f, xyz1, xyz2, ws.remainR, nullptr, ws.partial, EmdEpi{ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn}, ns, s,
+                     ws.perm1, mA);
+        if (ns > 1) emd_epi1_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL, ws.ratioL, ws.facL + (size_t)li * bn);
+        // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL             -> ratioR, facR, remainR
+        emd_sweep<2>(b, m, n, lvl2, 0.0f, xyz2, xyz1, ws.ratioL, nullptr, ws.partial, EmdEpi{ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm}, ns, s,
+                     ws.perm2, mB);
+        if (ns > 1) emd_epi2_kernel<<<(unsigned)((bm + 255) / 256), 256, 0, s>>>(m, ns, bm, ws.partial, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm);
+        // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR, row factor ratioL  -> remainL
+        emd_sweep<3>(b, n, m, lvl2, 0.0f, xyz1, xyz2, ws.ratioR, ws.ratioL, ws.partial, EmdEpi{ws.remainL, nullptr, nullptr}, ns, s, ws.perm1, mA);
+        if (ns > 1) emd_epi3_kernel<<<(unsigned)((bn + 255) / 256), 256, 0, s>>>(n, ns, bn, ws.partial, ws.remainL);
     }
     dim3 grid((unsigned)((n + 2 * MT_THREADS - 1) / (2 * MT_THREADS)), (unsigned)((m + MT_L - 1) / MT_L), (unsigned)b);
     RFNET_CHECK_ARG(grid.y <= 65535);

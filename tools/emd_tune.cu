@@ -12,10 +12,10 @@ float run(int b, int n, int nsplit, float lvl2, const float* x1, const float* x2
     nsplit = (chunks + cps - 1) / cps;
     const unsigned grid = (unsigned)(b * nrt * nsplit);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; ++i) emd_sweep_kernel<Q, false, false><<<grid, EMD_THREADS>>>(n, n, nrt, nsplit, cps, lvl2, 1e-9f, x1, x2, w, nullptr, partial);
+    for (int i = 0; i < 2; ++i) emd_sweep_kernel<Q, 1, false><<<grid, EMD_THREADS>>>(n, n, nrt, nsplit, cps, lvl2, 1e-9f, x1, x2, w, nullptr, partial, EmdEpi{w, partial, partial});
     cudaEventRecord(e0);
     const int it = 5;
-    for (int i = 0; i < it; ++i) emd_sweep_kernel<Q, false, false><<<grid, EMD_THREADS>>>(n, n, nrt, nsplit, cps, lvl2, 1e-9f, x1, x2, w, nullptr, partial);
+    for (int i = 0; i < it; ++i) emd_sweep_kernel<Q, 1, false><<<grid, EMD_THREADS>>>(n, n, nrt, nsplit, cps, lvl2, 1e-9f, x1, x2, w, nullptr, partial, EmdEpi{w, partial, partial});
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     ms /= it;
