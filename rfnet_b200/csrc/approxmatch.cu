@@ -7,8 +7,9 @@
 //   * every pass is the same reduction  S[row] = sum_c exp(level * d2(row, c)) * w[c]  ("weighted exp-sum sweep") with the
 //     roles of the two clouds swapped between passes; it runs on the whole chip: grid = clouds x row tiles x candidate
 //     splits, rows in registers as packed pairs (FADD2/FMUL2/FFMA2), candidates + weights broadcast from shared memory,
-//     one MUFU.EX2 per pair; partial sums go to a small buffer and a tiny epilogue kernel applies the pass's update rule
-//     (ratioL / consumption+ratioR / remainL) -- deterministic, no atomics;
+//     one MUFU.EX2 per pair; the pass's update rule (ratioL / consumption+ratioR / remainL) is applied by the sweep itself
+//     when a CTA sees all candidates, else partial sums go to a small buffer and a tiny epilogue kernel reduces them in
+//     split order -- deterministic, no atomics;
 //   * match is NOT accumulated level by level.  The per-level factors ratioL_j[k], ratioR_j[l] are kept (10*(n+m) floats per
 //     cloud) and match[l,k] = sum_j e_j(k,l) * ratioL_j[k] * ratioR_j[l] is written ONCE at the end: 4 B/pair of HBM
 //     traffic instead of 80, at the price of 9 more ex2 per pair (the j = -2 level has e = 1).
