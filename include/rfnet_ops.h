@@ -112,10 +112,15 @@ int rfnet_scatteraddpoint(int b, int n, int m, const float *out_g, const int *id
  * tf_ops/grouping/tf_grouping.cpp:67,146,177 (defined tf_ops/grouping/tf_grouping_g.cu:125-141).
  * radius is a DEVICE pointer to one float, as in the reference (tf_grouping.cpp:93-95).  Rows with no point in the
  * ball are filled with 0 (the reference leaves them uninitialised) and get pts_cnt 0.
+ * With a workspace (and 2048 <= n <= 32768) query_ball_point bins the dataset in a uniform grid and only tests the cells
+ * a ball touches; with workspace == NULL every query scans the whole dataset.  Identical results either way
+ * (RFNET_BALL_NO_GRID=1 forces the scan, for A/B tests).
  * groupPointGrad zero-fills grad_points itself (reference: tf_grouping.cpp:208).
  * ------------------------------------------------------------------------------------------------------------- */
+size_t rfnet_query_ball_point_workspace_bytes(int b, int n, int m);
 int rfnet_query_ball_point(int b, int n, int m, const float *radius, int nsample, const float *xyz1,
-                           const float *xyz2, int *idx, int *pts_cnt, rfnet_stream_t stream);
+                           const float *xyz2, int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes,
+                           rfnet_stream_t stream);
 int rfnet_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
                       rfnet_stream_t stream);
 size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, int m, int nsample);

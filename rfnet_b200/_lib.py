@@ -33,7 +33,8 @@ SIGNATURES = {
     "rfnet_gatherpoint": (_i, [_i, _i, _i, _p, _p, _p, _p]),
     "rfnet_scatteraddpoint_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_scatteraddpoint": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
-    "rfnet_query_ball_point": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "rfnet_query_ball_point_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_query_ball_point": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_group_point": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_group_point_grad_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
     "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),

@@ -9,6 +9,8 @@
 //
 // The predicate max(sqrtf(d2), 1e-20f) < r is evaluated without a square root: sqrt_rn is monotone, so it equals
 // d2 < T with T = min{t : sqrt_rn(t) >= r}; T is found once per thread by stepping nextafter around r*r.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "rfnet_ops.h"
 #include "segscatter.cuh"
@@ -109,6 +111,252 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m,
         int* __restrict__ row = idx + ((size_t)cloud * m + j) * nsample;
         // remaining slots repeat the first hit (tf_grouping_g.cu:26-29); rows without any hit are defined as 0 here
         for (int s = c + lane; s < nsample; s += 32) row[s] = first[u];
+        if (lane == 0) pts_cnt[(size_t)cloud * m + j] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Grid variant (used when the caller passes a workspace and the dataset has >= BG_MIN_POINTS points).
+// The hits of a query all lie in the cells of a uniform grid that its ball touches; with cells at least one radius wide
+// that is at most 3 x 3 x 3 of them.  ball_grid_kernel (one CTA per cloud) bins the dataset with a counting sort --
+// cell = ((cx * Gy) + cy) * Gz + cz, G = min(32, extent / r) per axis -- and stores
+// the cell offsets and the coordinates in cell order.  ball_query_grid_kernel gives a warp per query: it walks the <= 9 runs of
+// z-consecutive cells (contiguous in the sorted order), tests the SAME predicate on the same fused distance as the scan
+// kernel above, marks every hit in a per-warp bitmap over the dataset indices (shared memory), and reads the bitmap back in
+// index order: "the first nsample points inside the ball in index order" (tf_grouping_g.cu:17-31) computed from ~n/37
+// candidates instead of n, whatever the number of hits.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BG_CELLS = 32768;        // 32^3
+constexpr int BG_MIN_POINTS = 2048;
+constexpr int BG_MAX_POINTS = 32768;   // one bit per dataset point and warp in shared memory (4 KiB x 8 warps)
+struct BallGrid {
+    float lo[3], scale[3];   // cell coordinate along axis a: min(G[a] - 1, (int)((p[a] - lo[a]) * scale[a]))
+    int G[3], pad;
+};
+static inline size_t ball_grid_stride(int n) {   // bytes of workspace per cloud
+    return (sizeof(BallGrid) + sizeof(int) * (BG_CELLS + 1) + sizeof(int) * (size_t)n + sizeof(float) * 3 * (size_t)n + 63) & ~(size_t)63;
+}
+struct BallGridView {
+    const BallGrid* g;
+    const int* cell_start;     // BG_CELLS + 1
+    const int* sorted_idx;     // n: dataset indices in cell order
+    const float* sorted_xyz;   // n x 3 in cell order
+};
+__device__ __forceinline__ BallGridView ball_grid_view(const unsigned char* ws, size_t stride, int cloud, int n) {
+    const unsigned char* p = ws + stride * cloud;
+    BallGridView v;
+    v.g = reinterpret_cast<const BallGrid*>(p);                p += sizeof(BallGrid);
+    v.cell_start = reinterpret_cast<const int*>(p);            p += sizeof(int) * (BG_CELLS + 1);
+    v.sorted_idx = reinterpret_cast<const int*>(p);            p += sizeof(int) * (size_t)n;
+    v.sorted_xyz = reinterpret_cast<const float*>(p);
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) ball_grid_kernel(int n, const float* __restrict__ radius, const float* __restrict__ xyz1, unsigned char* __restrict__ ws,
+                                                         size_t stride) {
+    extern __shared__ unsigned cell[];   // BG_CELLS counters, then cursors; one pad word per 32 (CI)
+    __shared__ float red[6][32];
+    __shared__ unsigned wtot[32];
+    __shared__ BallGrid sg;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ pts = xyz1 + (size_t)cloud * n * 3;
+    const BallGridView v = ball_grid_view(ws, stride, cloud, n);
+    BallGrid* gout = const_cast<BallGrid*>(v.g);
+    int* cell_start = const_cast<int*>(v.cell_start);
+    int* sorted_idx = const_cast<int*>(v.sorted_idx);
+    float* sorted_xyz = const_cast<float*>(v.sorted_xyz);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto CI = [](unsigned c) -> unsigned { return c + (c >> 5); };
+    for (int i = tid; i < BG_CELLS + BG_CELLS / 32; i += 1024) cell[i] = 0u;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int i = tid; i < n; i += 1024)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float x = pts[(size_t)i * 3 + a];
+            lo[a] = fminf(lo[a], x);
+            hi[a] = fmaxf(hi[a], x);
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float r = radius[0];
+        for (int a = 0; a < 3; ++a) {
+            float l = red[a][0], h = red[3 + a][0];
+            for (int w2 = 1; w2 < 32; ++w2) { l = fminf(l, red[a][w2]); h = fmaxf(h, red[3 + a][w2]); }
+            const float ext = h - l;
+            int G = 1;
+            if (r > 0.f && ext > 0.f && ext / r < 1e6f) G = max(1, min(32, (int)(ext / r)));   // cells at least one radius wide
+            else if (r > 0.f && ext > 0.f) G = 32;
+            sg.lo[a] = l;
+            sg.scale[a] = ext > 0.f ? (float)G / ext : 0.f;
+            sg.G[a] = G;
+        }
+        sg.pad = 0;
+        *gout = sg;
+    }
+    __syncthreads();
+    const BallGrid g = sg;
+    auto code = [&](int i) -> unsigned {
+        unsigned c[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) c[a] = (unsigned)min(g.G[a] - 1, max(0, (int)((pts[(size_t)i * 3 + a] - g.lo[a]) * g.scale[a])));
+        return (c[0] * g.G[1] + c[1]) * g.G[2] + c[2];
+    };
+    for (int i = tid; i < n; i += 1024) atomicAdd(&cell[CI(code(i))], 1u);
+    __syncthreads();
+    unsigned sum = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) sum += cell[CI(tid * 32 + k)];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = wtot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        wtot[lane] = t;
+    }
+    __syncthreads();
+    const unsigned base = (warp ? wtot[warp - 1] : 0u) + incl - sum;
+    {
+        unsigned run = base;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const unsigned c = cell[CI(tid * 32 + k)];
+            cell[CI(tid * 32 + k)] = run;
+            cell_start[tid * 32 + k] = (int)run;
+            run += c;
+        }
+        if (tid == 1023) cell_start[BG_CELLS] = (int)run;   // == n
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) sorted_idx[atomicAdd(&cell[CI(code(i))], 1u)] = i;
+    __syncthreads();
+    // (the order of the points inside a cell is whatever the atomics produced: the query kernel sorts its hits anyway)
+    for (int p2 = tid; p2 < n; p2 += 1024) {
+        const int i = sorted_idx[p2];
+        sorted_xyz[(size_t)p2 * 3 + 0] = pts[(size_t)i * 3 + 0];
+        sorted_xyz[(size_t)p2 * 3 + 1] = pts[(size_t)i * 3 + 1];
+        sorted_xyz[(size_t)p2 * 3 + 2] = pts[(size_t)i * 3 + 2];
+    }
+}
+
+__global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_grid_kernel(int n, int m, const float* __restrict__ radius, int nsample,
+                                                                        const float* __restrict__ xyz2, const unsigned char* __restrict__ ws, size_t stride,
+                                                                        int* __restrict__ idx, int* __restrict__ pts_cnt) {
+    // one bit per dataset point and warp: hits are marked in whatever order the cells deliver them and read back in index order
+    __shared__ unsigned bitmap[BQ_WARPS][BG_MAX_POINTS / 32];
+    const int cloud = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BallGridView v = ball_grid_view(ws, stride, cloud, n);
+    const BallGrid g = *v.g;
+    const float r = radius[0];
+    const float T = ball_threshold(r);
+    const float rr = r * 1.0001f;   // the cell range is taken for a slightly larger ball: rounding can only add cells
+    unsigned* __restrict__ bm = bitmap[warp];
+    const int words = (n + 31) >> 5, rounds = (words + 31) >> 5;
+    for (int w = lane; w < words; w += 32) bm[w] = 0u;
+    __syncwarp();
+    for (int u = 0; u < BQ_QPW; ++u) {
+        const int j = (blockIdx.x * BQ_WARPS + warp) * BQ_QPW + u;
+        if (j >= m) break;   // warp-uniform
+        const float* q = xyz2 + ((size_t)cloud * m + j) * 3;
+        const float qc[3] = {q[0], q[1], q[2]};
+        int c0[3], c1[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float pad = rr + 1e-6f * (fabsf(qc[a]) + fabsf(g.lo[a]));   // + a few ulps of the coordinates, for radii near their resolution
+            c0[a] = min(g.G[a] - 1, max(0, (int)floorf((qc[a] - pad - g.lo[a]) * g.scale[a])));
+            c1[a] = min(g.G[a] - 1, max(0, (int)floorf((qc[a] + pad - g.lo[a]) * g.scale[a])));
+        }
+        // test the candidates of one run of z-consecutive cells, two warp-steps at a time: the loads are what this loop waits for
+        auto scan_run = [&](int rs, int e) {
+            for (int p0 = rs; p0 < e; p0 += 64) {
+                const int pa = p0 + lane, pb = pa + 32;
+                const bool va = pa < e, vb = pb < e;
+                const float* ca = v.sorted_xyz + (size_t)(va ? pa : 0) * 3;
+                const float* cb = v.sorted_xyz + (size_t)(vb ? pb : 0) * 3;
+                const float ax = __ldg(ca), ay = __ldg(ca + 1), az = __ldg(ca + 2), bx = __ldg(cb), by = __ldg(cb + 1), bz = __ldg(cb + 2);
+                // query + (-point): the operand order of the scan kernel (and of tf_grouping_g.cu:24)
+                const float da = sqdist3<true>(__fadd_rn(-ax, qc[0]), __fadd_rn(-ay, qc[1]), __fadd_rn(-az, qc[2]));
+                const float db = sqdist3<true>(__fadd_rn(-bx, qc[0]), __fadd_rn(-by, qc[1]), __fadd_rn(-bz, qc[2]));
+                if (va && da < T) {
+                    const int k = __ldg(v.sorted_idx + pa);
+                    atomicOr(&bm[k >> 5], 1u << (k & 31));
+                }
+                if (vb && db < T) {
+                    const int k = __ldg(v.sorted_idx + pb);
+                    atomicOr(&bm[k >> 5], 1u << (k & 31));
+                }
+            }
+        };
+        if (c1[0] - c0[0] <= 2 && c1[1] - c0[1] <= 2) {
+            // the usual case (cells are at least one radius wide): at most 3 x 3 runs; fetch all their bounds before any candidate
+            int rs[9], re[9];
+#pragma unroll
+            for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 3; ++b2) {
+                    const int cx = c0[0] + a2, cy = c0[1] + b2;
+                    const bool ok = cx <= c1[0] && cy <= c1[1];
+                    const int ca = ok ? (cx * g.G[1] + cy) * g.G[2] : 0;
+                    rs[a2 * 3 + b2] = ok ? __ldg(v.cell_start + ca + c0[2]) : 0;
+                    re[a2 * 3 + b2] = ok ? __ldg(v.cell_start + ca + c1[2] + 1) : 0;
+                }
+#pragma unroll
+            for (int rI = 0; rI < 9; ++rI) scan_run(rs[rI], re[rI]);
+        } else {   // a ball wider than three cells (radius close to the resolution of the coordinates): plain loops
+            for (int cx = c0[0]; cx <= c1[0]; ++cx)
+                for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+                    const int ca = (cx * g.G[1] + cy) * g.G[2];
+                    scan_run(v.cell_start[ca + c0[2]], v.cell_start[ca + c1[2] + 1]);
+                }
+        }
+        __syncwarp();
+        // read the bitmap back in index order (word w belongs to lane w % 32 in round w / 32), clearing it for the next query
+        int* __restrict__ row = idx + ((size_t)cloud * m + j) * nsample;
+        int total = 0;
+        for (int t = 0; t < rounds; ++t) {
+            const int wi = t * 32 + lane;
+            unsigned w = 0u;
+            if (wi < words) { w = bm[wi]; bm[wi] = 0u; }
+            if (!__any_sync(0xffffffffu, w != 0u)) continue;
+            const int c = __popc(w);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            int off = total + incl - c;
+            while (w && off < nsample) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                row[off++] = wi * 32 + bit;
+            }
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        const int c = min(total, nsample);
+        const int first = total ? row[0] : 0;   // rows without any hit are defined as 0 (the reference leaves them uninitialised)
+        for (int s2 = c + lane; s2 < nsample; s2 += 32) row[s2] = first;
         if (lane == 0) pts_cnt[(size_t)cloud * m + j] = c;
     }
 }
@@ -246,15 +494,32 @@ __global__ void __launch_bounds__(SS_WARPS * 32) selection_sort_kernel(int n, in
 
 using namespace rfnet;
 
+extern "C" size_t rfnet_query_ball_point_workspace_bytes(int b, int n, int m) {
+    (void)m;
+    if (b <= 0 || n < BG_MIN_POINTS || n > BG_MAX_POINTS) return 0;
+    return ball_grid_stride(n) * (size_t)b;
+}
+
 extern "C" int rfnet_query_ball_point(int b, int n, int m, const float* radius, int nsample, const float* xyz1, const float* xyz2,
-                                      int* idx, int* pts_cnt, rfnet_stream_t stream) {
+                                      int* idx, int* pts_cnt, void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0 && nsample > 0);  // tf_grouping.cpp:75
     if (b == 0 || m == 0) return 0;
     RFNET_CHECK_ARG(radius && xyz2 && idx && pts_cnt && (n == 0 || xyz1));
     RFNET_CHECK_ARG(b <= 65535);
+    cudaStream_t s = (cudaStream_t)stream;
     const int per_block = BQ_WARPS * BQ_QPW;
     dim3 grid((unsigned)((m + per_block - 1) / per_block), (unsigned)b);
-    ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt);
+    const char* no_grid = getenv("RFNET_BALL_NO_GRID");   // A/B switch for the tests: scan kernel only
+    if (workspace && n >= BG_MIN_POINTS && n <= BG_MAX_POINTS && workspace_bytes >= rfnet_query_ball_point_workspace_bytes(b, n, m) &&
+        !(no_grid && no_grid[0] == '1')) {
+        const size_t stride = ball_grid_stride(n);
+        const size_t smem = sizeof(unsigned) * (BG_CELLS + BG_CELLS / 32);
+        RFNET_CUDA(cudaFuncSetAttribute(ball_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ball_grid_kernel<<<b, 1024, smem, s>>>(n, radius, xyz1, (unsigned char*)workspace, stride);
+        ball_query_grid_kernel<<<grid, BQ_WARPS * 32, 0, s>>>(n, m, radius, nsample, xyz2, (const unsigned char*)workspace, stride, idx, pts_cnt);
+        return launch_status();
+    }
+    ball_query_kernel<<<grid, BQ_WARPS * 32, 0, s>>>(n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt);
     return launch_status();
 }
 

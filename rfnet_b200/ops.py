@@ -399,9 +399,12 @@ def query_ball_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, radius: torch.Te
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_query_ball_point_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(_lib.load().rfnet_query_ball_point(b, n, m, _ptr(radius), nsample, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt), _stream(xyz1)),
-                   "rfnet_query_ball_point")
+        _lib.check(lib.rfnet_query_ball_point(b, n, m, _ptr(radius), nsample, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt), _ptr(ws), wsb,
+                                              _stream(xyz1)), "rfnet_query_ball_point")
     return idx, cnt
 
 

@@ -27,6 +27,42 @@ def test_query_ball_point_bit_exact(cuda, rng, b, n, m, ns, r):
     assert np.array_equal(gi.cpu().numpy(), wi)
 
 
+@pytest.mark.parametrize("b,n,m,ns,r,kind", [(2, 16384, 2048, 32, 0.1, "cube"), (2, 5000, 777, 16, 0.07, "sphere"), (1, 3000, 300, 64, 0.3, "cube"),
+                                             (1, 4096, 200, 8, 2.5, "cube"), (1, 4096, 100, 32, 1e-5, "dup"), (1, 2048, 64, 4, 0.05, "outside"),
+                                             (1, 8000, 500, 32, 0.02, "line")])
+def test_query_ball_point_grid_equals_scan(cuda, b, n, m, ns, r, kind):
+    """From 2048 dataset points the op bins the dataset in a uniform grid and only tests the cells a ball touches; the
+    result must be IDENTICAL to the full scan (RFNET_BALL_NO_GRID=1): volumes, surfaces, a radius larger than the cloud (every
+    query overflows the hit buffer and is redone by the scan kernel), a radius below the coordinate resolution with duplicated
+    points, queries outside the dataset's bounding box, and a degenerate (collinear) cloud."""
+    import os
+    from rfnet_b200 import tf_grouping
+    g = torch.Generator(device="cpu").manual_seed(7 + n + m)
+    x1 = torch.rand((b, n, 3), generator=g) - 0.5
+    x2 = torch.rand((b, m, 3), generator=g) - 0.5
+    if kind == "sphere":
+        x1 = 0.5 * x1 / x1.norm(dim=-1, keepdim=True)
+        x2 = 0.5 * x2 / x2.norm(dim=-1, keepdim=True)
+    elif kind == "dup":
+        x1[:, n // 2:] = x1[:, : n - n // 2]
+        x2 = x1[:, :m].clone()
+    elif kind == "outside":
+        x2 = x2 * 3.0
+    elif kind == "line":
+        x1[:, :, 1:] = 0.25
+        x2[:, :, 1:] = 0.25
+    x1, x2 = x1.to(cuda), x2.to(cuda)
+    assert os.environ.get("RFNET_BALL_NO_GRID") is None
+    gi, gc = tf_grouping.query_ball_point(r, ns, x1, x2)
+    os.environ["RFNET_BALL_NO_GRID"] = "1"
+    try:
+        si, sc = tf_grouping.query_ball_point(r, ns, x1, x2)
+    finally:
+        del os.environ["RFNET_BALL_NO_GRID"]
+    assert torch.equal(gc, sc) and torch.equal(gi, si)
+    assert int(gc.min()) >= 0 and int(gc.max()) <= ns
+
+
 def test_ball_threshold_is_exact(cuda):
     """The sqrt-free predicate: on distances straddling r the kernel must agree with max(sqrtf(d2),1e-20f) < r."""
     from rfnet_b200 import tf_grouping

@@ -58,7 +58,7 @@ def test_bad_arguments_return_error_codes(cuda):
     z = ctypes.c_void_p(0)
     assert lib.rfnet_nn_distance(1, 4, z, 4, z, z, z, z, z, z, 0, 0, z) == 1          # cudaErrorInvalidValue: null pointers
     assert lib.rfnet_nn_distance(-1, 4, z, 4, z, z, z, z, z, z, 0, 0, z) == 1
-    assert lib.rfnet_query_ball_point(1, 4, 4, z, 0, z, z, z, z, z) == 1               # nsample must be positive (tf_grouping.cpp:75)
+    assert lib.rfnet_query_ball_point(1, 4, 4, z, 0, z, z, z, z, z, 0, z) == 1               # nsample must be positive (tf_grouping.cpp:75)
     assert lib.rfnet_nn_distance(0, 4, z, 4, z, z, z, z, z, z, 0, 0, z) == 0           # empty batch is a no-op
     assert b"invalid" in lib.rfnet_error_string(1)
     # entry points added for tf_ops/emd and select_top_k
