@@ -157,8 +157,11 @@ int rfnet_auction_match(int b, int n, const float *xyz1, const float *xyz2, int 
  * reference's CPU build does, so indices match it bit for bit.  three_interpolate_grad zero-fills grad_points
  * (reference: tf_interpolate.cpp:258).
  * ------------------------------------------------------------------------------------------------------------- */
-int rfnet_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
-                   rfnet_stream_t stream);
+/* three_nn takes an optional workspace: with it (and 512 <= m <= 4096 known points) the search runs over a uniform grid of
+ * the known cloud instead of scanning it; identical distances and indices (RFNET_THREENN_NO_GRID=1 forces the scan). */
+size_t rfnet_three_nn_workspace_bytes(int b, int n, int m);
+int rfnet_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, void *workspace,
+                   size_t workspace_bytes, rfnet_stream_t stream);
 int rfnet_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
                             float *out, rfnet_stream_t stream);
 size_t rfnet_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m);

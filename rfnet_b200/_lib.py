@@ -41,7 +41,8 @@ SIGNATURES = {
     "rfnet_knn_point": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_selection_sort": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_auction_match": (_i, [_i, _i, _p, _p, _p, _p, _p]),
-    "rfnet_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
+    "rfnet_three_nn_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_three_nn": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_three_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_three_interpolate_grad_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "rfnet_three_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),

@@ -8,7 +8,10 @@
 //   * three_interpolate evaluates (p1*w1 + p2*w2) + p3*w3 unfused.
 // three_nn uses the same machinery as nn_distance: queries in registers as packed pairs, candidates broadcast from shared
 // memory, a branch-free scan that only LISTS the candidate groups able to change a top 3, and an exact pass over the list.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "pointgrid.cuh"
 #include "rfnet_ops.h"
 #include "segscatter.cuh"
 
@@ -214,6 +217,107 @@ __global__ void __launch_bounds__(TN_THREADS, TN_MIN_CTAS) three_nn_kernel(int n
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// three_nn over a uniform grid (used when the caller passes a workspace and the known cloud has TG_MIN_POINTS ..
+// TG_MAX_POINTS points).  The known points are binned by ball_grid_kernel (pointgrid.cuh, ~2 points per cell, <= 16 cells
+// per axis); the grid (cell offsets, coordinates and indices in cell order) is staged in shared memory and every THREAD owns
+// one query: it visits its own cell, then the shells of cells around it, keeping the three smallest (distance, index)
+// pairs, and stops as soon as the third distance is strictly below the distance to the nearest face of the block of cells
+// visited so far -- no unvisited point can then enter, not even on a tie.
+// Same arithmetic as the scan kernel (unfused d2 of query + (-point)); the reference's "strict '<' while scanning in index
+// order" is the lexicographic order on (distance, index), which is what the insertion here uses, so ties resolve identically.
+// ~80 candidates per query instead of m.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TG_MIN_POINTS = 512;
+constexpr int TG_MAX_POINTS = 4096;
+constexpr int TG_GMAX = 16;
+constexpr int TG_THREADS = 256;
+
+__device__ __forceinline__ void top3_insert_lex(Top3& t, float d, int k) {
+    const bool p1 = d < t.d1 || (d == t.d1 && k < t.i1);
+    const bool p2 = d < t.d2 || (d == t.d2 && k < t.i2);
+    const bool p3 = d < t.d3 || (d == t.d3 && k < t.i3);
+    if (p1) {
+        t.d3 = t.d2; t.i3 = t.i2; t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = k;
+    } else if (p2) {
+        t.d3 = t.d2; t.i3 = t.i2; t.d2 = d; t.i2 = k;
+    } else if (p3) {
+        t.d3 = d; t.i3 = k;
+    }
+}
+
+__global__ void __launch_bounds__(TG_THREADS) three_nn_grid_kernel(int n, int m, const float* __restrict__ xyz1, const unsigned char* __restrict__ ws,
+                                                                   size_t stride, float* __restrict__ dist, int* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char tg_smem[];
+    const int cloud = blockIdx.y;
+    const BallGridView v = ball_grid_view(ws, stride, cloud, m);
+    const BallGrid g = *v.g;
+    const int ncells = g.G[0] * g.G[1] * g.G[2];
+    int* sStart = reinterpret_cast<int*>(tg_smem);                       // ncells + 1
+    int* sIdx = sStart + (TG_GMAX * TG_GMAX * TG_GMAX + 1);              // m
+    float* sXyz = reinterpret_cast<float*>(sIdx + m);                    // 3 m
+    for (int i = threadIdx.x; i <= ncells; i += TG_THREADS) sStart[i] = v.cell_start[i];
+    for (int i = threadIdx.x; i < m; i += TG_THREADS) sIdx[i] = v.sorted_idx[i];
+    for (int i = threadIdx.x; i < 3 * m; i += TG_THREADS) sXyz[i] = v.sorted_xyz[i];
+    __syncthreads();
+    const int qi = blockIdx.x * TG_THREADS + threadIdx.x;
+    if (qi >= n) return;
+    const float* q = xyz1 + ((size_t)cloud * n + qi) * 3;
+    const float qc[3] = {q[0], q[1], q[2]};
+    int cq[3];
+    float side[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        cq[a] = min(g.G[a] - 1, max(0, (int)floorf((qc[a] - g.lo[a]) * g.scale[a])));
+        side[a] = g.scale[a] > 0.f ? 1.0f / g.scale[a] : 0.f;
+    }
+    const float inf = __int_as_float(0x7f800000);
+    Top3 t;
+    t.d1 = t.d2 = t.d3 = inf;
+    t.i1 = t.i2 = t.i3 = 0;
+    const int rmax = max(max(g.G[0], g.G[1]), g.G[2]);
+    for (int rho = 0; rho < rmax; ++rho) {
+        const int x0 = max(0, cq[0] - rho), x1 = min(g.G[0] - 1, cq[0] + rho);
+        const int y0 = max(0, cq[1] - rho), y1 = min(g.G[1] - 1, cq[1] + rho);
+        const int z0 = max(0, cq[2] - rho), z1 = min(g.G[2] - 1, cq[2] + rho);
+        for (int cx = x0; cx <= x1; ++cx)
+            for (int cy = y0; cy <= y1; ++cy) {
+                const bool edge_xy = abs(cx - cq[0]) == rho || abs(cy - cq[1]) == rho;
+                const int cbase = (cx * g.G[1] + cy) * g.G[2];
+                // cells of this (cx, cy) column that belong to the shell: the whole z range on the rim, else only the two caps
+                for (int part = 0; part < 2; ++part) {
+                    int za, zb;
+                    if (edge_xy) {
+                        if (part) break;
+                        za = z0; zb = z1;
+                    } else {
+                        const int zc = part ? cq[2] + rho : cq[2] - rho;
+                        if (zc < 0 || zc >= g.G[2] || (part && rho == 0)) continue;
+                        za = zb = zc;
+                    }
+                    const int s = sStart[cbase + za], e = sStart[cbase + zb + 1];
+                    for (int p2 = s; p2 < e; ++p2) {
+                        const float d = sqdist3<false>(__fadd_rn(qc[0], -sXyz[p2 * 3]), __fadd_rn(qc[1], -sXyz[p2 * 3 + 1]), __fadd_rn(qc[2], -sXyz[p2 * 3 + 2]));
+                        top3_insert_lex(t, d, sIdx[p2]);
+                    }
+                }
+            }
+        // distance from the query to the nearest face of the visited block that has unvisited cells behind it
+        float bound = inf;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (cq[a] - rho > 0) bound = fminf(bound, qc[a] - (g.lo[a] + (float)(cq[a] - rho) * side[a]));
+            if (cq[a] + rho < g.G[a] - 1) bound = fminf(bound, (g.lo[a] + (float)(cq[a] + rho + 1) * side[a]) - qc[a]);
+        }
+        if (bound == inf) break;                       // the block covers the whole grid
+        bound = fmaxf(bound, 0.f) * 0.99999f;          // float rounding of the face positions
+        if (t.d3 < bound * bound) break;               // strictly closer than anything unvisited
+    }
+    const size_t o = ((size_t)cloud * n + qi) * 3;
+    dist[o] = t.d1; dist[o + 1] = t.d2; dist[o + 2] = t.d3;
+    idx[o] = t.i1; idx[o + 1] = t.i2; idx[o + 2] = t.i3;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // knn_point for 3-d points.  The reference builds the full (b, m, n) distance matrix with framework
 // ops and calls tf.nn.top_k(-dist) "ONLY SUPPORT CPU" (tf_ops/grouping/tf_grouping.py:48-73); this kernel never
 // materialises the matrix: one thread per query keeps its K best (distance, index) sorted in registers, candidates are
@@ -379,12 +483,33 @@ __global__ void three_interpolate_grad_seg_kernel(int n, int cv, int m, const VE
 
 using namespace rfnet;
 
-extern "C" int rfnet_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, rfnet_stream_t stream) {
+extern "C" size_t rfnet_three_nn_workspace_bytes(int b, int n, int m) {
+    (void)n;
+    if (b <= 0 || m < TG_MIN_POINTS || m > TG_MAX_POINTS) return 0;
+    return ball_grid_stride(m) * (size_t)b;
+}
+
+extern "C" int rfnet_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, void* workspace,
+                              size_t workspace_bytes, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
     if (b == 0 || n == 0) return 0;
     RFNET_CHECK_ARG(xyz1 && dist && idx && (m == 0 || xyz2) && b <= 65535);
+    cudaStream_t s = (cudaStream_t)stream;
+    const char* no_grid = getenv("RFNET_THREENN_NO_GRID");   // A/B switch for the tests: scan kernel only
+    if (workspace && m >= TG_MIN_POINTS && m <= TG_MAX_POINTS && workspace_bytes >= rfnet_three_nn_workspace_bytes(b, n, m) &&
+        !(no_grid && no_grid[0] == '1')) {
+        const size_t stride = ball_grid_stride(m);
+        const size_t gsmem = sizeof(unsigned) * (BG_CELLS + BG_CELLS / 32);
+        RFNET_CUDA(cudaFuncSetAttribute(ball_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        ball_grid_kernel<<<b, 1024, gsmem, s>>>(m, nullptr, TG_GMAX, xyz2, (unsigned char*)workspace, stride);
+        const size_t smem = sizeof(int) * (TG_GMAX * TG_GMAX * TG_GMAX + 1 + (size_t)m) + sizeof(float) * 3 * (size_t)m;
+        RFNET_CUDA(cudaFuncSetAttribute(three_nn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((n + TG_THREADS - 1) / TG_THREADS), (unsigned)b);
+        three_nn_grid_kernel<<<grid, TG_THREADS, smem, s>>>(n, m, xyz1, (const unsigned char*)workspace, stride, dist, idx);
+        return launch_status();
+    }
     dim3 grid((unsigned)((n + TN_THREADS * TN_Q - 1) / (TN_THREADS * TN_Q)), (unsigned)b);
-    three_nn_kernel<<<grid, TN_THREADS, 0, (cudaStream_t)stream>>>(n, m, xyz1, xyz2, dist, idx);
+    three_nn_kernel<<<grid, TN_THREADS, 0, s>>>(n, m, xyz1, xyz2, dist, idx);
     return launch_status();
 }
 

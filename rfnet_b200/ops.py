@@ -546,8 +546,11 @@ def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, t
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_three_nn_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(_lib.load().rfnet_three_nn(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _stream(xyz1)), "rfnet_three_nn")
+        _lib.check(lib.rfnet_three_nn(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _ptr(ws), wsb, _stream(xyz1)), "rfnet_three_nn")
     return dist, idx
 
 

@@ -133,6 +133,40 @@ def test_three_nn_bit_exact(cuda, rng, b, n, m):
     assert np.array_equal(gd.cpu().numpy(), wd)
 
 
+@pytest.mark.parametrize("b,n,m,kind", [(2, 16384, 2048, "cube"), (2, 5000, 4096, "sphere"), (1, 3000, 512, "dup"), (1, 2000, 1000, "outside"),
+                                        (1, 4000, 3000, "line"), (1, 1000, 600, "same")])
+def test_three_nn_grid_equals_scan(cuda, b, n, m, kind):
+    """With 512..4096 known points three_nn searches a uniform grid (own cell, then shells, until the third distance is closer
+    than any unvisited cell); distances AND indices must be identical to the full scan (RFNET_THREENN_NO_GRID=1), including
+    which of several equidistant points comes first."""
+    import os
+    from rfnet_b200 import tf_interpolate
+    g = torch.Generator(device="cpu").manual_seed(90 + n + m)
+    x1 = torch.rand((b, n, 3), generator=g) - 0.5
+    x2 = torch.rand((b, m, 3), generator=g) - 0.5
+    if kind == "sphere":
+        x1 = 0.5 * x1 / x1.norm(dim=-1, keepdim=True)
+        x2 = 0.5 * x2 / x2.norm(dim=-1, keepdim=True)
+    elif kind == "dup":
+        x2[:, m // 2:] = x2[:, : m - m // 2]          # every known point twice: ties between indices
+        x1[:, :200] = x2[:, :200]                     # zero distances
+    elif kind == "outside":
+        x1 = x1 * 4.0
+    elif kind == "line":
+        x2[:, :, 1:] = 0.1
+    elif kind == "same":
+        x2[:] = x2[:, :1]                              # all known points coincide: one cell, all distances equal
+    x1, x2 = x1.to(cuda), x2.to(cuda)
+    assert os.environ.get("RFNET_THREENN_NO_GRID") is None
+    gd, gi = tf_interpolate.three_nn(x1, x2)
+    os.environ["RFNET_THREENN_NO_GRID"] = "1"
+    try:
+        sd, si = tf_interpolate.three_nn(x1, x2)
+    finally:
+        del os.environ["RFNET_THREENN_NO_GRID"]
+    assert torch.equal(gi, si) and torch.equal(gd, sd)
+
+
 def test_three_nn_adversarial_order(cuda, rng):
     """Candidates sorted by DECREASING distance from the query cluster: every group improves the top 3, the per-query group
     list overflows and the kernel's exact re-scan path runs.  Still bit-exact."""
