@@ -6,7 +6,8 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- nn_distance forward + NnDistanceGrad, B=32 clouds per GPU, partial
 2048 points vs dense 16384 points, synthetic uniform [-0.5,0.5]^3 clouds.  One step = one pass over one
-batch.  Unit of work = point pair (2*B*N*M per step, two directed searches).  Batches are sharded over ranks with no
+batch = ONE C-ABI call (rfnet_chamfer_step: search, gradient + key unpack + sqrt partial sums, final reduction: three kernel
+launches).  Unit of work = point pair (2*B*N*M per step, two directed searches).  Batches are sharded over ranks with no
 data-path collective; the only exchange is the 16-byte all-reduce of the loss partial sums (weak scaling: B per GPU fixed).
 
 One JSON line on stdout (rank 0).  Besides the contract's keys it carries
@@ -14,8 +15,17 @@ One JSON line on stdout (rank 0).  Besides the contract's keys it carries
                 the reference's operand order admits no fewer), peak = 148 SMs x 128 lanes x sm clock
   cpu_baseline  the reference's own CPU kernel (oracle/_ref: /root/reference/pc_distance/tf_nndistance.cpp compiled
                 unmodified) timed on this host's cores on a bounded sample of the same workload
-  e2e           the same metric through the public API from pinned HOST buffers, copies inside the timed region
-  extra         north-star shape (B=32, 16384^2) and EMD clouds/s, measured after the timed region (not part of `value`)
+  e2e           the same metric through the public host-buffer API from pinned HOST buffers with EVERY output of the operator
+                (dist1, idx1, dist2, idx2, both gradients, loss sums) copied back, copies inside the timed region
+  extra         measured after the timed region on ALL ranks (max over ranks, scalar all-reduce included), not part of `value`:
+                  sustained        the same step looped >= 2 s, with the clocks sampled during the loop
+                  config3          EMD approx_match + match_cost forward + gradient, B=32 TOTAL (strong scaling: 32/N clouds per
+                                   GPU), n=m=2048 and 16384: clouds/s and fraction of the MUFU roofline
+                  config5          recon loss path: chamfer_big + earth_mover forward + backward on 16384-point clouds, B=64
+                                   TOTAL (64/N per GPU)
+                  north_star       nn_distance forward at B=32 (per GPU), N=M=16384
+                  config4          (rank 0) per-op milliseconds and HBM fraction of FPS / ball query / group / 3-NN / interpolate
+                  ref_gpu_kernel   (rank 0, N=1) the reference's own .cu recompiled for sm_100a, timed on the same inputs
 """
 import argparse
 import json
@@ -33,6 +43,7 @@ METRIC = "chamfer_nn_point_pairs_per_s"
 UNIT = "Gpairs/s"
 L2_BYTES = 126 * 1024 * 1024
 LANE_OPS_PER_PAIR = 6.0
+HBM_PEAK_FALLBACK = 6544.0         # GB/s, MEASURED_PEAKS.json of this pool (used when the file is absent)
 
 
 def parse():
@@ -44,7 +55,11 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the post-run extra measurements")
     ap.add_argument("--workload", default="chamfer", choices=["chamfer", "recon_loss"],
                     help="chamfer (default, the headline): BASELINE configs[1].  recon_loss: BASELINE configs[4], the recon_test loss "
-                         "path -- chamfer_big + earth_mover on 16384-point outputs vs GT, 8 clouds per GPU -- reported in clouds/s")
+                         "path -- chamfer_big + earth_mover forward + backward on 16384-point outputs vs GT, B=64 total -- in clouds/s")
+    ap.add_argument("--data-dir", default=None, help="recon_loss only: a PCN-style directory with partial/<id>.pcd and complete/<id>.pcd "
+                                                      "(recon_test.py:50-51); clouds are read with rfnet_b200.io_util instead of being synthesised")
+    ap.add_argument("--list-path", default=None, help="recon_loss --data-dir: file with one model id per line (recon_test.py:46-47)")
+    ap.add_argument("--results-dir", default="results", help="recon_loss --data-dir: where results.csv is written (recon_test.py:42-44)")
     return ap.parse_args()
 
 
@@ -52,6 +67,14 @@ def host_clouds(nclouds, npts, seed):
     import numpy as np
     rng = np.random.default_rng(seed)
     return (rng.random((nclouds, npts, 3), dtype=np.float32) - 0.5)
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return HBM_PEAK_FALLBACK, "fallback: this pool's measured copy bandwidth (MEASURED_PEAKS.json absent)"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -124,9 +147,10 @@ def run_reference_arm(args):
 class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag, self.ok = index, [], set(), None, threading.Event(), False
+        self.period, self.power = period, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -146,23 +170,157 @@ class ClockSampler(threading.Thread):
             for bit, name in self.REASONS.items():
                 if mask & bit:
                     self.reasons.add(name)
+            self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
         except Exception:
             pass
 
     def run(self):
         while not self.stop_flag.is_set():
             self.sample()
-            time.sleep(0.005)
+            time.sleep(self.period)
+
+    def stop(self):
+        self.stop_flag.set()
+        self.join()
 
     def result(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# helpers shared by both workloads
+# ------------------------------------------------------------------------------------------------------------------
+class Dist:
+    """Rank bookkeeping + the two collectives the bench itself needs (barrier, max of a timing)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        if self.world == 1:
+            return float(ms)
+        t = self.torch.tensor([ms], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, iters, warm=1):
+        """ms per call of fn: `warm` untimed calls, barrier + synchronize, `iters` calls between two CUDA events on the
+        current stream, barrier + synchronize, MAX over ranks."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1)) / iters
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def count_rfnet_launches(torch, fn):
+    """number of OUR kernels (namespace rfnet::) one call of fn launches, from CUPTI activity records"""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        return sum(1 for e in prof.events() if "rfnet" in e.name)
+    except Exception:
+        return None
+
+
+def mufu_peak(sm_max_hz):
+    return 148 * 16 * sm_max_hz
+
+
+def emd_shard_step(D, n, clouds_total, seed):
+    """EMD forward + gradient on this rank's slice of `clouds_total` clouds of n points (cost + both MatchCostGrad gradients,
+    no match matrix) followed by the path's only collective: the all-reduce of [sum cost / n, count] (earth_mover,
+    vv_recon.py:392-399).  Returns (callable, clouds on this rank)."""
+    torch, dist = D.torch, D.dist
+    from rfnet_b200 import losses, ops
+    lo, hi = losses.shard_bounds(clouds_total, D.rank, D.world)
+    nb = hi - lo
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x1 = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    x2 = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    res = torch.zeros(2, device=D.dev)
+
+    def step():
+        if nb:
+            cost, g1, g2 = ops.emd_cost_grad_op(x1, x2)
+            part = torch.stack([(cost / float(n)).sum(), cost.new_tensor(float(nb))])
+        else:
+            part = torch.zeros(2, device=D.dev)
+        if D.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        res.copy_(part)
+    return step, nb
+
+
+def recon_shard_step(D, n, clouds_total, seed):
+    """BASELINE configs[4]: chamfer_big + earth_mover of 16384-point outputs vs GT, forward + backward w.r.t. the output cloud,
+    on this rank's slice of `clouds_total` clouds, then the all-reduce of the six partial sums (vv_recon.py:381-399,484-493)."""
+    torch, dist = D.torch, D.dist
+    from rfnet_b200 import losses, ops
+    lo, hi = losses.shard_bounds(clouds_total, D.rank, D.world)
+    nb = hi - lo
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    gt = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    res = torch.zeros(6, device=D.dev)
+    f32, i32 = torch.float32, torch.int32
+    nbm = max(nb, 1)
+    o = dict(d1=torch.empty((nbm, n), dtype=f32, device=D.dev), i1=torch.empty((nbm, n), dtype=i32, device=D.dev),
+             d2=torch.empty((nbm, n), dtype=f32, device=D.dev), i2=torch.empty((nbm, n), dtype=i32, device=D.dev),
+             g1=torch.empty((nbm, n, 3), dtype=f32, device=D.dev), g2=torch.empty((nbm, n, 3), dtype=f32, device=D.dev), s=torch.zeros(4, device=D.dev))
+    ws = torch.empty(ops.nn_distance_workspace_bytes(nbm, n, n), dtype=torch.uint8, device=D.dev)
+    gd = torch.full((nbm, n), 0.25 / (clouds_total * n), device=D.dev)   # upstream of (mean sqrt d1 + mean sqrt d2) / 2 is applied by the caller
+
+    def step():
+        if nb:
+            ops.raw_chamfer_step(out, gt, gd, gd, o["d1"], o["i1"], o["d2"], o["i2"], o["g1"], o["g2"], o["s"], ws)
+            cost, e1, e2 = ops.emd_cost_grad_op(out, gt)
+            part = torch.cat([o["s"], torch.stack([(cost / float(n)).sum(), cost.new_tensor(float(nb))])])
+        else:
+            part = torch.zeros(6, device=D.dev)
+        if D.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        res.copy_(part)
+    return step, nb, res
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # second workload: BASELINE configs[4] (recon_test loss path), EMD-dominated -> clouds/s and the MUFU roofline
 # ------------------------------------------------------------------------------------------------------------------
-RB, RN = 8, 16384   # clouds per GPU (B=64 over 8 GPUs), points per cloud
+RB_TOTAL, RN = 64, 16384   # clouds in total (sharded over the ranks), points per cloud
 
 
 def emd_cpu_reference_rate(nclouds, n):
@@ -186,15 +344,53 @@ def emd_cpu_reference_rate(nclouds, n):
     return nclouds / dt, dt, cores, kind
 
 
-def run_recon_loss(args):
+def run_recon_files(args):
+    """recon_test.py's loss loop on real files (recon_test.py:46-68): per model read partial/complete PCDs, resample the
+    partial cloud to 3000 points, evaluate cd = chamfer_big(output, gt) and emd = fidelity_loss(partial, output) as the
+    reference does, and write results.csv.  There is no network here, so `output` is <data-dir>/completion/<id>.pcd when it
+    exists, else the ground truth with N(0, 0.01^2) noise (said so in the JSON line)."""
+    import numpy as np
     import torch
-    import torch.distributed as dist
-    from rfnet_b200 import _lib, losses
-    _lib.load()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from rfnet_b200 import io_util, losses
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    ids = [l.strip() for l in open(args.list_path)] if args.list_path else sorted(
+        os.path.relpath(os.path.join(r, f), os.path.join(args.data_dir, "complete"))[:-4]
+        for r, _, fs in os.walk(os.path.join(args.data_dir, "complete")) for f in fs if f.endswith(".pcd"))
+    ids = [i for i in ids if i]
+    rng = np.random.default_rng(0)
+    res = io_util.ResultsCsv(args.results_dir)
+    synthetic_outputs = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for mid in ids:
+        partial = io_util.resample_pcd(io_util.read_pcd(os.path.join(args.data_dir, "partial", mid + ".pcd")), 3000, rng)
+        complete = io_util.read_pcd(os.path.join(args.data_dir, "complete", mid + ".pcd"))
+        cpath = os.path.join(args.data_dir, "completion", mid + ".pcd")
+        if os.path.exists(cpath):
+            output = io_util.read_pcd(cpath)
+        else:
+            output = complete + rng.normal(0, 0.01, complete.shape)
+            synthetic_outputs += 1
+        tp = torch.from_numpy(np.ascontiguousarray(partial, dtype=np.float32))[None].to(dev)
+        tg = torch.from_numpy(np.ascontiguousarray(complete, dtype=np.float32))[None].to(dev)
+        to = torch.from_numpy(np.ascontiguousarray(output, dtype=np.float32))[None].to(dev)
+        cd, _ = losses.chamfer_big(to, tg)                     # recon_test.py:27
+        emd = losses.fidelity_loss(tp, to)                     # recon_test.py:28 (the column is named emd there)
+        res.add(mid if "/" in mid else "all/" + mid, float(cd), float(emd))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    per_cat = res.close()
+    print(json.dumps({"metric": "recon_test_models_per_s", "value": len(ids) / dt if dt > 0 else None, "unit": "models/s", "n_gpus": 1,
+                      "higher_is_better": True, "data": "files", "dtype": "f32",
+                      "config": {"workload": "recon_test.py loss loop over PCD files", "data_dir": args.data_dir, "models": len(ids),
+                                 "results_csv": os.path.join(args.results_dir, "results.csv"), "outputs_synthesised": synthetic_outputs},
+                      "per_category_cd_emd": per_cat}), flush=True)
+    return 0
+
+
+def run_recon_loss(args):
     if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return 0
         n_s = 2048   # the reference CPU kernel needs ~40 s and 2 GiB per 16384^2 cloud: time 2048^2 clouds, scale by (2048/16384)^2
@@ -207,111 +403,141 @@ def run_recon_loss(args):
         value = float(sum(rates) / len(rates)) / 64.0
         sample = "%d clouds of %d^2 per step on %d host threads; clouds/s scaled by 1/64 to 16384^2 (EXTRAPOLATED: work is n*m)" % (cores, n_s, cores)
         print(json.dumps({"impl": "reference", "metric": "recon_loss_clouds_per_s", "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "recon_test loss path CD+EMD 16384 pts", "sample": sample},
                           "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return 0
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    nsets = 3   # 3 x 2 x 1.5 MB of inputs: they fit L2, so every step first overwrites a 256 MiB buffer (2 x L2) to flush it
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    houts = torch.from_numpy(host_clouds(nsets * RB, RN, 500 + rank)).reshape(nsets, RB, RN, 3).pin_memory()
-    hgts = torch.from_numpy(host_clouds(nsets * RB, RN, 900 + rank)).reshape(nsets, RB, RN, 3).pin_memory()
-    douts, dgts = houts.to(dev), hgts.to(dev)
-    result = torch.zeros(2, device=dev)
+    if args.data_dir:
+        return run_recon_files(args)
+    from rfnet_b200 import _lib
+    _lib.load()
+    D = Dist()
+    torch = D.torch
+    steps = min(args.steps, 20)
+    warm = min(max(args.warmup, 3), 5)
+    step, nb, res = recon_shard_step(D, RN, RB_TOTAL, 500)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)
 
-    def step(i, from_host=False):
-        flush.zero_()
-        o = houts[i % nsets].to(dev, non_blocking=True) if from_host else douts[i % nsets]
-        g = hgts[i % nsets].to(dev, non_blocking=True) if from_host else dgts[i % nsets]
-        cd, _ = losses.sharded_chamfer_big(o, g)          # chamfer_big(output, gt), recon_test.py:27
-        emd = losses.sharded_earth_mover(o, g)            # earth_mover as in eval_one_batch, vv_recon.py:445-459
-        result.copy_(torch.stack([cd.detach(), emd.detach()]))
+    def flushed_step():
+        flush.zero_()          # inputs (2 x 12.6 MB at 64 clouds) fit L2: every step first overwrites a 256 MiB buffer
+        step()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(1, args.warmup)):
-        step(i)
-    barrier()
-    launches = None
-    try:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(0)
-            torch.cuda.synchronize()
-        launches = sum(1 for e in prof.events() if "rfnet" in e.name)
-    except Exception:
-        pass
-    sampler = ClockSampler(local)
+    for _ in range(warm):
+        flushed_step()
+    launches = count_rfnet_launches(torch, step)
+    sampler = ClockSampler(D.local)
     sampler.sample()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    sampler.stop_flag.set()
-    sampler.join()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = RB * world * args.steps / (ms * 1e-3)
-    # e2e: same step with the clouds coming from pinned host memory and the two loss scalars read back
-    k_e2e = max(2, min(args.steps, 10))
-    host_res = torch.empty(2).pin_memory()
-    barrier()
-    e0.record()
-    for i in range(k_e2e):
-        step(i, from_host=True)
-        host_res.copy_(result, non_blocking=True)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = RB * world * k_e2e / (float(t.item()) * 1e-3)
+    ms = D.timed(flushed_step, steps, warm=0)
+    sampler.stop()
+    value = RB_TOTAL / (ms * 1e-3)
     clocks = sampler.result()
     sm_max = (clocks["sm_max_mhz"] or 1965) * 1e6
-    mufu_peak = 148 * 16 * sm_max
-    achieved = RB * args.steps / (ms * 1e-3) * 30.0 * RN * RN    # algorithmic ex2 per second on this GPU (30 pair-passes per pair)
-    line = {"metric": "recon_loss_clouds_per_s", "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "recon_test loss path: chamfer_big + earth_mover, %d clouds/GPU of %d points vs GT (BASELINE configs[4])" % (RB, RN),
-                       "parallelism": "batch-sharded x%d, loss scalars all-reduced" % world,
-                       "l2": "flushed: every step begins by overwriting a 256 MiB buffer (2 x the 126 MB L2), ~0.04 ms inside the timed region",
-                       "emd": "fused approx_match + match_cost (rfnet_emd_cost): the %d GiB match tensor is never materialised" % (RB * RN * RN * 4 // 2 ** 30)},
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": 2 * RB * RN * 12, "d2h_bytes_per_step": 8, "steps": k_e2e,
-                                      "api": "rfnet_b200.losses.sharded_chamfer_big + sharded_earth_mover on pinned host clouds, losses read back"},
-            "gpu_launches": (launches or 0) * args.steps, "gpu_launches_per_step": launches,
-            "roofline": {"bound": "mufu_ex2_pipe (co-limited with the FP32 pipe)", "kernel": "rfnet::emd_sweep_kernel x30 (+ fused materialise/cost, nn_search)",
-                         "achieved": achieved / 1e12, "peak": mufu_peak / 1e12, "unit": "Tex2/s", "frac": achieved / mufu_peak,
-                         "peak_source": "148 SMs x 16 MUFU lanes x %.0f MHz (architectural)" % (sm_max / 1e6),
-                         "algorithmic_ex2_per_cloud": 30.0 * RN * RN, "traffic": None,
-                         "note": "whole step over the algorithmic 30*n*m ex2 of approx_match; the sweep kernel alone runs at 82% of the MUFU pipe (profiles/r1_emd_sweep_full.txt)"}}
-    if rank == 0 and world == 1:
+    achieved = value / D.world * 30.0 * RN * RN
+    line = {"metric": "recon_loss_clouds_per_s", "value": value, "unit": "clouds/s", "n_gpus": D.world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "recon_test loss path: chamfer_big + earth_mover forward + backward, %d clouds TOTAL of %d points vs GT (BASELINE configs[4])" % (RB_TOTAL, RN),
+                       "parallelism": "batch-sharded x%d (%d clouds on rank 0), six loss partial sums all-reduced" % (D.world, nb),
+                       "l2": "flushed: every step begins by overwriting a 256 MiB buffer (2 x the 126 MB L2), inside the timed region",
+                       "emd": "rfnet_emd_cost_grad: cost and both gradients without any (b, m, n) match tensor"},
+            "clocks": clocks, "gpu_launches": (launches or 0) * steps, "gpu_launches_per_step": launches,
+            "e2e": {"value": None, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "see --workload chamfer for the host-buffer e2e"},
+            "roofline": {"bound": "mufu_ex2_pipe (co-limited with the FP32 pipe)", "kernel": "rfnet::emd_sweep_kernel (21 sweeps) + emd_pair_kernel x2, nn_search",
+                         "achieved": achieved / 1e12, "peak": mufu_peak(sm_max) / 1e12, "unit": "Tex2/s", "frac": achieved / mufu_peak(sm_max),
+                         "peak_source": "148 SMs x 16 MUFU lanes x %.0f MHz (architectural)" % (sm_max / 1e6), "algorithmic_ex2_per_cloud": 30.0 * RN * RN,
+                         "traffic": None}}
+    if D.rank == 0 and D.world == 1:
         try:
             r, dt, cores, kind = emd_cpu_reference_rate(os.cpu_count() or 1, 2048)
             line["cpu_baseline"] = {"value": r / 64.0, "unit": "clouds/s", "cores": cores, "kind": kind,
                                     "sample": "%d clouds of 2048^2 (approx_match + match_cost CPU kernels), one per thread, %.1f s; scaled by 1/64 to 16384^2 (EXTRAPOLATED)" % (cores, dt)}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "clouds/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
-    if rank == 0:
+    if D.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# extras
+# ------------------------------------------------------------------------------------------------------------------
+def config4_block(D, sm_max):
+    """BASELINE configs[3] (the sampling / grouping / interpolation chain at B=32) on rank 0: ms per op and, for the HBM-bound
+    ones, algorithmic bytes / time against the measured copy bandwidth (SURVEY.md 8d byte counts)."""
+    torch = D.torch
+    from rfnet_b200 import ops, tf_grouping, tf_interpolate, tf_sampling
+    peak, peak_src = hbm_peak()
+    b, n, m, ns, c = 32, 16384, 2048, 32, 64
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x = (torch.rand((b, n, 3), generator=g) - 0.5).to(D.dev)
+
+    def t(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {"shape": "B=32, 16384 -> 2048 FPS points, r=0.1, nsample=32, c=3 and c=64", "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
+    ms = t(lambda: tf_sampling.farthest_point_sample(m, x), 5)
+    out["farthest_point_sample"] = {"ms": ms, "us_per_pick": ms * 1e3 / m}
+    idx = tf_sampling.farthest_point_sample(m, x)
+    q = tf_sampling.gather_point(x, idx)
+    ms = t(lambda: tf_grouping.query_ball_point(0.1, ns, x, q))
+    out["query_ball_point"] = {"ms": ms}
+    gi, _ = tf_grouping.query_ball_point(0.1, ns, x, q)
+    for cc in (3, c):
+        pts = torch.randn((b, n, cc), generator=g).to(D.dev)
+        ms = t(lambda: tf_grouping.group_point(pts, gi))
+        byts = 4.0 * b * m * ns * (cc + 1) + 4.0 * b * n * cc
+        out["group_point_c%d" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
+        go = torch.randn((b, m, ns, cc), generator=g).to(D.dev)
+        ms = t(lambda: ops.group_point_grad_op(pts, gi, go))
+        out["group_point_grad_c%d" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
+        del pts, go
+    ms = t(lambda: tf_interpolate.three_nn(x, q))
+    out["three_nn"] = {"ms": ms}
+    d3, i3 = tf_interpolate.three_nn(x, q)
+    w = 1.0 / torch.clamp(d3, min=1e-10)
+    w = w / w.sum(-1, keepdim=True)
+    feats = torch.randn((b, m, c), generator=g).to(D.dev)
+    ms = t(lambda: tf_interpolate.three_interpolate(feats, i3, w))
+    byts = 4.0 * b * n * (c + 6) + 4.0 * b * m * c
+    out["three_interpolate_c%d" % c] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
+    go = torch.randn((b, n, c), generator=g).to(D.dev)
+    ms = t(lambda: ops.three_interpolate_grad_op(feats, i3, w, go))
+    out["three_interpolate_grad_c%d" % c] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
+    return out
+
+
+def ref_gpu_kernel_block(D, d1s, d2s):
+    """The kernel to beat: the reference's own tf_nndistance .cu recompiled unchanged for sm_100a
+    (oracle/_ref/libref_gpu.so, the parity checker), timed on the bench's inputs after the timed region."""
+    torch = D.torch
+    try:
+        from oracle import ref
+        if not ref.available("gpu"):
+            return {"unavailable": "oracle/_ref/libref_gpu.so not built"}
+        x1, x2 = d1s[0], d2s[0]
+        spec = [((B, N), torch.float32), ((B, N), torch.int32), ((B, M), torch.float32), ((B, M), torch.int32)]
+        for _ in range(2):
+            ref.run_gpu("NnDistance", [x1, x2], spec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ref.run_gpu("NnDistance", [x1, x2], spec)
+        e1.record()
+        torch.cuda.synchronize()
+        return {"nn_distance_fwd_ms": e0.elapsed_time(e1) / 5, "what": "NmDistanceKernel (tf_ops/CD/tf_nndistance_g.cu:4-130) recompiled for sm_100a, B=32 2048 vs 16384"}
+    except Exception as ex:
+        return {"unavailable": repr(ex)}
 
 
 def main():
@@ -322,21 +548,12 @@ def main():
         return run_reference_arm(args)
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- rfnet_b200 has no CPU path (use --impl reference for the CPU arm)")
-    from rfnet_b200 import _lib, losses, ops, tf_approxmatch, tf_nndistance
+    from rfnet_b200 import _lib, losses, ops
     lib = _lib.load()
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+    D = Dist()
+    dist, world, rank, dev = D.dist, D.world, D.rank, D.dev
 
     # ---- inputs: enough distinct batches that consecutive steps never find their inputs in L2 (rotating sets > L2)
     set_bytes = B * (N + M) * 12
@@ -347,14 +564,18 @@ def main():
     gd1 = torch.full((B, N), 0.5 / (B * N * world), device=dev)   # upstream grads of a mean-type loss
     gd2 = torch.full((B, M), 0.5 / (B * M * world), device=dev)
     sums = torch.zeros(4, device=dev)
-
+    f32, i32 = torch.float32, torch.int32
+    o = dict(d1=torch.empty((B, N), dtype=f32, device=dev), i1=torch.empty((B, N), dtype=i32, device=dev),
+             d2=torch.empty((B, M), dtype=f32, device=dev), i2=torch.empty((B, M), dtype=i32, device=dev),
+             g1=torch.empty((B, N, 3), dtype=f32, device=dev), g2=torch.empty((B, M, 3), dtype=f32, device=dev))
+    parts = [torch.zeros(4, device=dev) for _ in range(2)]
+    ws = torch.empty(ops.nn_distance_workspace_bytes(B, N, M), dtype=torch.uint8, device=dev)
     pending = []
 
     def step(i):
-        x1, x2 = d1s[i % nsets], d2s[i % nsets]
-        dist1, idx1, dist2, idx2 = ops.nn_distance_op(x1, x2)
-        g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, idx1, gd2, idx2)
-        part = ops.chamfer_partial_sums_op(dist1, dist2)            # the loss-level reduction of chamfer_big (vv_recon.py:381-385)
+        part = parts[i & 1]
+        # one C-ABI call: search, then gradient + unpack + sqrt partial sums, then the fixed-order reduction (3 launches)
+        ops.raw_chamfer_step(d1s[i % nsets], d2s[i % nsets], gd1, gd2, o["d1"], o["i1"], o["d2"], o["i2"], o["g1"], o["g2"], part, ws)
         if world > 1:
             # the path's only collective: 16 bytes over NCCL/NVLink, on NCCL's own stream.  Nothing on the device consumes
             # the reduced loss, so the compute stream only joins it one step later (it overlaps the next step's kernels).
@@ -365,7 +586,6 @@ def main():
                 sums.copy_(done)
         else:
             sums.copy_(part)
-        return g1, g2
 
     def flush():
         while pending:
@@ -373,62 +593,41 @@ def main():
             work.wait()
             sums.copy_(done)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for i in range(args.warmup):
         step(i)
     flush()
-    barrier()
+    D.barrier()
+    launches_per_step = count_rfnet_launches(torch, lambda: (step(0), flush()))
+    D.barrier()
 
-    # ---- count OUR kernels in one step (CUPTI activity records, outside the timed region)
-    launches_per_step = None
-    try:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(0)
-            flush()
-            torch.cuda.synchronize()
-        launches_per_step = sum(1 for e in prof.events() if "rfnet" in e.name)
-    except Exception:
-        launches_per_step = None
-    barrier()
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(D.local)
     sampler.sample()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     flush()                                                         # every step's all-reduce has joined the compute stream
     e1.record()
-    barrier()
-    sampler.stop_flag.set()
-    sampler.join()
+    D.barrier()
+    sampler.stop()
     sampler.sample()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = D.max_ms(e0.elapsed_time(e1))
     pairs_per_step = 2.0 * B * N * M * world
     value = pairs_per_step * args.steps / (ms * 1e-3) / 1e9
+    clocks = sampler.result()
+    sm_max = (clocks["sm_max_mhz"] or 1965) * 1e6
 
     # ---- dominant kernel against its roofline: the forward search alone, CUDA events on its stream
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     f0.record()
     for i in range(args.steps):
-        ops.nn_distance_op(d1s[i % nsets], d2s[i % nsets])
+        ops.raw_nn_distance(d1s[i % nsets], d2s[i % nsets], o["d1"], o["i1"], o["d2"], o["i2"], ws)
     f1.record()
     torch.cuda.synchronize()
     fwd_ms = f0.elapsed_time(f1) / args.steps
-    clocks = sampler.result()
-    sm_max = (clocks["sm_max_mhz"] or 1965) * 1e6
     peak = 148 * 128 * sm_max / 1e12                               # T lane-ops/s at max clock
     achieved = 2.0 * B * N * M * LANE_OPS_PER_PAIR / (fwd_ms * 1e-3) / 1e12
     # measured FP32 pipe peak: a dependency-free FFMA2 stream on every SM (rfnet_probe_fp32)
@@ -444,75 +643,105 @@ def main():
     p1.record()
     torch.cuda.synchronize()
     peak_measured = lane_ops.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
-    roofline = {"bound": "fp32_fma_pipe", "kernel": "rfnet::nn_search_kernel (timed as the forward call: + 2 key-unpack kernels, ~1%)",
+    roofline = {"bound": "fp32_fma_pipe", "kernel": "rfnet::nn_search_kernel (timed as the forward call: + 1 key-unpack kernel, ~1%)",
                 "achieved": achieved, "peak": peak, "unit": "Tlaneop/s", "frac": achieved / peak,
                 "peak_source": "148 SMs x 128 FP32 lanes x %.0f MHz (architectural; MEASURED_PEAKS.json has no FP32-pipe figure)" % (sm_max / 1e6),
                 "peak_measured_ffma2_stream": peak_measured, "frac_of_measured": achieved / peak_measured,
-                "algorithmic_laneops_per_pair": LANE_OPS_PER_PAIR, "fwd_ms": fwd_ms,
+                "algorithmic_laneops_per_pair": LANE_OPS_PER_PAIR, "fwd_ms": fwd_ms, "step_ms": ms / args.steps,
+                "frac_whole_step": pairs_per_step / world * LANE_OPS_PER_PAIR / (ms / args.steps * 1e-3) / 1e12 / peak,
                 "traffic": 11852288, "traffic_note": "dram__bytes_read+write of one nn_search_kernel launch at this config, ncu --set full (profiles/r1_nn_search_full.txt); inputs are 7.08 MB, compute-bound"}
 
     # ---- e2e: the same step through the public host-buffer API (rfnet_b200.host.ChamferHostPipeline): every step copies
-    # its inputs from pinned host memory and its results (dist, idx, grads, loss sums) back; copies of neighbouring steps
-    # overlap the kernels on separate streams
+    # its inputs from pinned host memory and EVERY output of the operator back; copies of neighbouring steps overlap the
+    # kernels on separate streams, the cross-rank all-reduce runs on a side stream
     from rfnet_b200.host import ChamferHostPipeline
-    # read back per step: the loss partial sums (what the training loop fetches) and both distance arrays; gradients stay on the device
-    pipe = ChamferHostPipeline(B, N, M, dev, depth=3, grad_scale1=0.5 / (B * N * world), grad_scale2=0.5 / (B * M * world),
-                               outputs=("sums", "dist1", "dist2"))
     k_e2e = max(3, min(args.steps, 100))
-    for i in range(3):
-        pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
-    pipe.drain()
-    barrier()
-    e0.record()
-    for i in range(k_e2e):
-        pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
-    torch.cuda.current_stream().wait_stream(pipe.s_out)
-    e1.record()
-    barrier()
-    last = pipe.wait((pipe.count - 1) % pipe.depth)
-    e2e_loss = float((last["sums"][0] / last["sums"][1] + last["sums"][2] / last["sums"][3]) / 2)   # chamfer_big read back on the host
-    e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_per_step * k_e2e / (float(t.item()) * 1e-3) / 1e9
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-           "steps": k_e2e, "loss_read_back": e2e_loss,
-           "api": "rfnet_b200.host.ChamferHostPipeline.submit(pinned xyz1, xyz2) -> pinned loss sums + dist1 + dist2 (grads stay on device); 3-slot ring, copies overlap compute"}
 
-    # ---- extras (rank 0, not part of `value`): north-star shape and EMD
+    def run_e2e(outputs):
+        pipe = ChamferHostPipeline(B, N, M, dev, depth=3, grad_scale1=0.5 / (B * N * world), grad_scale2=0.5 / (B * M * world), outputs=outputs)
+        for i in range(3):
+            pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
+        pipe.drain()
+        D.barrier()
+        e0.record()
+        for i in range(k_e2e):
+            pipe.submit(h1[i % nsets], h2[i % nsets], losses.all_reduce_scalars)
+        torch.cuda.current_stream().wait_stream(pipe.s_out)
+        e1.record()
+        D.barrier()
+        last = pipe.wait((pipe.count - 1) % pipe.depth)
+        loss = float((last["sums"][0] / last["sums"][1] + last["sums"][2] / last["sums"][3]) / 2)   # chamfer_big read back on the host
+        v = pairs_per_step * k_e2e / (D.max_ms(e0.elapsed_time(e1)) * 1e-3) / 1e9
+        return v, pipe.h2d_bytes, pipe.d2h_bytes, loss
+
+    v_all, h2d, d2h_all, e2e_loss = run_e2e(ChamferHostPipeline.ALL_OUTPUTS)
+    v_loop, _, d2h_loop, _ = run_e2e(("sums",))
+    e2e = {"value": v_all, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all, "steps": k_e2e, "loss_read_back": e2e_loss,
+           "api": "rfnet_b200.host.ChamferHostPipeline.submit(pinned xyz1, xyz2) -> pinned dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, loss sums "
+                  "(every output of NnDistance + NnDistanceGrad); 3-slot ring, copies overlap compute, all-reduce on a side stream",
+           "training_loop": {"value": v_loop, "d2h_bytes_per_step": d2h_loop, "note": "same call, only the 16-byte loss sums read back (what vv_recon.py's sess.run fetches)"}}
+
+    # ---- extras (all ranks take part; rank 0 reports)
     extra = {}
-    if rank == 0 and not args.no_extra:
-        def timed(fn, iters):
-            fn()
-            torch.cuda.synchronize()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(iters):
-                fn()
-            b_.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b_) / iters
+    if not args.no_extra:
+        # sustained: the same step for >= 2 s (the timed region above is a burst of tens of milliseconds)
+        per = ms / args.steps
+        k_sus = max(args.steps, int(2200.0 / per))
+        s2 = ClockSampler(D.local, period=0.02)
+        s2.start()
+        D.barrier()
+        e0.record()
+        for i in range(k_sus):
+            step(i)
+        flush()
+        e1.record()
+        D.barrier()
+        s2.stop()
+        ms_sus = D.max_ms(e0.elapsed_time(e1))
+        extra["sustained"] = {"steps": k_sus, "seconds": ms_sus / 1e3, "value": pairs_per_step * k_sus / (ms_sus * 1e-3) / 1e9, "unit": UNIT,
+                              "ms_per_step": ms_sus / k_sus, "clocks": s2.result()}
+        # north-star shape: nn_distance forward, B=32 per GPU, 16384 x 16384
         g = torch.Generator(device="cpu").manual_seed(5)
         y1 = (torch.rand((B, M, 3), generator=g) - 0.5).to(dev)
         y2 = (torch.rand((B, M, 3), generator=g) - 0.5).to(dev)
-        ms_ns = timed(lambda: ops.nn_distance_op(y1, y2), 10)
+        ms_ns = D.timed(lambda: ops.nn_distance_op(y1, y2), 10)
         pr = 2.0 * B * M * M
-        extra["chamfer_nn_fwd_B32_16384x16384"] = {"ms": ms_ns, "Gpairs_per_s": pr / ms_ns / 1e6, "frac_fp32_peak": pr * LANE_OPS_PER_PAIR / (ms_ns * 1e-3) / 1e12 / peak}
-        for (eb, en) in ((32, 2048), (4, 16384)):
-            z1, z2 = y1[:eb, :en].contiguous(), y2[:eb, :en].contiguous()
-            ms_e = timed(lambda: tf_approxmatch.match_cost(z1, z2, tf_approxmatch.approx_match(z1, z2)), 3)
-            extra["emd_approx_match+match_cost_B%d_n%d" % (eb, en)] = {"ms": ms_e, "clouds_per_s": eb / ms_e * 1e3,
-                                                                      "frac_mufu_peak": eb / (ms_e * 1e-3) * 30.0 * en * en / (148 * 16 * sm_max)}
-            ms_f = timed(lambda: tf_approxmatch.emd_cost(z1, z2), 3)   # the loss-level call: cost without the match matrix
-            extra["emd_cost_fused_B%d_n%d" % (eb, en)] = {"ms": ms_f, "clouds_per_s": eb / ms_f * 1e3,
-                                                         "frac_mufu_peak": eb / (ms_f * 1e-3) * 30.0 * en * en / (148 * 16 * sm_max)}
+        extra["north_star_chamfer_nn_fwd_B32_16384x16384"] = {"ms": ms_ns, "Gpairs_per_s_per_gpu": pr / ms_ns / 1e6, "frac_fp32_peak": pr * LANE_OPS_PER_PAIR / (ms_ns * 1e-3) / 1e12 / peak}
         del y1, y2
+        # config 3: EMD forward + gradient, B=32 TOTAL sharded over the ranks (strong scaling), with the scalar all-reduce
+        c3 = {"what": "approx_match + match_cost + match_cost_grad as one matrix-free call per rank (rfnet_emd_cost_grad) on 32/N clouds, "
+                      "then the all-reduce of the loss partial sums; max over ranks", "scaling": "strong", "clouds_total": 32}
+        for en, iters in ((2048, 10), (16384, 3)):
+            stp, nb = emd_shard_step(D, en, 32, 40 + en)
+            ms_e = D.timed(stp, iters, warm=2)
+            cps = 32 / (ms_e * 1e-3)
+            c3["n%d" % en] = {"ms": ms_e, "clouds_per_s": cps, "clouds_per_gpu": nb, "launches": count_rfnet_launches(torch, stp),
+                              "frac_mufu_peak_per_gpu": cps / world * 30.0 * en * en / mufu_peak(sm_max)}
+            del stp
+        extra["config3_emd_fwd_grad_B32_total"] = c3
+        # config 5: recon loss path, B=64 TOTAL
+        stp, nb, _ = recon_shard_step(D, 16384, 64, 500)
+        ms_r = D.timed(stp, 2, warm=1)
+        extra["config5_recon_loss_fwd_bwd_B64_total"] = {"ms": ms_r, "clouds_per_s": 64 / (ms_r * 1e-3), "clouds_per_gpu": nb, "scaling": "strong",
+                                                         "frac_mufu_peak_per_gpu": 64 / (ms_r * 1e-3) / world * 30.0 * 16384 * 16384 / mufu_peak(sm_max),
+                                                         "what": "chamfer_big + earth_mover forward + backward on 16384-point clouds, six partial sums all-reduced"}
+        del stp
+        if rank == 0:
+            try:
+                extra["config4"] = config4_block(D, sm_max)
+            except Exception as ex:
+                extra["config4"] = {"error": repr(ex)}
+            if world == 1:
+                extra["ref_gpu_kernel"] = ref_gpu_kernel_block(D, d1s, d2s)
+                if "nn_distance_fwd_ms" in extra["ref_gpu_kernel"]:
+                    extra["ref_gpu_kernel"]["speedup_of_our_forward"] = extra["ref_gpu_kernel"]["nn_distance_fwd_ms"] / fwd_ms
+        D.barrier()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step": pairs_per_step, "clouds_per_gpu": B, "parallelism": "batch-sharded x%d, 16-byte loss all-reduce" % world,
-                       "l2": "rotating %d input batches (%.0f MB > 126 MB L2), one per step" % (nsets, nsets * set_bytes / 1e6)},
+                       "l2": "rotating %d input batches (%.0f MB > 126 MB L2), one per step" % (nsets, nsets * set_bytes / 1e6),
+                       "step": "one rfnet_chamfer_step call: nn_search_kernel + chamfer_epilogue_kernel + chamfer_epilogue_final_kernel (+3 memsets)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": (launches_per_step or 0) * args.steps, "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "extra": extra}
 
@@ -526,9 +755,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

@@ -64,17 +64,43 @@ size_t rfnet_chamfer_partial_sums_workspace_bytes(void);
 int rfnet_chamfer_partial_sums(int b, int n, int m, const float *dist1, const float *dist2, float *sums4,
                                void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
+/* One training step of the reference's chamfer_big (vv_recon.py:381-385, forward and backward) in one call and three
+ * kernel launches: nn_distance, NnDistanceGrad for the given upstream gradients grad_dist1 (b,n) / grad_dist2 (b,m), and the
+ * loss partial sums sums4 (as rfnet_chamfer_partial_sums).  Outputs are exactly those of the three separate calls:
+ * dist/idx bit-identical; gradients by the reference's float-reduction formulation (last bits depend on thread timing). */
+size_t rfnet_chamfer_step_workspace_bytes(int b, int n, int m);
+int rfnet_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                       const float *grad_dist2, float *dist1, int *idx1, float *dist2, int *idx2, float *grad_xyz1,
+                       float *grad_xyz2, float *sums4, void *workspace, size_t workspace_bytes, int flags,
+                       rfnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * approx_match / match_cost (EMD).  Replace approxmatchLauncher, matchcostLauncher, matchcostgradLauncher,
  * pc_distance/tf_approxmatch.cpp:141-143 (defined pc_distance/tf_approxmatch.cu:180-182,226-228,292-295).
  * match is (b, m, n): match[i, l, k] pairs xyz2[i,l] with xyz1[i,k] (tf_approxmatch.cu:152).  `temp` of the reference
  * ((b, 2(n+m)) floats, tf_approxmatch.cpp:168) becomes workspace.
- * Environment switches read at call time, for A/B testing only: RFNET_EMD_NO_PRUNE=1 (dense sweeps at every level),
- * RFNET_FPS_NO_PRUNE=1 (cluster kernel instead of the pruned one).  Results are bit-identical either way.
+ *
+ * Every cloud's result depends on that cloud and on (n, m, flags) only -- never on the batch size or on the position in
+ * the batch: evaluating a cloud alone, inside a batch of 32, or on another GPU of a sharded batch gives the same bits.
+ *
+ * flags (approxmatch, emd_cost, emd_cost_grad):
+ *   0 (default)                every sum of the iteration is ONE chain over the candidates in ascending order: the reference
+ *                              kernel's rounding order, term for term.  Differs from the reference binary only through the
+ *                              flushing exponential (terms < 1.2e-38) and the derived exponentials of the final pass
+ *                              (<= 1.1e-6 relative per matrix entry).
+ *   RFNET_EMD_EXACT            additionally the reference's non-flushing __expf, no pruning, every exponential of the final
+ *                              pass through the MUFU: match is bit-identical to the reference CUDA binary's.
+ *   RFNET_EMD_NO_PRUNE         dense sweeps at every level (A/B test of the exact pruning; identical results).
+ *   RFNET_EMD_SPLIT_SUMS       cut every sum into fixed-length pieces added in ascending order: more parallelism when the
+ *                              call holds only one or two small clouds, at the price of a different rounding order (the
+ *                              iteration is ill-conditioned: up to ~1e-3 of the largest entry).  Not combinable with EXACT.
  * ------------------------------------------------------------------------------------------------------------- */
+#define RFNET_EMD_EXACT 1
+#define RFNET_EMD_NO_PRUNE 2
+#define RFNET_EMD_SPLIT_SUMS 4
 size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m);
 int rfnet_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace,
-                      size_t workspace_bytes, rfnet_stream_t stream);
+                      size_t workspace_bytes, int flags, rfnet_stream_t stream);
 size_t rfnet_matchcost_workspace_bytes(int b, int n, int m);
 int rfnet_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,
                     void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
@@ -84,11 +110,17 @@ int rfnet_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz
 /* Fused approx_match + match_cost for the loss-level caller earth_mover (vv_recon.py:396-399: match = approx_match,
  * cost = match_cost, mean(cost / num_points)): the same sweeps as rfnet_approxmatch, then ONE pass that reduces
  * cost[i] = sum sqrt(d2) * match (b floats) while the matrix entries are still in registers.  `match` may be NULL:
- * the (b, m, n) matrix -- 1 GiB per cloud at 16384 x 16384 -- is then never written; pass a buffer to keep it for
- * rfnet_matchcostgrad. */
+ * the (b, m, n) matrix -- 1 GiB per cloud at 16384 x 16384 -- is then never written. */
 size_t rfnet_emd_cost_workspace_bytes(int b, int n, int m);
 int rfnet_emd_cost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *cost,
-                   void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+                   void *workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream);
+/* The training form of the same chain: approx_match -> match_cost AND matchcostgrad (tf_approxmatch.py:44-50), with no
+ * (b, m, n) matrix anywhere.  After the sweeps, two passes rebuild each matrix entry in registers from the per-level
+ * factors: one reduces cost and grad1 (b, n, 3), the other grad2 (b, m, 3); grad1/grad2 are what rfnet_matchcostgrad
+ * returns for the matrix rfnet_approxmatch would have written (before the grad_cost scaling of the Python wrapper). */
+size_t rfnet_emd_cost_grad_workspace_bytes(int b, int n, int m);
+int rfnet_emd_cost_grad(int b, int n, int m, const float *xyz1, const float *xyz2, float *cost, float *grad1,
+                        float *grad2, void *workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * sampling.  Replace farthestpointsamplingLauncher, gatherpointLauncher, scatteraddpointLauncher,
@@ -113,8 +145,7 @@ int rfnet_scatteraddpoint(int b, int n, int m, const float *out_g, const int *id
  * radius is a DEVICE pointer to one float, as in the reference (tf_grouping.cpp:93-95).  Rows with no point in the
  * ball are filled with 0 (the reference leaves them uninitialised) and get pts_cnt 0.
  * With a workspace (and 2048 <= n <= 32768) query_ball_point bins the dataset in a uniform grid and only tests the cells
- * a ball touches; with workspace == NULL every query scans the whole dataset.  Identical results either way
- * (RFNET_BALL_NO_GRID=1 forces the scan, for A/B tests).
+ * a ball touches; with workspace == NULL every query scans the whole dataset.  Identical results either way.
  * groupPointGrad zero-fills grad_points itself (reference: tf_grouping.cpp:208).
  * ------------------------------------------------------------------------------------------------------------- */
 size_t rfnet_query_ball_point_workspace_bytes(int b, int n, int m);
@@ -158,7 +189,7 @@ int rfnet_auction_match(int b, int n, const float *xyz1, const float *xyz2, int 
  * (reference: tf_interpolate.cpp:258).
  * ------------------------------------------------------------------------------------------------------------- */
 /* three_nn takes an optional workspace: with it (and 512 <= m <= 4096 known points) the search runs over a uniform grid of
- * the known cloud instead of scanning it; identical distances and indices (RFNET_THREENN_NO_GRID=1 forces the scan). */
+ * the known cloud instead of scanning it; identical distances and indices. */
 size_t rfnet_three_nn_workspace_bytes(int b, int n, int m);
 int rfnet_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, void *workspace,
                    size_t workspace_bytes, rfnet_stream_t stream);
@@ -178,7 +209,7 @@ int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float *grad_o
 int rfnet_nn_distance_host(int device, int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1,
                            int *idx1, float *dist2, int *idx2, int flags);
 int rfnet_emd_host(int device, int b, int n, int m, const float *xyz1, const float *xyz2, float *match_or_null,
-                   float *cost);
+                   float *cost, int flags);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Measurement helper (used by bench.py only): runs a dependent-free FP32 FFMA2 stream on every SM for `iters` rounds

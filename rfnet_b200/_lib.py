@@ -20,14 +20,18 @@ SIGNATURES = {
     "rfnet_nn_distance_grad": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_chamfer_partial_sums_workspace_bytes": (_z, []),
     "rfnet_chamfer_partial_sums": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "rfnet_chamfer_step_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_chamfer_step": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "rfnet_approxmatch_workspace_bytes": (_z, [_i, _i, _i]),
-    "rfnet_approxmatch": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "rfnet_approxmatch": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _i, _p]),
     "rfnet_matchcost_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_matchcost": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_matchcostgrad_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_matchcostgrad": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_emd_cost_workspace_bytes": (_z, [_i, _i, _i]),
-    "rfnet_emd_cost": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "rfnet_emd_cost": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _i, _p]),
+    "rfnet_emd_cost_grad_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_emd_cost_grad": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "rfnet_farthestpointsampling_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_farthestpointsampling": (_i, [_i, _i, _i, _p, _p, _z, _p, _p]),
     "rfnet_gatherpoint": (_i, [_i, _i, _i, _p, _p, _p, _p]),
@@ -47,7 +51,7 @@ SIGNATURES = {
     "rfnet_three_interpolate_grad_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "rfnet_three_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_nn_distance_host": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i]),
-    "rfnet_emd_host": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "rfnet_emd_host": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _i]),
     "rfnet_probe_fp32": (_i, [_i, _p, _p, _p]),
 }
 

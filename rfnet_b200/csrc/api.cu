@@ -59,7 +59,7 @@ extern "C" const char* rfnet_error_string(int code) { return cudaGetErrorString(
 
 extern "C" int rfnet_probe_fp32(int iters, float* sink, unsigned long long* lane_ops, rfnet_stream_t stream) {
     RFNET_CHECK_ARG(iters > 0 && sink && lane_ops);
-    const int blocks = kNumSMs * 4, threads = 512;
+    const int blocks = num_sms() * 4, threads = 512;
     probe_fp32_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
     *lane_ops = (unsigned long long)blocks * threads * (unsigned long long)iters * 64ull;
     return launch_status();
@@ -106,7 +106,7 @@ done:
     return rc ? rc : rc2;
 }
 
-extern "C" int rfnet_emd_host(int device, int b, int n, int m, const float* xyz1, const float* xyz2, float* match_or_null, float* cost) {
+extern "C" int rfnet_emd_host(int device, int b, int n, int m, const float* xyz1, const float* xyz2, float* match_or_null, float* cost, int flags) {
     RFNET_CHECK_ARG(b >= 0 && n > 0 && m > 0 && cost);
     if (b == 0) return 0;
     DeviceGuard guard;
@@ -116,18 +116,16 @@ extern "C" int rfnet_emd_host(int device, int b, int n, int m, const float* xyz1
     rc = host_stream(device, &s);
     if (rc) return rc;
     const size_t bn = (size_t)b * n, bm = (size_t)b * m, nm = (size_t)b * n * m;
-    size_t wsb = rfnet_approxmatch_workspace_bytes(b, n, m);
-    const size_t wsc = rfnet_matchcost_workspace_bytes(b, n, m);
-    if (wsc > wsb) wsb = wsc;
+    const size_t wsb = rfnet_emd_cost_workspace_bytes(b, n, m);
     const size_t o_x2 = (bn * 12 + 255) & ~(size_t)255, o_cost = (o_x2 + bm * 12 + 255) & ~(size_t)255;
-    const size_t o_match = (o_cost + (size_t)b * 4 + 255) & ~(size_t)255, o_ws = (o_match + nm * 4 + 255) & ~(size_t)255;
+    const size_t o_match = (o_cost + (size_t)b * 4 + 255) & ~(size_t)255, o_ws = (o_match + (match_or_null ? nm * 4 : 0) + 255) & ~(size_t)255;
     char* d = nullptr;
     HOST_TRY((int)cudaMallocAsync((void**)&d, o_ws + wsb + 256, s));
     HOST_TRY((int)cudaMemcpyAsync(d, xyz1, bn * 12, cudaMemcpyHostToDevice, s));
     HOST_TRY((int)cudaMemcpyAsync(d + o_x2, xyz2, bm * 12, cudaMemcpyHostToDevice, s));
-    HOST_TRY(rfnet_approxmatch(b, n, m, (const float*)d, (const float*)(d + o_x2), (float*)(d + o_match), d + o_ws, wsb, (rfnet_stream_t)s));
-    HOST_TRY(rfnet_matchcost(b, n, m, (const float*)d, (const float*)(d + o_x2), (const float*)(d + o_match), (float*)(d + o_cost), d + o_ws, wsb,
-                             (rfnet_stream_t)s));
+    // one call: the sweeps, then a single pass that reduces the cost and (only when asked for) stores the matrix
+    HOST_TRY(rfnet_emd_cost(b, n, m, (const float*)d, (const float*)(d + o_x2), match_or_null ? (float*)(d + o_match) : nullptr, (float*)(d + o_cost),
+                            d + o_ws, wsb, flags, (rfnet_stream_t)s));
     HOST_TRY((int)cudaMemcpyAsync(cost, d + o_cost, (size_t)b * 4, cudaMemcpyDeviceToHost, s));
     if (match_or_null) HOST_TRY((int)cudaMemcpyAsync(match_or_null, d + o_match, nm * 4, cudaMemcpyDeviceToHost, s));
 done:

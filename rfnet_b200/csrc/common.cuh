@@ -9,7 +9,20 @@
 
 namespace rfnet {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMsB200 = 148;  // B200; only the fallback of num_sms() when the attribute query fails
+
+// Multiprocessor count of the CURRENT device, queried once per device (launch heuristics scale grids with it).
+static inline int num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMsB200;
+    int v = cache[dev];
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsB200;
+        cache[dev] = v;   // benign race: every thread writes the same value
+    }
+    return v;
+}
 
 #define RFNET_CHECK_ARG(cond) \
     do {                      \
@@ -57,11 +70,19 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 // 2^x on the MUFU pipe.  The reference's __expf compiles to ex2.approx.f32 WITHOUT .ftz, which ptxas expands to
 // FSETP + FMUL + MUFU.EX2 + FMUL (halve the argument / square the result below 2^-126 so that denormal results survive).
 // The .ftz form is the bare MUFU.EX2: identical bits whenever the result is a normal number, and 0 instead of a denormal
-// (< 1.2e-38) otherwise -- a difference that cannot reach any output of approx_match (every sum it enters carries a 1e-9
-// regulariser or is compared against one), and buys ~25 % of the sweep's FMA-pipe time.
+// (< 1.2e-38) otherwise.  Dropped terms are below 1.2e-38 x weight (<= 1e9), i.e. < 1e-29 absolute in sums that carry a 1e-9
+// regulariser and in match entries: far inside every tolerance, but NOT bit-identical to the reference wherever such a term
+// exists -- the reference-order mode of approx_match therefore uses ex2_approx_full.  The ftz form buys ~25 % of the sweep's
+// FMA-pipe time and makes the exact pruning of the sharp levels possible (exact zeros).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// The reference's form (denormal results kept): used only where bit-for-bit agreement with its binary is asked for.
+__device__ __forceinline__ float ex2_approx_full(float x) {
+    float y;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 

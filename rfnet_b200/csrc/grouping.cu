@@ -9,7 +9,6 @@
 //
 // The predicate max(sqrtf(d2), 1e-20f) < r is evaluated without a square root: sqrt_rn is monotone, so it equals
 // d2 < T with T = min{t : sqrt_rn(t) >= r}; T is found once per thread by stepping nextafter around r*r.
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "pointgrid.cuh"
@@ -380,9 +379,7 @@ extern "C" int rfnet_query_ball_point(int b, int n, int m, const float* radius, 
     cudaStream_t s = (cudaStream_t)stream;
     const int per_block = BQ_WARPS * BQ_QPW;
     dim3 grid((unsigned)((m + per_block - 1) / per_block), (unsigned)b);
-    const char* no_grid = getenv("RFNET_BALL_NO_GRID");   // A/B switch for the tests: scan kernel only
-    if (workspace && n >= BG_MIN_POINTS && n <= BG_MAX_POINTS && workspace_bytes >= rfnet_query_ball_point_workspace_bytes(b, n, m) &&
-        !(no_grid && no_grid[0] == '1')) {
+    if (workspace && n >= BG_MIN_POINTS && n <= BG_MAX_POINTS && workspace_bytes >= rfnet_query_ball_point_workspace_bytes(b, n, m)) {
         const size_t stride = ball_grid_stride(n);
         const size_t smem = sizeof(unsigned) * (BG_CELLS + BG_CELLS / 32);
         RFNET_CUDA(cudaFuncSetAttribute(ball_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -8,7 +8,6 @@
 //   * three_interpolate evaluates (p1*w1 + p2*w2) + p3*w3 unfused.
 // three_nn uses the same machinery as nn_distance: queries in registers as packed pairs, candidates broadcast from shared
 // memory, a branch-free scan that only LISTS the candidate groups able to change a top 3, and an exact pass over the list.
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "pointgrid.cuh"
@@ -495,9 +494,7 @@ extern "C" int rfnet_three_nn(int b, int n, int m, const float* xyz1, const floa
     if (b == 0 || n == 0) return 0;
     RFNET_CHECK_ARG(xyz1 && dist && idx && (m == 0 || xyz2) && b <= 65535);
     cudaStream_t s = (cudaStream_t)stream;
-    const char* no_grid = getenv("RFNET_THREENN_NO_GRID");   // A/B switch for the tests: scan kernel only
-    if (workspace && m >= TG_MIN_POINTS && m <= TG_MAX_POINTS && workspace_bytes >= rfnet_three_nn_workspace_bytes(b, n, m) &&
-        !(no_grid && no_grid[0] == '1')) {
+    if (workspace && m >= TG_MIN_POINTS && m <= TG_MAX_POINTS && workspace_bytes >= rfnet_three_nn_workspace_bytes(b, n, m)) {
         const size_t stride = ball_grid_stride(m);
         const size_t gsmem = sizeof(unsigned) * (BG_CELLS + BG_CELLS / 32);
         RFNET_CUDA(cudaFuncSetAttribute(ball_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));

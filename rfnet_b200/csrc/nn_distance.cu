@@ -383,21 +383,71 @@ __global__ void chamfer_sums_final_kernel(size_t n1, size_t n2, const float* __r
 constexpr int NN_CTAS_PER_SM = NN_MIN_CTAS;  // resident CTAs per SM implied by the launch bounds
 
 // One work item = one chunk of candidates for one query tile.  Every item pays a fixed price (query loads, pipeline fill,
-// index resolution, key merge) worth roughly 48 candidates of scanning, and the grid runs in ceil(items / resident CTAs)
-// rounds; pick the chunk length that minimises rounds x (chunk + 48).
-static int pick_chunk(int b, int n, int m, int Q) {
-    const int TQ = NN_THREADS * Q;
-    const long slots = (long)kNumSMs * NN_CTAS_PER_SM;
-    int best_chunk = NN_TC;
-    long best_cost = -1;
-    for (int chunk = NN_TC; chunk >= 256; chunk >>= 1) {
-        const long items = (long)b * ((n + TQ - 1) / TQ) * ((m + chunk - 1) / chunk) + (long)b * ((m + TQ - 1) / TQ) * ((n + chunk - 1) / chunk);
-        const long rounds = (items + slots - 1) / slots;
-        const int longest = (n > m ? n : m) < chunk ? (n > m ? n : m) : chunk;
-        const long cost = rounds * (longest + 48);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunk = chunk; }
+// index resolution, key merge) worth roughly 48 candidates of scanning.  The hardware hands items to the resident CTA slots
+// in blockIdx order -- direction 0's items, then direction 1's -- so the launch time is the makespan of list-scheduling
+// two classes of equal-cost items on `slots` machines; nn_makespan evaluates that exactly (a handful of steps) and
+// pick_chunks takes the pair of chunk lengths (each an even split of its candidate range, rounded up to 8) that minimises it.
+// With one shared power-of-two chunk the bench shape ran 2.77 waves of work in 3 rounds (7 % idle); see DESIGN.md 4.1.
+static long nn_makespan(long slots, long cnt_a, long cost_a, long cnt_b, long cost_b) {
+    // slot groups (time at which the slots of the group become free, how many), kept sorted by time; at most a few entries
+    long gt[64], gc[64];
+    int ng = 1;
+    gt[0] = 0; gc[0] = slots;
+    long end = 0;
+    for (int cls = 0; cls < 2; ++cls) {
+        long left = cls ? cnt_b : cnt_a;
+        const long cost = cls ? cost_b : cost_a;
+        while (left > 0) {
+            // earliest group
+            int e = 0;
+            for (int i = 1; i < ng; ++i) if (gt[i] < gt[e]) e = i;
+            const long use = gc[e] < left ? gc[e] : left;
+            const long t1 = gt[e] + cost;
+            left -= use;
+            if (t1 > end) end = t1;
+            if (use == gc[e]) { gt[e] = t1; }
+            else { gc[e] -= use; if (ng < 64) { gt[ng] = t1; gc[ng] = use; ++ng; } }
+            // merge groups with equal time
+            for (int i = 0; i < ng; ++i)
+                for (int j = i + 1; j < ng; ++j)
+                    if (gt[i] == gt[j]) { gc[i] += gc[j]; gt[j] = gt[ng - 1]; gc[j] = gc[ng - 1]; --ng; --j; }
+        }
     }
-    return best_chunk;
+    return end;
+}
+static void pick_chunks(int b, int n, int m, int Q, int* chunk0, int* chunk1) {
+    struct Memo { int b, n, m, Q, sms, c0, c1; };
+    static thread_local Memo memo = {0, 0, 0, 0, 0, 0, 0};   // a pure function of its arguments: the memo only saves host time
+    const int sms = num_sms();
+    if (memo.b == b && memo.n == n && memo.m == m && memo.Q == Q && memo.sms == sms) { *chunk0 = memo.c0; *chunk1 = memo.c1; return; }
+    const int TQ = NN_THREADS * Q;
+    const long slots = (long)sms * NN_CTAS_PER_SM;
+    const long tiles0 = (long)b * ((n + TQ - 1) / TQ), tiles1 = (long)b * ((m + TQ - 1) / TQ);
+    auto lens = [](int nc, int* out) {   // even splits of nc into k pieces, rounded up to 8, between 256 and NN_TC candidates
+        int cnt = 0, last = 0;
+        for (int k = 1; k <= 64 && cnt < 64; ++k) {
+            int len = ((nc + k - 1) / k + 7) & ~7;
+            if (len > NN_TC) continue;
+            if (len < 256 && cnt > 0) break;
+            if (len != last) out[cnt++] = len;
+            last = len;
+        }
+        if (cnt == 0) out[cnt++] = NN_TC;
+        return cnt;
+    };
+    int l0[64], l1[64];
+    const int c0 = lens(m, l0), c1 = lens(n, l1);
+    long best = -1;
+    int b0 = NN_TC, b1 = NN_TC;
+    for (int i = 0; i < c0; ++i)
+        for (int j = 0; j < c1; ++j) {
+            const long k0 = (m + l0[i] - 1) / l0[i], k1 = (n + l1[j] - 1) / l1[j];
+            const long t = nn_makespan(slots, tiles0 * k0, (m < l0[i] ? m : l0[i]) + 48, tiles1 * k1, (n < l1[j] ? n : l1[j]) + 48);
+            if (best < 0 || t < best) { best = t; b0 = l0[i]; b1 = l1[j]; }
+        }
+    memo = {b, n, m, Q, sms, b0, b1};
+    *chunk0 = b0;
+    *chunk1 = b1;
 }
 
 static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, bool split) {
@@ -432,18 +482,9 @@ extern "C" size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m) {
     return (size_t)b * ((size_t)n + (size_t)m) * sizeof(unsigned long long);
 }
 
-extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
-                                 int* idx2, void* workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream) {
-    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
-    if (b == 0 || (n == 0 && m == 0)) return 0;
-    RFNET_CHECK_ARG(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n == 0 || m == 0) {
-        // no candidates: the reference's CPU kernel reports (0, 0) for every query of the non-empty side
-        if (n) { RFNET_CUDA(cudaMemsetAsync(dist1, 0, sizeof(float) * (size_t)b * n, s)); RFNET_CUDA(cudaMemsetAsync(idx1, 0, sizeof(int) * (size_t)b * n, s)); }
-        if (m) { RFNET_CUDA(cudaMemsetAsync(dist2, 0, sizeof(float) * (size_t)b * m, s)); RFNET_CUDA(cudaMemsetAsync(idx2, 0, sizeof(int) * (size_t)b * m, s)); }
-        return 0;
-    }
+// plan + key memset + search launch; *need0 / *need1 tell the caller which directions left their results as packed keys
+static int nn_search_launch(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2, int* idx2, void* workspace,
+                            size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out) {
     const int Q = pick_q(n < m ? n : m);
     NNParams p;
     p.d[0].q = xyz1; p.d[0].c = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1;
@@ -451,13 +492,14 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
     // written directly, no key merge and no extra launches
     const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
+    int chunk0 = NN_TC, chunk1 = NN_TC;
 #ifdef NN_FORCE_CHUNK
-    const int chunk = split ? NN_FORCE_CHUNK : NN_TC;   // tools/nn_tune.cu
+    if (split) chunk0 = chunk1 = NN_FORCE_CHUNK;   // tools/nn_tune.cu
 #else
-    const int chunk = split ? pick_chunk(b, n, m, Q) : NN_TC;
+    if (split) pick_chunks(b, n, m, Q, &chunk0, &chunk1);
 #endif
-    plan_direction(p.d[0], b, n, m, Q, chunk, split);
-    plan_direction(p.d[1], b, m, n, Q, chunk, split);
+    plan_direction(p.d[0], b, n, m, Q, chunk0, split);
+    plan_direction(p.d[1], b, m, n, Q, chunk1, split);
     unsigned long long* keys = (unsigned long long*)workspace;
     p.d[0].keys = keys;
     p.d[1].keys = keys ? keys + (size_t)b * n : nullptr;
@@ -474,11 +516,135 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     if (Q == 8) launch_search<8>(p, grid, fused, s);
     else if (Q == 4) launch_search<4>(p, grid, fused, s);
     else launch_search<2>(p, grid, fused, s);
+    *need0_out = need0;
+    *need1_out = need1;
+    return 0;
+}
+
+extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
+                                 int* idx2, void* workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
+    if (b == 0 || (n == 0 && m == 0)) return 0;
+    RFNET_CHECK_ARG(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        // no candidates: the reference's CPU kernel reports (0, 0) for every query of the non-empty side
+        if (n) { RFNET_CUDA(cudaMemsetAsync(dist1, 0, sizeof(float) * (size_t)b * n, s)); RFNET_CUDA(cudaMemsetAsync(idx1, 0, sizeof(int) * (size_t)b * n, s)); }
+        if (m) { RFNET_CUDA(cudaMemsetAsync(dist2, 0, sizeof(float) * (size_t)b * m, s)); RFNET_CUDA(cudaMemsetAsync(idx2, 0, sizeof(int) * (size_t)b * m, s)); }
+        return 0;
+    }
+    bool need0 = false, need1 = false;
+    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, flags, s, &need0, &need1); if (rc) return rc; }
     if (need0 || need1) {
         const size_t count0 = (size_t)b * n;
         const size_t begin = need0 ? 0 : count0, end = need1 ? count0 + (size_t)b * m : count0;
-        nn_unpack_keys_kernel<<<(unsigned)((end - begin + 255) / 256), 256, 0, s>>>(keys, dist1, idx1, count0, dist2, idx2, begin, end);
+        nn_unpack_keys_kernel<<<(unsigned)((end - begin + 255) / 256), 256, 0, s>>>((const unsigned long long*)workspace, dist1, idx1, count0, dist2, idx2, begin, end);
     }
+    return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One training step of chamfer_big (vv_recon.py:381-385 and its backward) in three launches: the search above, then ONE
+// epilogue over all points of both clouds -- unpack the merged keys into dist/idx, the own-point and scattered gradient
+// terms of NnDistanceGrad (tf_nndistance_g.cu:131-150, float reductions on zero-filled outputs as there), and the
+// per-block partial sums of sqrt(dist) -- and a one-block reduction of those partials in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CE_THREADS = 256;
+__global__ void __launch_bounds__(CE_THREADS) chamfer_epilogue_kernel(int n, int m, size_t total1, size_t total2, unsigned blocks1, int keyed1, int keyed2,
+                                                                      const unsigned long long* __restrict__ keys, const float* __restrict__ xyz1,
+                                                                      const float* __restrict__ xyz2, const float* __restrict__ gd1,
+                                                                      const float* __restrict__ gd2, float* __restrict__ dist1, int* __restrict__ idx1,
+                                                                      float* __restrict__ dist2, int* __restrict__ idx2, float* __restrict__ g1,
+                                                                      float* __restrict__ g2, float* __restrict__ partial) {
+    __shared__ float sW[CE_THREADS / 32];
+    const int dir = blockIdx.x >= blocks1;
+    const size_t t = (size_t)(blockIdx.x - (dir ? blocks1 : 0)) * CE_THREADS + threadIdx.x;
+    const size_t total = dir ? total2 : total1;
+    const int nq = dir ? m : n, nc = dir ? n : m;
+    float root = 0.f;
+    if (t < total) {
+        float d;
+        int j2;
+        float* __restrict__ dist = dir ? dist2 : dist1;
+        int* __restrict__ idx = dir ? idx2 : idx1;
+        if (dir ? keyed2 : keyed1) {
+            const unsigned long long k = keys[(dir ? total1 : 0) + t];
+            d = __uint_as_float((unsigned)(k >> 32));
+            j2 = (int)(unsigned)(k & 0xffffffffull);
+            dist[t] = d;
+            idx[t] = j2;
+        } else {
+            d = dist[t];
+            j2 = idx[t];
+        }
+        root = __fsqrt_rn(d);
+        const size_t cloud = t / nq;
+        const float g = (dir ? gd2 : gd1)[t] * 2.0f;
+        const float* __restrict__ a = (dir ? xyz2 : xyz1) + t * 3;
+        const size_t oi = (cloud * nc + j2) * 3;
+        const float* __restrict__ o = (dir ? xyz1 : xyz2) + oi;
+        float* __restrict__ gown = (dir ? g2 : g1) + t * 3;
+        float* __restrict__ goth = (dir ? g1 : g2) + oi;
+        const float tx = g * (a[0] - o[0]), ty = g * (a[1] - o[1]), tz = g * (a[2] - o[2]);
+        atomicAdd(gown + 0, tx); atomicAdd(gown + 1, ty); atomicAdd(gown + 2, tz);
+        atomicAdd(goth + 0, -tx); atomicAdd(goth + 1, -ty); atomicAdd(goth + 2, -tz);
+    }
+    root = warp_sum(root);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = root;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < CE_THREADS / 32; ++i) s += sW[i];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(512) chamfer_epilogue_final_kernel(size_t total1, size_t total2, unsigned blocks1, unsigned blocks2,
+                                                                     const float* __restrict__ partial, float* __restrict__ sums) {
+    // warps 0-7: direction 0, warps 8-15: direction 1; thread-strided partials, then a fixed tree: deterministic
+    __shared__ float sW[16];
+    const int dir = threadIdx.x >> 8, tid = threadIdx.x & 255;
+    const unsigned cnt = dir ? blocks2 : blocks1;
+    const float* __restrict__ p = partial + (dir ? blocks1 : 0);
+    float t = 0.f;
+    for (unsigned i = tid; i < cnt; i += 256) t += p[i];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sW[dir * 8 + i];
+        sums[dir * 2] = s;
+        sums[dir * 2 + 1] = (float)(dir ? total2 : total1);
+    }
+}
+
+static size_t chamfer_step_partials(int b, int n, int m) {
+    return ((size_t)b * n + CE_THREADS - 1) / CE_THREADS + ((size_t)b * m + CE_THREADS - 1) / CE_THREADS;
+}
+
+extern "C" size_t rfnet_chamfer_step_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    return rfnet_nn_distance_workspace_bytes(b, n, m) + sizeof(float) * chamfer_step_partials(b, n, m);
+}
+
+extern "C" int rfnet_chamfer_step(int b, int n, const float* xyz1, int m, const float* xyz2, const float* grad_dist1, const float* grad_dist2,
+                                  float* dist1, int* idx1, float* dist2, int* idx2, float* grad_xyz1, float* grad_xyz2, float* sums4, void* workspace,
+                                  size_t workspace_bytes, int flags, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b > 0 && n > 0 && m > 0);
+    RFNET_CHECK_ARG(xyz1 && xyz2 && grad_dist1 && grad_dist2 && dist1 && idx1 && dist2 && idx2 && grad_xyz1 && grad_xyz2 && sums4);
+    RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_chamfer_step_workspace_bytes(b, n, m));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t t1 = (size_t)b * n, t2 = (size_t)b * m;
+    RFNET_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * t1, s));
+    RFNET_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * t2, s));
+    bool need0 = false, need1 = false;
+    const size_t key_bytes = rfnet_nn_distance_workspace_bytes(b, n, m);
+    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, key_bytes, flags, s, &need0, &need1); if (rc) return rc; }
+    float* partial = reinterpret_cast<float*>((char*)workspace + key_bytes);
+    const unsigned blocks1 = (unsigned)((t1 + CE_THREADS - 1) / CE_THREADS), blocks2 = (unsigned)((t2 + CE_THREADS - 1) / CE_THREADS);
+    chamfer_epilogue_kernel<<<blocks1 + blocks2, CE_THREADS, 0, s>>>(n, m, t1, t2, blocks1, need0 ? 1 : 0, need1 ? 1 : 0, (const unsigned long long*)workspace,
+                                                                       xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, partial);
+    chamfer_epilogue_final_kernel<<<1, 512, 0, s>>>(t1, t2, blocks1, blocks2, partial, sums4);
     return launch_status();
 }
 

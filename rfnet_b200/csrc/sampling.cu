@@ -14,7 +14,6 @@
 // in a 64-bit key (distance bits | inverted tie rank) so the arg-max is a plain integer max.
 #include <cooperative_groups.h>
 
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "morton.cuh"
@@ -406,10 +405,9 @@ extern "C" int rfnet_farthestpointsampling(int b, int n, int m, const float* inp
     RFNET_CHECK_ARG(n > 0 && inp && out);
     cudaStream_t s = (cudaStream_t)stream;
     // pruned single-CTA kernel whenever the cloud fits one SM's shared memory and a workspace for the Morton order was given
-    // (RFNET_FPS_NO_PRUNE=1 forces the cluster kernel: used by the tests to compare the two)
-    const char* no_prune = getenv("RFNET_FPS_NO_PRUNE");
+    // (workspace == NULL selects the cluster kernel: the tests compare the two that way)
     // (worth its prologue -- sort, gather, boxes: ~50 us -- from a few hundred picks on)
-    if (n <= FPSP_MAX_POINTS && m >= 256 && workspace && workspace_bytes >= sizeof(int) * (size_t)b * n && !(no_prune && no_prune[0] == '1')) {
+    if (n <= FPSP_MAX_POINTS && m >= 256 && workspace && workspace_bytes >= sizeof(int) * (size_t)b * n) {
         int* perm = (int*)workspace;
         int rc = morton_sort(b, n, 0, inp, nullptr, perm, nullptr, s);
         if (rc) return rc;
@@ -430,7 +428,7 @@ extern "C" int rfnet_farthestpointsampling(int b, int n, int m, const float* inp
     // cluster size: enough CTAs that a slice fits 8 points/thread, more when few clouds would leave SMs idle
     int C = 1;
     while (C < FPS_MAX_CLUSTER && (n + C - 1) / C > FPS_THREADS * 8) C <<= 1;
-    while (C < FPS_MAX_CLUSTER && (long)b * C * 2 <= kNumSMs && (n + C - 1) / C > FPS_THREADS) C <<= 1;
+    while (C < FPS_MAX_CLUSTER && (long)b * C * 2 <= num_sms() && (n + C - 1) / C > FPS_THREADS) C <<= 1;
     const int per_cta = (n + C - 1) / C;
     const int P = (per_cta + FPS_THREADS - 1) / FPS_THREADS;
     const bool smem_cloud = (size_t)n * 12 <= 200 * 1024;

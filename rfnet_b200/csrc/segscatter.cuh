@@ -171,7 +171,7 @@ static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaS
         csr_fill_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor, c.list);
         dim3 gs((unsigned)((n + 255) / 256), (unsigned)b);
         csr_sort_short_kernel<<<gs, 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
-        csr_sort_long_kernel<<<kNumSMs, 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
+        csr_sort_long_kernel<<<num_sms(), 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
     }
     return launch_status();
 }

@@ -21,7 +21,7 @@ class ChamferHostPipeline:
         self.outputs = tuple(outputs)
         self.deterministic = bool(deterministic)   # atomic-free CSR scatter for the gradient (bit-reproducible, slower)
         dev = self.dev
-        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.s_in, self.s_out, self.s_red = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.x1 = [torch.empty((b, n, 3), device=dev) for _ in range(depth)]
         self.x2 = [torch.empty((b, m, 3), device=dev) for _ in range(depth)]
         # device-side results and scratch, one set per slot: the steady-state loop allocates nothing and calls the C ABI directly
@@ -39,6 +39,7 @@ class ChamferHostPipeline:
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_compute = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_red = [torch.cuda.Event() for _ in range(depth)]
         self.count = 0
         self.h2d_bytes = b * (n + m) * 12
         per = {"dist1": b * n * 4, "idx1": b * n * 4, "dist2": b * m * 4, "idx2": b * m * 4, "grad1": b * n * 12, "grad2": b * m * 12, "sums": 16}
@@ -46,8 +47,13 @@ class ChamferHostPipeline:
 
     def submit(self, h_xyz1, h_xyz2, reduce_fn=None):
         """Enqueue one batch (pinned host tensors).  Returns the slot whose `out` buffers will hold the results once
-        `wait(slot)` returns.  `reduce_fn` (optional) is applied to the 4 loss partial sums on the compute stream (e.g. an
-        all-reduce across ranks)."""
+        `wait(slot)` returns.  `reduce_fn` (optional) is applied in place to the 4 loss partial sums (e.g. an all-reduce
+        across ranks).  It runs on a SIDE stream that only the copy-out of the sums waits for: the collective's launch
+        latency and the slowest rank never sit between two batches on the compute stream."""
+        with torch.cuda.device(self.dev):
+            return self._submit(h_xyz1, h_xyz2, reduce_fn)
+
+    def _submit(self, h_xyz1, h_xyz2, reduce_fn):
         k = self.count % self.depth
         self.count += 1
         compute = torch.cuda.current_stream(self.dev)
@@ -61,14 +67,22 @@ class ChamferHostPipeline:
         compute.wait_event(self.ev_in[k])
         compute.wait_event(self.ev_out[k])   # the slot's device results were last read by the copy-out of batch count - depth
         r = self.dres[k]
-        ops.raw_nn_distance(self.x1[k], self.x2[k], r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["ws"])
-        ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"],
-                                 r["ws"] if self.deterministic else None)
-        ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
-        if reduce_fn is not None:
-            reduce_fn(r["sums"])              # in place (e.g. an all-reduce across ranks)
+        if self.deterministic:
+            ops.raw_nn_distance(self.x1[k], self.x2[k], r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["ws"])
+            ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"], r["ws"])
+            ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
+        else:
+            # search + one epilogue (unpack, gradient, sqrt partial sums) + one reduction: three launches
+            ops.raw_chamfer_step(self.x1[k], self.x2[k], self.gd1, self.gd2, r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["grad1"], r["grad2"],
+                                 r["sums"], r["ws"])
         self.ev_compute[k].record(compute)
         self.s_out.wait_event(self.ev_compute[k])
+        if reduce_fn is not None:
+            self.s_red.wait_event(self.ev_compute[k])
+            with torch.cuda.stream(self.s_red):
+                reduce_fn(r["sums"])          # in place
+                self.ev_red[k].record(self.s_red)
+            self.s_out.wait_event(self.ev_red[k])
         with torch.cuda.stream(self.s_out):
             o = self.out[k]
             for name in self.outputs:
@@ -82,5 +96,6 @@ class ChamferHostPipeline:
         return self.out[slot]
 
     def drain(self):
+        self.s_red.synchronize()
         self.s_out.synchronize()
         torch.cuda.current_stream(self.dev).synchronize()

@@ -67,10 +67,18 @@ def raw_chamfer_partial_sums(dist1, dist2, sums4, workspace):
                                                       _ptr(workspace), workspace.numel(), _stream(dist1)), "rfnet_chamfer_partial_sums")
 
 
+def raw_chamfer_step(xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, sums4, workspace, unfused=False):
+    """nn_distance + NnDistanceGrad + the chamfer partial sums: one C-ABI call, three kernel launches (rfnet_chamfer_step)."""
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    _lib.check(_lib.load().rfnet_chamfer_step(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(grad_dist2), _ptr(dist1), _ptr(idx1), _ptr(dist2),
+                                              _ptr(idx2), _ptr(grad_xyz1), _ptr(grad_xyz2), _ptr(sums4), _ptr(workspace), workspace.numel(),
+                                              1 if unfused else 0, _stream(xyz1)), "rfnet_chamfer_step")
+
+
 def nn_distance_workspace_bytes(b, n, m):
     lib = _lib.load()
     return max(int(lib.rfnet_nn_distance_workspace_bytes(b, n, m)), int(lib.rfnet_chamfer_partial_sums_workspace_bytes()),
-               int(lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m)), 16)
+               int(lib.rfnet_nn_distance_grad_workspace_bytes(b, n, m)), int(lib.rfnet_chamfer_step_workspace_bytes(b, n, m)), 16)
 
 
 # ------------------------------------------------------------------------------------------------------------ nn_distance
@@ -185,8 +193,8 @@ def _(dist1, dist2):
 
 # ------------------------------------------------------------------------------------------------------------ approx_match
 @torch.library.custom_op("rfnet::approx_match", mutates_args=(), device_types="cuda")
-def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> torch.Tensor:
-    # ApproxMatchGpuOp::Compute, pc_distance/tf_approxmatch.cpp:145-173
+def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor, flags: int = 0) -> torch.Tensor:
+    # ApproxMatchGpuOp::Compute, pc_distance/tf_approxmatch.cpp:145-173.  flags: EMD_EXACT | EMD_NO_PRUNE | EMD_SPLIT_SUMS (rfnet_ops.h)
     _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
     _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ApproxMatch expects (batch_size,num_points,3) xyz2 shape, and batch_size must match")
     xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
@@ -196,12 +204,12 @@ def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> torch.Tensor:
     wsb = lib.rfnet_approxmatch_workspace_bytes(b, n, m)
     ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(lib.rfnet_approxmatch(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match), _ptr(ws), wsb, _stream(xyz1)), "rfnet_approxmatch")
+        _lib.check(lib.rfnet_approxmatch(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match), _ptr(ws), wsb, int(flags), _stream(xyz1)), "rfnet_approxmatch")
     return match
 
 
 @approx_match_op.register_fake
-def _(xyz1, xyz2):
+def _(xyz1, xyz2, flags=0):
     return xyz1.new_empty((xyz1.shape[0], xyz2.shape[1], xyz1.shape[1]))
 
 
@@ -267,10 +275,15 @@ def _match_cost_backward(ctx, grad_cost):
 match_cost_op.register_autograd(_match_cost_backward, setup_context=_match_cost_setup)
 
 
+EMD_EXACT = 1        # RFNET_EMD_EXACT: bit-identical to the reference CUDA binary
+EMD_NO_PRUNE = 2     # RFNET_EMD_NO_PRUNE
+EMD_SPLIT_SUMS = 4   # RFNET_EMD_SPLIT_SUMS: split every sum (more parallelism for tiny batches, different rounding order)
+
+
 @torch.library.custom_op("rfnet::emd_cost", mutates_args=(), device_types="cuda")
-def emd_cost_op(xyz1: torch.Tensor, xyz2: torch.Tensor, keep_match: bool) -> tuple[torch.Tensor, torch.Tensor]:
+def emd_cost_op(xyz1: torch.Tensor, xyz2: torch.Tensor, keep_match: bool, flags: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
     # ApproxMatch followed by MatchCost (vv_recon.py:396-399) in one call: (cost (b,), match (b,m,n) or an empty tensor).
-    # Without keep_match the (b, m, n) matrix never reaches HBM.
+    # Without keep_match the (b, m, n) matrix never reaches HBM.  Not differentiable: training uses emd_cost_grad_op.
     _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
     _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ApproxMatch expects (batch_size,num_points,3) xyz2 shape, and batch_size must match")
     xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
@@ -281,40 +294,60 @@ def emd_cost_op(xyz1: torch.Tensor, xyz2: torch.Tensor, keep_match: bool) -> tup
     wsb = lib.rfnet_emd_cost_workspace_bytes(b, n, m)
     ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(lib.rfnet_emd_cost(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match) if keep_match else None, _ptr(cost), _ptr(ws), wsb,
+        _lib.check(lib.rfnet_emd_cost(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(match) if keep_match else None, _ptr(cost), _ptr(ws), wsb, int(flags),
                                       _stream(xyz1)), "rfnet_emd_cost")
     return cost, match
 
 
 @emd_cost_op.register_fake
-def _(xyz1, xyz2, keep_match):
+def _(xyz1, xyz2, keep_match, flags=0):
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     return xyz1.new_empty((b,)), xyz1.new_empty((b, m, n) if keep_match else (0,))
 
 
-def _emd_cost_setup(ctx, inputs, output):
-    xyz1, xyz2, keep_match = inputs
-    ctx.keep_match = keep_match
-    ctx.save_for_backward(xyz1, xyz2, output[1])
+@torch.library.custom_op("rfnet::emd_cost_grad", mutates_args=(), device_types="cuda")
+def emd_cost_grad_op(xyz1: torch.Tensor, xyz2: torch.Tensor, flags: int = 0) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    # ApproxMatch -> MatchCost together with MatchCostGrad for that match (tf_approxmatch.py:44-50), no (b,m,n) matrix anywhere:
+    # (cost (b,), grad1 (b,n,3), grad2 (b,m,3)); the gradients are d cost / d xyz for the match held constant.
+    _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ApproxMatch expects (batch_size,num_points,3) xyz1 shape")
+    _require(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ApproxMatch expects (batch_size,num_points,3) xyz2 shape, and batch_size must match")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    cost = torch.empty((b,), dtype=torch.float32, device=xyz1.device)
+    g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    lib = _lib.load()
+    wsb = lib.rfnet_emd_cost_grad_workspace_bytes(b, n, m)
+    ws = _workspace(wsb, xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        _lib.check(lib.rfnet_emd_cost_grad(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(cost), _ptr(g1), _ptr(g2), _ptr(ws), wsb, int(flags), _stream(xyz1)),
+                   "rfnet_emd_cost_grad")
+    return cost, g1, g2
 
 
-def _emd_cost_backward(ctx, grad_cost, grad_match):
-    # the match is a constant of the loss (NoGradient('ApproxMatch'), tf_approxmatch.py:19); d cost = MatchCostGrad
-    if not ctx.keep_match:
-        raise RuntimeError("emd_cost was called with keep_match=False: the match matrix needed by MatchCostGrad was not kept")
-    xyz1, xyz2, match = ctx.saved_tensors
-    g1, g2 = match_cost_grad_op(xyz1, xyz2, match)
+@emd_cost_grad_op.register_fake
+def _(xyz1, xyz2, flags=0):
+    return xyz1.new_empty((xyz1.shape[0],)), torch.empty_like(xyz1), torch.empty_like(xyz2)
+
+
+def _emd_cost_grad_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1], output[2])
+
+
+def _emd_cost_grad_backward(ctx, grad_cost, grad_g1, grad_g2):
+    # the match is a constant of the loss (NoGradient('ApproxMatch'), tf_approxmatch.py:19); d cost = MatchCostGrad scaled by
+    # grad_cost[:,None,None] (tf_approxmatch.py:50).  grad1 / grad2 themselves are not differentiated further.
+    g1, g2 = ctx.saved_tensors
     s = grad_cost[:, None, None]
     return g1 * s, g2 * s, None
 
 
-emd_cost_op.register_autograd(_emd_cost_backward, setup_context=_emd_cost_setup)
+emd_cost_grad_op.register_autograd(_emd_cost_grad_backward, setup_context=_emd_cost_grad_setup)
 
 
 # ------------------------------------------------------------------------------------------------------------ sampling
 @torch.library.custom_op("rfnet::farthest_point_sample", mutates_args=(), device_types="cuda")
-def farthest_point_sample_op(inp: torch.Tensor, npoint: int) -> torch.Tensor:
-    # FarthestPointSampleGpuOp, tf_ops/sampling/tf_sampling.cpp:95-123
+def farthest_point_sample_op(inp: torch.Tensor, npoint: int, pruned: bool = True) -> torch.Tensor:
+    # FarthestPointSampleGpuOp, tf_ops/sampling/tf_sampling.cpp:95-123.  pruned=False: no workspace -> the cluster kernel (same indices)
     _require(npoint > 0, "FarthestPointSample expects positive npoint")
     _require(inp.dim() == 3 and inp.shape[2] == 3, "FarthestPointSample expects (batch_size,num_points,3) inp shape")
     inp = _cuda_f32("inp", inp)
@@ -322,14 +355,17 @@ def farthest_point_sample_op(inp: torch.Tensor, npoint: int) -> torch.Tensor:
     out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
     lib = _lib.load()
     wsb = lib.rfnet_farthestpointsampling_workspace_bytes(b, n, npoint)
+    if not pruned and n <= 32768:
+        wsb = 0
     ws = _workspace(wsb, inp.device)
     with torch.cuda.device(inp.device):
-        _lib.check(lib.rfnet_farthestpointsampling(b, n, npoint, _ptr(inp), _ptr(ws), wsb, _ptr(out), _stream(inp)), "rfnet_farthestpointsampling")
+        _lib.check(lib.rfnet_farthestpointsampling(b, n, npoint, _ptr(inp), _ptr(ws) if wsb else _vp(0), wsb, _ptr(out), _stream(inp)),
+                   "rfnet_farthestpointsampling")
     return out
 
 
 @farthest_point_sample_op.register_fake
-def _(inp, npoint):
+def _(inp, npoint, pruned=True):
     return inp.new_empty((inp.shape[0], npoint), dtype=torch.int32)
 
 
@@ -388,8 +424,9 @@ gather_point_op.register_autograd(_gather_backward, setup_context=_gather_setup)
 
 # ------------------------------------------------------------------------------------------------------------ grouping
 @torch.library.custom_op("rfnet::query_ball_point", mutates_args=(), device_types="cuda")
-def query_ball_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, radius: torch.Tensor, nsample: int) -> tuple[torch.Tensor, torch.Tensor]:
-    # QueryBallPointGpuOp, tf_ops/grouping/tf_grouping.cpp:68-110 -- radius is a tensor input there too (:93-95)
+def query_ball_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, radius: torch.Tensor, nsample: int, grid: bool = True) -> tuple[torch.Tensor, torch.Tensor]:
+    # QueryBallPointGpuOp, tf_ops/grouping/tf_grouping.cpp:68-110 -- radius is a tensor input there too (:93-95).
+    # grid=False: no workspace -> every query scans the whole dataset (same results)
     _require(nsample > 0, "QueryBallPoint expects positive nsample")
     _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
     _require(xyz2.dim() == 3 and xyz2.shape[2] == 3, "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
@@ -400,16 +437,16 @@ def query_ball_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, radius: torch.Te
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     lib = _lib.load()
-    wsb = lib.rfnet_query_ball_point_workspace_bytes(b, n, m)
+    wsb = lib.rfnet_query_ball_point_workspace_bytes(b, n, m) if grid else 0
     ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(lib.rfnet_query_ball_point(b, n, m, _ptr(radius), nsample, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt), _ptr(ws), wsb,
+        _lib.check(lib.rfnet_query_ball_point(b, n, m, _ptr(radius), nsample, _ptr(xyz1), _ptr(xyz2), _ptr(idx), _ptr(cnt), _ptr(ws) if wsb else _vp(0), wsb,
                                               _stream(xyz1)), "rfnet_query_ball_point")
     return idx, cnt
 
 
 @query_ball_point_op.register_fake
-def _(xyz1, xyz2, radius, nsample):
+def _(xyz1, xyz2, radius, nsample, grid=True):
     b, m = xyz2.shape[0], xyz2.shape[1]
     return xyz1.new_empty((b, m, nsample), dtype=torch.int32), xyz1.new_empty((b, m), dtype=torch.int32)
 
@@ -537,8 +574,8 @@ def _(xyz1, xyz2):
 
 # ------------------------------------------------------------------------------------------------------------ interpolation
 @torch.library.custom_op("rfnet::three_nn", mutates_args=(), device_types="cuda")
-def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-    # ThreeNNOp, tf_ops/interpolation/tf_interpolate.cpp:157-187
+def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor, grid: bool = True) -> tuple[torch.Tensor, torch.Tensor]:
+    # ThreeNNOp, tf_ops/interpolation/tf_interpolate.cpp:157-187.  grid=False: no workspace -> the scan kernel (same results)
     _require(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ThreeNN expects (b,n,3) xyz1 shape")
     _require(xyz2.dim() == 3 and xyz2.shape[2] == 3, "ThreeNN expects (b,m,3) xyz2 shape")
     _require(xyz2.shape[0] == xyz1.shape[0], "ThreeNN expects xyz1 and xyz2 have same batch size")
@@ -547,15 +584,15 @@ def three_nn_op(xyz1: torch.Tensor, xyz2: torch.Tensor) -> tuple[torch.Tensor, t
     dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
     lib = _lib.load()
-    wsb = lib.rfnet_three_nn_workspace_bytes(b, n, m)
+    wsb = lib.rfnet_three_nn_workspace_bytes(b, n, m) if grid else 0
     ws = _workspace(wsb, xyz1.device)
     with torch.cuda.device(xyz1.device):
-        _lib.check(lib.rfnet_three_nn(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _ptr(ws), wsb, _stream(xyz1)), "rfnet_three_nn")
+        _lib.check(lib.rfnet_three_nn(b, n, m, _ptr(xyz1), _ptr(xyz2), _ptr(dist), _ptr(idx), _ptr(ws) if wsb else _vp(0), wsb, _stream(xyz1)), "rfnet_three_nn")
     return dist, idx
 
 
 @three_nn_op.register_fake
-def _(xyz1, xyz2):
+def _(xyz1, xyz2, grid=True):
     b, n = xyz1.shape[0], xyz1.shape[1]
     return xyz1.new_empty((b, n, 3)), xyz1.new_empty((b, n, 3), dtype=torch.int32)
 

@@ -2,7 +2,7 @@
 from . import ops
 
 
-def approx_match(xyz1, xyz2):
+def approx_match(xyz1, xyz2, exact=False):
     '''
 input:
 	xyz1 : batch_size * #dataset_points * 3
@@ -11,8 +11,10 @@ returns:
 	match : batch_size * #query_points * #dataset_points
 
 No gradient flows through approx_match (ops.NoGradient('ApproxMatch'), tf_approxmatch.py:19).
+Every sum follows the reference CUDA kernel's order; exact=True also uses its non-flushing exponential everywhere, which
+makes `match` bit-identical to the reference binary's (the parity mode, ~15 % slower).
     '''
-    return ops.approx_match_op(xyz1.detach(), xyz2.detach())
+    return ops.approx_match_op(xyz1.detach(), xyz2.detach(), ops.EMD_EXACT if exact else 0)
 
 
 def match_cost(xyz1, xyz2, match):
@@ -29,14 +31,18 @@ Differentiable w.r.t. xyz1 and xyz2 (not match), as RegisterGradient('MatchCost'
     return ops.match_cost_op(xyz1, xyz2, match.detach())
 
 
-def emd_cost(xyz1, xyz2):
+def emd_cost(xyz1, xyz2, exact=False):
     '''
 approx_match followed by match_cost, as every caller in the reference chains them (vv_recon.py:396-399), in one call:
 	cost : batch_size
-The match matrix is kept (for the gradient of match_cost) only when a gradient can be asked for; otherwise it is never
-written to memory.  Values equal match_cost(xyz1, xyz2, approx_match(xyz1, xyz2)) up to summation order.
+The (b, m, n) match matrix is never written to memory.  When a gradient can be asked for, cost and both MatchCostGrad
+gradients come out of the same call (two passes that rebuild the matrix entries in registers); values equal
+match_cost(xyz1, xyz2, approx_match(xyz1, xyz2)) and its gradient up to summation order.
     '''
     import torch
-    keep = torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad)
-    cost, _ = ops.emd_cost_op(xyz1, xyz2, keep)
+    flags = ops.EMD_EXACT if exact else 0
+    if torch.is_grad_enabled() and (xyz1.requires_grad or xyz2.requires_grad):
+        cost, _, _ = ops.emd_cost_grad_op(xyz1, xyz2, flags)
+        return cost
+    cost, _ = ops.emd_cost_op(xyz1, xyz2, False, flags)
     return cost

@@ -15,7 +15,9 @@ def meta(*shape, dtype=torch.float32):
 def test_signatures_match_reference_wrappers():
     # tf_ops/CD/tf_nndistance.py:9, pc_distance/tf_approxmatch.py:10,27, tf_sampling.py:29,48, tf_grouping.py:8,33,48, tf_interpolate.py:8,19
     assert list(inspect.signature(tf_nndistance.nn_distance).parameters)[:2] == ["xyz1", "xyz2"]
-    assert list(inspect.signature(tf_approxmatch.approx_match).parameters) == ["xyz1", "xyz2"]
+    # approx_match keeps the reference's two positional arguments; exact is an optional keyword (the bit-exact parity mode)
+    assert list(inspect.signature(tf_approxmatch.approx_match).parameters)[:2] == ["xyz1", "xyz2"]
+    assert inspect.signature(tf_approxmatch.approx_match).parameters["exact"].default is False
     assert list(inspect.signature(tf_approxmatch.match_cost).parameters) == ["xyz1", "xyz2", "match"]
     assert list(inspect.signature(tf_sampling.farthest_point_sample).parameters) == ["npoint", "inp"]
     assert list(inspect.signature(tf_sampling.gather_point).parameters) == ["inp", "idx"]
@@ -60,6 +62,9 @@ def test_output_shapes_and_dtypes_via_meta_tensors():
     assert cost.shape == (b,) and kept.shape == (b, m, n)
     cost, kept = torch.ops.rfnet.emd_cost(meta(b, n, 3), meta(b, m, 3), False)
     assert cost.shape == (b,) and kept.numel() == 0
+    cost, g1, g2 = torch.ops.rfnet.emd_cost_grad(meta(b, n, 3), meta(b, m, 3))
+    assert cost.shape == (b,) and g1.shape == (b, n, 3) and g2.shape == (b, m, 3)
+    assert torch.ops.rfnet.approx_match(meta(b, n, 3), meta(b, m, 3), 1).shape == (b, m, n)
     val, ki = torch.ops.rfnet.knn_point(meta(b, n, 3), meta(b, m, 3), 4)
     assert val.shape == ki.shape == (b, m, 4) and ki.dtype == torch.int32
 

@@ -1,17 +1,19 @@
-"""GPU parity of approx_match / match_cost / match_cost_grad against the CPU oracle and the reference CUDA kernels.
+"""GPU parity of approx_match / match_cost / match_cost_grad / the fused loss-level calls against the CPU oracle and the
+reference CUDA kernels (pc_distance/tf_approxmatch.cu recompiled unchanged for sm_100a, oracle/_ref/libref_gpu.so).
 
-Tolerances.  BASELINE.json asks for 1e-4 relative on EMD.  match_cost, match_cost_grad (for a GIVEN match) and the final
-loss meet it against every oracle.  The match MATRIX itself is a different matter: approx_match is an ill-conditioned
-float32 iteration -- perturbing each exp() by 1 ulp, or summing a row in a different order, moves entries of `match` by up
-to ~1e-4 of the largest entry (measured: float32 oracle vs the same code in float64 differs by 9e-5 at n=512; the
-reference's own CPU and GPU kernels differ by 6e-4).  So:
-  * against the reference CUDA kernel, in the configuration where our sums run in the reference's order (no candidate
-    split), `match` must agree to 1e-5 of its largest entry -- tighter than asked;
-  * against the CPU oracle (libm expf instead of MUFU ex2) and in split mode, `match` is held to
-    max(1e-4, 8 x noise band) of its largest entry, where the noise band is measured on the same inputs as
-    |float32 oracle - float64 oracle| (oracle.port.approx_match_noise_band: 1e-6 on most clouds, up to 4e-3 on some), and
-    never looser than MATCH_RTOL = 5e-2;
-    the well-conditioned quantities derived from it (cost, marginals) are held to 1e-4."""
+Tolerances.  BASELINE.json asks for 1e-4 relative on EMD.
+  * RFNET_EMD_EXACT: `match` must be BIT-IDENTICAL to the reference CUDA kernel's (torch.equal), for any batch size and at the
+    benchmarked shapes -- (32, 2048, 2048), (1 | 4, 16384, 16384); cost and gradients within 1e-4 (their reductions run in a
+    different order than the reference's one-block-per-cloud kernels).
+  * DEFAULT (flags = 0): every sum of the iteration still follows the reference's order; only the flushing exponential and
+    the derived exponentials of the final pass differ.  match within 1e-5 of its largest entry, cost / gradients within 1e-4.
+  * RFNET_EMD_SPLIT_SUMS (opt-in, for one or two small clouds): a different rounding order of the same terms.  approx_match
+    is an ill-conditioned float32 iteration (the reference's own CPU and GPU kernels differ by 6e-4), so this mode is held to
+    caps = 2 x the largest error MEASURED against the reference kernel at the benchmarked shapes
+    (tools/emd_parity_report.py -> profiles/r2_emd_parity.txt); cost, what the loss uses, still meets 1e-4.
+  * Against the CPU oracle (libm expf instead of MUFU ex2) `match` is held to max(1e-4, 8 x noise band measured on the same
+    inputs as |float32 oracle - float64 oracle|), capped at MATCH_CAP; cost to 1e-4.
+  * Results never depend on the batch: a cloud alone, in any batch, at any position gives the same bits (torch.equal)."""
 import numpy as np
 import pytest
 import torch
@@ -21,11 +23,22 @@ from oracle import port, ref
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4
-MATCH_RTOL = 5e-2
+MATCH_CAP = 2e-2          # never looser than this against the CPU oracle (noise-band rule above)
+# RFNET_EMD_SPLIT_SUMS vs the reference CUDA kernel, relative to the largest entry / value: 2 x measured (profiles/r2_emd_parity.txt)
+SPLIT_MATCH_VS_REF = 1.5e-3
+SPLIT_COST_VS_REF = 1e-4
+SPLIT_GRAD_VS_REF = 2.5e-3
+EXACT = 1                 # RFNET_EMD_EXACT
+NO_PRUNE = 2              # RFNET_EMD_NO_PRUNE
+SPLIT = 4                 # RFNET_EMD_SPLIT_SUMS
 
 
 def match_tol(x1, x2, want):
-    return port.approx_match_tolerance(x1, x2, want, cap=MATCH_RTOL)
+    return port.approx_match_tolerance(x1, x2, want, cap=MATCH_CAP)
+
+
+def relmax(got, want):
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
 
 
 def close(got, want, rtol=RTOL):
@@ -42,12 +55,13 @@ def t(a, dev):
 SHAPES = [(1, 1, 1), (2, 16, 16), (2, 100, 100), (1, 257, 130), (1, 64, 200), (2, 512, 512), (1, 1030, 1030)]
 
 
+@pytest.mark.parametrize("flags", [0, EXACT, SPLIT])
 @pytest.mark.parametrize("b,n,m", SHAPES)
-def test_approx_match_vs_oracle(cuda, rng, b, n, m):
-    from rfnet_b200 import tf_approxmatch
+def test_approx_match_vs_oracle(cuda, rng, b, n, m, flags):
+    from rfnet_b200 import ops
     x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
     want = port.approx_match(x1, x2)
-    got = tf_approxmatch.approx_match(t(x1, cuda), t(x2, cuda)).cpu().numpy()
+    got = ops.approx_match_op(t(x1, cuda), t(x2, cuda), flags).cpu().numpy()
     assert got.shape == (b, m, n)
     close(got, want, match_tol(x1, x2, want))
     # the well-conditioned functional of the plan: its cost, at the asked 1e-4
@@ -95,7 +109,7 @@ def test_earth_mover_autograd(cuda, rng):
     match = port.approx_match(x1n, x2n)
     cost = port.match_cost(x1n, x2n, match)
     assert abs(loss.item() - float((cost / n).mean())) <= RTOL * abs(float((cost / n).mean()))
-    # gradient for OUR match (the gradient is linear in match; match itself is compared above at MATCH_RTOL)
+    # gradient for OUR match (the gradient is linear in match; match itself is compared above)
     from rfnet_b200 import tf_approxmatch
     ours = tf_approxmatch.approx_match(x1.detach(), x2.detach()).cpu().numpy()
     w1, w2 = port.match_cost_grad(x1n, x2n, ours)
@@ -105,29 +119,113 @@ def test_earth_mover_autograd(cuda, rng):
     close(x1.grad.cpu().numpy(), o1 / (b * n), rtol=5e-3)
 
 
+def ref_emd(x1, x2):
+    """match, cost, grad1, grad2 of the reference CUDA kernels (tf_approxmatch.cu:1-295) on the default stream."""
+    b, n, m = x1.shape[0], x1.shape[1], x2.shape[1]
+    assert b * n * m < 2 ** 31, "the reference kernel indexes match with int (tf_approxmatch.cu:15)"
+    (match,) = ref.run_gpu("ApproxMatch", [x1, x2], [((b, m, n), torch.float32)])
+    (cost,) = ref.run_gpu("MatchCost", [x1, x2, match], [((b,), torch.float32)])
+    g1, g2 = ref.run_gpu("MatchCostGrad", [x1, x2, match], [((b, n, 3), torch.float32), ((b, m, 3), torch.float32)])
+    return match, cost, g1, g2
+
+
+def gen_clouds(b, n, m, seed, noisy=False, dev=None):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x1 = torch.rand((b, n, 3), generator=g) - 0.5
+    if noisy and n == m:   # second input distribution of SURVEY.md 8(d): GT + N(0, 0.01^2)
+        x2 = x1 + 0.01 * torch.randn((b, m, 3), generator=g)
+    else:
+        x2 = torch.rand((b, m, 3), generator=g) - 0.5
+    return x1.to(dev), x2.to(dev)
+
+
+# the first two shapes are the ones DESIGN.md quotes for small clouds; the rest are BASELINE.json configs[2] as benchmarked
+# (B=32 n=m=2048; n=m=16384 alone and as the 4-cloud shard of an 8-GPU run), plus ragged / unequal sizes
+REF_SHAPES = [(600, 256, 256, False), (1200, 128, 300, False), (2, 512, 512, False), (1, 1000, 3000, False), (3, 1030, 2049, False),
+              (32, 2048, 2048, False), (32, 2048, 2048, True), (1, 16384, 16384, False), (4, 16384, 16384, False), (2, 16384, 16384, True)]
+
+
 @pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
-@pytest.mark.parametrize("b,n,m,rtol", [(600, 256, 256, 1e-5), (1200, 128, 300, 1e-5), (2, 512, 512, MATCH_RTOL), (1, 2048, 2048, MATCH_RTOL), (1, 1000, 3000, MATCH_RTOL)])
-def test_emd_vs_reference_cuda_kernels(cuda, rng, b, n, m, rtol):
-    """Against the reference's own CUDA kernels (tf_approxmatch.cu recompiled for sm_100a), same inputs.  The first two
-    shapes have enough clouds that no candidate split is used: sums run in the reference's order -> 1e-5."""
+@pytest.mark.parametrize("b,n,m,noisy", REF_SHAPES)
+def test_exact_and_default_vs_reference_cuda_kernels(cuda, b, n, m, noisy):
+    """Against the reference's own CUDA kernels, same inputs, any batch size.
+    RFNET_EMD_EXACT: `match` bit-identical.  Default: match within 1e-5 of its largest entry.  Both: cost and gradients within
+    1e-4 -- tighter than north_star asks, at the shapes that are benchmarked."""
     from rfnet_b200 import ops, tf_approxmatch
-    x1, x2 = t(cloud(rng, b, n), cuda), t(cloud(rng, b, m), cuda)
-    (want,) = ref.run_gpu("ApproxMatch", [x1, x2], [((b, m, n), torch.float32)])
-    got = tf_approxmatch.approx_match(x1, x2)
-    if rtol >= 1e-4:
-        rtol = match_tol(x1.cpu().numpy(), x2.cpu().numpy(), None)
-    close(got.cpu().numpy(), want.cpu().numpy(), rtol)
-    if rtol < 1e-4:
-        frac_equal = float((got == want).float().mean())
-        print("bitwise-equal fraction of match entries: %.6f" % frac_equal)
-        assert frac_equal > 0.95
-    (wcost,) = ref.run_gpu("MatchCost", [x1, x2, want], [((b,), torch.float32)])
-    gcost = tf_approxmatch.match_cost(x1, x2, want)
-    assert np.allclose(gcost.cpu().numpy(), wcost.cpu().numpy(), rtol=RTOL)
-    wg1, wg2 = ref.run_gpu("MatchCostGrad", [x1, x2, want], [((b, n, 3), torch.float32), ((b, m, 3), torch.float32)])
-    g1, g2 = ops.match_cost_grad_op(x1, x2, want)
-    close(g1.cpu().numpy(), wg1.cpu().numpy())
-    close(g2.cpu().numpy(), wg2.cpu().numpy())
+    x1, x2 = gen_clouds(b, n, m, 4000 + b + n + m, noisy, cuda)
+    want, wcost, wg1, wg2 = ref_emd(x1, x2)
+    got = ops.approx_match_op(x1, x2, EXACT)
+    assert torch.equal(got, want), "exact mode: rel-to-max err %.3e, bitwise-equal fraction %.6f" % (relmax(got, want), float((got == want).float().mean()))
+    del got
+    got = ops.approx_match_op(x1, x2, 0)
+    err = relmax(got, want)
+    print("default match vs reference kernel: rel-to-max err %.3e, bitwise-equal fraction %.6f" % (err, float((got == want).float().mean())))
+    assert err <= 1e-5
+    # cost of OUR match by OUR kernels vs cost of the reference's match by the reference's kernel
+    assert torch.allclose(tf_approxmatch.match_cost(x1, x2, got), wcost, rtol=RTOL, atol=0)
+    del got
+    for flags in (0, EXACT):
+        fcost, _ = ops.emd_cost_op(x1, x2, False, flags)
+        assert torch.allclose(fcost, wcost, rtol=RTOL, atol=0)
+        ccost, g1, g2 = ops.emd_cost_grad_op(x1, x2, flags)
+        assert torch.allclose(ccost, wcost, rtol=RTOL, atol=0)
+        assert relmax(g1, wg1) <= RTOL and relmax(g2, wg2) <= RTOL
+    # match_cost / match_cost_grad for a GIVEN (the reference's) match
+    assert torch.allclose(tf_approxmatch.match_cost(x1, x2, want), wcost, rtol=RTOL, atol=0)
+    h1, h2 = ops.match_cost_grad_op(x1, x2, want)
+    assert relmax(h1, wg1) <= RTOL and relmax(h2, wg2) <= RTOL
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+@pytest.mark.parametrize("b,n,m,noisy", [(32, 2048, 2048, False), (32, 2048, 2048, True), (4, 16384, 16384, False), (2, 16384, 16384, True),
+                                          (2, 512, 512, False), (1, 1000, 3000, False)])
+def test_split_sums_vs_reference_cuda_kernels(cuda, b, n, m, noisy):
+    """The opt-in split plan against the reference CUDA kernels at the benchmarked shapes.  Caps = 2 x the errors measured
+    by tools/emd_parity_report.py (profiles/r2_emd_parity.txt); cost -- what the loss uses -- at north_star's 1e-4."""
+    from rfnet_b200 import ops
+    x1, x2 = gen_clouds(b, n, m, 4000 + b + n + m, noisy, cuda)
+    want, wcost, wg1, wg2 = ref_emd(x1, x2)
+    got = ops.approx_match_op(x1, x2, SPLIT)
+    cost, g1, g2 = ops.emd_cost_grad_op(x1, x2, SPLIT)
+    e_match, e_g1, e_g2 = relmax(got, want), relmax(g1, wg1), relmax(g2, wg2)
+    e_cost = float(((cost - wcost).abs() / wcost.abs()).max())
+    print("split sums vs reference kernel: match %.3e, cost %.3e, grad1 %.3e, grad2 %.3e" % (e_match, e_cost, e_g1, e_g2))
+    assert e_match <= SPLIT_MATCH_VS_REF
+    assert e_cost <= SPLIT_COST_VS_REF
+    assert e_g1 <= SPLIT_GRAD_VS_REF and e_g2 <= SPLIT_GRAD_VS_REF
+
+
+@pytest.mark.parametrize("flags", [0, EXACT, SPLIT])
+@pytest.mark.parametrize("n,batches", [(2048, (1, 4, 8, 32)), (300, (1, 7, 600)), (16384, (1, 4))])
+def test_results_do_not_depend_on_the_batch(cuda, n, batches, flags):
+    """A cloud's match, cost and gradients are the same BITS alone, inside any batch and at any position of it -- although
+    the launch geometry (threads per CTA, CTAs per cloud) changes with the batch size.  This is what makes batch sharding
+    over GPUs value-preserving."""
+    from rfnet_b200 import ops
+    bmax = max(batches)
+    x1, x2 = gen_clouds(bmax, n, n, 77 + n, False, cuda)
+    full_cost, full_g1, full_g2 = ops.emd_cost_grad_op(x1, x2, flags)
+    full_match = ops.approx_match_op(x1, x2, flags) if bmax * n * n <= 1 << 28 else None
+    for b in batches:
+        if b == bmax:
+            continue
+        for lo in (0, bmax - b):     # first and last b clouds of the big batch
+            a, c = x1[lo:lo + b].contiguous(), x2[lo:lo + b].contiguous()
+            cost, g1, g2 = ops.emd_cost_grad_op(a, c, flags)
+            assert torch.equal(cost, full_cost[lo:lo + b]) and torch.equal(g1, full_g1[lo:lo + b]) and torch.equal(g2, full_g2[lo:lo + b])
+            c2, _ = ops.emd_cost_op(a, c, False, flags)
+            assert torch.equal(c2, cost)
+            if full_match is not None:
+                assert torch.equal(ops.approx_match_op(a, c, flags), full_match[lo:lo + b])
+
+
+def test_flag_combinations(cuda, rng):
+    from rfnet_b200 import ops
+    x = t(cloud(rng, 1, 64), cuda)
+    with pytest.raises(Exception, match="invalid"):
+        ops.approx_match_op(x, x, EXACT | SPLIT)       # a bit-exact split sum does not exist
+    with pytest.raises(Exception, match="invalid"):
+        ops.approx_match_op(x, x, 64)
 
 
 def test_emd_full_size_properties(cuda):
@@ -151,12 +249,22 @@ def test_emd_full_size_properties(cuda):
     part_cost = tf_approxmatch.match_cost(x1[:, sl].contiguous(), x2, match[:, :, sl].contiguous())
     assert abs(part_cost.item() - part.item()) <= 1e-4 * abs(part.item())
     assert 0 < part_cost.item() < cost.item()
+    # the matrix-free calls agree with the matrix: cost and both gradients in float64 from `match`
+    fcost, g1, g2 = torch.ops.rfnet.emd_cost_grad(x1, x2, 0)
+    dfull = torch.cdist(x2.double(), x1.double())[0]          # (m, n)
+    assert abs(fcost.item() - float((match[0].double() * dfull).sum())) <= 1e-5 * fcost.item()
+    wgt = match[0].double() / dfull.clamp_min(1e-10)           # match * rsqrt(d2)
+    want_g1 = x1[0].double() * wgt.sum(0)[:, None] - wgt.t() @ x2[0].double()
+    want_g2 = x2[0].double() * wgt.sum(1)[:, None] - wgt @ x1[0].double()
+    assert float((g1[0].double() - want_g1).abs().max()) <= 1e-5 * float(want_g1.abs().max())
+    assert float((g2[0].double() - want_g2).abs().max()) <= 1e-5 * float(want_g2.abs().max())
 
 
-@pytest.mark.parametrize("b,n,m", [(1, 1, 1), (2, 100, 100), (1, 257, 130), (1, 64, 200), (3, 512, 512), (1, 1030, 1030), (600, 256, 256)])
+@pytest.mark.parametrize("b,n,m", [(1, 1, 1), (2, 100, 100), (1, 257, 130), (1, 64, 200), (3, 512, 512), (1, 1030, 1030), (600, 256, 256), (2, 2048, 5000)])
 def test_emd_cost_fused(cuda, rng, b, n, m):
     """rfnet_emd_cost (approx_match + match_cost in one call, vv_recon.py:396-399): the cost equals the two-op chain at 1e-5;
-    with keep_match the matrix written is bit-identical to approx_match's; without it no matrix exists."""
+    with keep_match the matrix written is bit-identical to approx_match's; without it no matrix exists.
+    rfnet_emd_cost_grad adds both gradients of the chain, still without a matrix."""
     from rfnet_b200 import ops, tf_approxmatch
     x1n, x2n = cloud(rng, b, n), cloud(rng, b, m)
     x1, x2 = t(x1n, cuda), t(x2n, cuda)
@@ -169,9 +277,16 @@ def test_emd_cost_fused(cuda, rng, b, n, m):
     assert torch.equal(kept, match)
     assert torch.equal(cost1, cost0)
     assert np.allclose(tf_approxmatch.emd_cost(x1, x2).cpu().numpy(), chain, rtol=1e-5, atol=1e-7)
+    cost2, g1, g2 = ops.emd_cost_grad_op(x1, x2)
+    assert torch.equal(cost2, cost0)
+    c1, c2 = ops.match_cost_grad_op(x1, x2, match)     # the two-op chain's gradient, from the stored matrix
+    assert relmax(g1, c1) <= 1e-5 and relmax(g2, c2) <= 1e-5
     if b * n * m <= 1 << 21:
         want = port.match_cost(x1n, x2n, port.approx_match(x1n, x2n))
         assert np.allclose(cost0.cpu().numpy(), want, rtol=RTOL, atol=1e-7)
+        w1, w2 = port.match_cost_grad(x1n, x2n, match.cpu().numpy())
+        close(g1.cpu().numpy(), w1)
+        close(g2.cpu().numpy(), w2)
 
 
 def test_emd_cost_fused_edge_and_grad(cuda, rng):
@@ -180,17 +295,22 @@ def test_emd_cost_fused_edge_and_grad(cuda, rng):
     pts = t(cloud(rng, 2, 8), cuda)
     cost, _ = ops.emd_cost_op(empty, pts, False)
     assert cost.tolist() == [0.0, 0.0]
-    # gradient path keeps the matrix and equals the two-op chain's gradient exactly (same match, same grad kernel)
+    cost, g1, g2 = ops.emd_cost_grad_op(empty, pts)
+    assert cost.tolist() == [0.0, 0.0] and g1.shape == (2, 0, 3) and float(g2.abs().max()) == 0.0
+    # autograd through the matrix-free call equals the two-op chain's gradient (same entries, different summation order),
+    # including a non-trivial upstream gradient per cloud (tf_approxmatch.py:50)
     x1 = t(cloud(rng, 2, 300), cuda).requires_grad_(True)
     x2 = t(cloud(rng, 2, 300), cuda).requires_grad_(True)
-    tf_approxmatch.emd_cost(x1, x2).sum().backward()
+    wgt = torch.tensor([0.25, -3.0], device=cuda)
+    (tf_approxmatch.emd_cost(x1, x2) * wgt).sum().backward()
     g1, g2 = x1.grad.clone(), x2.grad.clone()
     x1.grad = x2.grad = None
-    tf_approxmatch.match_cost(x1, x2, tf_approxmatch.approx_match(x1, x2)).sum().backward()
-    assert torch.equal(g1, x1.grad) and torch.equal(g2, x2.grad)
-    with pytest.raises(RuntimeError, match="keep_match=False"):
-        c, _ = ops.emd_cost_op(x1, x2, False)
-        c.sum().backward()
+    (tf_approxmatch.match_cost(x1, x2, tf_approxmatch.approx_match(x1, x2)) * wgt).sum().backward()
+    assert relmax(g1, x1.grad) <= 1e-5 and relmax(g2, x2.grad) <= 1e-5
+    # without a gradient being asked for, the cost-only kernel runs and gives the same bits
+    with torch.no_grad():
+        c0 = tf_approxmatch.emd_cost(x1, x2)
+    assert torch.equal(c0, tf_approxmatch.emd_cost(x1, x2).detach())
 
 
 @pytest.mark.parametrize("b,n,m,kind", [(2, 4096, 4096, "cube"), (1, 5000, 4100, "cube"), (1, 4096, 8192, "sphere"), (130, 4096, 4096, "cube"),
@@ -198,9 +318,8 @@ def test_emd_cost_fused_edge_and_grad(cuda, rng):
 def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
     """From 4096 points per cloud the three sharpest levels run as pruned sweeps (Morton-ordered rows, per-cluster candidate
     masks).  Skipped terms are exact zeros and the surviving ones are added in the same order, so the plan must be
-    BIT-IDENTICAL to the dense sweeps' (RFNET_EMD_NO_PRUNE=1), split or not (b = 130 runs unsplit)."""
-    import os
-    from rfnet_b200 import ops, tf_approxmatch
+    BIT-IDENTICAL to the dense sweeps' (flags = RFNET_EMD_NO_PRUNE), with whole-row chains and with split sums."""
+    from rfnet_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(1000 + n + m + b)
     def pts(count):
         x = torch.rand((b, count, 3), generator=g) - 0.5
@@ -209,15 +328,12 @@ def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
             x[:, : count // 16] = x[:, count // 16: 2 * (count // 16)]
         return x.to(cuda)
     x1, x2 = pts(n), pts(m)
-    assert os.environ.get("RFNET_EMD_NO_PRUNE") is None
-    pruned = tf_approxmatch.approx_match(x1, x2)
-    cost_pruned, _ = ops.emd_cost_op(x1, x2, False)
-    os.environ["RFNET_EMD_NO_PRUNE"] = "1"
-    try:
-        dense = tf_approxmatch.approx_match(x1, x2)
-        cost_dense, _ = ops.emd_cost_op(x1, x2, False)
-    finally:
-        del os.environ["RFNET_EMD_NO_PRUNE"]
-    assert torch.equal(pruned, dense)
-    assert torch.equal(cost_pruned, cost_dense)
-    assert float(dense.sum()) > 0.9 * b * min(n, m)
+    for base in (0, SPLIT):
+        pruned = ops.approx_match_op(x1, x2, base)
+        cost_pruned, g1p, g2p = ops.emd_cost_grad_op(x1, x2, base)
+        dense = ops.approx_match_op(x1, x2, base | NO_PRUNE)
+        cost_dense, g1d, g2d = ops.emd_cost_grad_op(x1, x2, base | NO_PRUNE)
+        assert torch.equal(pruned, dense)
+        assert torch.equal(cost_pruned, cost_dense) and torch.equal(g1p, g1d) and torch.equal(g2p, g2d)
+        assert float(dense.sum()) > 0.9 * b * min(n, m)
+        del pruned, dense

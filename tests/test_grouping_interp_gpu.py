@@ -35,7 +35,6 @@ def test_query_ball_point_grid_equals_scan(cuda, b, n, m, ns, r, kind):
     result must be IDENTICAL to the full scan (RFNET_BALL_NO_GRID=1): volumes, surfaces, a radius larger than the cloud (every
     query overflows the hit buffer and is redone by the scan kernel), a radius below the coordinate resolution with duplicated
     points, queries outside the dataset's bounding box, and a degenerate (collinear) cloud."""
-    import os
     from rfnet_b200 import tf_grouping
     g = torch.Generator(device="cpu").manual_seed(7 + n + m)
     x1 = torch.rand((b, n, 3), generator=g) - 0.5
@@ -52,13 +51,8 @@ def test_query_ball_point_grid_equals_scan(cuda, b, n, m, ns, r, kind):
         x1[:, :, 1:] = 0.25
         x2[:, :, 1:] = 0.25
     x1, x2 = x1.to(cuda), x2.to(cuda)
-    assert os.environ.get("RFNET_BALL_NO_GRID") is None
     gi, gc = tf_grouping.query_ball_point(r, ns, x1, x2)
-    os.environ["RFNET_BALL_NO_GRID"] = "1"
-    try:
-        si, sc = tf_grouping.query_ball_point(r, ns, x1, x2)
-    finally:
-        del os.environ["RFNET_BALL_NO_GRID"]
+    si, sc = torch.ops.rfnet.query_ball_point(x1, x2, torch.tensor([r], dtype=torch.float32, device=cuda), ns, False)   # no workspace: scan
     assert torch.equal(gc, sc) and torch.equal(gi, si)
     assert int(gc.min()) >= 0 and int(gc.max()) <= ns
 
@@ -88,6 +82,32 @@ def test_query_ball_point_vs_reference_cuda_kernel(cuda, rng):
     wi, wc = ref.run_gpu("QueryBallPoint", [x1, x2, r], [((b, m, ns), torch.int32), ((b, m), torch.int32)], attrs={"nsample": ns}, zero_outputs=True)
     gi, gc = tf_grouping.query_ball_point(r, ns, x1, x2)
     assert torch.equal(gc, wc) and torch.equal(gi, wi)
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+def test_config4_full_shape_vs_reference_cuda_kernels(cuda):
+    """BASELINE config 4 at full size (B=32, dataset 16384, queries = the 2048 FPS points, r=0.1, nsample=32): idx and pts_cnt
+    of EVERY query equal the reference CUDA kernel's (tf_grouping_g.cu:3-36), grid and scan variants; group_point (c=3, c=64)
+    and its gradient equal the reference kernels' (:40-78; the gradient within float-atomic rounding)."""
+    from rfnet_b200 import ops, tf_grouping, tf_sampling
+    g = torch.Generator(device="cpu").manual_seed(11)
+    b, n, m, ns = 32, 16384, 2048, 32
+    x = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    q = tf_sampling.gather_point(x, tf_sampling.farthest_point_sample(m, x))
+    r = torch.tensor([0.1], device=cuda)
+    wi, wc = ref.run_gpu("QueryBallPoint", [x, q, r], [((b, m, ns), torch.int32), ((b, m), torch.int32)], attrs={"nsample": ns}, zero_outputs=True)
+    gi, gc = tf_grouping.query_ball_point(r, ns, x, q)
+    assert torch.equal(gc, wc) and torch.equal(gi, wi)
+    si, sc = torch.ops.rfnet.query_ball_point(x, q, r, ns, False)
+    assert torch.equal(sc, wc) and torch.equal(si, wi)
+    for c in (3, 64):
+        pts = torch.randn((b, n, c), generator=g).to(cuda)
+        (wg,) = ref.run_gpu("GroupPoint", [pts, wi], [((b, m, ns, c), torch.float32)])
+        assert torch.equal(tf_grouping.group_point(pts, gi), wg)
+        go = torch.randn((b, m, ns, c), generator=g).to(cuda)
+        (wgg,) = ref.run_gpu("GroupPointGrad", [pts, wi, go], [((b, n, c), torch.float32)], zero_outputs=True)
+        gg = ops.group_point_grad_op(pts, gi, go)
+        assert float((gg - wgg).abs().max()) <= 1e-5 * float(wgg.abs().max())
 
 
 @pytest.mark.parametrize("c", [1, 3, 16, 64, 6])
@@ -139,7 +159,6 @@ def test_three_nn_grid_equals_scan(cuda, b, n, m, kind):
     """With 512..4096 known points three_nn searches a uniform grid (own cell, then shells, until the third distance is closer
     than any unvisited cell); distances AND indices must be identical to the full scan (RFNET_THREENN_NO_GRID=1), including
     which of several equidistant points comes first."""
-    import os
     from rfnet_b200 import tf_interpolate
     g = torch.Generator(device="cpu").manual_seed(90 + n + m)
     x1 = torch.rand((b, n, 3), generator=g) - 0.5
@@ -157,13 +176,8 @@ def test_three_nn_grid_equals_scan(cuda, b, n, m, kind):
     elif kind == "same":
         x2[:] = x2[:, :1]                              # all known points coincide: one cell, all distances equal
     x1, x2 = x1.to(cuda), x2.to(cuda)
-    assert os.environ.get("RFNET_THREENN_NO_GRID") is None
     gd, gi = tf_interpolate.three_nn(x1, x2)
-    os.environ["RFNET_THREENN_NO_GRID"] = "1"
-    try:
-        sd, si = tf_interpolate.three_nn(x1, x2)
-    finally:
-        del os.environ["RFNET_THREENN_NO_GRID"]
+    sd, si = torch.ops.rfnet.three_nn(x1, x2, False)   # no workspace: the scan kernel
     assert torch.equal(gi, si) and torch.equal(gd, sd)
 
 

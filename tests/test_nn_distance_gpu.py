@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import cloud
-from oracle import port
+from oracle import port, ref
 
 pytestmark = pytest.mark.gpu
 
@@ -75,6 +75,30 @@ def test_nn_distance_large_property(cuda):
     full = torch.cdist(x1d, x2d) ** 2
     assert np.allclose(full.min(dim=2).values.cpu().numpy(), d1, rtol=1e-5, atol=1e-9)
     assert np.allclose(full.min(dim=1).values.cpu().numpy(), d2, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+@pytest.mark.parametrize("b,n,m", [(32, 2048, 16384), (4, 16384, 16384), (32, 16384, 16384)])
+def test_nn_distance_full_shapes_vs_reference_cuda_kernel(cuda, b, n, m):
+    """BASELINE config 2 (B=32, 2048 vs 16384), the north-star shape (B=32, 16384^2) and its 8-GPU shard (B=4): ALL four
+    outputs bit-identical with the reference's own CUDA kernel (tf_ops/CD/tf_nndistance_g.cu == pc_distance/tf_nndistance.cu,
+    recompiled unchanged for sm_100a) -- every distance and every index of every query, in both directions; then the gradient
+    for those indices against the reference's NnDistanceGrad kernel (float atomics: order-dependent last bits -> 1e-5)."""
+    from rfnet_b200 import ops, tf_nndistance
+    g = torch.Generator(device="cpu").manual_seed(20 + b + n)
+    x1 = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    x2 = (torch.rand((b, m, 3), generator=g) - 0.5).to(cuda)
+    want = ref.run_gpu("NnDistance", [x1, x2], [((b, n), torch.float32), ((b, n), torch.int32), ((b, m), torch.float32), ((b, m), torch.int32)])
+    got = tf_nndistance.nn_distance(x1, x2)
+    for gt, w in zip(got, want):
+        assert torch.equal(gt, w)
+    gd1 = torch.rand((b, n), generator=g).to(cuda)
+    gd2 = torch.rand((b, m), generator=g).to(cuda)
+    w1, w2 = ref.run_gpu("NnDistanceGrad", [x1, x2, gd1, want[1], gd2, want[3]], [((b, n, 3), torch.float32), ((b, m, 3), torch.float32)])
+    for det in (False, True):
+        g1, g2 = ops.nn_distance_grad_op(x1, x2, gd1, got[1], gd2, got[3], det)
+        assert float((g1 - w1).abs().max()) <= 1e-5 * float(w1.abs().max())
+        assert float((g2 - w2).abs().max()) <= 1e-5 * float(w2.abs().max())
 
 
 def test_nn_distance_grad_many_queries_share_one_neighbour(cuda, rng):
@@ -192,3 +216,27 @@ def test_host_pipeline_matches_direct_ops(cuda, rng):
         assert np.allclose(out["grad1"].numpy(), g1, rtol=1e-5, atol=1e-9) and np.allclose(out["grad2"].numpy(), g2, rtol=1e-5, atol=1e-9)
         assert np.allclose(out["sums"].numpy()[0], np.sqrt(want[0].astype(np.float64)).sum(), rtol=1e-5)
     pipe.drain()
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 300, 257), (3, 2048, 5000), (32, 2048, 16384), (4, 16384, 16384), (1, 1, 7)])
+def test_chamfer_step_equals_separate_calls(cuda, b, n, m):
+    """rfnet_chamfer_step (search + one epilogue + one reduction) against nn_distance, nn_distance_grad and
+    chamfer_partial_sums called one after the other: dist / idx bit-identical, gradients and sums to float rounding."""
+    from rfnet_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(b * 7 + n)
+    x1 = (torch.rand((b, n, 3), generator=g) - 0.5).to(cuda)
+    x2 = (torch.rand((b, m, 3), generator=g) - 0.5).to(cuda)
+    gd1, gd2 = torch.rand((b, n), generator=g).to(cuda), torch.rand((b, m), generator=g).to(cuda)
+    d1, i1, d2, i2 = ops.nn_distance_op(x1, x2)
+    w1, w2 = ops.nn_distance_grad_op(x1, x2, gd1, i1, gd2, i2, True)          # deterministic reference-order gradient
+    wsum = ops.chamfer_partial_sums_op(d1, d2)
+    f32, i32 = torch.float32, torch.int32
+    o = dict(d1=torch.empty((b, n), dtype=f32, device=cuda), i1=torch.empty((b, n), dtype=i32, device=cuda),
+             d2=torch.empty((b, m), dtype=f32, device=cuda), i2=torch.empty((b, m), dtype=i32, device=cuda),
+             g1=torch.empty((b, n, 3), dtype=f32, device=cuda), g2=torch.empty((b, m, 3), dtype=f32, device=cuda), s=torch.empty(4, device=cuda))
+    ws = torch.empty(ops.nn_distance_workspace_bytes(b, n, m), dtype=torch.uint8, device=cuda)
+    for _ in range(2):   # twice: the call must re-initialise everything it accumulates into
+        ops.raw_chamfer_step(x1, x2, gd1, gd2, o["d1"], o["i1"], o["d2"], o["i2"], o["g1"], o["g2"], o["s"], ws)
+    assert torch.equal(o["d1"], d1) and torch.equal(o["i1"], i1) and torch.equal(o["d2"], d2) and torch.equal(o["i2"], i2)
+    assert float((o["g1"] - w1).abs().max()) <= 1e-5 * float(w1.abs().max()) and float((o["g2"] - w2).abs().max()) <= 1e-5 * float(w2.abs().max())
+    assert torch.allclose(o["s"], wsum, rtol=1e-5)

@@ -49,7 +49,6 @@ def test_fps_pruned_equals_cluster_kernel(cuda, b, n, m, kind):
     """The pruned kernel (Morton clusters whose box is out of reach of a pick are skipped) against the cluster kernel that
     updates every point at every pick (RFNET_FPS_NO_PRUNE=1): identical indices, on volumes, surfaces, lattices (massive
     ties) and duplicated points."""
-    import os
     from rfnet_b200 import tf_sampling
     g = torch.Generator(device="cpu").manual_seed(50 + n + m)
     x = torch.rand((b, n, 3), generator=g) - 0.5
@@ -60,13 +59,8 @@ def test_fps_pruned_equals_cluster_kernel(cuda, b, n, m, kind):
     elif kind == "dup":
         x[:, n // 2:] = x[:, : n - n // 2]
     x = x.to(cuda)
-    assert os.environ.get("RFNET_FPS_NO_PRUNE") is None
     pruned = tf_sampling.farthest_point_sample(m, x)
-    os.environ["RFNET_FPS_NO_PRUNE"] = "1"
-    try:
-        full = tf_sampling.farthest_point_sample(m, x)
-    finally:
-        del os.environ["RFNET_FPS_NO_PRUNE"]
+    full = torch.ops.rfnet.farthest_point_sample(x, m, False)    # no workspace: the cluster kernel
     assert torch.equal(pruned, full)
 
 
@@ -78,6 +72,18 @@ def test_fps_vs_reference_cuda_kernel(cuda, rng, b, n, m):
     (want,) = ref.run_gpu("FarthestPointSample", [x], [((b, m), torch.int32)], attrs={"npoint": m})
     got = tf_sampling.farthest_point_sample(m, x)
     assert torch.equal(got, want)
+
+
+@pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
+def test_fps_config4_full_shape_vs_reference_cuda_kernel(cuda):
+    """BASELINE config 4 at full size (B=32, 16384 -> 2048): every index of every cloud equals the reference CUDA kernel's
+    (tf_sampling_g.cu:105-170), for the pruned kernel and for the cluster kernel."""
+    from rfnet_b200 import tf_sampling
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = (torch.rand((32, 16384, 3), generator=g) - 0.5).to(cuda)
+    (want,) = ref.run_gpu("FarthestPointSample", [x], [((32, 2048), torch.int32)], attrs={"npoint": 2048})
+    assert torch.equal(tf_sampling.farthest_point_sample(2048, x), want)
+    assert torch.equal(torch.ops.rfnet.farthest_point_sample(x, 2048, False), want)
 
 
 def test_fps_full_size_properties(cuda):

@@ -11,6 +11,8 @@ rnd = lambda b, n: (torch.rand((b, n, 3), generator=g) - 0.5).to(dev)
 x1, x2 = rnd(1, 4100), rnd(1, 4096)
 m = tf_approxmatch.approx_match(x1, x2)                 # pruned sweeps (Morton sort, masks), ragged sizes
 c, _ = ops.emd_cost_op(x1, x2, False)
+cg, g1, g2 = ops.emd_cost_grad_op(x1, x2)              # matrix-free cost + both gradients (split sweeps, fused pass 3 + pass 1)
+mr_ = ops.approx_match_op(x1[:, :700].contiguous(), x2[:, :515].contiguous(), 1)   # reference-order mode, ragged
 x = rnd(2, 5003)
 idx = tf_sampling.farthest_point_sample(300, x)         # pruned FPS, ragged last cluster
 q = tf_sampling.gather_point(x, idx)
