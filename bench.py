@@ -260,7 +260,7 @@ def mufu_peak(sm_max_hz):
     return 148 * 16 * sm_max_hz
 
 
-def emd_shard_step(D, n, clouds_total, seed):
+def emd_shard_step(D, n, clouds_total, seed, flags=0):
     """EMD forward + gradient on this rank's slice of `clouds_total` clouds of n points (cost + both MatchCostGrad gradients,
     no match matrix) followed by the path's only collective: the all-reduce of [sum cost / n, count] (earth_mover,
     vv_recon.py:392-399).  Returns (callable, clouds on this rank)."""
@@ -275,7 +275,7 @@ def emd_shard_step(D, n, clouds_total, seed):
 
     def step():
         if nb:
-            cost, g1, g2 = ops.emd_cost_grad_op(x1, x2)
+            cost, g1, g2 = ops.emd_cost_grad_op(x1, x2, flags)
             part = torch.stack([(cost / float(n)).sum(), cost.new_tensor(float(nb))])
         else:
             part = torch.zeros(2, device=D.dev)
@@ -499,8 +499,13 @@ def config4_block(D, sm_max):
         out["group_point_c%d" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
         go = torch.randn((b, m, ns, cc), generator=g).to(D.dev)
         ms = t(lambda: ops.group_point_grad_op(pts, gi, go))
-        out["group_point_grad_c%d" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
-        del pts, go
+        out["group_point_grad_c%d" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak,
+                                            "note": "standalone call: builds the inverted index (6 small launches) and sums"}
+        plan = ops.scatter_plan_op(gi.reshape(b, -1), n)
+        ms = t(lambda: ops.group_point_grad_planned_op(go, plan, n))
+        out["group_point_grad_c%d_planned" % cc] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak,
+                                                    "note": "what autograd runs: the inverted index was built at forward time"}
+        del pts, go, plan
     ms = t(lambda: tf_interpolate.three_nn(x, q))
     out["three_nn"] = {"ms": ms}
     d3, i3 = tf_interpolate.three_nn(x, q)
@@ -513,6 +518,9 @@ def config4_block(D, sm_max):
     go = torch.randn((b, n, c), generator=g).to(D.dev)
     ms = t(lambda: ops.three_interpolate_grad_op(feats, i3, w, go))
     out["three_interpolate_grad_c%d" % c] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
+    plan = ops.scatter_plan_op(i3.reshape(b, -1), m)
+    ms = t(lambda: ops.three_interpolate_grad_planned_op(go, w, plan, m))
+    out["three_interpolate_grad_c%d_planned" % c] = {"ms": ms, "GB_per_s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peak}
     return out
 
 
@@ -712,12 +720,16 @@ def main():
         c3 = {"what": "approx_match + match_cost + match_cost_grad as one matrix-free call per rank (rfnet_emd_cost_grad) on 32/N clouds, "
                       "then the all-reduce of the loss partial sums; max over ranks", "scaling": "strong", "clouds_total": 32}
         for en, iters in ((2048, 10), (16384, 3)):
-            stp, nb = emd_shard_step(D, en, 32, 40 + en)
-            ms_e = D.timed(stp, iters, warm=2)
-            cps = 32 / (ms_e * 1e-3)
-            c3["n%d" % en] = {"ms": ms_e, "clouds_per_s": cps, "clouds_per_gpu": nb, "launches": count_rfnet_launches(torch, stp),
-                              "frac_mufu_peak_per_gpu": cps / world * 30.0 * en * en / mufu_peak(sm_max)}
-            del stp
+            for flags, tag in ((0, ""), (4, "_split_sums")):
+                stp, nb = emd_shard_step(D, en, 32, 40 + en, flags)
+                ms_e = D.timed(stp, iters, warm=2)
+                cps = 32 / (ms_e * 1e-3)
+                c3["n%d%s" % (en, tag)] = {"ms": ms_e, "clouds_per_s": cps, "clouds_per_gpu": nb, "launches": count_rfnet_launches(torch, stp),
+                                           "frac_mufu_peak_per_gpu": cps / world * 30.0 * en * en / mufu_peak(sm_max)}
+                del stp
+        c3["modes"] = ("default: every sum one chain in the reference kernel's order (match within 1e-5 of the reference CUDA kernel, bit-identical with "
+                       "RFNET_EMD_EXACT); *_split_sums: RFNET_EMD_SPLIT_SUMS, each sum cut into pieces (more parallelism per cloud, different "
+                       "rounding order: up to 1e-3 of the largest match entry)")
         extra["config3_emd_fwd_grad_B32_total"] = c3
         # config 5: recon loss path, B=64 TOTAL
         stp, nb, _ = recon_shard_step(D, 16384, 64, 500)

@@ -37,6 +37,9 @@ const char *rfnet_error_string(int code);
  * direction 2.  d2 is evaluated as fma(dz,dz, fma(dx,dx, dy*dy)) -- the contraction of the reference's GPU binary --
  * unless RFNET_NN_UNFUSED is set in flags, which gives ((dx*dx)+(dy*dy))+(dz*dz) as in the reference's CPU build
  * (pc_distance/tf_nndistance.cpp:21-43).  workspace may be NULL when rfnet_nn_distance_workspace_bytes() returns 0.
+ * Non-finite coordinates: a query whose distances are all NaN reports (+inf, 0) -- the reference reports (NaN-free seed
+ * 1e38-style garbage / NaN depending on the build); three_nn ignores NaN distances exactly as the reference's strict '<'
+ * does.  Results are only specified for finite inputs.
  * ------------------------------------------------------------------------------------------------------------- */
 #define RFNET_NN_UNFUSED 1
 size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m);
@@ -74,6 +77,22 @@ int rfnet_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2
                        float *grad_xyz2, float *sums4, void *workspace, size_t workspace_bytes, int flags,
                        rfnet_stream_t stream);
 
+/* merge_layer of the reference's model (vv_recon.py:132-139, always called with knum = 1): every new point is pulled towards
+ * its nearest raw point,
+ *     out[j] = new[j] + exp(-d2 / (1e-8 + decfactor^2)) * (raw[nn(j)] - new[j]),     d2 = |raw[nn(j)] - new[j]|^2,
+ * nn(j) = NnDistance's idx2 for (raw, new).  The reference chains NnDistance (both directions), GroupPoint and five framework
+ * ops; this is ONE directed search and one epilogue.  decfactor is a DEVICE pointer to one float (a trained variable there).
+ * idx (b, n_new) is returned for the backward: rfnet_merge_layer_grad gives, for an upstream gradient grad_out (b, n_new, 3),
+ * grad_new (b, n_new, 3), the rows grad_raw_rows (b, n_new, 3) to be scatter-added into raw by idx (rfnet_scatteraddpoint or a
+ * scatter plan), and rfnet_merge_layer_grad_partials(b, n_new) partial sums of d out / d decfactor (add them up). */
+size_t rfnet_merge_layer_workspace_bytes(int b, int n_raw, int n_new);
+int rfnet_merge_layer(int b, int n_raw, const float *raw, int n_new, const float *newpts, const float *decfactor,
+                      float *out, int *idx, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
+size_t rfnet_merge_layer_grad_partials(int b, int n_new);
+int rfnet_merge_layer_grad(int b, int n_raw, const float *raw, int n_new, const float *newpts, const int *idx,
+                           const float *decfactor, const float *grad_out, float *grad_new, float *grad_raw_rows,
+                           float *dec_partial, rfnet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * approx_match / match_cost (EMD).  Replace approxmatchLauncher, matchcostLauncher, matchcostgradLauncher,
  * pc_distance/tf_approxmatch.cpp:141-143 (defined pc_distance/tf_approxmatch.cu:180-182,226-228,292-295).
@@ -90,7 +109,10 @@ int rfnet_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2
  *                              (<= 1.1e-6 relative per matrix entry).
  *   RFNET_EMD_EXACT            additionally the reference's non-flushing __expf, no pruning, every exponential of the final
  *                              pass through the MUFU: match is bit-identical to the reference CUDA binary's.
- *   RFNET_EMD_NO_PRUNE         dense sweeps at every level (A/B test of the exact pruning; identical results).
+ *   RFNET_EMD_PRUNE            run the three sharpest levels as exactly-pruned sweeps (Morton-ordered rows, per-cluster candidate
+ *                              masks; terms that the flushing exponential makes exactly 0 are skipped): identical results.
+ *                              Opt-in: on B200 it only pays for large batches of large clouds.
+ *   RFNET_EMD_NO_PRUNE         dense sweeps at every level (overrides RFNET_EMD_PRUNE).
  *   RFNET_EMD_SPLIT_SUMS       cut every sum into fixed-length pieces added in ascending order: more parallelism when the
  *                              call holds only one or two small clouds, at the price of a different rounding order (the
  *                              iteration is ill-conditioned: up to ~1e-3 of the largest entry).  Not combinable with EXACT.
@@ -98,6 +120,7 @@ int rfnet_chamfer_step(int b, int n, const float *xyz1, int m, const float *xyz2
 #define RFNET_EMD_EXACT 1
 #define RFNET_EMD_NO_PRUNE 2
 #define RFNET_EMD_SPLIT_SUMS 4
+#define RFNET_EMD_PRUNE 8
 size_t rfnet_approxmatch_workspace_bytes(int b, int n, int m);
 int rfnet_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, void *workspace,
                       size_t workspace_bytes, int flags, rfnet_stream_t stream);
@@ -158,6 +181,18 @@ size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, int m, int ns
 int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
+/* Scatter plans.  Every gradient of a gather (gather_point, group_point, three_interpolate) adds rows of an upstream gradient
+ * into the points they were gathered from.  The atomic-free path inverts the index tensor first; that inverse -- a "plan" --
+ * depends on idx only, so it can be built ONCE, off the critical path (e.g. at forward time), and shared by every gradient that
+ * goes through the same idx (the xyz and the feature grouping of one layer).  idx is read as (b, rows) targets in
+ * [0, n_targets): group_point: rows = m * nsample, n_targets = n; gather_point: rows = m; three_interpolate: rows = 3 n,
+ * n_targets = m.  The *_planned gradients equal rfnet_<op>_grad with a workspace bit for bit. */
+size_t rfnet_scatter_plan_bytes(int b, int n_targets, int rows);
+int rfnet_scatter_plan_build(int b, int n_targets, int rows, const int *idx, void *plan, size_t plan_bytes,
+                             rfnet_stream_t stream);
+int rfnet_group_point_grad_planned(int b, int n, int c, int m, int nsample, const float *grad_out, const void *plan,
+                                   size_t plan_bytes, float *grad_points, rfnet_stream_t stream);
+
 /* knn_point for 3-d points, k <= 32.  The reference has no kernel for it: tf_ops/grouping/tf_grouping.py:48-73 materialises
  * the (b, m, n) distance matrix with framework ops and calls tf.nn.top_k(-dist) on the CPU.  xyz1 = dataset (b,n,3),
  * xyz2 = queries (b,m,3); val (b,m,k) = NEGATED squared distances in descending order (i.e. nearest first), idx (b,m,k). */
@@ -199,6 +234,9 @@ size_t rfnet_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m);
 int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
                                  const float *weight, float *grad_points, void *workspace, size_t workspace_bytes,
                                  rfnet_stream_t stream);
+
+int rfnet_three_interpolate_grad_planned(int b, int n, int c, int m, const float *grad_out, const float *weight,
+                                         const void *plan, size_t plan_bytes, float *grad_points, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points: what a CPU-side caller (e.g. the reference's DEVICE_CPU OpKernels,

@@ -22,6 +22,10 @@ SIGNATURES = {
     "rfnet_chamfer_partial_sums": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "rfnet_chamfer_step_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_chamfer_step": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
+    "rfnet_merge_layer_workspace_bytes": (_z, [_i, _i, _i]),
+    "rfnet_merge_layer": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "rfnet_merge_layer_grad_partials": (_z, [_i, _i]),
+    "rfnet_merge_layer_grad": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rfnet_approxmatch_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_approxmatch": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _i, _p]),
     "rfnet_matchcost_workspace_bytes": (_z, [_i, _i, _i]),
@@ -42,6 +46,10 @@ SIGNATURES = {
     "rfnet_group_point": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_group_point_grad_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
     "rfnet_group_point_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "rfnet_scatter_plan_bytes": (_z, [_i, _i, _i]),
+    "rfnet_scatter_plan_build": (_i, [_i, _i, _i, _p, _p, _z, _p]),
+    "rfnet_group_point_grad_planned": (_i, [_i, _i, _i, _i, _i, _p, _p, _z, _p, _p]),
+    "rfnet_three_interpolate_grad_planned": (_i, [_i, _i, _i, _i, _p, _p, _p, _z, _p, _p]),
     "rfnet_knn_point": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "rfnet_selection_sort": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "rfnet_auction_match": (_i, [_i, _i, _p, _p, _p, _p, _p]),

@@ -66,10 +66,9 @@ __host__ __device__ inline float emd_level(int li) {  // li = 0..9  ->  j = 7..-
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Sweep plan: a function of the cloud sizes and the flags only (NOT of the batch size -- see the header).
-// B200 tuning (profiles/r1_emd_tune_*.txt, r2_emd_tune.txt): the sweep is MUFU-bound and wants ~40 resident warps per SM;
-// Q = 4 rows per thread with the candidate range cut into many short splits is the best or within 1 % of the best grid at
-// every batch size from 1 to 32 clouds, so no batch-dependent choice is needed.
+// Split plan (RFNET_EMD_SPLIT_SUMS only): a function of the cloud sizes, NOT of the batch size -- see the header.
+// B200 tuning (profiles/r2_emd_tune.txt): Q = 4 rows per thread with the candidate range cut into many short splits is the
+// best or within 1 % of the best grid at every batch size from 1 to 32 clouds, so no batch-dependent choice is needed.
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepPlan { int Q, nrt, nsplit, split_len; };
 static int emd_split_len(int nc) {
@@ -77,7 +76,6 @@ static int emd_split_len(int nc) {
     if ((nc + sl - 1) / sl > EMD_MAX_SPLITS) sl = (((nc + EMD_MAX_SPLITS - 1) / EMD_MAX_SPLITS) + 31) / 32 * 32;
     return sl;
 }
-// the split plan (RFNET_EMD_SPLIT_SUMS); without that flag every row sum is one chain and no plan is needed
 static SweepPlan emd_plan(int nr, int nc) {
     SweepPlan p;
     p.Q = nr >= EMD_THREADS * 4 ? 4 : 2;
@@ -90,28 +88,38 @@ static SweepPlan emd_plan(int nr, int nc) {
 // Workspace layout (floats), per call:
 //   remainL [b*n] remainR [b*m] ratioL [b*n] ratioR [b*m]                      running state of the current level
 //   facL [EMD_LEVELS][b*n]  facR [EMD_LEVELS][b*m]                             per-level factors for the final pass
-//   partial                                                                    sweep partial sums (two sets for the fused sweep)
+//   partial                                                                    sweep partial sums (split sums only; two sets for the fused sweep)
+//   pairA1/pairZ1, pairA2/pairZ2                                               the clouds as candidate PAIRS (see emd_row_kernel)
+//   perm1, perm2, maskA, maskB                                                 Morton orders + candidate masks of the pruned levels
+constexpr int EMD_PRUNE_LEVELS = 3;          // levels the masks are built for (layout of the mask words)
+constexpr int EMD_PRUNED_SWEEP_LEVELS = 2;   // levels that run as pruned sweeps
+constexpr int EMD_CLUSTER = 32;         // rows of one warp of the row kernel: one per lane
 struct EmdWs {
     float *remainL, *remainR, *ratioL, *ratioR, *facL, *facR, *partial;
+    float4 *pairA1, *pairA2;     // (x0, x1, y0, y1) of candidates 2i, 2i+1
+    float2 *pairZ1, *pairZ2;     // (z0, z1)
     int *perm1, *perm2;          // Morton order of xyz1 / xyz2 (pruned sweeps only)
     unsigned *maskA, *maskB;     // candidate masks: rows = xyz1 clusters vs xyz2 candidates (passes 1, 3) / the reverse (pass 2)
 };
-// pruned sweeps pay off (and their sort fits shared memory) for clouds of 4096 .. 32768 points
-static bool emd_prune_enabled(int n, int m) { return n >= 4096 && m >= 4096 && n <= 32768 && m <= 32768; }
-static size_t emd_mask_words(int b, int nr, int nc) { return (size_t)b * ((nr + 127) / 128) * 3 * ((nc + 31) / 32); }
+// exact pruning pays off from about a thousand points per cloud; the Morton sort handles up to 32768
+static bool emd_prune_enabled(int n, int m) { return n >= 1024 && m >= 1024 && n <= MORTON_SORT_MAX && m <= MORTON_SORT_MAX; }
+static size_t emd_mask_words(int b, int nr, int nc) { return (size_t)b * ((nr + EMD_CLUSTER - 1) / EMD_CLUSTER) * EMD_PRUNE_LEVELS * ((nc + 31) / 32); }
+static int emd_npad(int n) { return (((n + 1) / 2) + 1) & ~1; }   // candidate pairs per cloud, padded to an even count (16-byte rows of float2)
 static size_t emd_partial_floats(int b, int n, int m) {
     const size_t rows1 = 2 * (size_t)n * emd_plan(n, m).nsplit;   // rows = xyz1: the fused sweep keeps two sums per row
     const size_t rows2 = (size_t)m * emd_plan(m, n).nsplit;
-    return (size_t)b * (rows1 > rows2 ? rows1 : rows2);
+    return ((size_t)b * (rows1 > rows2 ? rows1 : rows2) + 3) & ~(size_t)3;
 }
 static size_t emd_ws_floats(int b, int n, int m) {
-    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    const size_t bn = (((size_t)b * n) + 3) & ~(size_t)3, bm = (((size_t)b * m) + 3) & ~(size_t)3;
     size_t f = 2 * (bn + bm) + (size_t)EMD_LEVELS * (bn + bm) + emd_partial_floats(b, n, m);
+    f += 6 * (size_t)b * (emd_npad(n) + emd_npad(m));
     if (emd_prune_enabled(n, m)) f += bn + bm + emd_mask_words(b, n, m) + emd_mask_words(b, m, n);
     return (f + 3) & ~(size_t)3;
 }
 static EmdWs emd_carve(float* w, int b, int n, int m) {
-    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
+    // every block starts on a 16-byte boundary (the workspace itself must be 16-byte aligned: cudaMalloc / torch give 256+)
+    const size_t bn = (((size_t)b * n) + 3) & ~(size_t)3, bm = (((size_t)b * m) + 3) & ~(size_t)3;
     EmdWs s;
     s.remainL = w; w += bn;
     s.remainR = w; w += bm;
@@ -120,6 +128,10 @@ static EmdWs emd_carve(float* w, int b, int n, int m) {
     s.facL = w; w += EMD_LEVELS * bn;
     s.facR = w; w += EMD_LEVELS * bm;
     s.partial = w; w += emd_partial_floats(b, n, m);
+    s.pairA1 = reinterpret_cast<float4*>(w); w += 4 * (size_t)b * emd_npad(n);
+    s.pairA2 = reinterpret_cast<float4*>(w); w += 4 * (size_t)b * emd_npad(m);
+    s.pairZ1 = reinterpret_cast<float2*>(w); w += 2 * (size_t)b * emd_npad(n);
+    s.pairZ2 = reinterpret_cast<float2*>(w); w += 2 * (size_t)b * emd_npad(m);
     s.perm1 = reinterpret_cast<int*>(w); w += bn;
     s.perm2 = reinterpret_cast<int*>(w); w += bm;
     s.maskA = reinterpret_cast<unsigned*>(w); w += emd_mask_words(b, n, m);
@@ -132,7 +144,7 @@ __device__ __forceinline__ float emd_ex2(float x) { return EXACT ? ex2_approx_fu
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weighted exp-sum sweep:  sum[cloud][row] = init + sum_{c ascending} ex2(lvl2 * d2(row, c)) * w[c]
-//   rows: (b, nr, 3), cands: (b, nc, 3), w: (b, nc).  grid.x = b * nrt * nsplit.  Q rows per thread (Q/2 packed pairs).
+//   rows: (b, nr, 3), cands: (b, nc, 3), w: (b, nc).
 // The accumulation is the reference binary's, term by term and in candidate order:
 //   MODE 1 (pass 1, tf_approxmatch.cu:26-59):   acc = fma(e, w[c], acc), acc starts at 1e-9     -> ratioL = remainL / acc
 //   MODE 2 (pass 2, :75-108):                   acc = fma(e, w[c], acc)                          -> consumption, ratioR, remainR
@@ -141,18 +153,17 @@ __device__ __forceinline__ float emd_ex2(float x) { return EXACT ? ex2_approx_fu
 //            pair, two exponentials, two chains; the rule of pass 3 is applied first, then pass 1's on the updated remainL.
 // UNIT: the last level (j = -2) has level = 0, i.e. e = ex2(0 * d2) = 1 for every pair; the same chain is run without
 // distances or exponentials.  In MODE 4 UNIT refers to the next level (the fused pair j = -1, -2).
-// With nsplit == 1 the thread owns the complete sum of its rows and applies the rule itself; with splits the partial sums
-// are reduced in split order by emd_epi_kernel.  (Fusing the split case too, through a last-CTA ticket, was measured slower.)
-// PRUNED (Q = 4, MODE 1..3): see below.
 // ---------------------------------------------------------------------------------------------------------------
 struct SweepArgs {
-    int nr, nc, nrt, nsplit, split_len, nwords;
+    int nr, nc, nrt, nsplit, split_len, nwords, npad, tma;
     float lvl2, lvl2b, init0;
     const float *rows, *cands, *w, *wb, *rowfac;
-    float *partial, *partial_b;
+    const float4* pairA;           // row kernel: the candidates as pairs, (b, npad)
+    const float2* pairZ;
+    float *partial, *partial_b;    // split sums
     float *remain, *ratio, *fac;   // MODE 1, 3, 4: remainL / ratioL / facL[level (MODE 4: next level)]   MODE 2: remainR / ratioR / facR[level]
-    const int* perm;               // PRUNED: Morton order of the rows
-    const unsigned* mask;          // PRUNED: the level's candidate-mask words of cluster 0 of cloud 0
+    const int* perm;               // pruned: Morton order of the rows
+    const unsigned* mask;          // pruned: the level's candidate-mask words of cluster 0 of cloud 0
 };
 template <int MODE>
 __device__ __forceinline__ void emd_apply(float* __restrict__ remain, float* __restrict__ ratio, float* __restrict__ fac, size_t idx, float sum, float sumb) {
@@ -180,16 +191,28 @@ __device__ __forceinline__ void emd_apply(float* __restrict__ remain, float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Exact pruning of the three sharpest levels (j = 7, 6, 5: e = exp(-4^j d2) with 4^j = 16384, 4096, 1024).
+// emd_row_kernel -- the default sweep: ONE ROW PER THREAD, candidates taken two at a time as the packed pair.
+// Every row sum is a single sequential chain over all candidates in ascending order -- the reference thread's chain,
+// acc = fma(e_l, w_l, acc) for l = 0, 1, 2, ... -- so results carry the reference's rounding order whatever the batch
+// size, and (rows being independent) do not depend on how rows are spread over threads, CTAs or GPUs.
+// FP32 cost per pair-pass equals the row-packed kernel's (7 packed issues + 2 scalar FFMA per two candidates against 8
+// packed issues per two rows), with four times as many threads for the same rows: 4 clouds of 16384 points already give
+// every SM 14 warps.
+// Candidates come pre-paired from emd_pairs_kernel -- (x0, x1, y0, y1), (z0, z1) per pair, written once per call -- and are
+// staged chunk by chunk in shared memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier, double buffered) together
+// with the weight pairs: no thread spends an instruction on staging and the next chunk lands while this one is consumed.
+// (Clouds whose size is not a multiple of 4 take plain loads: the weight rows are then not 16-byte aligned.)
+//
+// PRUNED: exact pruning of the three sharpest levels (j = 7, 6, 5: e = exp(-4^j d2) with 4^j = 16384, 4096, 1024).
 // ex2.approx.ftz returns EXACTLY 0 once its argument is below -126, i.e. for d2 > 0.0053 / 0.021 / 0.085, and a zero term
 // leaves the accumulator bit-identical (fma(0, w, acc) == acc).  At those levels almost every pair is such a no-op, so:
 //   * morton_sort_kernel orders each cloud along a Morton curve (one CTA per cloud, counting sort in shared memory);
-//     a warp of the pruned sweep then owns 128 CONSECUTIVE points of that order: a spatially tight cluster;
+//     a warp then owns 32 CONSECUTIVE points of that order: a spatially tight cluster;
 //   * emd_mask_kernel marks, per cluster and level, the candidates whose distance to the cluster's bounding box still
 //     allows a non-zero term;
-//   * the PRUNED sweep is the dense one restricted to marked candidates, visited in ASCENDING candidate order:
-//     every row sum goes through the same sequence of non-trivial fma's as in the dense sweep, so the result is bit-for-bit
-//     the dense one (tests/test_emd_gpu.py::test_pruned_sweeps_are_exact) -- only the row -> thread assignment changes.
+//   * the warp visits only candidate pairs with a marked member, in ASCENDING order: every row sum goes through the same
+//     sequence of non-trivial fma's as in the dense sweep, so the result is bit-for-bit the dense one
+//     (tests/test_emd_gpu.py::test_pruned_sweeps_are_exact) -- only the row -> thread assignment changes.
 // The masks depend on the points only: built once per call for both roles (rows = xyz1 / rows = xyz2), used by 9 sweeps.
 //
 // Margin.  A candidate is dropped when lvl2 * dbox2 <= EMD_PRUNE_ARG = -130, where dbox2 is the squared distance from the
@@ -199,18 +222,300 @@ __device__ __forceinline__ void emd_apply(float* __restrict__ remain, float* __r
 // 1e-4 in the argument of the exponential.  The sweep's own argument for that pair is therefore below -130 + 1e-4 < -126,
 // where ex2.approx.ftz is exactly 0: a margin of 4 units covers the rounding by four orders of magnitude.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int EMD_PRUNE_LEVELS = 3;
-constexpr int EMD_CLUSTER = 128;        // rows of one warp of the pruned sweep (4 per lane)
 constexpr float EMD_PRUNE_ARG = -130.0f;
+constexpr int ROW_CP = 128;         // candidate pairs per staged chunk
+#ifndef EMD_ROW_UNROLL_VALUE
+#define EMD_ROW_UNROLL_VALUE 8
+#endif
+constexpr int EMD_ROW_UNROLL = EMD_ROW_UNROLL_VALUE;   // candidate pairs per unrolled step (tools/emd_tune.cu)
 
-template <int Q, int MODE, bool UNIT, bool PRUNED, bool EXACT, int NT = EMD_THREADS>
-__global__ void __launch_bounds__(NT) emd_sweep_kernel(const __grid_constant__ SweepArgs a) {
+template <int MODE, bool UNIT, bool EXACT, int NT>
+__global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ SweepArgs a) {
     constexpr bool P3 = MODE == 3 || MODE == 4;
     constexpr bool DUAL = MODE == 4;
-    static_assert(!PRUNED || (Q == 4 && !DUAL && !UNIT && !EXACT), "pruned sweeps: Q = 4, single level, ftz exponential");
+    constexpr bool COORDS = !UNIT || DUAL;      // a unit-level single sweep needs the weights only
+    __shared__ __align__(128) float4 sA[2][ROW_CP];
+    __shared__ __align__(16) float2 sZ[2][ROW_CP];
+    __shared__ __align__(16) float2 sW[2][ROW_CP];
+    __shared__ __align__(16) float2 sV[DUAL ? 2 : 1][DUAL ? ROW_CP : 2];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x % a.nrt;
+    const int cloud = blockIdx.x / a.nrt;
+    const int nr = a.nr, nc = a.nc;
+    const float* __restrict__ wbase = a.w + (size_t)cloud * nc;
+    const float* __restrict__ vbase = DUAL ? a.wb + (size_t)cloud * nc : nullptr;
+    const float4* __restrict__ Abase = a.pairA + (size_t)cloud * a.npad;
+    const float2* __restrict__ Zbase = a.pairZ + (size_t)cloud * a.npad;
+    const int pos = tile * NT + tid;
+    const bool valid = pos < nr;
+    const int row = valid ? pos : 0;
+    const size_t ridx = (size_t)cloud * nr + row;
+    // the row NEGATED in both halves: (cand + (-row)) == cand - row exactly
+    const float* rp = a.rows + ridx * 3;
+    const float2 RX = make_float2(-rp[0], -rp[0]), RY = make_float2(-rp[1], -rp[1]), RZ = make_float2(-rp[2], -rp[2]);
+    float rfs = 1.f;
+    if (P3) rfs = a.rowfac[ridx];
+    const float2 RF = make_float2(rfs, rfs);
+    const float2 L2 = make_float2(a.lvl2, a.lvl2), L2B = make_float2(a.lvl2b, a.lvl2b);
+    float acc = a.init0, accb = 1e-9f;   // pass 1 (also the fused one of the next level) starts at 1e-9 (tf_approxmatch.cu:36)
+
+    const int npairs = (nc + 1) / 2;
+    const int nchunks = (npairs + ROW_CP - 1) / ROW_CP;
+    const bool tma = a.tma != 0;
+    if (tma) {
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    auto issue = [&](int ci) {   // thread 0 only: start the bulk copies of chunk ci (nc % 4 == 0: every size is a multiple of 16 bytes)
+        const int p0 = ci * ROW_CP;
+        const unsigned cp = (unsigned)min(ROW_CP, npairs - p0);
+        const int bf = ci & 1;
+        mbar_expect_tx(&bar[bf], cp * ((COORDS ? 24u : 0u) + 8u + (DUAL ? 8u : 0u)));
+        if (COORDS) {
+            tma_bulk_g2s(sA[bf], Abase + p0, cp * 16u, &bar[bf]);
+            tma_bulk_g2s(sZ[bf], Zbase + p0, cp * 8u, &bar[bf]);
+        }
+        tma_bulk_g2s(sW[bf], wbase + 2 * p0, cp * 8u, &bar[bf]);
+        if (DUAL) tma_bulk_g2s(sV[bf], vbase + 2 * p0, cp * 8u, &bar[bf]);
+    };
+    if (tma && tid == 0) issue(0);
+
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int p0 = ci * ROW_CP;
+        const int cp = min(ROW_CP, npairs - p0);
+        const int bf = tma ? (ci & 1) : 0;
+        if (tma) {
+            if (tid == 0 && ci + 1 < nchunks) issue(ci + 1);   // the other buffer was released by the barrier that ended chunk ci - 1
+            mbar_wait(&bar[bf], (ci >> 1) & 1);
+        } else {
+            for (int i = tid; i < cp; i += NT) {
+                const int ca = 2 * (p0 + i), cb = ca + 1;
+                if (COORDS) { sA[0][i] = Abase[p0 + i]; sZ[0][i] = Zbase[p0 + i]; }
+                // a phantom second member of the last pair (odd nc) carries weight 0: fma(e, 0, acc) == acc
+                sW[0][i] = make_float2(wbase[ca], cb < nc ? wbase[cb] : 0.f);
+                if (DUAL) sV[0][i] = make_float2(vbase[ca], cb < nc ? vbase[cb] : 0.f);
+            }
+            __syncthreads();
+        }
+        // (A hand-made software pipeline -- exponentials of group g + 1 issued before the fma chain of group g -- was measured
+        // 25 % SLOWER than letting ptxas schedule the unrolled loop: the register copies and clamps cost more than the stalls.)
+        auto step = [&](int i) {
+            const float2 w = sW[bf][i];
+            if (UNIT && !DUAL) {
+                // e == 1: fma(1, w, acc) == acc + w and fma(rf * 1, w, acc) == fma(rf, w, acc), bit for bit
+                if (P3) { acc = __fmaf_rn(rfs, w.x, acc); acc = __fmaf_rn(rfs, w.y, acc); }
+                else { acc = __fadd_rn(acc, w.x); acc = __fadd_rn(acc, w.y); }
+            } else {
+                const float4 A = sA[bf][i];
+                const float2 Z = sZ[bf][i];
+                const float2 dx = __fadd2_rn(make_float2(A.x, A.y), RX);
+                const float2 dy = __fadd2_rn(make_float2(A.z, A.w), RY);
+                const float2 dz = __fadd2_rn(Z, RZ);
+                const float2 d2 = sqdist3x2<true>(dx, dy, dz);
+                const float2 x = __fmul2_rn(d2, L2);
+                float2 e = make_float2(emd_ex2<EXACT>(x.x), emd_ex2<EXACT>(x.y));
+                if (P3) e = __fmul2_rn(RF, e);
+                acc = __fmaf_rn(e.x, w.x, acc);
+                acc = __fmaf_rn(e.y, w.y, acc);
+                if (DUAL) {
+                    const float2 v = sV[bf][i];
+                    if (UNIT) {
+                        accb = __fadd_rn(accb, v.x);
+                        accb = __fadd_rn(accb, v.y);
+                    } else {
+                        const float2 xb = __fmul2_rn(d2, L2B);
+                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.x), v.x, accb);
+                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.y), v.y, accb);
+                    }
+                }
+            }
+        };
+        {
+            EMD_PRAGMA_UNROLL(EMD_ROW_UNROLL)
+            for (int i = 0; i < cp; ++i) step(i);
+        }
+        __syncthreads();   // everyone is done with this buffer before it is refilled
+    }
+    if (valid) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx, acc, accb);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// emd_pruned_kernel -- the same chain restricted to the candidate pairs that can contribute at a sharp level (RFNET_EMD_PRUNE).
+// A warp owns one 32-row Morton cluster.  It walks the cluster's candidate mask 32 words at a time, COMPACTS the indices of
+// the pairs with a marked member into a per-warp list (ascending), and every 32 listed pairs: each lane gathers one pair
+// (coordinates + weights, three small loads, all in flight together) into a per-warp shared-memory tile, then the warp runs
+// the dense, unrolled chain loop over the tile.  Work and traffic are proportional to the surviving pairs, the inner loop has
+// the dense kernel's instruction-level parallelism, and there is no block-wide barrier.  (The first pruned variant staged
+// every candidate and visited marked pairs one by one: it took as long as a dense sweep -- profiles/r2_emd_launches_*.csv.)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PG_WARPS = 4;
+template <int MODE>
+__global__ void __launch_bounds__(PG_WARPS * 32) emd_pruned_kernel(const __grid_constant__ SweepArgs a) {
+    constexpr bool P3 = MODE == 3;
+    static_assert(MODE >= 1 && MODE <= 3, "one sharp level per pruned sweep");
+    __shared__ int sList[PG_WARPS][64];
+    __shared__ __align__(16) float4 sA[PG_WARPS][32];
+    __shared__ __align__(8) float2 sZ[PG_WARPS][32];
+    __shared__ __align__(8) float2 sW[PG_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nr = a.nr, nc = a.nc;
+    const int nclusters = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
+    const int cpc = (nclusters + PG_WARPS - 1) / PG_WARPS;        // CTAs per cloud
+    const int cloud = blockIdx.x / cpc;
+    const int cluster = (blockIdx.x % cpc) * PG_WARPS + warp;
+    if (cluster >= nclusters) return;                              // warp-uniform; no block barrier below
+    const int pos = cluster * EMD_CLUSTER + lane;
+    const bool valid = pos < nr;
+    const int row = a.perm[(size_t)cloud * nr + (valid ? pos : cluster * EMD_CLUSTER)];
+    const size_t ridx = (size_t)cloud * nr + row;
+    const float* rp = a.rows + ridx * 3;
+    const float2 RX = make_float2(-rp[0], -rp[0]), RY = make_float2(-rp[1], -rp[1]), RZ = make_float2(-rp[2], -rp[2]);
+    float rfs = 1.f;
+    if (P3) rfs = a.rowfac[ridx];
+    const float2 RF = make_float2(rfs, rfs);
+    const float2 L2 = make_float2(a.lvl2, a.lvl2);
+    float acc = a.init0;
+    const float* __restrict__ wbase = a.w + (size_t)cloud * nc;
+    const float4* __restrict__ Abase = a.pairA + (size_t)cloud * a.npad;
+    const float2* __restrict__ Zbase = a.pairZ + (size_t)cloud * a.npad;
+    const unsigned* __restrict__ mrow = a.mask + ((size_t)cloud * nclusters + cluster) * EMD_PRUNE_LEVELS * a.nwords;
+    int* list = sList[warp];
+
+    auto flush = [&](int cnt) {   // gather the first cnt (<= 32) listed pairs, then chain them in order
+        if (lane < cnt) {
+            const int i = list[lane];
+            sA[warp][lane] = __ldg(Abase + i);
+            sZ[warp][lane] = __ldg(Zbase + i);
+            const int ca = 2 * i, cb = ca + 1;
+            sW[warp][lane] = make_float2(__ldg(wbase + ca), cb < nc ? __ldg(wbase + cb) : 0.f);   // a phantom member carries weight 0
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const float4 A = sA[warp][k];
+            const float2 Z = sZ[warp][k], w = sW[warp][k];
+            const float2 dx = __fadd2_rn(make_float2(A.x, A.y), RX);
+            const float2 dy = __fadd2_rn(make_float2(A.z, A.w), RY);
+            const float2 dz = __fadd2_rn(Z, RZ);
+            const float2 x = __fmul2_rn(sqdist3x2<true>(dx, dy, dz), L2);
+            float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));   // the unmarked member of a listed pair gives an exact 0
+            if (P3) e = __fmul2_rn(RF, e);
+            acc = __fmaf_rn(e.x, w.x, acc);
+            acc = __fmaf_rn(e.y, w.y, acc);
+        }
+        __syncwarp();
+    };
+
+    int count = 0;   // listed, not yet processed (warp-uniform, < 32 between words)
+    for (int w0 = 0; w0 < a.nwords; w0 += 32) {
+        const unsigned myword = (w0 + lane < a.nwords) ? mrow[w0 + lane] : 0u;
+        unsigned nonzero = __ballot_sync(0xffffffffu, myword != 0u);
+        while (nonzero) {
+            const int wl = __ffs(nonzero) - 1;
+            nonzero &= nonzero - 1;
+            const unsigned bits = __shfl_sync(0xffffffffu, myword, wl);
+            const unsigned pm = (bits | (bits >> 1)) & 0x55555555u;      // bit 2j set: pair j of this word has a marked member
+            if (lane < 16 && ((pm >> (2 * lane)) & 1u))
+                list[count + __popc(pm & ((1u << (2 * lane)) - 1u))] = (w0 + wl) * 16 + lane;
+            count += __popc(pm);
+            __syncwarp();
+            if (count >= 32) {
+                flush(32);
+                const int rest = count - 32;                              // <= 15
+                const int v = lane < rest ? list[32 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) list[lane] = v;
+                __syncwarp();
+                count = rest;
+            }
+        }
+    }
+    if (count > 0) flush(count);
+    if (valid) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx, acc, 0.f);
+}
+
+// The clouds as candidate pairs, written once per call: A[i] = (x0, x1, y0, y1), Z[i] = (z0, z1) of candidates 2i, 2i+1;
+// entries past the cloud's end are zero (finite coordinates; their weights are zero or never read).
+__global__ void emd_pairs_kernel(int n, int npad, const float* __restrict__ xyz, float4* __restrict__ A, float2* __restrict__ Z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    const size_t cloud = blockIdx.y;
+    const float* __restrict__ p = xyz + cloud * (size_t)n * 3;
+    const int ca = 2 * i, cb = 2 * i + 1;
+    float x0 = 0.f, y0 = 0.f, z0 = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (ca < n) { x0 = p[ca * 3]; y0 = p[ca * 3 + 1]; z0 = p[ca * 3 + 2]; }
+    if (cb < n) { x1 = p[cb * 3]; y1 = p[cb * 3 + 1]; z1 = p[cb * 3 + 2]; }
+    A[cloud * npad + i] = make_float4(x0, x1, y0, y1);
+    Z[cloud * npad + i] = make_float2(z0, z1);
+}
+
+// grid = (32-row clusters, clouds), 256 threads.  mask[((cloud * nclusters + cluster) * 3 + lev) * nwords + word]
+__global__ void __launch_bounds__(256) emd_mask_kernel(int nr, int nc, int nwords, const float* __restrict__ rows, const int* __restrict__ perm,
+                                                       const float* __restrict__ cands, float l0, float l1, float l2, unsigned* __restrict__ mask) {
+    __shared__ float box[6];
+    const int cloud = blockIdx.y, cluster = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float inf = __int_as_float(0x7f800000);
+    if (tid < 32) {   // bounding box of the cluster's (up to) 32 rows: one warp
+        float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+        const int s = cluster * EMD_CLUSTER + tid;
+        if (s < nr) {
+            const float* p = rows + ((size_t)cloud * nr + perm[(size_t)cloud * nr + s]) * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) lo[a] = hi[a] = p[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+            if (tid == 0) { box[a] = lo[a]; box[3 + a] = hi[a]; }
+        }
+    }
+    __syncthreads();
+    const float lo0 = box[0], lo1 = box[1], lo2 = box[2], hi0 = box[3], hi1 = box[4], hi2 = box[5];
+    unsigned* __restrict__ out = mask + ((size_t)cloud * gridDim.x + cluster) * EMD_PRUNE_LEVELS * nwords;
+    const float* __restrict__ cb = cands + (size_t)cloud * nc * 3;
+    for (int c = tid; c < nwords * 32; c += 256) {
+        float d2 = inf;
+        if (c < nc) {
+            const float vx = cb[(size_t)c * 3], vy = cb[(size_t)c * 3 + 1], vz = cb[(size_t)c * 3 + 2];
+            const float dx = fmaxf(fmaxf(lo0 - vx, vx - hi0), 0.f), dy = fmaxf(fmaxf(lo1 - vy, vy - hi1), 0.f), dz = fmaxf(fmaxf(lo2 - vz, vz - hi2), 0.f);
+            d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // distance to the box
+        }
+        const bool valid = c < nc;
+        const unsigned w0 = __ballot_sync(0xffffffffu, valid && l0 * d2 > EMD_PRUNE_ARG);
+        const unsigned w1 = __ballot_sync(0xffffffffu, valid && l1 * d2 > EMD_PRUNE_ARG);
+        const unsigned w2 = __ballot_sync(0xffffffffu, valid && l2 * d2 > EMD_PRUNE_ARG);
+        if (lane == 0) {
+            out[c >> 5] = w0;
+            out[nwords + (c >> 5)] = w1;
+            out[2 * nwords + (c >> 5)] = w2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// emd_sweep_kernel -- the split-sum variant (RFNET_EMD_SPLIT_SUMS): Q rows per thread as packed pairs, the candidate range
+// of a sum cut into `nsplit` pieces handled by different CTAs (grid.x = b * nrt * nsplit); partial sums go to a small buffer
+// and emd_epi_kernel adds them in split order and applies the pass's rule -- deterministic, no atomics, but a different
+// rounding order than the reference's single chain.  Worth it only when a call holds one or two small clouds.
+// (Fusing the epilogue through a last-CTA ticket was measured slower.)
+// ---------------------------------------------------------------------------------------------------------------
+template <int Q, int MODE, bool UNIT>
+__global__ void __launch_bounds__(EMD_THREADS) emd_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    constexpr bool P3 = MODE == 3 || MODE == 4;
+    constexpr bool DUAL = MODE == 4;
     __shared__ __align__(16) float4 sC[EMD_TC];
     __shared__ float sB[DUAL ? EMD_TC : 1];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int bid = blockIdx.x;
     const int split = bid % a.nsplit;
     const int tile = (bid / a.nsplit) % a.nrt;
@@ -220,23 +525,10 @@ __global__ void __launch_bounds__(NT) emd_sweep_kernel(const __grid_constant__ S
     const float* __restrict__ cbase = a.cands + (size_t)cloud * nc * 3;
     const float* __restrict__ wbase = a.w + (size_t)cloud * nc;
     const float* __restrict__ wbbase = DUAL ? a.wb + (size_t)cloud * nc : nullptr;
-
-    // rows of this thread: dense = tile-strided; pruned = the warp's cluster of 128 consecutive Morton positions, 32 per q
     int row[Q];
-    const unsigned* __restrict__ mrow = nullptr;
-    if (PRUNED) {
-        const int nclusters = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
-        const int cluster = tile * (NT * Q / EMD_CLUSTER) + warp;
-        const int* __restrict__ pbase = a.perm + (size_t)cloud * nr;
-        const int s0 = cluster * EMD_CLUSTER + lane;
+    const int r0 = tile * (EMD_THREADS * Q) + tid;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) row[q] = (s0 + 32 * q) < nr ? pbase[s0 + 32 * q] : -1;
-        mrow = a.mask + ((size_t)cloud * nclusters + min(cluster, nclusters - 1)) * EMD_PRUNE_LEVELS * a.nwords;
-    } else {
-        const int r0 = tile * (NT * Q) + tid;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) row[q] = (r0 + q * NT) < nr ? r0 + q * NT : -1;
-    }
+    for (int q = 0; q < Q; ++q) row[q] = (r0 + q * EMD_THREADS) < nr ? r0 + q * EMD_THREADS : -1;
     float2 rx[Q / 2], ry[Q / 2], rz[Q / 2], rf[Q / 2], acc[Q / 2], accb[Q / 2];
     const float a0 = split == 0 ? a.init0 : 0.0f;
     const float b0 = split == 0 ? 1e-9f : 0.0f;   // pass 1 of the next level starts at 1e-9 (tf_approxmatch.cu:36)
@@ -256,44 +548,12 @@ __global__ void __launch_bounds__(NT) emd_sweep_kernel(const __grid_constant__ S
         accb[h] = make_float2(b0, b0);
     }
     const float2 L2 = make_float2(a.lvl2, a.lvl2), L2B = make_float2(a.lvl2b, a.lvl2b);
-
-    auto step = [&](int k) {
-        const float4 c = sC[k];
-        const float2 cw = make_float2(c.w, c.w);
-        float2 cwb = make_float2(0.f, 0.f);
-        if (DUAL) { const float t = sB[k]; cwb = make_float2(t, t); }
-#pragma unroll
-        for (int h = 0; h < Q / 2; ++h) {
-            if (UNIT && !DUAL) {
-                // e == 1: fma(1, w, acc) == acc + w and fma(rf * 1, w, acc) == fma(rf, w, acc), bit for bit
-                acc[h] = P3 ? __ffma2_rn(rf[h], cw, acc[h]) : __fadd2_rn(acc[h], cw);
-            } else {
-                const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // the sign of the difference is irrelevant after squaring
-                const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
-                const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
-                const float2 d2 = sqdist3x2<true>(dx, dy, dz);
-                const float2 x = __fmul2_rn(d2, L2);
-                float2 e = make_float2(emd_ex2<EXACT>(x.x), emd_ex2<EXACT>(x.y));
-                if (P3) e = __fmul2_rn(rf[h], e);
-                acc[h] = __ffma2_rn(e, cw, acc[h]);
-                if (DUAL) {
-                    if (UNIT) {
-                        accb[h] = __fadd2_rn(accb[h], cwb);
-                    } else {
-                        const float2 xb = __fmul2_rn(d2, L2B);
-                        accb[h] = __ffma2_rn(make_float2(emd_ex2<EXACT>(xb.x), emd_ex2<EXACT>(xb.y)), cwb, accb[h]);
-                    }
-                }
-            }
-        }
-    };
-
     const int c_begin = split * a.split_len;
     const int c_end = min(nc, c_begin + a.split_len);
     for (int c0 = c_begin; c0 < c_end; c0 += EMD_TC) {
         const int len = min(EMD_TC, c_end - c0);
         __syncthreads();
-        for (int i = tid; i < EMD_TC; i += NT) {
+        for (int i = tid; i < EMD_TC; i += EMD_THREADS) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padded candidates carry weight 0: fma(e, 0, acc) == acc
             float vb = 0.f;
             if (i < len) {
@@ -304,27 +564,37 @@ __global__ void __launch_bounds__(NT) emd_sweep_kernel(const __grid_constant__ S
             sC[i] = v;
             if (DUAL) sB[i] = vb;
         }
-        if (PRUNED) {
-            // this warp's mask words for the chunk (c0 is a multiple of 32): lane i holds word i
-            const int wi0 = c0 >> 5;
-            const unsigned myword = (lane < EMD_TC / 32 && wi0 + lane < a.nwords) ? mrow[wi0 + lane] : 0u;
-            __syncthreads();
-#pragma unroll 1
-            for (int wi = 0; wi < EMD_TC / 32; ++wi) {
-                unsigned bits = __shfl_sync(0xffffffffu, myword, wi);
-                if (wi * 32 >= len) bits = 0u;
-                else if (len - wi * 32 < 32) bits &= (1u << (len - wi * 32)) - 1u;   // candidates past the split's end belong to the next split
-                while (bits) {
-                    const int k = wi * 32 + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    step(k);
+        __syncthreads();
+        const int len2 = (len + EMD_UNROLL - 1) / EMD_UNROLL * EMD_UNROLL;  // padded entries carry weight 0 (EMD_TC % EMD_UNROLL == 0)
+        EMD_PRAGMA_UNROLL(EMD_UNROLL)
+        for (int k = 0; k < len2; ++k) {
+            const float4 c = sC[k];
+            const float2 cw = make_float2(c.w, c.w);
+            float2 cwb = make_float2(0.f, 0.f);
+            if (DUAL) { const float t = sB[k]; cwb = make_float2(t, t); }
+#pragma unroll
+            for (int h = 0; h < Q / 2; ++h) {
+                if (UNIT && !DUAL) {
+                    acc[h] = P3 ? __ffma2_rn(rf[h], cw, acc[h]) : __fadd2_rn(acc[h], cw);
+                } else {
+                    const float2 dx = __fadd2_rn(rx[h], make_float2(c.x, c.x));  // the sign of the difference is irrelevant after squaring
+                    const float2 dy = __fadd2_rn(ry[h], make_float2(c.y, c.y));
+                    const float2 dz = __fadd2_rn(rz[h], make_float2(c.z, c.z));
+                    const float2 d2 = sqdist3x2<true>(dx, dy, dz);
+                    const float2 x = __fmul2_rn(d2, L2);
+                    float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+                    if (P3) e = __fmul2_rn(rf[h], e);
+                    acc[h] = __ffma2_rn(e, cw, acc[h]);
+                    if (DUAL) {
+                        if (UNIT) {
+                            accb[h] = __fadd2_rn(accb[h], cwb);
+                        } else {
+                            const float2 xb = __fmul2_rn(d2, L2B);
+                            accb[h] = __ffma2_rn(make_float2(ex2_approx(xb.x), ex2_approx(xb.y)), cwb, accb[h]);
+                        }
+                    }
                 }
             }
-        } else {
-            __syncthreads();
-            const int len2 = (len + EMD_UNROLL - 1) / EMD_UNROLL * EMD_UNROLL;  // padded entries carry weight 0 (EMD_TC % EMD_UNROLL == 0)
-            EMD_PRAGMA_UNROLL(EMD_UNROLL)
-            for (int k = 0; k < len2; ++k) step(k);
         }
     }
     if (a.nsplit == 1) {   // complete sums: apply the pass's rule here
@@ -343,150 +613,7 @@ __global__ void __launch_bounds__(NT) emd_sweep_kernel(const __grid_constant__ S
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// The same sweep with ONE ROW PER THREAD and the candidates taken two at a time as the packed pair: the default kernel.
-// Every row sum is a single sequential chain over all candidates in ascending order -- the reference thread's chain,
-// acc = fma(e_l, w_l, acc) for l = 0, 1, 2, ... -- so results carry the reference's rounding order whatever the batch
-// size, and (rows being independent) do not depend on how rows are spread over threads, CTAs or GPUs.
-// Four times as many threads as the Q = 4 kernel for the same rows: 4 clouds of 16384 points already give every SM ~14
-// warps, and the unrolled candidate loop keeps 8 independent exponentials per thread in flight.  FP32 cost per pair-pass
-// is unchanged (7 packed issues + 2 scalar FFMA per two candidates against 8 packed issues per two rows).
-// Shared memory holds candidate PAIRS as structure-of-arrays float4's: (x0, x1, y0, y1), (z0, z1, w0, w1).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int EMD_ROW_UNROLL = 4;   // candidate pairs per unrolled step
-template <int MODE, bool UNIT, bool EXACT, int NT>
-__global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ SweepArgs a) {
-    constexpr bool P3 = MODE == 3 || MODE == 4;
-    constexpr bool DUAL = MODE == 4;
-    __shared__ __align__(16) float4 sA[EMD_TC / 2];
-    __shared__ __align__(16) float4 sBv[EMD_TC / 2];
-    __shared__ __align__(8) float2 sWB[DUAL ? EMD_TC / 2 : 1];
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x % a.nrt;
-    const int cloud = blockIdx.x / a.nrt;
-    const int nr = a.nr, nc = a.nc;
-    const float* __restrict__ cbase = a.cands + (size_t)cloud * nc * 3;
-    const float* __restrict__ wbase = a.w + (size_t)cloud * nc;
-    const float* __restrict__ wbbase = DUAL ? a.wb + (size_t)cloud * nc : nullptr;
-    const int row = tile * NT + tid;
-    const bool valid = row < nr;
-    const size_t ridx = (size_t)cloud * nr + (valid ? row : 0);
-    // the row NEGATED in both halves: (cand + (-row)) == cand - row exactly
-    const float* rp = a.rows + ridx * 3;
-    const float2 RX = make_float2(-rp[0], -rp[0]), RY = make_float2(-rp[1], -rp[1]), RZ = make_float2(-rp[2], -rp[2]);
-    float rfs = 1.f;
-    if (P3) rfs = a.rowfac[ridx];
-    const float2 RF = make_float2(rfs, rfs);
-    const float2 L2 = make_float2(a.lvl2, a.lvl2), L2B = make_float2(a.lvl2b, a.lvl2b);
-    float acc = a.init0, accb = 1e-9f;   // pass 1 (also the fused one of the next level) starts at 1e-9 (tf_approxmatch.cu:36)
-
-    for (int c0 = 0; c0 < nc; c0 += EMD_TC) {
-        const int len = min(EMD_TC, nc - c0);
-        __syncthreads();
-        for (int i = tid; i < EMD_TC / 2; i += NT) {
-            // padded candidates carry weight 0 and finite coordinates: fma(e, 0, acc) == acc
-            float x0 = 0.f, y0 = 0.f, z0 = 0.f, w0 = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f, w1 = 0.f, v0 = 0.f, v1 = 0.f;
-            const int ca = 2 * i, cb = 2 * i + 1;
-            if (ca < len) { const float* c = cbase + (size_t)(c0 + ca) * 3; x0 = c[0]; y0 = c[1]; z0 = c[2]; w0 = wbase[c0 + ca]; if (DUAL) v0 = wbbase[c0 + ca]; }
-            if (cb < len) { const float* c = cbase + (size_t)(c0 + cb) * 3; x1 = c[0]; y1 = c[1]; z1 = c[2]; w1 = wbase[c0 + cb]; if (DUAL) v1 = wbbase[c0 + cb]; }
-            sA[i] = make_float4(x0, x1, y0, y1);
-            sBv[i] = make_float4(z0, z1, w0, w1);
-            if (DUAL) sWB[i] = make_float2(v0, v1);
-        }
-        __syncthreads();
-        const int npairs = (len + 1) / 2;
-        const int np4 = (npairs + EMD_ROW_UNROLL - 1) / EMD_ROW_UNROLL * EMD_ROW_UNROLL;   // entries up to EMD_TC / 2 are padded with weight 0
-        EMD_PRAGMA_UNROLL(EMD_ROW_UNROLL)
-        for (int i = 0; i < np4; ++i) {
-            const float4 A = sA[i], Bv = sBv[i];
-            if (UNIT && !DUAL) {
-                // e == 1: fma(1, w, acc) == acc + w and fma(rf * 1, w, acc) == fma(rf, w, acc), bit for bit
-                if (P3) { acc = __fmaf_rn(rfs, Bv.z, acc); acc = __fmaf_rn(rfs, Bv.w, acc); }
-                else { acc = __fadd_rn(acc, Bv.z); acc = __fadd_rn(acc, Bv.w); }
-            } else {
-                const float2 dx = __fadd2_rn(make_float2(A.x, A.y), RX);
-                const float2 dy = __fadd2_rn(make_float2(A.z, A.w), RY);
-                const float2 dz = __fadd2_rn(make_float2(Bv.x, Bv.y), RZ);
-                const float2 d2 = sqdist3x2<true>(dx, dy, dz);
-                const float2 x = __fmul2_rn(d2, L2);
-                float2 e = make_float2(emd_ex2<EXACT>(x.x), emd_ex2<EXACT>(x.y));
-                if (P3) e = __fmul2_rn(RF, e);
-                acc = __fmaf_rn(e.x, Bv.z, acc);
-                acc = __fmaf_rn(e.y, Bv.w, acc);
-                if (DUAL) {
-                    const float2 wb = sWB[i];
-                    if (UNIT) {
-                        accb = __fadd_rn(accb, wb.x);
-                        accb = __fadd_rn(accb, wb.y);
-                    } else {
-                        const float2 xb = __fmul2_rn(d2, L2B);
-                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.x), wb.x, accb);
-                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.y), wb.y, accb);
-                    }
-                }
-            }
-        }
-    }
-    if (valid) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx, acc, accb);
-}
-
-// grid = (clusters of rows, clouds), 256 threads.  mask[((cloud * nclusters + cluster) * 3 + lev) * nwords + word]
-__global__ void __launch_bounds__(256) emd_mask_kernel(int nr, int nc, int nwords, const float* __restrict__ rows, const int* __restrict__ perm,
-                                                       const float* __restrict__ cands, float l0, float l1, float l2, unsigned* __restrict__ mask) {
-    __shared__ float red[6][8];
-    const int cloud = blockIdx.y, cluster = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float inf = __int_as_float(0x7f800000);
-    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-    const int s = cluster * EMD_CLUSTER + tid;
-    if (tid < EMD_CLUSTER && s < nr) {
-        const float* p = rows + ((size_t)cloud * nr + perm[(size_t)cloud * nr + s]) * 3;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) lo[a] = hi[a] = p[a];
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-        }
-        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float l = red[a][0], h = red[3 + a][0];
-        for (int w2 = 1; w2 < 8; ++w2) { l = fminf(l, red[a][w2]); h = fmaxf(h, red[3 + a][w2]); }
-        lo[a] = l;
-        hi[a] = h;
-    }
-    unsigned* __restrict__ out = mask + ((size_t)cloud * gridDim.x + cluster) * EMD_PRUNE_LEVELS * nwords;
-    const float* __restrict__ cb = cands + (size_t)cloud * nc * 3;
-    for (int c = tid; c < nwords * 32; c += 256) {
-        float d2 = inf;
-        if (c < nc) {
-            d2 = 0.f;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float v = cb[(size_t)c * 3 + a];
-                const float d = fmaxf(fmaxf(lo[a] - v, v - hi[a]), 0.f);   // distance to the box along this axis
-                d2 = fmaf(d, d, d2);
-            }
-        }
-        const bool valid = c < nc;
-        const unsigned w0 = __ballot_sync(0xffffffffu, valid && l0 * d2 > EMD_PRUNE_ARG);
-        const unsigned w1 = __ballot_sync(0xffffffffu, valid && l1 * d2 > EMD_PRUNE_ARG);
-        const unsigned w2 = __ballot_sync(0xffffffffu, valid && l2 * d2 > EMD_PRUNE_ARG);
-        if (lane == 0) {
-            out[c >> 5] = w0;
-            out[nwords + (c >> 5)] = w1;
-            out[2 * nwords + (c >> 5)] = w2;
-        }
-    }
-}
-
-// ---- epilogue: one thread per row; sum the split partials in fixed order, then the pass's update rule ------------
+// ---- epilogue of the split sums: one thread per row; add the split partials in fixed order, then the pass's rule ----
 __device__ __forceinline__ float emd_sum_partials(const float* __restrict__ partial, size_t cloud, int nsplit, int nr, int r) {
     float s = partial[(cloud * nsplit) * nr + r];
     for (int sp = 1; sp < nsplit; ++sp) s += partial[(cloud * nsplit + sp) * nr + r];
@@ -837,94 +964,90 @@ __global__ void __launch_bounds__(MV_THREADS) matchcost_v4_kernel(int n, int m, 
     }
 }
 
-// grad1 partials over an l-range: thread owns 4 k (12 accumulators), same partial layout as matchcostgrad1_kernel
-__global__ void __launch_bounds__(MV_THREADS) matchcostgrad1_v4_kernel(int n, int m, int nlt, const float* __restrict__ xyz1,
-                                                                       const float* __restrict__ xyz2, const float* __restrict__ match,
-                                                                       float* __restrict__ partial) {
-    __shared__ float sP[G1_L * 3];
-    const int cloud = blockIdx.z;
-    const int k4 = (blockIdx.x * MV_THREADS + threadIdx.x) * 4;
-    const int l0 = blockIdx.y * G1_L;
-    const int nl = min(G1_L, m - l0);
-    for (int i = threadIdx.x; i < nl * 3; i += MV_THREADS) sP[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
-    __syncthreads();
-    if (k4 >= n) return;
-    const Pts4 q = load_pts4_neg(xyz1 + ((size_t)cloud * n + k4) * 3);
-    const float4* __restrict__ mp = reinterpret_cast<const float4*>(match + ((size_t)cloud * m + l0) * n + k4);
-    const size_t stride = (size_t)(n >> 2);
-    float2 gx01 = make_float2(0.f, 0.f), gx23 = gx01, gy01 = gx01, gy23 = gx01, gz01 = gx01, gz23 = gx01;
-#pragma unroll 4
-    for (int l = 0; l < nl; ++l) {
-        const float4 mv = __ldg(mp + (size_t)l * stride);
-        const float px = sP[l * 3], py = sP[l * 3 + 1], pz = sP[l * 3 + 2];
-        // e = p2 - p1 (packed); grad1 accumulates (p1 - p2) * s = e * (-s)
-        const float2 ex01 = __fadd2_rn(q.nx01, make_float2(px, px)), ey01 = __fadd2_rn(q.ny01, make_float2(py, py)), ez01 = __fadd2_rn(q.nz01, make_float2(pz, pz));
-        const float2 ex23 = __fadd2_rn(q.nx23, make_float2(px, px)), ey23 = __fadd2_rn(q.ny23, make_float2(py, py)), ez23 = __fadd2_rn(q.nz23, make_float2(pz, pz));
-        const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
-        const float2 ns01 = make_float2(-mv.x * rsqrtf(fmaxf(d01.x, 1e-20f)), -mv.y * rsqrtf(fmaxf(d01.y, 1e-20f)));
-        const float2 ns23 = make_float2(-mv.z * rsqrtf(fmaxf(d23.x, 1e-20f)), -mv.w * rsqrtf(fmaxf(d23.y, 1e-20f)));
-        gx01 = __ffma2_rn(ex01, ns01, gx01); gy01 = __ffma2_rn(ey01, ns01, gy01); gz01 = __ffma2_rn(ez01, ns01, gz01);
-        gx23 = __ffma2_rn(ex23, ns23, gx23); gy23 = __ffma2_rn(ey23, ns23, gy23); gz23 = __ffma2_rn(ez23, ns23, gz23);
-    }
-    float* o = partial + (((size_t)cloud * nlt + blockIdx.y) * n + k4) * 3;  // 12 consecutive floats, 16-byte aligned
-    reinterpret_cast<float4*>(o)[0] = make_float4(gx01.x, gy01.x, gz01.x, gx01.y);
-    reinterpret_cast<float4*>(o)[1] = make_float4(gy01.y, gz01.y, gx23.x, gy23.x);
-    reinterpret_cast<float4*>(o)[2] = make_float4(gz23.x, gx23.y, gy23.y, gz23.y);
-}
-
-// grad2: one warp per l, 16 rows per CTA sharing shared-memory tiles of xyz1 (stored negated, structure-of-arrays, so the
-// differences p2 - p1 are FADD2 with a broadcast scalar on packed pairs); lanes stride k in float4 chunks of `match`
-constexpr int G2V_WARPS = 16;
-constexpr int G2V_TILE = 1024;  // points of xyz1 per tile (12 KiB)
-__global__ void __launch_bounds__(G2V_WARPS * 32) matchcostgrad2_v4_kernel(int n, int m, const float* __restrict__ xyz1,
-                                                                           const float* __restrict__ xyz2, const float* __restrict__ match,
-                                                                           float* __restrict__ grad2) {
-    __shared__ __align__(16) float sx[G2V_TILE], sy[G2V_TILE], sz[G2V_TILE];
-    const int cloud = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l = blockIdx.x * G2V_WARPS + warp;
-    const bool live = l < m;
-    float x2 = 0.f, y2 = 0.f, z2 = 0.f;
-    if (live) {
-        const float* q = xyz2 + ((size_t)cloud * m + l) * 3;
-        x2 = q[0]; y2 = q[1]; z2 = q[2];
-    }
-    const float2 X2 = make_float2(x2, x2), Y2 = make_float2(y2, y2), Z2 = make_float2(z2, z2);
-    const float* __restrict__ a = xyz1 + (size_t)cloud * n * 3;
-    const float* __restrict__ mrow = match + ((size_t)cloud * m + (live ? l : 0)) * n;
-    float2 gx = make_float2(0.f, 0.f), gy = gx, gz = gx;
-    for (int t0 = 0; t0 < n; t0 += G2V_TILE) {
-        const int len = min(G2V_TILE, n - t0);  // multiple of 4
+// ---------------------------------------------------------------------------------------------------------------
+// match_cost gradient for a GIVEN matrix in ONE streaming pass over `match` (4 B per pair, the HBM floor); the reference
+// reads it twice (matchcostgrad1 + matchcostgrad2, tf_approxmatch.cu:229-291) and so did the first version here.
+// CTA = 128 consecutive k (a float4 of one matrix row per lane) x GF_LT rows l; warp w takes rows l = w, w + 8, ...
+//   t(k,l) = match[l,k] * rsqrt(max(d2, 1e-20)) * (p2_l - p1_k)
+//   grad1[k] = -sum_l t : 12 accumulators per lane across the whole l range, summed over the 8 warps at the end
+//   grad2[l] = +sum_k t : the lane's 4-pair partial goes to a rotated (bank-conflict-free) shared-memory slab, 64 rows at a
+//              time; 192 threads then add the 32 lane partials of one (l, component) each -- 4 instructions per row and lane
+//              where a shuffle tree would cost 30.
+// Partials over l-ranges (grad1) and k-tiles (grad2) are summed in a fixed order by emd_grad_reduce_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GF_THREADS = 256, GF_WARPS = 8, GF_KT = 128, GF_LC = 64, GF_LT = 512, GF_UN = 4;
+__global__ void __launch_bounds__(GF_THREADS, 3) matchcostgrad_fused_kernel(int n, int m, int nkt, int nlt, const float* __restrict__ xyz1,
+                                                                            const float* __restrict__ xyz2, const float* __restrict__ match,
+                                                                            float* __restrict__ part1, float* __restrict__ part2) {
+    __shared__ float sP2[GF_LC * 3];
+    __shared__ float sG[GF_LC * 3 * 32];
+    const int cloud = blockIdx.z, kt = blockIdx.x, lt = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k4 = kt * GF_KT + lane * 4;
+    const bool live = k4 < n;   // n % 4 == 0: a quad is either entirely inside or entirely outside
+    Pts4 q;
+    q.nx01 = q.nx23 = q.ny01 = q.ny23 = q.nz01 = q.nz23 = make_float2(0.f, 0.f);
+    if (live) q = load_pts4_neg(xyz1 + ((size_t)cloud * n + k4) * 3);
+    float2 ax01 = make_float2(0.f, 0.f), ax23 = ax01, ay01 = ax01, ay23 = ax01, az01 = ax01, az23 = ax01;   // sum_l t for the lane's four k
+    const float* __restrict__ mbase = match + (size_t)cloud * m * n + k4;
+    const int l_end = min(m, (lt + 1) * GF_LT);
+    for (int l0 = lt * GF_LT; l0 < l_end; l0 += GF_LC) {
+        const int nl = min(GF_LC, l_end - l0);
+        __syncthreads();   // the previous chunk's reduction has finished with sG and sP2
+        for (int i = tid; i < nl * 3; i += GF_THREADS) sP2[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
         __syncthreads();
-        for (int i4 = threadIdx.x * 4; i4 < len; i4 += G2V_WARPS * 32 * 4) {  // four points per thread: 3 float4 in, 3 float4 out
-            const float4* src = reinterpret_cast<const float4*>(a + (size_t)(t0 + i4) * 3);
-            const float4 A = __ldg(src), B = __ldg(src + 1), C = __ldg(src + 2);
-            *reinterpret_cast<float4*>(&sx[i4]) = make_float4(-A.x, -A.w, -B.z, -C.y);
-            *reinterpret_cast<float4*>(&sy[i4]) = make_float4(-A.y, -B.x, -B.w, -C.z);
-            *reinterpret_cast<float4*>(&sz[i4]) = make_float4(-A.z, -B.y, -C.x, -C.w);
-        }
-        __syncthreads();
-        if (live) {
-#pragma unroll 2
-            for (int k4 = lane * 4; k4 < len; k4 += 128) {
-                const float4 mv = __ldg(reinterpret_cast<const float4*>(mrow + t0 + k4));
-                const float4 NX = *reinterpret_cast<const float4*>(&sx[k4]), NY = *reinterpret_cast<const float4*>(&sy[k4]), NZ = *reinterpret_cast<const float4*>(&sz[k4]);
-                // e = p2 - p1 for the four points (packed pairs 01, 23)
-                const float2 ex01 = __fadd2_rn(make_float2(NX.x, NX.y), X2), ex23 = __fadd2_rn(make_float2(NX.z, NX.w), X2);
-                const float2 ey01 = __fadd2_rn(make_float2(NY.x, NY.y), Y2), ey23 = __fadd2_rn(make_float2(NY.z, NY.w), Y2);
-                const float2 ez01 = __fadd2_rn(make_float2(NZ.x, NZ.y), Z2), ez23 = __fadd2_rn(make_float2(NZ.z, NZ.w), Z2);
-                const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
-                const float2 s01 = __fmul2_rn(make_float2(mv.x, mv.y), make_float2(rsqrtf(fmaxf(d01.x, 1e-20f)), rsqrtf(fmaxf(d01.y, 1e-20f))));
-                const float2 s23 = __fmul2_rn(make_float2(mv.z, mv.w), make_float2(rsqrtf(fmaxf(d23.x, 1e-20f)), rsqrtf(fmaxf(d23.y, 1e-20f))));
-                gx = __ffma2_rn(ex01, s01, gx); gy = __ffma2_rn(ey01, s01, gy); gz = __ffma2_rn(ez01, s01, gz);
-                gx = __ffma2_rn(ex23, s23, gx); gy = __ffma2_rn(ey23, s23, gy); gz = __ffma2_rn(ez23, s23, gz);
+#pragma unroll 1
+        for (int j0 = 0; j0 < GF_LC / GF_WARPS; j0 += GF_UN) {
+            float4 mv[GF_UN];
+#pragma unroll
+            for (int u = 0; u < GF_UN; ++u) {   // all loads of the step first: GF_UN x 16 B in flight per lane
+                const int li = warp + GF_WARPS * (j0 + u);
+                mv[u] = (live && li < nl) ? __ldcs(reinterpret_cast<const float4*>(mbase + (size_t)(l0 + li) * n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < GF_UN; ++u) {
+                const int li = warp + GF_WARPS * (j0 + u);
+                if (li < nl) {
+                    const float px = sP2[li * 3], py = sP2[li * 3 + 1], pz = sP2[li * 3 + 2];
+                    const float2 ex01 = __fadd2_rn(q.nx01, make_float2(px, px)), ey01 = __fadd2_rn(q.ny01, make_float2(py, py)), ez01 = __fadd2_rn(q.nz01, make_float2(pz, pz));
+                    const float2 ex23 = __fadd2_rn(q.nx23, make_float2(px, px)), ey23 = __fadd2_rn(q.ny23, make_float2(py, py)), ez23 = __fadd2_rn(q.nz23, make_float2(pz, pz));
+                    const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
+                    const float2 s01 = __fmul2_rn(make_float2(mv[u].x, mv[u].y), make_float2(rsqrt_approx(fmaxf(d01.x, 1e-20f)), rsqrt_approx(fmaxf(d01.y, 1e-20f))));
+                    const float2 s23 = __fmul2_rn(make_float2(mv[u].z, mv[u].w), make_float2(rsqrt_approx(fmaxf(d23.x, 1e-20f)), rsqrt_approx(fmaxf(d23.y, 1e-20f))));
+                    ax01 = __ffma2_rn(ex01, s01, ax01); ay01 = __ffma2_rn(ey01, s01, ay01); az01 = __ffma2_rn(ez01, s01, az01);
+                    ax23 = __ffma2_rn(ex23, s23, ax23); ay23 = __ffma2_rn(ey23, s23, ay23); az23 = __ffma2_rn(ez23, s23, az23);
+                    const float2 gx = __ffma2_rn(ex01, s01, __fmul2_rn(ex23, s23)), gy = __ffma2_rn(ey01, s01, __fmul2_rn(ey23, s23)),
+                                 gz = __ffma2_rn(ez01, s01, __fmul2_rn(ez23, s23));
+                    const int r = li * 3;
+                    sG[(r + 0) * 32 + ((lane + r + 0) & 31)] = gx.x + gx.y;
+                    sG[(r + 1) * 32 + ((lane + r + 1) & 31)] = gy.x + gy.y;
+                    sG[(r + 2) * 32 + ((lane + r + 2) & 31)] = gz.x + gz.y;
+                }
             }
         }
+        __syncthreads();
+        if (tid < nl * 3) {   // one (row, component) per thread: add the 32 lane partials in lane order
+            float t = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) t += sG[tid * 32 + ((i + tid) & 31)];
+            part2[(((size_t)cloud * nkt + kt) * m + l0) * 3 + tid] = t;
+        }
     }
-    const float sx_ = warp_sum(gx.x + gx.y), sy_ = warp_sum(gy.x + gy.y), sz_ = warp_sum(gz.x + gz.y);
-    if (live && lane == 0) {
-        float* o = grad2 + ((size_t)cloud * m + l) * 3;
-        o[0] = sx_; o[1] = sy_; o[2] = sz_;
+    // grad1: add the eight warps' accumulators (each saw different rows l of the same 128 k) and negate
+    __syncthreads();
+    float* sW = sG + warp * (GF_KT * 3);   // 8 x 384 floats <= the 6144 of sG
+    sW[(lane * 4 + 0) * 3 + 0] = ax01.x; sW[(lane * 4 + 0) * 3 + 1] = ay01.x; sW[(lane * 4 + 0) * 3 + 2] = az01.x;
+    sW[(lane * 4 + 1) * 3 + 0] = ax01.y; sW[(lane * 4 + 1) * 3 + 1] = ay01.y; sW[(lane * 4 + 1) * 3 + 2] = az01.y;
+    sW[(lane * 4 + 2) * 3 + 0] = ax23.x; sW[(lane * 4 + 2) * 3 + 1] = ay23.x; sW[(lane * 4 + 2) * 3 + 2] = az23.x;
+    sW[(lane * 4 + 3) * 3 + 0] = ax23.y; sW[(lane * 4 + 3) * 3 + 1] = ay23.y; sW[(lane * 4 + 3) * 3 + 2] = az23.y;
+    __syncthreads();
+    for (int i = tid; i < GF_KT * 3; i += GF_THREADS) {
+        if (kt * GF_KT + i / 3 < n) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < GF_WARPS; ++w) t += sG[w * (GF_KT * 3) + i];
+            part1[(((size_t)cloud * nlt + lt) * n + (size_t)kt * GF_KT) * 3 + i] = -t;
+        }
     }
 }
 
@@ -941,49 +1064,48 @@ static void emd_launch_row(const SweepArgs& a, unsigned grid, bool unit, bool ex
 }
 template <int Q, int MODE>
 static void emd_launch_split(const SweepArgs& a, unsigned grid, bool unit, cudaStream_t s) {
-    if (unit) emd_sweep_kernel<Q, MODE, true, false, false><<<grid, EMD_THREADS, 0, s>>>(a);
-    else emd_sweep_kernel<Q, MODE, false, false, false><<<grid, EMD_THREADS, 0, s>>>(a);
+    if (unit) emd_sweep_kernel<Q, MODE, true><<<grid, EMD_THREADS, 0, s>>>(a);
+    else emd_sweep_kernel<Q, MODE, false><<<grid, EMD_THREADS, 0, s>>>(a);
 }
-// One sweep (+ its epilogue kernel when the candidates are split).  rows/cands: the two clouds in the roles of this pass.
-// MODE 4: lvl2b / wb describe pass 1 of the next level.  mask != nullptr selects the pruned sweep (MODE 1..3, nr >= 512).
+// One sweep.  rows/cands: the two clouds in the roles of this pass; pairA/pairZ: the candidates' pair layout.
+// MODE 4: lvl2b / wb describe pass 1 of the next level.  mask != nullptr selects the pruned form (MODE 1..3).
 // Kernel choice never changes a result except through RFNET_EMD_SPLIT_SUMS (the only thing that reorders a sum):
-//   default      one chain per row: emd_row_kernel (a thread per row), or the pruned sweep (a warp per 128-row cluster) at the sharp levels
-//   SPLIT_SUMS   emd_sweep_kernel<Q> over candidate splits + emd_epi_kernel
+//   default      one chain per row: emd_row_kernel, 128 or 64 threads per CTA by the number of rows in the call
+//   SPLIT_SUMS   emd_sweep_kernel<Q> over candidate splits + emd_epi_kernel (dense at every level)
 template <int MODE>
-static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b, const float* rows, const float* cands, const float* w, const float* wb,
-                      const float* rowfac, float* remain, float* ratio, float* fac, float* partial, const int* perm, const unsigned* mask,
-                      cudaStream_t s) {
+static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b, const float* rows, const float* cands, const float4* pairA,
+                      const float2* pairZ, const float* w, const float* wb, const float* rowfac, float* remain, float* ratio, float* fac,
+                      float* partial, const int* perm, const unsigned* mask, cudaStream_t s) {
     SweepArgs a;
-    a.nr = nr; a.nc = nc; a.nwords = (nc + 31) / 32;
+    a.nr = nr; a.nc = nc; a.nwords = (nc + 31) / 32; a.npad = emd_npad(nc);
     a.lvl2 = lvl2; a.lvl2b = lvl2b; a.init0 = MODE == 1 ? 1e-9f : 0.0f;
     a.rows = rows; a.cands = cands; a.w = w; a.wb = wb; a.rowfac = rowfac;
+    a.pairA = pairA; a.pairZ = pairZ;
     a.partial = partial; a.partial_b = partial;
     a.remain = remain; a.ratio = ratio; a.fac = fac;
     a.perm = perm; a.mask = mask;
+    // bulk copies need 16-byte aligned weight rows: cloud stride nc * 4 bytes
+    a.tma = (nc % 4 == 0) && ((((uintptr_t)w | (uintptr_t)(wb ? wb : w) | (uintptr_t)pairA | (uintptr_t)pairZ) & 15u) == 0);
     const bool exact = (flags & RFNET_EMD_EXACT) != 0;
     const bool unit = MODE == 4 ? lvl2b == 0.0f : lvl2 == 0.0f;
-    const int sms = num_sms();
     if (!(flags & RFNET_EMD_SPLIT_SUMS)) {
-        a.nsplit = 1; a.split_len = (nc + 31) / 32 * 32;
-        if (mask && MODE != 4) {
-            // a warp per 128-row cluster; one-warp CTAs when four-warp CTAs would leave SMs idle
-            const long clusters = (long)b * ((nr + EMD_CLUSTER - 1) / EMD_CLUSTER);
+        a.nsplit = 1; a.split_len = nc;
+        if (mask != nullptr && MODE != 4) {
+            // (the fused sweep is never pruned: each level has its own, tighter mask)
             constexpr int PM = MODE == 4 ? 1 : MODE;
-            if (clusters >= 8L * sms) {
-                a.nrt = (nr + 4 * EMD_CLUSTER - 1) / (4 * EMD_CLUSTER);
-                emd_sweep_kernel<4, PM, false, true, false, 128><<<(unsigned)(b * a.nrt), 128, 0, s>>>(a);
-            } else {
-                a.nrt = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
-                emd_sweep_kernel<4, PM, false, true, false, 32><<<(unsigned)(b * a.nrt), 32, 0, s>>>(a);
-            }
+            const int nclusters = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
+            a.nrt = (nclusters + PG_WARPS - 1) / PG_WARPS;
+            emd_pruned_kernel<PM><<<(unsigned)(b * a.nrt), PG_WARPS * 32, 0, s>>>(a);
             return;
         }
-        if ((long)b * nr >= 256L * sms) {
-            a.nrt = (nr + 127) / 128;
-            emd_launch_row<MODE, 128>(a, (unsigned)(b * a.nrt), unit, exact, s);
-        } else {
+        // 64-thread CTAs beat 128-thread ones at every size (profiles/r2_emd_tune.txt); one-warp CTAs when even those leave fewer
+        // than ~12 CTAs per SM (finer balance over the SMs, no block barrier)
+        if ((long)b * nr >= 768L * num_sms()) {
             a.nrt = (nr + 63) / 64;
             emd_launch_row<MODE, 64>(a, (unsigned)(b * a.nrt), unit, exact, s);
+        } else {
+            a.nrt = (nr + 31) / 32;
+            emd_launch_row<MODE, 32>(a, (unsigned)(b * a.nrt), unit, exact, s);
         }
         return;
     }
@@ -991,14 +1113,8 @@ static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b,
     a.nrt = p.nrt; a.nsplit = p.nsplit; a.split_len = p.split_len;
     a.partial_b = partial + (size_t)b * nr * p.nsplit;
     const unsigned grid = (unsigned)(b * p.nrt * p.nsplit);
-    if (mask && p.Q == 4 && MODE != 4) {
-        constexpr int PM = MODE == 4 ? 1 : MODE;
-        emd_sweep_kernel<4, PM, false, true, false><<<grid, EMD_THREADS, 0, s>>>(a);
-    } else if (p.Q == 4) {
-        emd_launch_split<4, MODE>(a, grid, unit, s);
-    } else {
-        emd_launch_split<2, MODE>(a, grid, unit, s);
-    }
+    if (p.Q == 4) emd_launch_split<4, MODE>(a, grid, unit, s);
+    else emd_launch_split<2, MODE>(a, grid, unit, s);
     if (p.nsplit > 1) {
         const size_t total = (size_t)b * nr;
         emd_epi_kernel<MODE><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(nr, p.nsplit, total, a.partial, a.partial_b, remain, ratio, fac);
@@ -1043,8 +1159,17 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
     emd_init_kernel<<<(unsigned)((bn + bm + 255) / 256), 256, 0, s>>>(bn, bm, multiL, multiR, ws.remainL, ws.remainR);
     EmdLevels lv;
     for (int li = 0; li < EMD_LEVELS; ++li) lv.lvl2[li] = emd_level(li) * LOG2E;
-    // exact pruning of the three sharpest levels (see emd_sweep_kernel<PRUNED>); relies on the ftz exponential's exact zeros
-    const bool prune = emd_prune_enabled(n, m) && !(flags & (RFNET_EMD_NO_PRUNE | RFNET_EMD_EXACT));
+    const bool split = (flags & RFNET_EMD_SPLIT_SUMS) != 0;
+    if (!split) {   // the clouds as candidate pairs for the row kernel
+        const int np1 = emd_npad(n), np2 = emd_npad(m);
+        emd_pairs_kernel<<<dim3((unsigned)((np1 + 255) / 256), (unsigned)b), 256, 0, s>>>(n, np1, xyz1, ws.pairA1, ws.pairZ1);
+        emd_pairs_kernel<<<dim3((unsigned)((np2 + 255) / 256), (unsigned)b), 256, 0, s>>>(m, np2, xyz2, ws.pairA2, ws.pairZ2);
+    }
+    // exact pruning of the three sharpest levels (see emd_row_kernel); relies on the flushing exponential's exact zeros
+    // Measured on B200 (profiles/r2_emd_launches_*.csv): a pruned sweep visits few pairs but one at a time (no unrolling across
+    // the gaps of the mask), and at 4 clouds of 16384 points it takes as long as a dense sweep while also breaking up the
+    // fused pass-3 + pass-1 sweeps -- so pruning is opt-in (RFNET_EMD_PRUNE) until the compacted-gather variant lands.
+    const bool prune = (flags & RFNET_EMD_PRUNE) && emd_prune_enabled(n, m) && !(flags & (RFNET_EMD_NO_PRUNE | RFNET_EMD_EXACT | RFNET_EMD_SPLIT_SUMS));
     const int nwA = (m + 31) / 32, nwB = (n + 31) / 32;
     if (prune) {
         { const int rc = morton_sort(b, n, m, xyz1, xyz2, ws.perm1, ws.perm2, s); if (rc) return rc; }
@@ -1053,26 +1178,29 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
         emd_mask_kernel<<<dim3((unsigned)((m + EMD_CLUSTER - 1) / EMD_CLUSTER), (unsigned)b), 256, 0, s>>>(m, n, nwB, xyz2, ws.perm2, xyz1, lv.lvl2[0],
                                                                                                        lv.lvl2[1], lv.lvl2[2], ws.maskB);
     }
-    auto maskA = [&](int li) -> const unsigned* { return prune && li < EMD_PRUNE_LEVELS ? ws.maskA + (size_t)li * nwA : nullptr; };
-    auto maskB = [&](int li) -> const unsigned* { return prune && li < EMD_PRUNE_LEVELS ? ws.maskB + (size_t)li * nwB : nullptr; };
+    // levels 7 and 6 keep ~4 % / ~14 % of the pairs of a uniform 16384-point cloud; level 5 keeps ~58 %: not worth the gathers
+    auto maskA = [&](int li) -> const unsigned* { return prune && li < EMD_PRUNED_SWEEP_LEVELS ? ws.maskA + (size_t)li * nwA : nullptr; };
+    auto maskB = [&](int li) -> const unsigned* { return prune && li < EMD_PRUNED_SWEEP_LEVELS ? ws.maskB + (size_t)li * nwB : nullptr; };
     // pass 1 of the first level: rows = xyz1 (k), candidates = xyz2 (l) weighted by remainR            -> ratioL, facL[0]
-    emd_sweep<1>(b, n, m, flags, lv.lvl2[0], 0.f, xyz1, xyz2, ws.remainR, nullptr, nullptr, ws.remainL, ws.ratioL, ws.facL, ws.partial, ws.perm1, maskA(0), s);
+    emd_sweep<1>(b, n, m, flags, lv.lvl2[0], 0.f, xyz1, xyz2, ws.pairA2, ws.pairZ2, ws.remainR, nullptr, nullptr, ws.remainL, ws.ratioL, ws.facL, ws.partial,
+                 ws.perm1, maskA(0), s);
     for (int li = 0; li < EMD_LEVELS; ++li) {
         const float lvl2 = lv.lvl2[li];
         // pass 2: rows = xyz2 (l), candidates = xyz1 (k) weighted by ratioL                           -> ratioR, facR[li], remainR
-        emd_sweep<2>(b, m, n, flags, lvl2, 0.f, xyz2, xyz1, ws.ratioL, nullptr, nullptr, ws.remainR, ws.ratioR, ws.facR + (size_t)li * bm, ws.partial,
-                     ws.perm2, maskB(li), s);
+        emd_sweep<2>(b, m, n, flags, lvl2, 0.f, xyz2, xyz1, ws.pairA1, ws.pairZ1, ws.ratioL, nullptr, nullptr, ws.remainR, ws.ratioR,
+                     ws.facR + (size_t)li * bm, ws.partial, ws.perm2, maskB(li), s);
         // pass 3: rows = xyz1 (k), candidates = xyz2 (l) weighted by ratioR, row factor ratioL         -> remainL
         // fused with pass 1 of level li + 1 (weights remainR, already final)                          -> ratioL, facL[li + 1]
         // unless one of the two runs as a pruned sweep (each has its own, tighter candidate mask)
         const bool last = li == EMD_LEVELS - 1;
         if (!last && !maskA(li) && !maskA(li + 1)) {
-            emd_sweep<4>(b, n, m, flags, lvl2, lv.lvl2[li + 1], xyz1, xyz2, ws.ratioR, ws.remainR, ws.ratioL, ws.remainL, ws.ratioL,
+            emd_sweep<4>(b, n, m, flags, lvl2, lv.lvl2[li + 1], xyz1, xyz2, ws.pairA2, ws.pairZ2, ws.ratioR, ws.remainR, ws.ratioL, ws.remainL, ws.ratioL,
                          ws.facL + (size_t)(li + 1) * bn, ws.partial, nullptr, nullptr, s);
         } else {
-            emd_sweep<3>(b, n, m, flags, lvl2, 0.f, xyz1, xyz2, ws.ratioR, nullptr, ws.ratioL, ws.remainL, nullptr, nullptr, ws.partial, ws.perm1, maskA(li), s);
+            emd_sweep<3>(b, n, m, flags, lvl2, 0.f, xyz1, xyz2, ws.pairA2, ws.pairZ2, ws.ratioR, nullptr, ws.ratioL, ws.remainL, nullptr, nullptr, ws.partial,
+                         ws.perm1, maskA(li), s);
             if (!last)
-                emd_sweep<1>(b, n, m, flags, lv.lvl2[li + 1], 0.f, xyz1, xyz2, ws.remainR, nullptr, nullptr, ws.remainL, ws.ratioL,
+                emd_sweep<1>(b, n, m, flags, lv.lvl2[li + 1], 0.f, xyz1, xyz2, ws.pairA2, ws.pairZ2, ws.remainR, nullptr, nullptr, ws.remainL, ws.ratioL,
                              ws.facL + (size_t)(li + 1) * bn, ws.partial, ws.perm1, maskA(li + 1), s);
         }
     }
@@ -1115,7 +1243,7 @@ using namespace rfnet;
 
 // EXACT excludes the split sums (a different rounding order) -- asking for both is a caller error
 static bool emd_flags_ok(int flags) {
-    if (flags & ~(RFNET_EMD_EXACT | RFNET_EMD_NO_PRUNE | RFNET_EMD_SPLIT_SUMS)) return false;
+    if (flags & ~(RFNET_EMD_EXACT | RFNET_EMD_NO_PRUNE | RFNET_EMD_SPLIT_SUMS | RFNET_EMD_PRUNE)) return false;
     return !((flags & RFNET_EMD_EXACT) && (flags & RFNET_EMD_SPLIT_SUMS));
 }
 
@@ -1205,7 +1333,9 @@ extern "C" int rfnet_matchcost(int b, int n, int m, const float* xyz1, const flo
 
 extern "C" size_t rfnet_matchcostgrad_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return sizeof(float) * 3 * (size_t)b * n * ((m + G1_L - 1) / G1_L);
+    const size_t legacy = sizeof(float) * 3 * (size_t)b * n * ((m + G1_L - 1) / G1_L);
+    const size_t fused = sizeof(float) * 3 * (size_t)b * ((size_t)n * ((m + GF_LT - 1) / GF_LT) + (size_t)m * ((n + GF_KT - 1) / GF_KT));
+    return legacy > fused ? legacy : fused;
 }
 
 extern "C" int rfnet_matchcostgrad(int b, int n, int m, const float* xyz1, const float* xyz2, const float* match, float* grad1, float* grad2,
@@ -1219,24 +1349,25 @@ extern "C" int rfnet_matchcostgrad(int b, int n, int m, const float* xyz1, const
         return 0;
     }
     RFNET_CHECK_ARG(xyz1 && xyz2 && match && grad1 && grad2 && workspace && workspace_bytes >= rfnet_matchcostgrad_workspace_bytes(b, n, m) && b <= 65535);
-    const int nlt = (m + G1_L - 1) / G1_L;
-    RFNET_CHECK_ARG(nlt <= 65535);
-    const size_t bn = (size_t)b * n;
+    const size_t bn = (size_t)b * n, bm = (size_t)b * m;
     const bool vec = (n % 4 == 0) && ((((uintptr_t)match | (uintptr_t)xyz1 | (uintptr_t)workspace) & 15u) == 0);
     if (vec) {
-        dim3 g1((unsigned)((n + MV_THREADS * 4 - 1) / (MV_THREADS * 4)), (unsigned)nlt, (unsigned)b);
-        matchcostgrad1_v4_kernel<<<g1, MV_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
-    } else {
-        dim3 g1((unsigned)((n + G1_THREADS - 1) / G1_THREADS), (unsigned)nlt, (unsigned)b);
-        matchcostgrad1_kernel<<<g1, G1_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
+        // one pass over the matrix: both gradients from a single read
+        const int nkt = (n + GF_KT - 1) / GF_KT, nlt = (m + GF_LT - 1) / GF_LT;
+        RFNET_CHECK_ARG(nlt <= 65535);
+        float* part1 = (float*)workspace;
+        float* part2 = part1 + 3 * bn * nlt;
+        matchcostgrad_fused_kernel<<<dim3((unsigned)nkt, (unsigned)nlt, (unsigned)b), GF_THREADS, 0, s>>>(n, m, nkt, nlt, xyz1, xyz2, match, part1, part2);
+        emd_grad_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, nlt, bn, part1, grad1);
+        emd_grad_reduce_kernel<<<(unsigned)((bm * 3 + 255) / 256), 256, 0, s>>>(m, nkt, bm, part2, grad2);
+        return launch_status();
     }
+    const int nlt = (m + G1_L - 1) / G1_L;
+    RFNET_CHECK_ARG(nlt <= 65535);
+    dim3 g1((unsigned)((n + G1_THREADS - 1) / G1_THREADS), (unsigned)nlt, (unsigned)b);
+    matchcostgrad1_kernel<<<g1, G1_THREADS, 0, s>>>(n, m, nlt, xyz1, xyz2, match, (float*)workspace);
     matchcostgrad1_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, nlt, bn, (const float*)workspace, grad1);
-    if (vec) {
-        dim3 g2((unsigned)((m + G2V_WARPS - 1) / G2V_WARPS), (unsigned)b);
-        matchcostgrad2_v4_kernel<<<g2, G2V_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
-    } else {
-        dim3 g2((unsigned)((m + G2_WARPS - 1) / G2_WARPS), (unsigned)b);
-        matchcostgrad2_kernel<<<g2, G2_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
-    }
+    dim3 g2((unsigned)((m + G2_WARPS - 1) / G2_WARPS), (unsigned)b);
+    matchcostgrad2_kernel<<<g2, G2_WARPS * 32, 0, s>>>(n, m, xyz1, xyz2, match, grad2);
     return launch_status();
 }

@@ -233,16 +233,42 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_grid_kernel(int n, i
 
 // out[i,j,k,:] = points[i, idx[i,j,k], :]                                         (tf_grouping_g.cu:40-57)
 // grid.y = cloud, so all index arithmetic inside a cloud is 32-bit (64-bit divisions dominated the first version)
+// GP_E output vectors per thread, GP_E * 256 consecutive vectors per CTA: all index loads of a thread are issued first,
+// then all row loads, then the stores -- GP_E independent 16-byte gathers in flight per thread instead of one dependent
+// idx -> row chain (0.62 -> see profiles/r2_gathers.txt of the measured copy bandwidth at c = 64).  Stores are streaming
+// (st.global.cs): the output is written once and never re-read here, so it should not evict `points` from L2.
+constexpr int GP_E = 4;
 template <typename VEC>
-__global__ void group_point_kernel(int n, int cv, unsigned rows_per_cloud, const VEC* __restrict__ points, const int* __restrict__ idx,
-                                   VEC* __restrict__ out) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output vector of this cloud
-    const unsigned row = t / (unsigned)cv;
-    if (row >= rows_per_cloud) return;
-    const unsigned l = t - row * (unsigned)cv;
+__device__ __forceinline__ void store_streaming(VEC* p, VEC v);
+template <>
+__device__ __forceinline__ void store_streaming<float4>(float4* p, float4 v) { __stcs(p, v); }
+template <>
+__device__ __forceinline__ void store_streaming<float>(float* p, float v) { __stcs(p, v); }
+template <typename VEC>
+__global__ void __launch_bounds__(256) group_point_kernel(int n, int cv, unsigned rows_per_cloud, const VEC* __restrict__ points, const int* __restrict__ idx,
+                                                         VEC* __restrict__ out) {
     const size_t cloud = blockIdx.y;
-    const size_t grow = cloud * rows_per_cloud + row;
-    out[grow * cv + l] = __ldg(points + (cloud * n + (size_t)idx[grow]) * cv + l);
+    const unsigned total = rows_per_cloud * (unsigned)cv;       // output vectors of this cloud (< 2^31, checked by the caller)
+    const unsigned e0 = blockIdx.x * (256u * GP_E) + threadIdx.x;
+    const int* __restrict__ id = idx + cloud * rows_per_cloud;
+    const VEC* __restrict__ P = points + cloud * (size_t)n * cv;
+    VEC* __restrict__ O = out + cloud * (size_t)total;
+    unsigned l[GP_E];
+    int src[GP_E];
+#pragma unroll
+    for (int u = 0; u < GP_E; ++u) {
+        const unsigned e = e0 + u * 256u;
+        const unsigned row = e / (unsigned)cv;
+        l[u] = e - row * (unsigned)cv;
+        src[u] = e < total ? __ldg(id + row) : -1;
+    }
+    VEC v[GP_E];
+#pragma unroll
+    for (int u = 0; u < GP_E; ++u)
+        if (src[u] >= 0) v[u] = __ldg(P + (size_t)src[u] * cv + l[u]);
+#pragma unroll
+    for (int u = 0; u < GP_E; ++u)
+        if (src[u] >= 0) store_streaming<VEC>(O + e0 + u * 256u, v[u]);
 }
 
 // grad_points[i, idx[i,j,k], :] += grad_out[i,j,k,:]  after zero-fill                (tf_grouping_g.cu:61-78, tf_grouping.cpp:208)
@@ -401,10 +427,10 @@ extern "C" int rfnet_group_point(int b, int n, int c, int m, int nsample, const 
     const size_t rpc = (size_t)m * nsample;
     RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
-        dim3 grid((unsigned)((rpc * (c / 4) + 255) / 256), (unsigned)b);
+        dim3 grid((unsigned)((rpc * (c / 4) + 256 * GP_E - 1) / (256 * GP_E)), (unsigned)b);
         group_point_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
     } else {
-        dim3 grid((unsigned)((rpc * c + 255) / 256), (unsigned)b);
+        dim3 grid((unsigned)((rpc * c + 256 * GP_E - 1) / (256 * GP_E)), (unsigned)b);
         group_point_kernel<float><<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, points, idx, out);
     }
     return launch_status();
@@ -414,6 +440,19 @@ extern "C" size_t rfnet_group_point_grad_workspace_bytes(int b, int n, int c, in
     (void)c;
     if (b <= 0 || n <= 0) return 0;
     return seg::csr_bytes(b, n, (size_t)(m > 0 ? m : 0) * (nsample > 0 ? nsample : 0));
+}
+
+// the atomic-free sum over a built CSR (rfnet_group_point_grad with a workspace = build + this)
+static int group_point_grad_from_csr(int b, int n, int c, size_t rpc, const float* grad_out, const seg::Csr& csr, float* grad_points, cudaStream_t s) {
+    const bool vec = c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0;
+    if (vec) {
+        dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
+        group_point_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)grad_out, csr.offset, csr.list, (float4*)grad_points);
+    } else {
+        dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
+        group_point_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, csr.offset, csr.list, grad_points);
+    }
+    return launch_status();
 }
 
 extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int* idx, float* grad_points,
@@ -432,14 +471,7 @@ extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, c
         seg::Csr csr = seg::csr_carve(workspace, b, n, rpc);
         const int rc = seg::csr_build(csr, b, n, rpc, idx, s);
         if (rc) return rc;
-        if (vec) {
-            dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
-            group_point_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, (unsigned)rpc, (const float4*)grad_out, csr.offset, csr.list, (float4*)grad_points);
-        } else {
-            dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
-            group_point_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, csr.offset, csr.list, grad_points);
-        }
-        return launch_status();
+        return group_point_grad_from_csr(b, n, c, rpc, grad_out, csr, grad_points, s);
     }
     // no workspace: the reference's formulation (zero-fill + float reductions), order-dependent in the last bits
     RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, s));
@@ -452,6 +484,32 @@ extern "C" int rfnet_group_point_grad(int b, int n, int c, int m, int nsample, c
         group_point_grad_kernel<<<grid, 256, 0, s>>>(n, c, (unsigned)rpc, grad_out, idx, grad_points);
     }
     return launch_status();
+}
+
+// ---- scatter plans: the inverted index of an idx tensor, built once (e.g. while the forward gather runs) and reused by every
+// gradient that scatters through the same idx.  idx is read as (b, rows) targets in [0, n_targets).
+extern "C" size_t rfnet_scatter_plan_bytes(int b, int n_targets, int rows) {
+    if (b <= 0 || n_targets <= 0 || rows < 0) return 0;
+    return seg::csr_bytes(b, n_targets, (size_t)rows);
+}
+
+extern "C" int rfnet_scatter_plan_build(int b, int n_targets, int rows, const int* idx, void* plan, size_t plan_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n_targets >= 0 && rows >= 0);
+    if (b == 0 || n_targets == 0) return 0;
+    RFNET_CHECK_ARG(plan && plan_bytes >= rfnet_scatter_plan_bytes(b, n_targets, rows) && (rows == 0 || idx) && b <= 65535);
+    seg::Csr csr = seg::csr_carve(plan, b, n_targets, (size_t)rows);
+    return seg::csr_build(csr, b, n_targets, (size_t)rows, idx, (cudaStream_t)stream);
+}
+
+extern "C" int rfnet_group_point_grad_planned(int b, int n, int c, int m, int nsample, const float* grad_out, const void* plan, size_t plan_bytes,
+                                              float* grad_points, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0 && nsample >= 0);
+    const size_t rpc = (size_t)m * nsample;
+    if ((size_t)b * n * c == 0) return 0;
+    RFNET_CHECK_ARG(grad_points && plan && (rpc == 0 || grad_out) && rpc < 0x7fffffffull && plan_bytes >= rfnet_scatter_plan_bytes(b, n, (int)rpc));
+    RFNET_CHECK_ARG(b <= 65535 && rpc * (size_t)c < 0x7fffffffull && (size_t)n * c < 0x7fffffffull);
+    const seg::Csr csr = seg::csr_carve(const_cast<void*>(plan), b, n, rpc);
+    return group_point_grad_from_csr(b, n, c, rpc, grad_out, csr, grad_points, (cudaStream_t)stream);
 }
 
 extern "C" int rfnet_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, rfnet_stream_t stream) {

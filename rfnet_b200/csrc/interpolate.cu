@@ -36,7 +36,11 @@ __device__ __forceinline__ void top3_insert(Top3& t, float d, int k) {  // tf_in
 
 // the same insertion without branches (3 compares, 5 min/max, 5 selects): identical results, including which index stays
 // ahead among equal distances (strict '<' everywhere)
+// A NaN distance fails every '<' of the reference's insertion and is ignored there; fminf/fmaxf would instead shift the
+// stored distances (fmaxf(d2, NaN) == d2).  NaN is therefore replaced by +inf, which also fails every strict compare
+// against finite values and against the 1e40 -> +inf seeds.
 __device__ __forceinline__ void top3_insert_bf(Top3& t, float d, int k) {
+    d = (d != d) ? __int_as_float(0x7f800000) : d;
     const bool p1 = d < t.d1, p2 = d < t.d2, p3 = d < t.d3;
     t.i3 = p3 ? (p2 ? t.i2 : k) : t.i3;
     t.i2 = p2 ? (p1 ? t.i1 : k) : t.i2;
@@ -53,6 +57,13 @@ __device__ __forceinline__ void top3_insert_bf(Top3& t, float d, int k) {
 //            per-query list in shared memory.  The 3rd smallest group minimum is an upper bound of the true 3rd smallest
 //            distance, and fused / unfused evaluation differ by < 3e-7 relative, so every group holding a candidate
 //            that the reference's scan would insert is on the list (about 3 ln(groups) entries per query).
+//            Margin (u = 2^-24).  Both evaluations start from the SAME rounded differences dx, dy, dz; on those, the unfused
+//            sum ((dx*dx)+(dy*dy))+(dz*dz) and the fused fma(dz,dz, fma(dx,dx, dy*dy)) are each within 3u relative of the exact
+//            dx^2+dy^2+dz^2 (one product and at most two sum roundings per non-negative term).  The reference inserts
+//            candidate c when unf(c) < d3, its running 3rd smallest unfused distance, and d3 <= G3_unf, the 3rd smallest
+//            unfused group minimum of the groups before c's.  So fused(c) <= unf(c)(1+6u) < G3_unf (1+6u) <= G3_fused (1+12u),
+//            and c's group minimum gm <= fused(c).  The list test is gm <= fl(G3_fused * 1.000001f) with 1.000001f = 1 + 18u
+//            and one more rounding: >= G3_fused (1 + 16.9u) > G3_fused (1 + 12u): every such group is listed.
 //   resolve  the listed groups, in scan order, go through the reference's exact code: UNFUSED distance, strict-'<'
 //            insertion.  Unlisted groups cannot change the top 3, so the state after each tile is the reference's.
 // A query whose list overflows (adversarially ordered candidates) re-scans the tile with the exact code.
@@ -388,20 +399,50 @@ __device__ __forceinline__ float4 blend3<float4>(float4 a, float4 b, float4 c, f
     return make_float4(blend3<float>(a.x, b.x, c.x, w1, w2, w3), blend3<float>(a.y, b.y, c.y, w1, w2, w3),
                        blend3<float>(a.z, b.z, c.z, w1, w2, w3), blend3<float>(a.w, b.w, c.w, w1, w2, w3));
 }
-// grid.y = cloud: 32-bit index arithmetic inside a cloud
+// grid.y = cloud: 32-bit index arithmetic inside a cloud.  TI_E output vectors per thread: the 3 * TI_E indices and weights
+// are loaded first, then the 3 * TI_E rows, then blended and stored with streaming stores (written once, never re-read here).
+constexpr int TI_E = 2;
 template <typename VEC>
-__global__ void three_interpolate_kernel(int m, int cv, int n, const VEC* __restrict__ points, const int* __restrict__ idx,
-                                         const float* __restrict__ weight, VEC* __restrict__ out) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned j = t / (unsigned)cv;
-    if (j >= (unsigned)n) return;
-    const unsigned l = t - j * (unsigned)cv;
+__device__ __forceinline__ void ti_store(VEC* p, VEC v);
+template <>
+__device__ __forceinline__ void ti_store<float4>(float4* p, float4 v) { __stcs(p, v); }
+template <>
+__device__ __forceinline__ void ti_store<float>(float* p, float v) { __stcs(p, v); }
+template <typename VEC>
+__global__ void __launch_bounds__(256) three_interpolate_kernel(int m, int cv, int n, const VEC* __restrict__ points, const int* __restrict__ idx,
+                                                               const float* __restrict__ weight, VEC* __restrict__ out) {
     const size_t cloud = blockIdx.y;
-    const size_t row = cloud * n + j;
-    const int* id = idx + row * 3;
-    const float* w = weight + row * 3;
-    const VEC* P = points + cloud * (size_t)m * cv + l;
-    out[row * cv + l] = blend3<VEC>(__ldg(P + (size_t)id[0] * cv), __ldg(P + (size_t)id[1] * cv), __ldg(P + (size_t)id[2] * cv), w[0], w[1], w[2]);
+    const unsigned total = (unsigned)n * (unsigned)cv;
+    const unsigned e0 = blockIdx.x * (256u * TI_E) + threadIdx.x;
+    const int* __restrict__ id = idx + cloud * (size_t)n * 3;
+    const float* __restrict__ wt = weight + cloud * (size_t)n * 3;
+    const VEC* __restrict__ P = points + cloud * (size_t)m * cv;
+    VEC* __restrict__ O = out + cloud * (size_t)total;
+    unsigned l[TI_E];
+    int i0[TI_E], i1[TI_E], i2[TI_E];
+    float w0[TI_E], w1[TI_E], w2[TI_E];
+#pragma unroll
+    for (int u = 0; u < TI_E; ++u) {
+        const unsigned e = e0 + u * 256u;
+        const unsigned j = e / (unsigned)cv;
+        l[u] = e - j * (unsigned)cv;
+        i0[u] = -1;
+        if (e < total) {
+            i0[u] = __ldg(id + j * 3); i1[u] = __ldg(id + j * 3 + 1); i2[u] = __ldg(id + j * 3 + 2);
+            w0[u] = __ldg(wt + j * 3); w1[u] = __ldg(wt + j * 3 + 1); w2[u] = __ldg(wt + j * 3 + 2);
+        }
+    }
+    VEC a[TI_E], b[TI_E], c[TI_E];
+#pragma unroll
+    for (int u = 0; u < TI_E; ++u)
+        if (i0[u] >= 0) {
+            a[u] = __ldg(P + (size_t)i0[u] * cv + l[u]);
+            b[u] = __ldg(P + (size_t)i1[u] * cv + l[u]);
+            c[u] = __ldg(P + (size_t)i2[u] * cv + l[u]);
+        }
+#pragma unroll
+    for (int u = 0; u < TI_E; ++u)
+        if (i0[u] >= 0) ti_store<VEC>(O + e0 + u * 256u, blend3<VEC>(a[u], b[u], c[u], w0[u], w1[u], w2[u]));
 }
 
 // grad_points[i, i_t, l] += grad_out[i,j,l] * w_t  after zero-fill             (tf_interpolate.cpp:131-153, :258)
@@ -519,10 +560,10 @@ extern "C" int rfnet_three_interpolate(int b, int m, int c, int n, const float* 
     cudaStream_t s = (cudaStream_t)stream;
     RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull);
     if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
-        dim3 grid((unsigned)(((size_t)n * (c / 4) + 255) / 256), (unsigned)b);
+        dim3 grid((unsigned)(((size_t)n * (c / 4) + 256 * TI_E - 1) / (256 * TI_E)), (unsigned)b);
         three_interpolate_kernel<float4><<<grid, 256, 0, s>>>(m, c / 4, n, (const float4*)points, idx, weight, (float4*)out);
     } else {
-        dim3 grid((unsigned)(((size_t)n * c + 255) / 256), (unsigned)b);
+        dim3 grid((unsigned)(((size_t)n * c + 256 * TI_E - 1) / (256 * TI_E)), (unsigned)b);
         three_interpolate_kernel<float><<<grid, 256, 0, s>>>(m, c, n, points, idx, weight, out);
     }
     return launch_status();
@@ -532,6 +573,31 @@ extern "C" size_t rfnet_three_interpolate_grad_workspace_bytes(int b, int n, int
     (void)c;
     if (b <= 0 || m <= 0) return 0;
     return seg::csr_bytes(b, m, (size_t)(n > 0 ? n : 0) * 3);
+}
+
+static int three_interpolate_grad_from_csr(int b, int n, int c, int m, const float* grad_out, const float* weight, const seg::Csr& csr, float* grad_points,
+                                           cudaStream_t s) {
+    const bool vec = c % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)grad_points) & 15u) == 0;
+    if (vec) {
+        dim3 grid((unsigned)(((size_t)m * (c / 4) + 255) / 256), (unsigned)b);
+        three_interpolate_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, m, (const float4*)grad_out, weight, csr.offset, csr.list, (float4*)grad_points);
+    } else {
+        dim3 grid((unsigned)(((size_t)m * c + 255) / 256), (unsigned)b);
+        three_interpolate_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, m, grad_out, weight, csr.offset, csr.list, grad_points);
+    }
+    return launch_status();
+}
+
+// three_interpolate's gradient over a scatter plan of idx read as (b, 3n) targets in [0, m) (rfnet_scatter_plan_build)
+extern "C" int rfnet_three_interpolate_grad_planned(int b, int n, int c, int m, const float* grad_out, const float* weight, const void* plan,
+                                                    size_t plan_bytes, float* grad_points, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n >= 0 && c >= 0 && m >= 0);
+    if ((size_t)b * m * c == 0) return 0;
+    RFNET_CHECK_ARG(grad_points && plan && (n == 0 || (grad_out && weight)));
+    RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull && (size_t)m * c < 0x7fffffffull && (size_t)n * 3 < 0x7fffffffull);
+    RFNET_CHECK_ARG(plan_bytes >= seg::csr_bytes(b, m, (size_t)n * 3));
+    const seg::Csr csr = seg::csr_carve(const_cast<void*>(plan), b, m, (size_t)n * 3);
+    return three_interpolate_grad_from_csr(b, n, c, m, grad_out, weight, csr, grad_points, (cudaStream_t)stream);
 }
 
 extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
@@ -548,14 +614,7 @@ extern "C" int rfnet_three_interpolate_grad(int b, int n, int c, int m, const fl
         seg::Csr csr = seg::csr_carve(workspace, b, m, (size_t)n * 3);
         const int rc = seg::csr_build(csr, b, m, (size_t)n * 3, idx, s);   // idx (b, n, 3) read as (b, 3n) source entries
         if (rc) return rc;
-        if (vec) {
-            dim3 grid((unsigned)(((size_t)m * (c / 4) + 255) / 256), (unsigned)b);
-            three_interpolate_grad_seg_kernel<float4><<<grid, 256, 0, s>>>(n, c / 4, m, (const float4*)grad_out, weight, csr.offset, csr.list, (float4*)grad_points);
-        } else {
-            dim3 grid((unsigned)(((size_t)m * c + 255) / 256), (unsigned)b);
-            three_interpolate_grad_seg_kernel<float><<<grid, 256, 0, s>>>(n, c, m, grad_out, weight, csr.offset, csr.list, grad_points);
-        }
-        return launch_status();
+        return three_interpolate_grad_from_csr(b, n, c, m, grad_out, weight, csr, grad_points, s);
     }
     RFNET_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, s));
     if (rows == 0) return 0;

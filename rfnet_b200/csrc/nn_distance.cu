@@ -483,8 +483,9 @@ extern "C" size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m) {
 }
 
 // plan + key memset + search launch; *need0 / *need1 tell the caller which directions left their results as packed keys
+// dirs: 1 = xyz1 queries against xyz2 only, 2 = xyz2 queries against xyz1 only, 3 = both
 static int nn_search_launch(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2, int* idx2, void* workspace,
-                            size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out) {
+                            size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out, int dirs = 3) {
     const int Q = pick_q(n < m ? n : m);
     NNParams p;
     p.d[0].q = xyz1; p.d[0].c = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1;
@@ -500,6 +501,8 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
 #endif
     plan_direction(p.d[0], b, n, m, Q, chunk0, split);
     plan_direction(p.d[1], b, m, n, Q, chunk1, split);
+    if (!(dirs & 1)) { p.d[0].items = 0; p.d[0].nsplit = 1; }   // a direction without items launches no CTA and merges no keys
+    if (!(dirs & 2)) { p.d[1].items = 0; p.d[1].nsplit = 1; }
     unsigned long long* keys = (unsigned long long*)workspace;
     p.d[0].keys = keys;
     p.d[1].keys = keys ? keys + (size_t)b * n : nullptr;
@@ -543,6 +546,7 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
     return launch_status();
 }
 
+namespace rfnet {
 // ---------------------------------------------------------------------------------------------------------------
 // One training step of chamfer_big (vv_recon.py:381-385 and its backward) in three launches: the search above, then ONE
 // epilogue over all points of both clouds -- unpack the merged keys into dist/idx, the own-point and scattered gradient
@@ -616,6 +620,112 @@ __global__ void __launch_bounds__(512) chamfer_epilogue_final_kernel(size_t tota
         sums[dir * 2] = s;
         sums[dir * 2 + 1] = (float)(dir ? total2 : total1);
     }
+}
+
+}  // namespace rfnet
+
+namespace rfnet {
+// ---------------------------------------------------------------------------------------------------------------
+// merge_layer of the reference's model (vv_recon.py:132-139, called with knum = 1): every new point is pulled towards its
+// nearest raw point,  out = new + exp(-d2 / (1e-8 + dec^2)) * (raw[nn] - new),  d2 = |raw[nn] - new|^2 summed as the framework
+// does ((dx*dx + dy*dy) + dz*dz).  The reference chains NnDistance (both directions), GroupPoint and five framework ops;
+// here: ONE directed search (new -> raw) and one epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void merge_layer_kernel(int n_raw, int n_new, size_t total, int keyed, const unsigned long long* __restrict__ keys,
+                                   const float* __restrict__ raw, const float* __restrict__ newp, const float* __restrict__ dec,
+                                   int* __restrict__ idx, float* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int j;
+    if (keyed) {
+        j = (int)(unsigned)(keys[t] & 0xffffffffull);
+        idx[t] = j;
+    } else {
+        j = idx[t];
+    }
+    const size_t cloud = t / n_new;
+    const float* r = raw + (cloud * n_raw + j) * 3;
+    const float* q = newp + t * 3;
+    const float dx = __fsub_rn(r[0], q[0]), dy = __fsub_rn(r[1], q[1]), dz = __fsub_rn(r[2], q[2]);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float dc = dec[0];
+    const float ratio = expf(-d2 / (1e-8f + dc * dc));
+    out[t * 3 + 0] = __fadd_rn(q[0], __fmul_rn(ratio, dx));
+    out[t * 3 + 1] = __fadd_rn(q[1], __fmul_rn(ratio, dy));
+    out[t * 3 + 2] = __fadd_rn(q[2], __fmul_rn(ratio, dz));
+}
+// backward of the above for an upstream gradient g (b, n_new, 3), idx held constant (NoGradient of the index, as in the
+// reference's graph).  With diff = raw[nn] - new, s = 1e-8 + dec^2, r = exp(-d2/s), a = <g, diff>:
+//   g_new      = g (1 - r) + a (2 r / s) diff
+//   g_raw_rows = g r - a (2 r / s) diff            (rows to be scatter-added into raw by idx: GroupPointGrad with nsample = 1)
+//   g_dec     += a r d2 (2 dec / s^2)              (per-block partial sums, fixed order)
+__global__ void __launch_bounds__(256) merge_layer_grad_kernel(int n_raw, int n_new, size_t total, const float* __restrict__ raw,
+                                                               const float* __restrict__ newp, const int* __restrict__ idx, const float* __restrict__ dec,
+                                                               const float* __restrict__ g, float* __restrict__ g_new, float* __restrict__ g_rows,
+                                                               float* __restrict__ dec_partial) {
+    __shared__ float sW[8];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float gd = 0.f;
+    if (t < total) {
+        const size_t cloud = t / n_new;
+        const float* r = raw + (cloud * n_raw + idx[t]) * 3;
+        const float* q = newp + t * 3;
+        const float dx = r[0] - q[0], dy = r[1] - q[1], dz = r[2] - q[2];
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        const float dc = dec[0];
+        const float s = 1e-8f + dc * dc;
+        const float ratio = expf(-d2 / s);
+        const float gx = g[t * 3], gy = g[t * 3 + 1], gz = g[t * 3 + 2];
+        const float a = gx * dx + gy * dy + gz * dz;
+        const float k = a * (2.0f * ratio / s);
+        g_new[t * 3 + 0] = gx * (1.0f - ratio) + k * dx;
+        g_new[t * 3 + 1] = gy * (1.0f - ratio) + k * dy;
+        g_new[t * 3 + 2] = gz * (1.0f - ratio) + k * dz;
+        g_rows[t * 3 + 0] = gx * ratio - k * dx;
+        g_rows[t * 3 + 1] = gy * ratio - k * dy;
+        g_rows[t * 3 + 2] = gz * ratio - k * dz;
+        gd = a * ratio * d2 * (2.0f * dc / (s * s));
+    }
+    gd = warp_sum(gd);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = gd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int i = 0; i < 8; ++i) v += sW[i];
+        dec_partial[blockIdx.x] = v;
+    }
+}
+}  // namespace rfnet
+
+extern "C" size_t rfnet_merge_layer_workspace_bytes(int b, int n_raw, int n_new) { return rfnet_nn_distance_workspace_bytes(b, n_raw, n_new); }
+
+extern "C" int rfnet_merge_layer(int b, int n_raw, const float* raw, int n_new, const float* newpts, const float* decfactor, float* out, int* idx,
+                                 void* workspace, size_t workspace_bytes, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n_raw > 0 && n_new >= 0);
+    if (b == 0 || n_new == 0) return 0;
+    RFNET_CHECK_ARG(raw && newpts && decfactor && out && idx && workspace && workspace_bytes >= rfnet_merge_layer_workspace_bytes(b, n_raw, n_new));
+    cudaStream_t s = (cudaStream_t)stream;
+    bool need0 = false, need1 = false;
+    // direction 2 only: queries = new points, candidates = raw points.  Distances are not needed (the epilogue recomputes d2 the
+    // framework's way), so the dist output of the search goes to the front of the output buffer and is overwritten afterwards
+    { const int rc = nn_search_launch(b, n_raw, raw, n_new, newpts, nullptr, nullptr, out, idx, workspace, workspace_bytes, 0, s, &need0, &need1, 2); if (rc) return rc; }
+    const size_t total = (size_t)b * n_new;
+    const unsigned long long* keys = (const unsigned long long*)workspace + (size_t)b * n_raw;
+    merge_layer_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n_raw, n_new, total, need1 ? 1 : 0, keys, raw, newpts, decfactor, idx, out);
+    return launch_status();
+}
+
+extern "C" size_t rfnet_merge_layer_grad_partials(int b, int n_new) { return ((size_t)(b > 0 ? b : 0) * (n_new > 0 ? n_new : 0) + 255) / 256; }
+
+extern "C" int rfnet_merge_layer_grad(int b, int n_raw, const float* raw, int n_new, const float* newpts, const int* idx, const float* decfactor,
+                                      const float* grad_out, float* grad_new, float* grad_raw_rows, float* dec_partial, rfnet_stream_t stream) {
+    RFNET_CHECK_ARG(b >= 0 && n_raw > 0 && n_new >= 0);
+    if (b == 0 || n_new == 0) return 0;
+    RFNET_CHECK_ARG(raw && newpts && idx && decfactor && grad_out && grad_new && grad_raw_rows && dec_partial);
+    const size_t total = (size_t)b * n_new;
+    merge_layer_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_raw, n_new, total, raw, newpts, idx, decfactor, grad_out,
+                                                                                               grad_new, grad_raw_rows, dec_partial);
+    return launch_status();
 }
 
 static size_t chamfer_step_partials(int b, int n, int m) {

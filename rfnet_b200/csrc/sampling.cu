@@ -179,7 +179,15 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(int n, int 
 // cloud is ordered along a Morton curve (morton.cuh) and cut into clusters of 32 consecutive points -- one register slot
 // across a warp -- each with a bounding box and the maximum running distance of its points.  A cluster whose box is
 // farther from p than that maximum (dmin2(box, p) >= max temp, with a 1e-6 relative margin for the rounding of the two
-// expressions) cannot change: it is skipped, exactly.  After a few dozen picks that is all but a handful of the 512
+// expressions) cannot change: it is skipped, exactly.
+// Margin (u = 2^-24).  The kernel's d2(x, p) = fma(dz,dz, fma(dx,dx, dy*dy)) on rounded differences is within 5u relative of
+// the exact squared distance (dy^2 term: 2u from the difference, u from the product, u from each fma; the others fewer; all
+// terms are non-negative).  dmin2 is the same expression on the per-axis distances to the box: also within 5u of the exact
+// box distance, which is <= the exact distance to any point x of the cluster.  Hence d2_computed(x, p) >= dmin2 * (1 - 10u).
+// The test skips when fl(dmin2 * 0.999999f) >= cmax; 0.999999f = 1 - 17u and the product adds one rounding, so a skipped
+// cluster has dmin2 * (1 - 16u) >= cmax >= temp[x], i.e. d2_computed(x, p) >= dmin2 * (1 - 10u) > temp[x] for all its points:
+// min(temp[x], d2) == temp[x], bit for bit.  16u against the 10u needed.
+// After a few dozen picks that is all but a handful of the 512
 // clusters, so a pick costs one box test per lane, the update of the few live clusters, two REDUX arg-maxes and ONE block
 // barrier (measured 0.75 us against 0.93 us for the cluster-wide exchange above; the rest is the latency of the chained warp votes).
 // Running distances, tie ranks and the cluster summaries live in registers; the Morton-ordered coordinates in shared memory

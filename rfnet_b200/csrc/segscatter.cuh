@@ -8,6 +8,10 @@
 // float sums run over each segment in ascending source order: the result is bit-reproducible run to run, and no float
 // atomic is issued.  Segments longer than kSegSortMax keep the claim order (still correct, just not order-stable); that
 // only happens when one point receives more than 8192 contributions.
+// Sorting by segment length: <= 16 entries: insertion sort by one thread; <= 1024: rank sort by one warp through shared
+// memory; <= 8192: bitonic network by one CTA in shared memory (O(L log^2 L): ~20 us for 8192 entries -- the first version
+// ran an O(L^2) transposition sort in global memory there, several milliseconds when a clustered cloud gave a few points
+// thousands of hits each).
 #pragma once
 #include "common.cuh"
 
@@ -21,8 +25,9 @@ struct Csr {
     int* offset;      // (b, n+1)  exclusive prefix of the per-target counts
     int* cursor;      // (b, n)    counts, then fill cursors
     int* list;        // (b, R)    source rows grouped by target, ascending inside a segment
-    int* long_count;  // (1)       number of queued long segments   (directly before cursor: one memset clears both)
-    int2* long_list;  // (b * n)   (cloud, target) of segments longer than kSegThread
+    int* long_count;  // (1)       number of queued long segments   (directly before cursor: one memset clears the counters and cursor)
+    int* vlong_count; // (1)       number of queued very long segments (kSegSmem < L <= kSegSortMax), directly before long_count
+    int2* long_list;  // (b * n)   (cloud, target): long segments from the front, very long ones from the back
 };
 static inline size_t csr_bytes(int b, int n, size_t R) {
     return sizeof(int) * ((size_t)b * (n + 1) + 4 + (size_t)b * n + (size_t)b * R + 2 * (size_t)b * n) + 64;
@@ -32,6 +37,7 @@ static inline Csr csr_carve(void* ws, int b, int n, size_t R) {
     int* p = reinterpret_cast<int*>(ws);
     c.long_list = reinterpret_cast<int2*>(p);  p += 2 * (size_t)b * n;      // 8-byte aligned: first
     c.offset = p;                              p += (size_t)b * (n + 1);
+    c.vlong_count = p;                         p += 1;
     c.long_count = p;                          p += 1;
     c.cursor = p;                              p += (size_t)b * n;
     c.list = p;
@@ -99,8 +105,8 @@ static __global__ void csr_fill_kernel(int n, unsigned R, const int* __restrict_
 // typically referenced a handful of times -- are insertion-sorted by ONE THREAD per target; longer ones are queued
 // (integer atomic on a counter) for the warp-per-segment kernel below.  grid (ceil(n/256), b)
 constexpr int kSegThread = 16;
-static __global__ void csr_sort_short_kernel(int n, unsigned R, const int* __restrict__ offset, int* __restrict__ list, int* __restrict__ long_count,
-                                             int2* __restrict__ long_list) {
+static __global__ void csr_sort_short_kernel(int n, unsigned R, size_t queue_len, const int* __restrict__ offset, int* __restrict__ list,
+                                             int* __restrict__ long_count, int* __restrict__ vlong_count, int2* __restrict__ long_list) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (unsigned)n) return;
     const size_t cloud = blockIdx.y;
@@ -117,7 +123,8 @@ static __global__ void csr_sort_short_kernel(int n, unsigned R, const int* __res
         }
         return;
     }
-    if (L <= kSegSortMax) long_list[atomicAdd(long_count, 1)] = make_int2((int)cloud, (int)t);
+    if (L <= kSegSmem) long_list[atomicAdd(long_count, 1)] = make_int2((int)cloud, (int)t);
+    else if (L <= kSegSortMax) long_list[queue_len - 1 - (size_t)atomicAdd(vlong_count, 1)] = make_int2((int)cloud, (int)t);
 }
 
 // persistent warps over the queue of long segments.  The rank of an entry is the number of smaller entries.
@@ -132,35 +139,55 @@ static __global__ void __launch_bounds__(256) csr_sort_long_kernel(int n, unsign
         const int beg = offset[cloud * (n + 1) + ct.y], end = offset[cloud * (n + 1) + ct.y + 1];
         const int L = end - beg;
         int* seg = list + cloud * R + beg;
-        if (L <= kSegSmem) {
-            int* s = seg_smem + warp * kSegSmem;
-            for (int i = lane; i < L; i += 32) s[i] = seg[i];
-            __syncwarp();
-            for (int i = lane; i < L; i += 32) {
-                const int v = s[i];
-                int rank = 0;
-                for (int o = 0; o < L; ++o) rank += (s[o] < v) ? 1 : 0;
-                seg[rank] = v;
-            }
-            __syncwarp();
-        } else {
-            // kSegSmem < L <= kSegSortMax: in-place odd-even transposition sort over global memory, cooperative across the
-            // warp -- O(L^2 / 64) steps per lane, only reached when one point collects thousands of contributions
-            for (int pass = 0; pass < L; ++pass) {
-                for (int i = (pass & 1) + 2 * lane; i + 1 < L; i += 64) {
-                    const int a = seg[i], b2 = seg[i + 1];
-                    if (a > b2) { seg[i] = b2; seg[i + 1] = a; }
-                }
-                __syncwarp();
-            }
+        int* s = seg_smem + warp * kSegSmem;   // L <= kSegSmem by construction of the queue
+        for (int i = lane; i < L; i += 32) s[i] = seg[i];
+        __syncwarp();
+        for (int i = lane; i < L; i += 32) {
+            const int v = s[i];
+            int rank = 0;
+            for (int o = 0; o < L; ++o) rank += (s[o] < v) ? 1 : 0;
+            seg[rank] = v;
         }
+        __syncwarp();
+    }
+}
+
+// one CTA per very long segment (kSegSmem < L <= kSegSortMax): bitonic network over shared memory, padded with INT_MAX
+static __global__ void __launch_bounds__(512) csr_sort_vlong_kernel(int n, unsigned R, size_t queue_len, const int* __restrict__ offset, int* __restrict__ list,
+                                                                    const int* __restrict__ vlong_count, const int2* __restrict__ long_list) {
+    __shared__ int s[kSegSortMax];
+    const int total = *vlong_count;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int2 ct = long_list[queue_len - 1 - (size_t)w];
+        const size_t cloud = (size_t)ct.x;
+        const int beg = offset[cloud * (n + 1) + ct.y], end = offset[cloud * (n + 1) + ct.y + 1];
+        const int L = end - beg;
+        int* seg = list + cloud * R + beg;
+        int P = 1;
+        while (P < L) P <<= 1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < L ? seg[i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const int a = s[i], b2 = s[x];
+                        const bool up = (i & k) == 0;
+                        if ((a > b2) == up) { s[i] = b2; s[x] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = threadIdx.x; i < L; i += blockDim.x) seg[i] = s[i];
     }
 }
 
 // Builds the CSR for idx (b, R) -> targets [0, n).  All work is stream-ordered; `ws` must hold csr_bytes(b, n, R).
 static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaStream_t s) {
     if (b == 0 || n == 0) return 0;
-    RFNET_CUDA(cudaMemsetAsync(c.long_count, 0, sizeof(int) * ((size_t)b * n + 1), s));  // long_count and cursor are adjacent
+    RFNET_CUDA(cudaMemsetAsync(c.vlong_count, 0, sizeof(int) * ((size_t)b * n + 2), s));  // vlong_count, long_count and cursor are adjacent
     if (R) {
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
         csr_count_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor);
@@ -170,8 +197,10 @@ static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaS
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
         csr_fill_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor, c.list);
         dim3 gs((unsigned)((n + 255) / 256), (unsigned)b);
-        csr_sort_short_kernel<<<gs, 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
+        const size_t queue_len = (size_t)b * n;
+        csr_sort_short_kernel<<<gs, 256, 0, s>>>(n, (unsigned)R, queue_len, c.offset, c.list, c.long_count, c.vlong_count, c.long_list);
         csr_sort_long_kernel<<<num_sms(), 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
+        csr_sort_vlong_kernel<<<num_sms(), 512, 0, s>>>(n, (unsigned)R, queue_len, c.offset, c.list, c.vlong_count, c.long_list);
     }
     return launch_status();
 }

@@ -56,13 +56,14 @@ def sampling(npoint, xyz):
 
 
 def merge_layer(rawpts, newpts, decfactor):
-    """vv_recon.py:132-139: pull every new point towards its nearest raw point with weight exp(-d2 / (1e-8 + decfactor^2))."""
-    _, _, _, idx2 = tf_nndistance.nn_distance(rawpts, newpts)
-    grouped_xyz = tf_grouping.group_point(rawpts, idx2.unsqueeze(-1))            # (b, npoint_new, 1, 3)
-    diff = grouped_xyz - newpts.unsqueeze(2)
-    dismat = (diff * diff).sum(-1, keepdim=True)
-    ratio = torch.exp(-dismat / (1e-8 + decfactor * decfactor))
-    return newpts + (ratio * diff).sum(2)
+    """vv_recon.py:132-139: pull every new point towards its nearest raw point with weight exp(-d2 / (1e-8 + decfactor^2)).
+    One fused operator (rfnet::merge_layer: a single directed nearest-neighbour search + one epilogue kernel) instead of the
+    reference's NnDistance + GroupPoint + five framework ops; differentiable w.r.t. both clouds and decfactor."""
+    from . import ops
+    if not isinstance(decfactor, torch.Tensor):
+        decfactor = torch.tensor([float(decfactor)], dtype=torch.float32, device=newpts.device)
+    out, _ = ops.merge_layer_op(rawpts, newpts, decfactor)
+    return out
 
 
 def re_chamfer(gt, pred, part=8):

@@ -191,6 +191,70 @@ def _(dist1, dist2):
     return dist1.new_empty((4,))
 
 
+# ------------------------------------------------------------------------------------------------------------ merge_layer
+@torch.library.custom_op("rfnet::merge_layer", mutates_args=(), device_types="cuda")
+def merge_layer_op(rawpts: torch.Tensor, newpts: torch.Tensor, decfactor: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    # vv_recon.py:132-139 (knum = 1) in one directed search + one epilogue: (refine_pts (b, n_new, 3), idx (b, n_new))
+    _require(rawpts.dim() == 3 and rawpts.shape[2] == 3 and newpts.dim() == 3 and newpts.shape[2] == 3, "merge_layer expects (b,n,3) point sets")
+    _require(rawpts.shape[0] == newpts.shape[0], "merge_layer expects rawpts and newpts have same batch size")
+    _require(rawpts.shape[1] > 0, "merge_layer expects a non-empty raw cloud")
+    rawpts, newpts, decfactor = _cuda_f32("rawpts", rawpts), _cuda_f32("newpts", newpts), _cuda_f32("decfactor", decfactor).reshape(-1)
+    _require(decfactor.numel() == 1, "merge_layer expects a one-element decfactor (vv_recon.py:211)")
+    b, nr, nn = rawpts.shape[0], rawpts.shape[1], newpts.shape[1]
+    out = torch.empty_like(newpts)
+    idx = torch.empty((b, nn), dtype=torch.int32, device=newpts.device)
+    lib = _lib.load()
+    wsb = lib.rfnet_merge_layer_workspace_bytes(b, nr, nn)
+    ws = _workspace(wsb, newpts.device)
+    with torch.cuda.device(newpts.device):
+        _lib.check(lib.rfnet_merge_layer(b, nr, _ptr(rawpts), nn, _ptr(newpts), _ptr(decfactor), _ptr(out), _ptr(idx), _ptr(ws), wsb, _stream(newpts)),
+                   "rfnet_merge_layer")
+    return out, idx
+
+
+@merge_layer_op.register_fake
+def _(rawpts, newpts, decfactor):
+    return torch.empty_like(newpts), newpts.new_empty((newpts.shape[0], newpts.shape[1]), dtype=torch.int32)
+
+
+@torch.library.custom_op("rfnet::merge_layer_grad", mutates_args=(), device_types="cuda")
+def merge_layer_grad_op(rawpts: torch.Tensor, newpts: torch.Tensor, decfactor: torch.Tensor, idx: torch.Tensor,
+                        grad_out: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    # -> (grad_new (b,n_new,3), grad_raw_rows (b,n_new,3) to be scattered into rawpts by idx, partial sums of d/d decfactor)
+    rawpts, newpts, grad_out = _cuda_f32("rawpts", rawpts), _cuda_f32("newpts", newpts), _cuda_f32("grad_out", grad_out)
+    decfactor, idx = _cuda_f32("decfactor", decfactor).reshape(-1), _cuda_i32("idx", idx)
+    b, nr, nn = rawpts.shape[0], rawpts.shape[1], newpts.shape[1]
+    lib = _lib.load()
+    g_new, g_rows = torch.empty_like(newpts), torch.empty_like(newpts)
+    part = torch.zeros((max(int(lib.rfnet_merge_layer_grad_partials(b, nn)), 1),), dtype=torch.float32, device=newpts.device)
+    with torch.cuda.device(newpts.device):
+        _lib.check(lib.rfnet_merge_layer_grad(b, nr, _ptr(rawpts), nn, _ptr(newpts), _ptr(idx), _ptr(decfactor), _ptr(grad_out), _ptr(g_new), _ptr(g_rows),
+                                              _ptr(part), _stream(newpts)), "rfnet_merge_layer_grad")
+    return g_new, g_rows, part
+
+
+@merge_layer_grad_op.register_fake
+def _(rawpts, newpts, decfactor, idx, grad_out):
+    return torch.empty_like(newpts), torch.empty_like(newpts), newpts.new_empty((1,))
+
+
+def _merge_setup(ctx, inputs, output):
+    rawpts, newpts, decfactor = inputs
+    ctx.dec_shape = decfactor.shape
+    ctx.save_for_backward(rawpts, newpts, decfactor, output[1])
+
+
+def _merge_backward(ctx, grad_out, grad_idx):
+    rawpts, newpts, decfactor, idx = ctx.saved_tensors
+    g_new, g_rows, part = merge_layer_grad_op(rawpts, newpts, decfactor, idx, grad_out.contiguous())
+    # scatter the rows into the raw cloud: GroupPointGrad with one sample per row (the reference's graph: group_point's gradient)
+    g_raw = group_point_grad_planned_op(g_rows.unsqueeze(2), scatter_plan_cached(idx, rawpts.shape[1]), rawpts.shape[1])
+    return g_raw, g_new, part.sum().reshape(ctx.dec_shape)
+
+
+merge_layer_op.register_autograd(_merge_backward, setup_context=_merge_setup)
+
+
 # ------------------------------------------------------------------------------------------------------------ approx_match
 @torch.library.custom_op("rfnet::approx_match", mutates_args=(), device_types="cuda")
 def approx_match_op(xyz1: torch.Tensor, xyz2: torch.Tensor, flags: int = 0) -> torch.Tensor:
@@ -278,6 +342,7 @@ match_cost_op.register_autograd(_match_cost_backward, setup_context=_match_cost_
 EMD_EXACT = 1        # RFNET_EMD_EXACT: bit-identical to the reference CUDA binary
 EMD_NO_PRUNE = 2     # RFNET_EMD_NO_PRUNE
 EMD_SPLIT_SUMS = 4   # RFNET_EMD_SPLIT_SUMS: split every sum (more parallelism for tiny batches, different rounding order)
+EMD_PRUNE = 8        # RFNET_EMD_PRUNE: exactly-pruned sweeps at the three sharpest levels (identical results)
 
 
 @torch.library.custom_op("rfnet::emd_cost", mutates_args=(), device_types="cuda")
@@ -342,6 +407,77 @@ def _emd_cost_grad_backward(ctx, grad_cost, grad_g1, grad_g2):
 
 
 emd_cost_grad_op.register_autograd(_emd_cost_grad_backward, setup_context=_emd_cost_grad_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------ scatter plans
+@torch.library.custom_op("rfnet::scatter_plan", mutates_args=(), device_types="cuda")
+def scatter_plan_op(idx: torch.Tensor, n_targets: int) -> torch.Tensor:
+    """The inverted index ("plan") of idx read as (b, rows) targets in [0, n_targets): what the atomic-free gradient scatters
+    need, built once -- at forward time, off the backward's critical path -- and shared by every gradient through the same idx."""
+    idx = _cuda_i32("idx", idx)
+    b = idx.shape[0]
+    rows = idx.numel() // max(b, 1)
+    lib = _lib.load()
+    nbytes = lib.rfnet_scatter_plan_bytes(b, n_targets, rows)
+    plan = _workspace(nbytes, idx.device)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.rfnet_scatter_plan_build(b, n_targets, rows, _ptr(idx), _ptr(plan), nbytes, _stream(idx)), "rfnet_scatter_plan_build")
+    return plan
+
+
+@scatter_plan_op.register_fake
+def _(idx, n_targets):
+    return idx.new_empty((1,), dtype=torch.uint8)
+
+
+@torch.library.custom_op("rfnet::group_point_grad_planned", mutates_args=(), device_types="cuda")
+def group_point_grad_planned_op(grad_out: torch.Tensor, plan: torch.Tensor, n: int) -> torch.Tensor:
+    # GroupPointGradGpuOp (tf_grouping.cpp:178-212) over a plan of its idx; grad_out (b, m, nsample, c) -> (b, n, c)
+    grad_out = _cuda_f32("grad_out", grad_out)
+    b, m, ns, c = grad_out.shape
+    g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(_lib.load().rfnet_group_point_grad_planned(b, n, c, m, ns, _ptr(grad_out), _ptr(plan), plan.numel(), _ptr(g), _stream(grad_out)),
+                   "rfnet_group_point_grad_planned")
+    return g
+
+
+@group_point_grad_planned_op.register_fake
+def _(grad_out, plan, n):
+    return grad_out.new_empty((grad_out.shape[0], n, grad_out.shape[3]))
+
+
+@torch.library.custom_op("rfnet::three_interpolate_grad_planned", mutates_args=(), device_types="cuda")
+def three_interpolate_grad_planned_op(grad_out: torch.Tensor, weight: torch.Tensor, plan: torch.Tensor, m: int) -> torch.Tensor:
+    # ThreeInterpolateGradOp (tf_interpolate.cpp:226-262) over a plan of its idx; grad_out (b, n, c) -> (b, m, c)
+    grad_out, weight = _cuda_f32("grad_out", grad_out), _cuda_f32("weight", weight)
+    b, n, c = grad_out.shape
+    g = torch.empty((b, m, c), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(_lib.load().rfnet_three_interpolate_grad_planned(b, n, c, m, _ptr(grad_out), _ptr(weight), _ptr(plan), plan.numel(), _ptr(g),
+                                                                    _stream(grad_out)), "rfnet_three_interpolate_grad_planned")
+    return g
+
+
+@three_interpolate_grad_planned_op.register_fake
+def _(grad_out, weight, plan, m):
+    return grad_out.new_empty((grad_out.shape[0], m, grad_out.shape[2]))
+
+
+# plans of the idx tensors seen most recently: the xyz and the feature grouping of one layer share one (SURVEY.md 8a a9).
+# An entry keeps its idx tensor alive, so its address cannot be recycled while the entry exists; _version guards in-place edits.
+_PLAN_CACHE = []
+_PLAN_CACHE_SIZE = 4
+
+
+def scatter_plan_cached(idx, n_targets):
+    for e in _PLAN_CACHE:
+        if e[0] is idx and e[1] == idx._version and e[2] == n_targets:
+            return e[3]
+    plan = scatter_plan_op(idx.reshape(idx.shape[0], -1), n_targets)
+    _PLAN_CACHE.insert(0, (idx, idx._version, n_targets, plan))
+    del _PLAN_CACHE[_PLAN_CACHE_SIZE:]
+    return plan
 
 
 # ------------------------------------------------------------------------------------------------------------ sampling
@@ -411,12 +547,14 @@ def _(inp, idx, out_g):
 
 
 def _gather_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    inp, idx = inputs
+    ctx.n = inp.shape[1]
+    ctx.save_for_backward(scatter_plan_cached(idx, inp.shape[1]))   # the inverted index, built while the forward runs
 
 
 def _gather_backward(ctx, out_g):
-    inp, idx = ctx.saved_tensors  # tf_ops/sampling/tf_sampling.py:43-47
-    return gather_point_grad_op(inp, idx, out_g), None
+    (plan,) = ctx.saved_tensors  # tf_ops/sampling/tf_sampling.py:43-47; gather_point's gradient is group_point's with nsample = 1
+    return group_point_grad_planned_op(out_g.contiguous().unsqueeze(2), plan, ctx.n), None
 
 
 gather_point_op.register_autograd(_gather_backward, setup_context=_gather_setup)
@@ -495,12 +633,14 @@ def _(points, idx, grad_out):
 
 
 def _group_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    points, idx = inputs
+    ctx.n = points.shape[1]
+    ctx.save_for_backward(scatter_plan_cached(idx, points.shape[1]))   # the inverted index, built while the forward runs
 
 
 def _group_backward(ctx, grad_out):
-    points, idx = ctx.saved_tensors  # tf_ops/grouping/tf_grouping.py:42-46
-    return group_point_grad_op(points, idx, grad_out), None
+    (plan,) = ctx.saved_tensors  # tf_ops/grouping/tf_grouping.py:42-46
+    return group_point_grad_planned_op(grad_out.contiguous(), plan, ctx.n), None
 
 
 group_point_op.register_autograd(_group_backward, setup_context=_group_setup)
@@ -525,6 +665,24 @@ def knn_point_op(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.
 def _(xyz1, xyz2, k):
     b, m = xyz2.shape[0], xyz2.shape[1]
     return xyz1.new_empty((b, m, k)), xyz1.new_empty((b, m, k), dtype=torch.int32)
+
+
+def _knn_setup(ctx, inputs, output):
+    xyz1, xyz2, _k = inputs
+    ctx.save_for_backward(xyz1, xyz2, output[1])
+
+
+def _knn_backward(ctx, grad_val, grad_idx):
+    # val[b,j,t] = -|xyz1[b, idx[b,j,t]] - xyz2[b,j]|^2  (the reference's top_k(-dist) is differentiable in the same way):
+    # d val / d xyz2[j] = +2 (x - q), d val / d xyz1[idx] = -2 (x - q); the scatter into xyz1 is group_point's gradient kernel
+    xyz1, xyz2, idx = ctx.saved_tensors
+    diff = group_point_op(xyz1, idx) - xyz2.unsqueeze(2)                 # (b, m, k, 3)
+    w = (2.0 * grad_val).unsqueeze(-1) * diff
+    g1 = group_point_grad_planned_op((-w).contiguous(), scatter_plan_cached(idx, xyz1.shape[1]), xyz1.shape[1])
+    return g1, w.sum(2), None
+
+
+knn_point_op.register_autograd(_knn_backward, setup_context=_knn_setup)
 
 
 @torch.library.custom_op("rfnet::selection_sort", mutates_args=(), device_types="cuda")
@@ -647,12 +805,14 @@ def _(points, idx, weight, grad_out):
 
 
 def _interp_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    points, idx, weight = inputs
+    ctx.m = points.shape[1]
+    ctx.save_for_backward(weight, scatter_plan_cached(idx, points.shape[1]))   # the inverted index, built while the forward runs
 
 
 def _interp_backward(ctx, grad_out):
-    points, idx, weight = ctx.saved_tensors  # tf_ops/interpolation/tf_interpolate.py:29-34
-    return three_interpolate_grad_op(points, idx, weight, grad_out), None, None
+    weight, plan = ctx.saved_tensors  # tf_ops/interpolation/tf_interpolate.py:29-34
+    return three_interpolate_grad_planned_op(grad_out.contiguous(), weight, plan, ctx.m), None, None
 
 
 three_interpolate_op.register_autograd(_interp_backward, setup_context=_interp_setup)

@@ -58,11 +58,13 @@ def knn_point(k, xyz1, xyz2):
         idx: (batch_size, npoint, k) int32 array, indices to input points
 
     The reference implements this with framework ops only (tf.nn.top_k on a materialised (b,m,n) matrix, "ONLY SUPPORT
-    CPU", tf_grouping.py:64-73).  For 3-d CUDA points and k <= 32 this uses the rfnet::knn_point kernel, which never builds
-    the matrix; any other input (feature vectors, large k) takes the reference's framework formulation.
+    CPU", tf_grouping.py:64-73).  Here it is the rfnet::knn_point kernel, which never builds the matrix: 3-d float32 CUDA
+    points and k <= 32 (what the model uses).  Anything else is an error -- there is no framework fallback.
+    val is differentiable w.r.t. both clouds (as top_k(-dist) is in the reference); ties keep the lowest index first.
     '''
-    if xyz1.is_cuda and xyz1.shape[-1] == 3 and xyz2.shape[-1] == 3 and 0 < int(k) <= min(32, xyz1.shape[1]) and xyz1.dtype == torch.float32:
-        return ops.knn_point_op(xyz1.detach(), xyz2.detach(), int(k))
-    dist = ((xyz1[:, None, :, :] - xyz2[:, :, None, :]) ** 2).sum(-1)
-    val, idx = torch.topk(-dist, k=int(k), dim=-1)
-    return val, idx.to(torch.int32)
+    if xyz1.shape[-1] != 3 or xyz2.shape[-1] != 3:
+        raise ValueError("knn_point: the kernel handles 3-d points (got %d-d); the reference's framework formulation for feature "
+                         "vectors is not reproduced" % xyz1.shape[-1])
+    if not 0 < int(k) <= min(32, xyz1.shape[1]):
+        raise ValueError("knn_point: the kernel handles 0 < k <= min(32, ndataset) (got k=%d, ndataset=%d)" % (int(k), xyz1.shape[1]))
+    return ops.knn_point_op(xyz1, xyz2, int(k))

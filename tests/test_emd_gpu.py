@@ -31,6 +31,7 @@ SPLIT_GRAD_VS_REF = 2.5e-3
 EXACT = 1                 # RFNET_EMD_EXACT
 NO_PRUNE = 2              # RFNET_EMD_NO_PRUNE
 SPLIT = 4                 # RFNET_EMD_SPLIT_SUMS
+PRUNE = 8                 # RFNET_EMD_PRUNE
 
 
 def match_tol(x1, x2, want):
@@ -314,11 +315,11 @@ def test_emd_cost_fused_edge_and_grad(cuda, rng):
 
 
 @pytest.mark.parametrize("b,n,m,kind", [(2, 4096, 4096, "cube"), (1, 5000, 4100, "cube"), (1, 4096, 8192, "sphere"), (130, 4096, 4096, "cube"),
-                                        (1, 16384, 16384, "sphere")])
+                                        (1, 16384, 16384, "sphere"), (3, 1030, 2049, "cube")])
 def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
-    """From 4096 points per cloud the three sharpest levels run as pruned sweeps (Morton-ordered rows, per-cluster candidate
-    masks).  Skipped terms are exact zeros and the surviving ones are added in the same order, so the plan must be
-    BIT-IDENTICAL to the dense sweeps' (flags = RFNET_EMD_NO_PRUNE), with whole-row chains and with split sums."""
+    """With RFNET_EMD_PRUNE (clouds of 1024 .. 32768 points) the three sharpest levels run as pruned sweeps (Morton-ordered rows,
+    per-cluster candidate masks).  Skipped terms are exact zeros and the surviving ones are added in the same order, so the plan
+    must be BIT-IDENTICAL to the dense sweeps'."""
     from rfnet_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(1000 + n + m + b)
     def pts(count):
@@ -328,12 +329,10 @@ def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
             x[:, : count // 16] = x[:, count // 16: 2 * (count // 16)]
         return x.to(cuda)
     x1, x2 = pts(n), pts(m)
-    for base in (0, SPLIT):
-        pruned = ops.approx_match_op(x1, x2, base)
-        cost_pruned, g1p, g2p = ops.emd_cost_grad_op(x1, x2, base)
-        dense = ops.approx_match_op(x1, x2, base | NO_PRUNE)
-        cost_dense, g1d, g2d = ops.emd_cost_grad_op(x1, x2, base | NO_PRUNE)
-        assert torch.equal(pruned, dense)
-        assert torch.equal(cost_pruned, cost_dense) and torch.equal(g1p, g1d) and torch.equal(g2p, g2d)
-        assert float(dense.sum()) > 0.9 * b * min(n, m)
-        del pruned, dense
+    pruned = ops.approx_match_op(x1, x2, PRUNE)
+    cost_pruned, g1p, g2p = ops.emd_cost_grad_op(x1, x2, PRUNE)
+    dense = ops.approx_match_op(x1, x2, 0)
+    cost_dense, g1d, g2d = ops.emd_cost_grad_op(x1, x2, PRUNE | NO_PRUNE)
+    assert torch.equal(pruned, dense)
+    assert torch.equal(cost_pruned, cost_dense) and torch.equal(g1p, g1d) and torch.equal(g2p, g2d)
+    assert float(dense.sum()) > 0.9 * b * min(n, m)

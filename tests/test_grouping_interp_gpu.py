@@ -293,3 +293,96 @@ def test_knn_point_kernel_bit_exact(cuda, rng, b, n, m, k):
     d = ((t(x1, cuda)[:, None] - t(x2, cuda)[:, :, None]) ** 2).sum(-1)
     tv, _ = torch.topk(-d, k=k, dim=-1)
     assert torch.allclose(gv, tv, rtol=1e-5, atol=1e-7)
+
+
+def test_knn_point_gradient_and_errors(cuda, rng):
+    """val = top_k(-dist) is differentiable in the reference (framework ops); the kernel path registers the same gradient:
+    d val / d query = 2 (x - q), d val / d dataset[idx] = -2 (x - q), scattered with the atomic-free group_point gradient."""
+    from rfnet_b200 import tf_grouping
+    b, n, m, k = 2, 300, 50, 6
+    x1 = t(cloud(rng, b, n), cuda).requires_grad_(True)
+    x2 = t(cloud(rng, b, m), cuda).requires_grad_(True)
+    wgt = torch.randn((b, m, k), generator=torch.Generator(device="cpu").manual_seed(3)).to(cuda)
+    val, idx = tf_grouping.knn_point(k, x1, x2)
+    (val * wgt).sum().backward()
+    g1, g2 = x1.grad.clone(), x2.grad.clone()
+    x1.grad = x2.grad = None
+    d = ((x1[:, None] - x2[:, :, None]) ** 2).sum(-1)                         # the reference's formulation
+    tv, ti = torch.topk(-d, k=k, dim=-1)
+    assert torch.equal(ti.to(torch.int32), idx)
+    (tv * wgt).sum().backward()
+    assert torch.allclose(g1, x1.grad, rtol=1e-5, atol=1e-6) and torch.allclose(g2, x2.grad, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError, match="3-d points"):
+        tf_grouping.knn_point(4, torch.zeros((1, 8, 5), device=cuda), torch.zeros((1, 2, 5), device=cuda))
+    with pytest.raises(ValueError, match="k <= min"):
+        tf_grouping.knn_point(40, torch.zeros((1, 64, 3), device=cuda), torch.zeros((1, 2, 3), device=cuda))
+
+
+@pytest.mark.parametrize("c", [3, 16])
+def test_scatter_plans_equal_unplanned_gradients(cuda, rng, c):
+    """A scatter plan (the inverted idx, built once) gives the same bits as the gradient that builds its own, for group_point,
+    gather_point and three_interpolate; autograd builds the plan at forward time and shares it between calls on the same idx."""
+    from rfnet_b200 import ops, tf_grouping, tf_interpolate, tf_sampling
+    b, n, m, ns = 2, 400, 150, 8
+    pts = rng.standard_normal((b, n, c)).astype(np.float32)
+    idx = rng.integers(0, n, size=(b, m, ns)).astype(np.int32)
+    go = rng.standard_normal((b, m, ns, c)).astype(np.float32)
+    tp, ti, tg = t(pts, cuda), t(idx, cuda), t(go, cuda)
+    want = ops.group_point_grad_op(tp, ti, tg)
+    plan = ops.scatter_plan_op(ti.reshape(b, -1), n)
+    assert torch.equal(ops.group_point_grad_planned_op(tg, plan, n), want)
+    assert np.array_equal(want.cpu().numpy(), port.group_point_grad(pts, idx, go))
+    # autograd: two gathers through the same idx share one plan; results unchanged
+    a1 = tp.clone().requires_grad_(True)
+    a2 = tp.clone().requires_grad_(True)
+    (tf_grouping.group_point(a1, ti) * tg).sum().backward()
+    n_plans = len(ops._PLAN_CACHE)
+    (tf_grouping.group_point(a2, ti) * tg).sum().backward()
+    assert len(ops._PLAN_CACHE) == n_plans                                    # cache hit: no new plan
+    assert torch.equal(a1.grad, want) and torch.equal(a2.grad, want)
+    # three_interpolate: idx (b, n3, 3) into m known points
+    n3 = 500
+    i3 = rng.integers(0, m, size=(b, n3, 3)).astype(np.int32)
+    w3 = rng.random((b, n3, 3)).astype(np.float32)
+    feats = rng.standard_normal((b, m, c)).astype(np.float32)
+    g3 = rng.standard_normal((b, n3, c)).astype(np.float32)
+    want3 = ops.three_interpolate_grad_op(t(feats, cuda), t(i3, cuda), t(w3, cuda), t(g3, cuda))
+    plan3 = ops.scatter_plan_op(t(i3, cuda).reshape(b, -1), m)
+    assert torch.equal(ops.three_interpolate_grad_planned_op(t(g3, cuda), t(w3, cuda), plan3, m), want3)
+    assert np.array_equal(want3.cpu().numpy(), port.three_interpolate_grad(feats, i3, w3, g3))
+    f = t(feats, cuda).requires_grad_(True)
+    (tf_interpolate.three_interpolate(f, t(i3, cuda), t(w3, cuda)) * t(g3, cuda)).sum().backward()
+    assert torch.equal(f.grad, want3)
+    # gather_point: group_point's gradient with one sample per row
+    if c == 3:
+        gi = rng.integers(0, n, size=(b, m)).astype(np.int32)
+        og = rng.standard_normal((b, m, 3)).astype(np.float32)
+        x = tp.clone().requires_grad_(True)
+        tf_sampling.gather_point(x, t(gi, cuda)).backward(t(og, cuda))
+        assert np.array_equal(x.grad.cpu().numpy(), port.gather_point_grad(pts, gi, og))
+
+
+def test_scatter_gradient_every_segment_length_class(cuda, rng):
+    """Segments of the inverted index are sorted by one thread (<= 16 entries), one warp (<= 1024), one CTA (bitonic, <= 8192)
+    or left in claim order (longer): the gradient must equal the sequential oracle in every sorted class, and the long classes
+    must not be slow (the first version's O(L^2) global-memory sort took tens of milliseconds at L = 8192)."""
+    import time
+    from rfnet_b200 import ops
+    b, n, c = 2, 64, 4
+    lengths = [1, 5, 16, 17, 300, 1024, 1025, 5000, 8192]
+    rows = sum(lengths)
+    idx = np.concatenate([np.full(L, t_, np.int32) for t_, L in enumerate(lengths)])
+    perm = rng.permutation(rows)
+    idx = np.stack([idx[perm], idx[rng.permutation(rows)]])[:, :, None]      # (b, rows, 1): target t_ receives lengths[t_] rows
+    go = rng.standard_normal((b, rows, 1, c)).astype(np.float32)
+    pts = np.zeros((b, n, c), np.float32)
+    want = port.group_point_grad(pts, idx, go)
+    tp, ti, tg = t(pts, cuda), t(idx, cuda), t(go, cuda)
+    got = ops.group_point_grad_op(tp, ti, tg)
+    assert np.array_equal(got.cpu().numpy(), want)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ops.group_point_grad_op(tp, ti, tg)
+    torch.cuda.synchronize()
+    assert (time.perf_counter() - t0) / 5 < 2e-3, "a long-segment sort is slow again"

@@ -17,10 +17,10 @@ float run(int b, int n, int split_len, float lvl2, const float* x1, const float*
     a.perm = nullptr; a.mask = nullptr;
     const unsigned grid = (unsigned)(b * a.nrt * a.nsplit);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; ++i) emd_sweep_kernel<Q, MODE, false, false, false><<<grid, EMD_THREADS>>>(a);
+    for (int i = 0; i < 2; ++i) emd_sweep_kernel<Q, MODE, false><<<grid, EMD_THREADS>>>(a);
     cudaEventRecord(e0);
     const int it = 5;
-    for (int i = 0; i < it; ++i) emd_sweep_kernel<Q, MODE, false, false, false><<<grid, EMD_THREADS>>>(a);
+    for (int i = 0; i < it; ++i) emd_sweep_kernel<Q, MODE, false><<<grid, EMD_THREADS>>>(a);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     ms /= it;
@@ -31,11 +31,11 @@ float run(int b, int n, int split_len, float lvl2, const float* x1, const float*
 }
 
 template <int MODE, int NT>
-float run_row(int b, int n, float lvl2, const float* x1, const float* x2, const float* w, float* scratch) {
+float run_row(int b, int n, float lvl2, const float* x1, const float* x2, const float* w, float* scratch, float4* pA, float2* pZ) {
     SweepArgs a;
-    a.nr = n; a.nc = n; a.nrt = (n + NT - 1) / NT; a.nsplit = 1; a.split_len = n; a.nwords = (n + 31) / 32;
+    a.nr = n; a.nc = n; a.nrt = (n + NT - 1) / NT; a.nsplit = 1; a.split_len = n; a.nwords = (n + 31) / 32; a.npad = emd_npad(n); a.tma = (n % 4 == 0);
     a.lvl2 = lvl2; a.lvl2b = lvl2 * 0.25f; a.init0 = 1e-9f;
-    a.rows = x1; a.cands = x2; a.w = w; a.wb = w; a.rowfac = w;
+    a.rows = x1; a.cands = x2; a.w = w; a.wb = w; a.rowfac = w; a.pairA = pA; a.pairZ = pZ;
     a.partial = nullptr; a.partial_b = nullptr;
     a.remain = scratch; a.ratio = scratch + (size_t)b * n; a.fac = scratch + 2 * (size_t)b * n;
     a.perm = nullptr; a.mask = nullptr;
@@ -49,7 +49,7 @@ float run_row(int b, int n, float lvl2, const float* x1, const float* x2, const 
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     ms /= it;
     const double pp = (double)b * n * n * (MODE == 4 ? 2 : 1);
-    printf("  mode %d ROW kernel NT=%3d (one chain per row)   grid=%6u (%5.1f CTAs/SM): %8.3f ms  %.2f Tpair-pass/s  MUFU %.1f%%\n", MODE, NT, grid,
+    printf("  mode %d ROW kernel NT=%3d unroll %d (one chain per row)   grid=%6u (%5.1f CTAs/SM): %8.3f ms  %.2f Tpair-pass/s  MUFU %.1f%%\n", MODE, NT, EMD_ROW_UNROLL, grid,
            grid / 148.0, ms, pp / ms / 1e9, 100.0 * pp / (ms * 1e-3) / (148.0 * 16 * 1.965e9));
     return ms;
 }
@@ -72,11 +72,17 @@ int main() {
         cudaMemset(scratch, 0, (size_t)b * n * 3 * 4);
         printf("b=%d n=m=%d, level -64\n", b, n);
         const float lvl2 = -64.0f * LOG2E;
-        run_row<1, 128>(b, n, lvl2, x1, x2, w, scratch);
-        run_row<1, 64>(b, n, lvl2, x1, x2, w, scratch);
-        run_row<4, 128>(b, n, lvl2, x1, x2, w, scratch);
-        run_row<4, 64>(b, n, lvl2, x1, x2, w, scratch);
-        for (int sl : {128, 512, 2048}) {
+        float4* pA; float2* pZ;
+        cudaMalloc(&pA, (size_t)b * emd_npad(n) * 16); cudaMalloc(&pZ, (size_t)b * emd_npad(n) * 8);
+        emd_pairs_kernel<<<dim3((unsigned)((emd_npad(n) + 255) / 256), (unsigned)b), 256>>>(n, emd_npad(n), x2, pA, pZ);
+        run_row<1, 128>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<1, 64>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<1, 32>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<4, 128>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<4, 64>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<4, 32>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        cudaFree(pA); cudaFree(pZ);
+        for (int sl : {512}) {
             if (sl > n || (n + sl - 1) / sl > 256) continue;
             run<2, 1>(b, n, sl, lvl2, x1, x2, w, partial, scratch);
             run<4, 1>(b, n, sl, lvl2, x1, x2, w, partial, scratch);

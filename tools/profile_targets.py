@@ -11,10 +11,13 @@ what = sys.argv[1] if len(sys.argv) > 1 else "emd16k"
 if what in ("emd16k", "emd2k"):
     b, n = (4, 16384) if what == "emd16k" else (32, 2048)
     x1, x2 = rnd(b, n), rnd(b, n)
+    flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     for _ in range(2):
-        m = tf_approxmatch.approx_match(x1, x2)
+        m = ops.approx_match_op(x1, x2, flags)
         c = tf_approxmatch.match_cost(x1, x2, m)
-        ops.match_cost_grad_op(x1, x2, m)
+        ops.match_cost_grad_op(x1, x2, m)              # one-pass gradient from a stored matrix
+        del m
+        ops.emd_cost_grad_op(x1, x2, flags)            # matrix-free cost + both gradients
 elif what == "fps":
     x = rnd(32, 16384)
     for _ in range(2):
@@ -30,6 +33,9 @@ elif what == "config4":
         grp = tf_grouping.group_point(f, bi)
         d, i3 = tf_interpolate.three_nn(x, q)
         w = torch.rand((32, 16384, 3), device=dev)
-        tf_interpolate.three_interpolate(torch.randn((32, 2048, 64), device=dev), i3, w)
+        feats = torch.randn((32, 2048, 64), device=dev)
+        tf_interpolate.three_interpolate(feats, i3, w)
+        ops.group_point_grad_op(f, bi, grp)
+        ops.three_interpolate_grad_op(feats, i3, w, f)
 torch.cuda.synchronize()
 print("done", what)

@@ -44,7 +44,7 @@ if "nn" in which:
             line += " | reference kernel %.3f ms = %.1f Gpairs/s | speedup %.2fx" % (rmn, pairs / rmn / 1e6, rmn / mn)
         print(line, flush=True)
 if "emd" in which:
-    for (b, n) in [(32, 2048), (4, 2048), (32, 1024), (32, 64), (4, 16384), (8, 16384), (1, 16384)]:
+    for (b, n) in [(32, 2048), (4, 2048), (32, 1024), (32, 64), (4, 16384), (8, 16384), (1, 16384), (32, 16384)]:
         x1, x2 = rnd(b, n, 3), rnd(b, n, 4)
         med, mn = timeit(lambda: tf_approxmatch.approx_match(x1, x2), warm=2, iters=5)
         match = tf_approxmatch.approx_match(x1, x2)
@@ -52,7 +52,8 @@ if "emd" in which:
         gmed, gmn = timeit(lambda: ops.match_cost_grad_op(x1, x2, match), warm=2, iters=5)
         _, xmn = timeit(lambda: ops.approx_match_op(x1, x2, 1), warm=2, iters=5)
         _, smn = timeit(lambda: ops.approx_match_op(x1, x2, 4), warm=2, iters=5)
-        line = "emd b=%d n=m=%d: approx_match %.3f ms (%.1f clouds/s) [exact mode %.3f ms, split sums %.3f ms], match_cost %.3f ms, grad %.3f ms" % (b, n, mn, b / mn * 1e3, xmn, smn, cmn, gmn)
+        _, pmn = timeit(lambda: ops.approx_match_op(x1, x2, 8), warm=2, iters=5)
+        line = "emd b=%d n=m=%d: approx_match %.3f ms (%.1f clouds/s) [exact mode %.3f ms, split sums %.3f ms, pruned %.3f ms], match_cost %.3f ms, grad %.3f ms" % (b, n, mn, b / mn * 1e3, xmn, smn, pmn, cmn, gmn)
         if have_ref and b * n * n < 2 ** 31:
             rmed, rmn = timeit(lambda: ref.run_gpu("ApproxMatch", [x1, x2], [((b, n, n), torch.float32)]), warm=1, iters=2)
             line += " | reference approxmatch %.3f ms (%.1f clouds/s) speedup %.1fx" % (rmn, b / rmn * 1e3, rmn / mn)
