@@ -285,7 +285,7 @@ def emd_shard_step(D, n, clouds_total, seed, flags=0):
     return step, nb
 
 
-def recon_shard_step(D, n, clouds_total, seed):
+def recon_shard_step(D, n, clouds_total, seed, host_inputs=None):
     """BASELINE configs[4]: chamfer_big + earth_mover of 16384-point outputs vs GT, forward + backward w.r.t. the output cloud,
     on this rank's slice of `clouds_total` clouds, then the all-reduce of the six partial sums (vv_recon.py:381-399,484-493)."""
     torch, dist = D.torch, D.dist
@@ -293,8 +293,11 @@ def recon_shard_step(D, n, clouds_total, seed):
     lo, hi = losses.shard_bounds(clouds_total, D.rank, D.world)
     nb = hi - lo
     g = torch.Generator(device="cpu").manual_seed(seed)
-    out = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
-    gt = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    if host_inputs is None:
+        out = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+        gt = (torch.rand((clouds_total, n, 3), generator=g) - 0.5)[lo:hi].contiguous().to(D.dev)
+    else:   # device buffers the caller refills from pinned host memory every step
+        out, gt = torch.empty_like(host_inputs[0], device=D.dev), torch.empty_like(host_inputs[1], device=D.dev)
     res = torch.zeros(6, device=D.dev)
     f32, i32 = torch.float32, torch.int32
     nbm = max(nb, 1)
@@ -314,6 +317,8 @@ def recon_shard_step(D, n, clouds_total, seed):
         if D.world > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM)
         res.copy_(part)
+    if host_inputs is not None:
+        return step, nb, res, (out, gt)
     return step, nb, res
 
 
@@ -433,6 +438,23 @@ def run_recon_loss(args):
     sampler.stop()
     value = RB_TOTAL / (ms * 1e-3)
     clocks = sampler.result()
+    # e2e: the same step with this rank's clouds coming from pinned HOST memory every step and the six loss sums read back
+    from rfnet_b200 import losses as _losses
+    lo, hi = _losses.shard_bounds(RB_TOTAL, D.rank, D.world)
+    g = torch.Generator(device="cpu").manual_seed(500)
+    h_out = (torch.rand((RB_TOTAL, RN, 3), generator=g) - 0.5)[lo:hi].contiguous().pin_memory()
+    h_gt = (torch.rand((RB_TOTAL, RN, 3), generator=g) - 0.5)[lo:hi].contiguous().pin_memory()
+    host_res = torch.empty(6).pin_memory()
+    e_step, _, e_res, e_bufs = recon_shard_step(D, RN, RB_TOTAL, 500, host_inputs=(h_out, h_gt))
+
+    def e2e_step():
+        e_bufs[0].copy_(h_out, non_blocking=True)
+        e_bufs[1].copy_(h_gt, non_blocking=True)
+        e_step()
+        host_res.copy_(e_res, non_blocking=True)
+    k_e2e = max(2, min(steps, 5))
+    ms_e2e = D.timed(e2e_step, k_e2e, warm=1)
+    e2e_value = RB_TOTAL / (ms_e2e * 1e-3)
     sm_max = (clocks["sm_max_mhz"] or 1965) * 1e6
     achieved = value / D.world * 30.0 * RN * RN
     line = {"metric": "recon_loss_clouds_per_s", "value": value, "unit": "clouds/s", "n_gpus": D.world, "steps": steps, "warmup": warm,
@@ -442,7 +464,8 @@ def run_recon_loss(args):
                        "l2": "flushed: every step begins by overwriting a 256 MiB buffer (2 x the 126 MB L2), inside the timed region",
                        "emd": "rfnet_emd_cost_grad: cost and both gradients without any (b, m, n) match tensor"},
             "clocks": clocks, "gpu_launches": (launches or 0) * steps, "gpu_launches_per_step": launches,
-            "e2e": {"value": None, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "see --workload chamfer for the host-buffer e2e"},
+            "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": 2 * (hi - lo) * RN * 12, "d2h_bytes_per_step": 24, "steps": k_e2e,
+                    "api": "per step: this rank's output and GT clouds copied from pinned host memory, rfnet_chamfer_step + rfnet_emd_cost_grad, six loss sums read back"},
             "roofline": {"bound": "mufu_ex2_pipe (co-limited with the FP32 pipe)", "kernel": "rfnet::emd_sweep_kernel (21 sweeps) + emd_pair_kernel x2, nn_search",
                          "achieved": achieved / 1e12, "peak": mufu_peak(sm_max) / 1e12, "unit": "Tex2/s", "frac": achieved / mufu_peak(sm_max),
                          "peak_source": "148 SMs x 16 MUFU lanes x %.0f MHz (architectural)" % (sm_max / 1e6), "algorithmic_ex2_per_cloud": 30.0 * RN * RN,

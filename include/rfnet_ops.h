@@ -109,9 +109,10 @@ int rfnet_merge_layer_grad(int b, int n_raw, const float *raw, int n_new, const 
  *                              (<= 1.1e-6 relative per matrix entry).
  *   RFNET_EMD_EXACT            additionally the reference's non-flushing __expf, no pruning, every exponential of the final
  *                              pass through the MUFU: match is bit-identical to the reference CUDA binary's.
- *   RFNET_EMD_PRUNE            run the three sharpest levels as exactly-pruned sweeps (Morton-ordered rows, per-cluster candidate
- *                              masks; terms that the flushing exponential makes exactly 0 are skipped): identical results.
- *                              Opt-in: on B200 it only pays for large batches of large clouds.
+ *   RFNET_EMD_PRUNE            force the exactly-pruned sweeps of the two sharpest levels (curve-ordered rows, per-cluster
+ *                              candidate masks; terms that the flushing exponential makes exactly 0 are skipped) for clouds of
+ *                              1024 .. 32768 points.  They are used by default wherever they pay (from ~32768 rows per call of
+ *                              clouds with >= 2048 points); results are bit-identical either way.
  *   RFNET_EMD_NO_PRUNE         dense sweeps at every level (overrides RFNET_EMD_PRUNE).
  *   RFNET_EMD_SPLIT_SUMS       cut every sum into fixed-length pieces added in ascending order: more parallelism when the
  *                              call holds only one or two small clouds, at the price of a different rounding order (the

@@ -102,7 +102,7 @@ struct EmdWs {
     unsigned *maskA, *maskB;     // candidate masks: rows = xyz1 clusters vs xyz2 candidates (passes 1, 3) / the reverse (pass 2)
 };
 // exact pruning pays off from about a thousand points per cloud; the Morton sort handles up to 32768
-static bool emd_prune_enabled(int n, int m) { return n >= 1024 && m >= 1024 && n <= MORTON_SORT_MAX && m <= MORTON_SORT_MAX; }
+static bool emd_prune_enabled(int n, int m) { return n >= 1024 && m >= 1024 && n <= MORTON_SORT_MAX && m <= MORTON_SORT_MAX; }   // (2048 by default, see emd_run)
 static size_t emd_mask_words(int b, int nr, int nc) { return (size_t)b * ((nr + EMD_CLUSTER - 1) / EMD_CLUSTER) * EMD_PRUNE_LEVELS * ((nc + 31) / 32); }
 static int emd_npad(int n) { return (((n + 1) / 2) + 1) & ~1; }   // candidate pairs per cloud, padded to an even count (16-byte rows of float2)
 static size_t emd_partial_floats(int b, int n, int m) {
@@ -1166,10 +1166,12 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
         emd_pairs_kernel<<<dim3((unsigned)((np2 + 255) / 256), (unsigned)b), 256, 0, s>>>(m, np2, xyz2, ws.pairA2, ws.pairZ2);
     }
     // exact pruning of the three sharpest levels (see emd_row_kernel); relies on the flushing exponential's exact zeros
-    // Measured on B200 (profiles/r2_emd_launches_*.csv): a pruned sweep visits few pairs but one at a time (no unrolling across
-    // the gaps of the mask), and at 4 clouds of 16384 points it takes as long as a dense sweep while also breaking up the
-    // fused pass-3 + pass-1 sweeps -- so pruning is opt-in (RFNET_EMD_PRUNE) until the compacted-gather variant lands.
-    const bool prune = (flags & RFNET_EMD_PRUNE) && emd_prune_enabled(n, m) && !(flags & (RFNET_EMD_NO_PRUNE | RFNET_EMD_EXACT | RFNET_EMD_SPLIT_SUMS));
+    // Pruned and dense sweeps give the same bits, so this choice may depend on the batch: the prologue (curve order + masks,
+    // ~0.2 ms for 4 clouds of 16384 points) pays from about 32768 rows per call (measured, profiles/r2_timings_emd.txt: B=32
+    // 2048^2 -5 %, B=4 16384^2 -12 %, B=32 16384^2 -14 %; B=4 2048^2 and B=32 1024^2 would lose 5-7 %).
+    const bool big = n >= 2048 && m >= 2048 && ((n >= 4096 && m >= 4096) || (long)b * (n > m ? n : m) >= 32768);
+    const bool prune = emd_prune_enabled(n, m) && (big || (flags & RFNET_EMD_PRUNE)) &&
+                       !(flags & (RFNET_EMD_NO_PRUNE | RFNET_EMD_EXACT | RFNET_EMD_SPLIT_SUMS));
     const int nwA = (m + 31) / 32, nwB = (n + 31) / 32;
     if (prune) {
         { const int rc = morton_sort(b, n, m, xyz1, xyz2, ws.perm1, ws.perm2, s); if (rc) return rc; }

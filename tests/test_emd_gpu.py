@@ -317,9 +317,9 @@ def test_emd_cost_fused_edge_and_grad(cuda, rng):
 @pytest.mark.parametrize("b,n,m,kind", [(2, 4096, 4096, "cube"), (1, 5000, 4100, "cube"), (1, 4096, 8192, "sphere"), (130, 4096, 4096, "cube"),
                                         (1, 16384, 16384, "sphere"), (3, 1030, 2049, "cube")])
 def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
-    """With RFNET_EMD_PRUNE (clouds of 1024 .. 32768 points) the three sharpest levels run as pruned sweeps (Morton-ordered rows,
-    per-cluster candidate masks).  Skipped terms are exact zeros and the surviving ones are added in the same order, so the plan
-    must be BIT-IDENTICAL to the dense sweeps'."""
+    """The two sharpest levels run as pruned sweeps (Hilbert-ordered rows, per-cluster candidate masks, compacted gathers) --
+    by default where they pay, forced here with RFNET_EMD_PRUNE.  Skipped terms are exact zeros and the surviving ones are
+    added in the same order, so the plan must be BIT-IDENTICAL to the dense sweeps' (RFNET_EMD_NO_PRUNE)."""
     from rfnet_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(1000 + n + m + b)
     def pts(count):
@@ -331,7 +331,7 @@ def test_pruned_sweeps_are_exact(cuda, b, n, m, kind):
     x1, x2 = pts(n), pts(m)
     pruned = ops.approx_match_op(x1, x2, PRUNE)
     cost_pruned, g1p, g2p = ops.emd_cost_grad_op(x1, x2, PRUNE)
-    dense = ops.approx_match_op(x1, x2, 0)
+    dense = ops.approx_match_op(x1, x2, NO_PRUNE)
     cost_dense, g1d, g2d = ops.emd_cost_grad_op(x1, x2, PRUNE | NO_PRUNE)
     assert torch.equal(pruned, dense)
     assert torch.equal(cost_pruned, cost_dense) and torch.equal(g1p, g1d) and torch.equal(g2p, g2d)

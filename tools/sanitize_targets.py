@@ -12,7 +12,21 @@ x1, x2 = rnd(1, 4100), rnd(1, 4096)
 m = tf_approxmatch.approx_match(x1, x2)                 # pruned sweeps (Morton sort, masks), ragged sizes
 c, _ = ops.emd_cost_op(x1, x2, False)
 cg, g1, g2 = ops.emd_cost_grad_op(x1, x2)              # matrix-free cost + both gradients (split sweeps, fused pass 3 + pass 1)
-mr_ = ops.approx_match_op(x1[:, :700].contiguous(), x2[:, :515].contiguous(), 1)   # reference-order mode, ragged
+mr_ = ops.approx_match_op(x1[:, :700].contiguous(), x2[:, :515].contiguous(), 1)   # exact mode, ragged (plain-load staging: 515 % 4 != 0)
+mp_ = ops.emd_cost_grad_op(x1, x2, 8)                  # compacted-gather pruned sweeps (Hilbert order, masks)
+ms_ = ops.emd_cost_grad_op(x1[:, :1030].contiguous(), x2[:, :900].contiguous(), 4)  # split sums + epilogue kernels
+mg_ = ops.match_cost_grad_op(x1[:, :1028].contiguous(), x2[:, :700].contiguous(), m[:, :700, :1028].contiguous())   # one-pass gradient
+from rfnet_b200 import losses
+raw, new = rnd(2, 900), rnd(2, 300)
+dec = torch.tensor([0.05], device=dev, requires_grad=True)
+nw = new.clone().requires_grad_(True)
+losses.merge_layer(raw, nw, dec).sum().backward()      # fused merge_layer forward + backward (scatter plan)
+f32, i32 = torch.float32, torch.int32
+a1, a2 = rnd(3, 2048), rnd(3, 5000)
+o = [torch.empty((3, 2048), dtype=f32, device=dev), torch.empty((3, 2048), dtype=i32, device=dev), torch.empty((3, 5000), dtype=f32, device=dev),
+     torch.empty((3, 5000), dtype=i32, device=dev), torch.empty((3, 2048, 3), device=dev), torch.empty((3, 5000, 3), device=dev), torch.empty(4, device=dev)]
+ws = torch.empty(ops.nn_distance_workspace_bytes(3, 2048, 5000), dtype=torch.uint8, device=dev)
+ops.raw_chamfer_step(a1, a2, torch.ones((3, 2048), device=dev), torch.ones((3, 5000), device=dev), *o, ws)   # fused chamfer step
 x = rnd(2, 5003)
 idx = tf_sampling.farthest_point_sample(300, x)         # pruned FPS, ragged last cluster
 q = tf_sampling.gather_point(x, idx)
