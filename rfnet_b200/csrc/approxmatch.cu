@@ -229,7 +229,7 @@ constexpr int ROW_CP = 128;         // candidate pairs per staged chunk
 #endif
 constexpr int EMD_ROW_UNROLL = EMD_ROW_UNROLL_VALUE;   // candidate pairs per unrolled step (tools/emd_tune.cu)
 
-template <int MODE, bool UNIT, bool EXACT, int NT>
+template <int MODE, bool UNIT, bool EXACT, int NT, int R = 1>
 __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ SweepArgs a) {
     constexpr bool P3 = MODE == 3 || MODE == 4;
     constexpr bool DUAL = MODE == 4;
@@ -247,18 +247,26 @@ __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ Swe
     const float* __restrict__ vbase = DUAL ? a.wb + (size_t)cloud * nc : nullptr;
     const float4* __restrict__ Abase = a.pairA + (size_t)cloud * a.npad;
     const float2* __restrict__ Zbase = a.pairZ + (size_t)cloud * a.npad;
-    const int pos = tile * NT + tid;
-    const bool valid = pos < nr;
-    const int row = valid ? pos : 0;
-    const size_t ridx = (size_t)cloud * nr + row;
-    // the row NEGATED in both halves: (cand + (-row)) == cand - row exactly
-    const float* rp = a.rows + ridx * 3;
-    const float2 RX = make_float2(-rp[0], -rp[0]), RY = make_float2(-rp[1], -rp[1]), RZ = make_float2(-rp[2], -rp[2]);
-    float rfs = 1.f;
-    if (P3) rfs = a.rowfac[ridx];
-    const float2 RF = make_float2(rfs, rfs);
+    // R rows per thread, each with its own chain(s): the candidate loads of a step are shared by the R rows (R = 2 halves the
+    // shared-memory instructions per pair-pass: LDS and MUFU share the MIO queue, the top stall of the R = 1 kernel at small batches)
+    bool valid[R];
+    size_t ridx[R];
+    float2 RX[R], RY[R], RZ[R], RF[R];
+    float rfs[R], acc[R], accb[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int pos = tile * (NT * R) + r * NT + tid;
+        valid[r] = pos < nr;
+        ridx[r] = (size_t)cloud * nr + (valid[r] ? pos : 0);
+        // the row NEGATED in both halves: (cand + (-row)) == cand - row exactly
+        const float* rp = a.rows + ridx[r] * 3;
+        RX[r] = make_float2(-rp[0], -rp[0]); RY[r] = make_float2(-rp[1], -rp[1]); RZ[r] = make_float2(-rp[2], -rp[2]);
+        rfs[r] = P3 ? a.rowfac[ridx[r]] : 1.f;
+        RF[r] = make_float2(rfs[r], rfs[r]);
+        acc[r] = a.init0;
+        accb[r] = 1e-9f;   // pass 1 (also the fused one of the next level) starts at 1e-9 (tf_approxmatch.cu:36)
+    }
     const float2 L2 = make_float2(a.lvl2, a.lvl2), L2B = make_float2(a.lvl2b, a.lvl2b);
-    float acc = a.init0, accb = 1e-9f;   // pass 1 (also the fused one of the next level) starts at 1e-9 (tf_approxmatch.cu:36)
 
     const int npairs = (nc + 1) / 2;
     const int nchunks = (npairs + ROW_CP - 1) / ROW_CP;
@@ -308,29 +316,36 @@ __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ Swe
             const float2 w = sW[bf][i];
             if (UNIT && !DUAL) {
                 // e == 1: fma(1, w, acc) == acc + w and fma(rf * 1, w, acc) == fma(rf, w, acc), bit for bit
-                if (P3) { acc = __fmaf_rn(rfs, w.x, acc); acc = __fmaf_rn(rfs, w.y, acc); }
-                else { acc = __fadd_rn(acc, w.x); acc = __fadd_rn(acc, w.y); }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (P3) { acc[r] = __fmaf_rn(rfs[r], w.x, acc[r]); acc[r] = __fmaf_rn(rfs[r], w.y, acc[r]); }
+                    else { acc[r] = __fadd_rn(acc[r], w.x); acc[r] = __fadd_rn(acc[r], w.y); }
+                }
             } else {
                 const float4 A = sA[bf][i];
                 const float2 Z = sZ[bf][i];
-                const float2 dx = __fadd2_rn(make_float2(A.x, A.y), RX);
-                const float2 dy = __fadd2_rn(make_float2(A.z, A.w), RY);
-                const float2 dz = __fadd2_rn(Z, RZ);
-                const float2 d2 = sqdist3x2<true>(dx, dy, dz);
-                const float2 x = __fmul2_rn(d2, L2);
-                float2 e = make_float2(emd_ex2<EXACT>(x.x), emd_ex2<EXACT>(x.y));
-                if (P3) e = __fmul2_rn(RF, e);
-                acc = __fmaf_rn(e.x, w.x, acc);
-                acc = __fmaf_rn(e.y, w.y, acc);
-                if (DUAL) {
-                    const float2 v = sV[bf][i];
-                    if (UNIT) {
-                        accb = __fadd_rn(accb, v.x);
-                        accb = __fadd_rn(accb, v.y);
-                    } else {
-                        const float2 xb = __fmul2_rn(d2, L2B);
-                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.x), v.x, accb);
-                        accb = __fmaf_rn(emd_ex2<EXACT>(xb.y), v.y, accb);
+                float2 v = make_float2(0.f, 0.f);
+                if (DUAL) v = sV[bf][i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float2 dx = __fadd2_rn(make_float2(A.x, A.y), RX[r]);
+                    const float2 dy = __fadd2_rn(make_float2(A.z, A.w), RY[r]);
+                    const float2 dz = __fadd2_rn(Z, RZ[r]);
+                    const float2 d2 = sqdist3x2<true>(dx, dy, dz);
+                    const float2 x = __fmul2_rn(d2, L2);
+                    float2 e = make_float2(emd_ex2<EXACT>(x.x), emd_ex2<EXACT>(x.y));
+                    if (P3) e = __fmul2_rn(RF[r], e);
+                    acc[r] = __fmaf_rn(e.x, w.x, acc[r]);
+                    acc[r] = __fmaf_rn(e.y, w.y, acc[r]);
+                    if (DUAL) {
+                        if (UNIT) {
+                            accb[r] = __fadd_rn(accb[r], v.x);
+                            accb[r] = __fadd_rn(accb[r], v.y);
+                        } else {
+                            const float2 xb = __fmul2_rn(d2, L2B);
+                            accb[r] = __fmaf_rn(emd_ex2<EXACT>(xb.x), v.x, accb[r]);
+                            accb[r] = __fmaf_rn(emd_ex2<EXACT>(xb.y), v.y, accb[r]);
+                        }
                     }
                 }
             }
@@ -341,7 +356,9 @@ __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ Swe
         }
         __syncthreads();   // everyone is done with this buffer before it is refilled
     }
-    if (valid) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx, acc, accb);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (valid[r]) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx[r], acc[r], accb[r]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -680,11 +697,15 @@ struct PairArgs {
     float* match;                        // WRITE (ROLE 1 only): (b, n_oth, n_own)
     float* cost_partial;                 // COST: one float per CTA
     float* grad_partial;                 // GRAD: (b, gridDim.y, n_own, 3)
+    float* grad2_partial;                // GRAD2: (b, gridDim.x * 4, n_oth, 3): one slice per warp (64 own points)
     EmdLevels lv;
 };
-template <int ROLE, bool WRITE, bool COST, bool GRAD, bool EXACT>
+template <int ROLE, bool WRITE, bool COST, bool GRAD, bool GRAD2, bool EXACT>
 __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_constant__ PairArgs a) {
     static_assert(!WRITE || ROLE == 1, "the matrix is written k-contiguous: own = xyz1");
+    static_assert(!GRAD2 || (ROLE == 1 && GRAD), "the one-pass form: grad1 in registers, grad2 through the per-warp slab");
+    constexpr int LB = GRAD2 ? 4 : 2;                 // others per unrolled batch
+    __shared__ float sG2[GRAD2 ? MT_THREADS / 32 : 1][GRAD2 ? LB * 3 * 32 : 1];
     __shared__ __align__(16) float4 sP[MT_L];       // x, y, z of the other point
     __shared__ __align__(16) float sF[MT_L][12];    // its factors, j = 0..9 (+2 pad)
     __shared__ float sW[MT_THREADS / 32];
@@ -719,8 +740,21 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
         }
         __syncthreads();
         float* __restrict__ out = WRITE ? a.match + ((size_t)cloud * n_oth + l0) * n_own : nullptr;
-#pragma unroll 2
-        for (int l = 0; l < nl; ++l) {
+#pragma unroll 1
+        for (int lb = 0; lb < nl; lb += LB) {
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            const int l = lb + u;
+            if (l >= nl) {
+                if (GRAD2) {   // a ragged tail still has to clear its slab rows
+                    const int lane_ = threadIdx.x & 31, r_ = u * 3;
+                    float* slab_ = sG2[threadIdx.x >> 5];
+                    slab_[(r_ + 0) * 32 + ((lane_ + r_ + 0) & 31)] = 0.f;
+                    slab_[(r_ + 1) * 32 + ((lane_ + r_ + 1) & 31)] = 0.f;
+                    slab_[(r_ + 2) * 32 + ((lane_ + r_ + 2) & 31)] = 0.f;
+                }
+                continue;
+            }
             const float4 q = sP[l];
             const float4 f0 = *reinterpret_cast<const float4*>(&sF[l][0]), f1 = *reinterpret_cast<const float4*>(&sF[l][4]), f2 = *reinterpret_cast<const float4*>(&sF[l][8]);
             const float fx[EMD_LEVELS] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y};
@@ -773,11 +807,34 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
                 if (GRAD) {
                     // dx = other - own; the gradient wants (own - other) * s
                     const float2 ns = make_float2(-s.x, -s.y);
-                    gx = __ffma2_rn(make_float2(va ? dx.x : 0.f, vb ? dx.y : 0.f), ns, gx);
+                    const float2 dxg = make_float2(va ? dx.x : 0.f, vb ? dx.y : 0.f);
+                    gx = __ffma2_rn(dxg, ns, gx);
                     gy = __ffma2_rn(dy, ns, gy);
                     gz = __ffma2_rn(dz, ns, gz);
+                    if (GRAD2) {
+                        // the other point's gradient, sum over k of match * (other - own) * rsqrt: this lane's two k's go to the
+                        // warp's slab (rotated: conflict-free lane-wise writes and row-wise reads), reduced below every LB rows
+                        const float2 px = __fmul2_rn(dxg, s), py = __fmul2_rn(dy, s), pz = __fmul2_rn(dz, s);
+                        const int lane_ = threadIdx.x & 31, r_ = u * 3;
+                        float* slab_ = sG2[threadIdx.x >> 5];
+                        slab_[(r_ + 0) * 32 + ((lane_ + r_ + 0) & 31)] = px.x + px.y;
+                        slab_[(r_ + 1) * 32 + ((lane_ + r_ + 1) & 31)] = py.x + py.y;
+                        slab_[(r_ + 2) * 32 + ((lane_ + r_ + 2) & 31)] = pz.x + pz.y;
+                    }
                 }
             }
+        }
+        if (GRAD2) {
+            const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+            __syncwarp();
+            if (lane_ < LB * 3 && lb + lane_ / 3 < nl) {   // one (other point, component) per lane: the 32 lane partials in lane order
+                float t = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) t += sG2[warp_][lane_ * 32 + ((i + lane_) & 31)];
+                a.grad2_partial[(((size_t)cloud * (gridDim.x * (MT_THREADS / 32)) + blockIdx.x * (MT_THREADS / 32) + warp_) * n_oth + l0 + lb) * 3 + lane_] = t;
+            }
+            __syncwarp();
+        }
         }
     }
     if (GRAD) {
@@ -967,20 +1024,23 @@ __global__ void __launch_bounds__(MV_THREADS) matchcost_v4_kernel(int n, int m, 
 // ---------------------------------------------------------------------------------------------------------------
 // match_cost gradient for a GIVEN matrix in ONE streaming pass over `match` (4 B per pair, the HBM floor); the reference
 // reads it twice (matchcostgrad1 + matchcostgrad2, tf_approxmatch.cu:229-291) and so did the first version here.
-// CTA = 128 consecutive k (a float4 of one matrix row per lane) x GF_LT rows l; warp w takes rows l = w, w + 8, ...
+// CTA = 128 consecutive k (a float4 of one matrix row per lane) x GF_LT rows l; warp w takes GF_LT / 8 consecutive rows
 //   t(k,l) = match[l,k] * rsqrt(max(d2, 1e-20)) * (p2_l - p1_k)
 //   grad1[k] = -sum_l t : 12 accumulators per lane across the whole l range, summed over the 8 warps at the end
-//   grad2[l] = +sum_k t : the lane's 4-pair partial goes to a rotated (bank-conflict-free) shared-memory slab, 64 rows at a
-//              time; 192 threads then add the 32 lane partials of one (l, component) each -- 4 instructions per row and lane
-//              where a shuffle tree would cost 30.
+//   grad2[l] = +sum_k t : the lane's 4-pair partial goes to a rotated (bank-conflict-free) per-WARP shared-memory slab, 8 rows
+//              at a time; 24 lanes then add the 32 lane partials of one (l, component) each -- ~4 instructions per row and
+//              lane where a shuffle tree would cost 30, and no block-wide barrier anywhere in the row loop (a first version
+//              with a CTA-wide slab and two barriers per 64 rows drained the load pipeline at every barrier: 0.53 of HBM).
 // Partials over l-ranges (grad1) and k-tiles (grad2) are summed in a fixed order by emd_grad_reduce_kernel.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GF_THREADS = 256, GF_WARPS = 8, GF_KT = 128, GF_LC = 64, GF_LT = 512, GF_UN = 4;
-__global__ void __launch_bounds__(GF_THREADS, 3) matchcostgrad_fused_kernel(int n, int m, int nkt, int nlt, const float* __restrict__ xyz1,
+constexpr int GF_THREADS = 256, GF_WARPS = 8, GF_KT = 128, GF_LT = 512, GF_UN = 8;
+constexpr int GF_RPW = GF_LT / GF_WARPS;   // consecutive rows l per warp
+__global__ void __launch_bounds__(GF_THREADS, 2) matchcostgrad_fused_kernel(int n, int m, int nkt, int nlt, const float* __restrict__ xyz1,
                                                                             const float* __restrict__ xyz2, const float* __restrict__ match,
                                                                             float* __restrict__ part1, float* __restrict__ part2) {
-    __shared__ float sP2[GF_LC * 3];
-    __shared__ float sG[GF_LC * 3 * 32];
+    // per-warp slab of lane partials: [row of the batch][component][lane, rotated by the row index so that both the lane-wise
+    // writes and the row-wise reads are bank-conflict free].  Warps never wait for each other inside the row loop.
+    __shared__ float sG[GF_WARPS][GF_UN * 3 * 32];
     const int cloud = blockIdx.z, kt = blockIdx.x, lt = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k4 = kt * GF_KT + lane * 4;
@@ -990,52 +1050,46 @@ __global__ void __launch_bounds__(GF_THREADS, 3) matchcostgrad_fused_kernel(int 
     if (live) q = load_pts4_neg(xyz1 + ((size_t)cloud * n + k4) * 3);
     float2 ax01 = make_float2(0.f, 0.f), ax23 = ax01, ay01 = ax01, ay23 = ax01, az01 = ax01, az23 = ax01;   // sum_l t for the lane's four k
     const float* __restrict__ mbase = match + (size_t)cloud * m * n + k4;
-    const int l_end = min(m, (lt + 1) * GF_LT);
-    for (int l0 = lt * GF_LT; l0 < l_end; l0 += GF_LC) {
-        const int nl = min(GF_LC, l_end - l0);
-        __syncthreads();   // the previous chunk's reduction has finished with sG and sP2
-        for (int i = tid; i < nl * 3; i += GF_THREADS) sP2[i] = xyz2[((size_t)cloud * m + l0) * 3 + i];
-        __syncthreads();
+    const float* __restrict__ p2 = xyz2 + (size_t)cloud * m * 3;
+    float* __restrict__ slab = sG[warp];
+    const int l_begin = lt * GF_LT + warp * GF_RPW;
+    const int l_end = min(m, l_begin + GF_RPW);
 #pragma unroll 1
-        for (int j0 = 0; j0 < GF_LC / GF_WARPS; j0 += GF_UN) {
-            float4 mv[GF_UN];
+    for (int l0 = l_begin; l0 < l_end; l0 += GF_UN) {
+        float4 mv[GF_UN];
 #pragma unroll
-            for (int u = 0; u < GF_UN; ++u) {   // all loads of the step first: GF_UN x 16 B in flight per lane
-                const int li = warp + GF_WARPS * (j0 + u);
-                mv[u] = (live && li < nl) ? __ldcs(reinterpret_cast<const float4*>(mbase + (size_t)(l0 + li) * n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int u = 0; u < GF_UN; ++u)   // all loads of the batch first: GF_UN x 16 B in flight per lane
+            mv[u] = (live && l0 + u < l_end) ? __ldcs(reinterpret_cast<const float4*>(mbase + (size_t)(l0 + u) * n)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < GF_UN; ++u) {
-                const int li = warp + GF_WARPS * (j0 + u);
-                if (li < nl) {
-                    const float px = sP2[li * 3], py = sP2[li * 3 + 1], pz = sP2[li * 3 + 2];
-                    const float2 ex01 = __fadd2_rn(q.nx01, make_float2(px, px)), ey01 = __fadd2_rn(q.ny01, make_float2(py, py)), ez01 = __fadd2_rn(q.nz01, make_float2(pz, pz));
-                    const float2 ex23 = __fadd2_rn(q.nx23, make_float2(px, px)), ey23 = __fadd2_rn(q.ny23, make_float2(py, py)), ez23 = __fadd2_rn(q.nz23, make_float2(pz, pz));
-                    const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
-                    const float2 s01 = __fmul2_rn(make_float2(mv[u].x, mv[u].y), make_float2(rsqrt_approx(fmaxf(d01.x, 1e-20f)), rsqrt_approx(fmaxf(d01.y, 1e-20f))));
-                    const float2 s23 = __fmul2_rn(make_float2(mv[u].z, mv[u].w), make_float2(rsqrt_approx(fmaxf(d23.x, 1e-20f)), rsqrt_approx(fmaxf(d23.y, 1e-20f))));
-                    ax01 = __ffma2_rn(ex01, s01, ax01); ay01 = __ffma2_rn(ey01, s01, ay01); az01 = __ffma2_rn(ez01, s01, az01);
-                    ax23 = __ffma2_rn(ex23, s23, ax23); ay23 = __ffma2_rn(ey23, s23, ay23); az23 = __ffma2_rn(ez23, s23, az23);
-                    const float2 gx = __ffma2_rn(ex01, s01, __fmul2_rn(ex23, s23)), gy = __ffma2_rn(ey01, s01, __fmul2_rn(ey23, s23)),
-                                 gz = __ffma2_rn(ez01, s01, __fmul2_rn(ez23, s23));
-                    const int r = li * 3;
-                    sG[(r + 0) * 32 + ((lane + r + 0) & 31)] = gx.x + gx.y;
-                    sG[(r + 1) * 32 + ((lane + r + 1) & 31)] = gy.x + gy.y;
-                    sG[(r + 2) * 32 + ((lane + r + 2) & 31)] = gz.x + gz.y;
-                }
-            }
+        for (int u = 0; u < GF_UN; ++u) {
+            const int l = min(l0 + u, m - 1);   // rows past the end carry match == 0: they add exact zeros
+            const float px = __ldg(p2 + (size_t)l * 3), py = __ldg(p2 + (size_t)l * 3 + 1), pz = __ldg(p2 + (size_t)l * 3 + 2);
+            const float2 ex01 = __fadd2_rn(q.nx01, make_float2(px, px)), ey01 = __fadd2_rn(q.ny01, make_float2(py, py)), ez01 = __fadd2_rn(q.nz01, make_float2(pz, pz));
+            const float2 ex23 = __fadd2_rn(q.nx23, make_float2(px, px)), ey23 = __fadd2_rn(q.ny23, make_float2(py, py)), ez23 = __fadd2_rn(q.nz23, make_float2(pz, pz));
+            const float2 d01 = sqdist3x2<true>(ex01, ey01, ez01), d23 = sqdist3x2<true>(ex23, ey23, ez23);
+            const float2 s01 = __fmul2_rn(make_float2(mv[u].x, mv[u].y), make_float2(rsqrt_approx(fmaxf(d01.x, 1e-20f)), rsqrt_approx(fmaxf(d01.y, 1e-20f))));
+            const float2 s23 = __fmul2_rn(make_float2(mv[u].z, mv[u].w), make_float2(rsqrt_approx(fmaxf(d23.x, 1e-20f)), rsqrt_approx(fmaxf(d23.y, 1e-20f))));
+            ax01 = __ffma2_rn(ex01, s01, ax01); ay01 = __ffma2_rn(ey01, s01, ay01); az01 = __ffma2_rn(ez01, s01, az01);
+            ax23 = __ffma2_rn(ex23, s23, ax23); ay23 = __ffma2_rn(ey23, s23, ay23); az23 = __ffma2_rn(ez23, s23, az23);
+            const float2 gx = __ffma2_rn(ex01, s01, __fmul2_rn(ex23, s23)), gy = __ffma2_rn(ey01, s01, __fmul2_rn(ey23, s23)),
+                         gz = __ffma2_rn(ez01, s01, __fmul2_rn(ez23, s23));
+            const int r = u * 3;
+            slab[(r + 0) * 32 + ((lane + r + 0) & 31)] = gx.x + gx.y;
+            slab[(r + 1) * 32 + ((lane + r + 1) & 31)] = gy.x + gy.y;
+            slab[(r + 2) * 32 + ((lane + r + 2) & 31)] = gz.x + gz.y;
         }
-        __syncthreads();
-        if (tid < nl * 3) {   // one (row, component) per thread: add the 32 lane partials in lane order
+        __syncwarp();
+        if (lane < GF_UN * 3 && l0 + lane / 3 < l_end) {   // one (row, component) per lane: add the 32 lane partials in lane order
             float t = 0.f;
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) t += sG[tid * 32 + ((i + tid) & 31)];
-            part2[(((size_t)cloud * nkt + kt) * m + l0) * 3 + tid] = t;
+            for (int i = 0; i < 32; ++i) t += slab[lane * 32 + ((i + lane) & 31)];
+            part2[(((size_t)cloud * nkt + kt) * m + l0) * 3 + lane] = t;   // GF_UN consecutive rows: 3 * GF_UN consecutive floats
         }
+        __syncwarp();
     }
     // grad1: add the eight warps' accumulators (each saw different rows l of the same 128 k) and negate
-    __syncthreads();
-    float* sW = sG + warp * (GF_KT * 3);   // 8 x 384 floats <= the 6144 of sG
+    __shared__ float sW1[GF_WARPS][GF_KT * 3];
+    float* sW = sW1[warp];
     sW[(lane * 4 + 0) * 3 + 0] = ax01.x; sW[(lane * 4 + 0) * 3 + 1] = ay01.x; sW[(lane * 4 + 0) * 3 + 2] = az01.x;
     sW[(lane * 4 + 1) * 3 + 0] = ax01.y; sW[(lane * 4 + 1) * 3 + 1] = ay01.y; sW[(lane * 4 + 1) * 3 + 2] = az01.y;
     sW[(lane * 4 + 2) * 3 + 0] = ax23.x; sW[(lane * 4 + 2) * 3 + 1] = ay23.x; sW[(lane * 4 + 2) * 3 + 2] = az23.x;
@@ -1045,7 +1099,7 @@ __global__ void __launch_bounds__(GF_THREADS, 3) matchcostgrad_fused_kernel(int 
         if (kt * GF_KT + i / 3 < n) {
             float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < GF_WARPS; ++w) t += sG[w * (GF_KT * 3) + i];
+            for (int w = 0; w < GF_WARPS; ++w) t += sW1[w][i];
             part1[(((size_t)cloud * nlt + lt) * n + (size_t)kt * GF_KT) * 3 + i] = -t;
         }
     }
@@ -1122,10 +1176,10 @@ static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b,
 }
 
 // ---- final pass launcher ----------------------------------------------------------------------------------------
-template <int ROLE, bool WRITE, bool COST, bool GRAD>
+template <int ROLE, bool WRITE, bool COST, bool GRAD, bool GRAD2>
 static void emd_launch_pair(const PairArgs& a, dim3 grid, bool exact, cudaStream_t s) {
-    if (exact) emd_pair_kernel<ROLE, WRITE, COST, GRAD, true><<<grid, MT_THREADS, 0, s>>>(a);
-    else emd_pair_kernel<ROLE, WRITE, COST, GRAD, false><<<grid, MT_THREADS, 0, s>>>(a);
+    if (exact) emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, true><<<grid, MT_THREADS, 0, s>>>(a);
+    else emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, false><<<grid, MT_THREADS, 0, s>>>(a);
 }
 static dim3 emd_pair_grid(int b, int n_own, int n_oth) {
     const int ot = emd_pair_tile(n_oth);
@@ -1139,6 +1193,10 @@ static size_t emd_cost_partials(int b, int n, int m) {
 static size_t emd_grad_partials(int b, int n_own, int n_oth) {
     const dim3 g = emd_pair_grid(b, n_own, n_oth);
     return g.y > 1 ? (size_t)b * g.y * n_own * 3 : 0;   // a single tile of others writes the gradient directly
+}
+static size_t emd_grad2_partials(int b, int n_own, int n_oth) {   // one slice per warp of the own-point tiles
+    const dim3 g = emd_pair_grid(b, n_own, n_oth);
+    return (size_t)b * g.x * (MT_THREADS / 32) * n_oth * 3;
 }
 __global__ void emd_grad_reduce_kernel(int n, int nt, size_t bn, const float* __restrict__ partial, float* __restrict__ grad) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over bn*3
@@ -1211,29 +1269,25 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
     PairArgs pa;
     pa.n_own = n; pa.n_oth = m; pa.ot_len = emd_pair_tile(m); pa.b_own = bn; pa.b_oth = bm;
     pa.own = xyz1; pa.oth = xyz2; pa.fac_own = ws.facL; pa.fac_oth = ws.facR;
-    pa.match = match; pa.cost_partial = extra; pa.grad_partial = nullptr; pa.lv = lv;
+    pa.match = match; pa.cost_partial = extra; pa.grad_partial = nullptr; pa.grad2_partial = nullptr; pa.lv = lv;
     const dim3 g1 = emd_pair_grid(b, n, m);
     RFNET_CHECK_ARG(g1.y <= 65535 && g1.z <= 65535);
     if (grad1) {
+        // ONE pass over all pairs: cost and grad1 in the registers of the thread that owns the xyz1 point, grad2 through per-warp
+        // slabs (a first version ran a second pass with the roles swapped: twice the exponentials)
         float* gp1 = extra + emd_cost_partials(b, n, m);
-        pa.grad_partial = g1.y > 1 ? gp1 : grad1;
-        emd_launch_pair<1, false, true, true>(pa, g1, exact, s);
-        if (g1.y > 1) emd_grad_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, (int)g1.y, bn, gp1, grad1);
-        PairArgs pb = pa;
-        pb.n_own = m; pb.n_oth = n; pb.ot_len = emd_pair_tile(n); pb.b_own = bm; pb.b_oth = bn;
-        pb.own = xyz2; pb.oth = xyz1; pb.fac_own = ws.facR; pb.fac_oth = ws.facL; pb.match = nullptr; pb.cost_partial = nullptr;
-        const dim3 g2 = emd_pair_grid(b, m, n);
-        RFNET_CHECK_ARG(g2.y <= 65535);
         float* gp2 = gp1 + emd_grad_partials(b, n, m);
-        pb.grad_partial = g2.y > 1 ? gp2 : grad2;
-        emd_launch_pair<2, false, false, true>(pb, g2, exact, s);
-        if (g2.y > 1) emd_grad_reduce_kernel<<<(unsigned)((bm * 3 + 255) / 256), 256, 0, s>>>(m, (int)g2.y, bm, gp2, grad2);
+        pa.grad_partial = g1.y > 1 ? gp1 : grad1;
+        pa.grad2_partial = gp2;
+        emd_launch_pair<1, false, true, true, true>(pa, g1, exact, s);
+        if (g1.y > 1) emd_grad_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, (int)g1.y, bn, gp1, grad1);
+        emd_grad_reduce_kernel<<<(unsigned)((bm * 3 + 255) / 256), 256, 0, s>>>(m, (int)(g1.x * (MT_THREADS / 32)), bm, gp2, grad2);
     } else if (match && cost) {
-        emd_launch_pair<1, true, true, false>(pa, g1, exact, s);
+        emd_launch_pair<1, true, true, false, false>(pa, g1, exact, s);
     } else if (cost) {
-        emd_launch_pair<1, false, true, false>(pa, g1, exact, s);
+        emd_launch_pair<1, false, true, false, false>(pa, g1, exact, s);
     } else {
-        emd_launch_pair<1, true, false, false>(pa, g1, exact, s);
+        emd_launch_pair<1, true, false, false, false>(pa, g1, exact, s);
     }
     if (cost) reduce_partials_kernel<<<b, 256, 0, s>>>((int)(g1.x * g1.y), extra, cost);
     return launch_status();
@@ -1284,7 +1338,7 @@ extern "C" int rfnet_emd_cost(int b, int n, int m, const float* xyz1, const floa
 
 extern "C" size_t rfnet_emd_cost_grad_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return (emd_ws_floats(b, n, m) + emd_cost_partials(b, n, m) + emd_grad_partials(b, n, m) + emd_grad_partials(b, m, n)) * sizeof(float);
+    return (emd_ws_floats(b, n, m) + emd_cost_partials(b, n, m) + emd_grad_partials(b, n, m) + emd_grad2_partials(b, n, m)) * sizeof(float);
 }
 
 extern "C" int rfnet_emd_cost_grad(int b, int n, int m, const float* xyz1, const float* xyz2, float* cost, float* grad1, float* grad2,

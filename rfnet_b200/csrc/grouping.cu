@@ -325,7 +325,13 @@ __global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC
     const int* __restrict__ seg = list + cloud * R;
     const VEC* __restrict__ G = grad_out + cloud * (size_t)R * cv + l;
     VEC acc = vec_zero<VEC>();
-    for (int e = beg; e < end; ++e) acc = vec_add<VEC>(acc, __ldg(G + (size_t)seg[e] * cv));
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {   // four source rows in flight; added in ascending order, as the sequential reference does
+        const int s0 = seg[e], s1 = seg[e + 1], s2 = seg[e + 2], s3 = seg[e + 3];
+        const VEC g0 = __ldg(G + (size_t)s0 * cv), g1 = __ldg(G + (size_t)s1 * cv), g2 = __ldg(G + (size_t)s2 * cv), g3 = __ldg(G + (size_t)s3 * cv);
+        acc = vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(acc, g0), g1), g2), g3);
+    }
+    for (; e < end; ++e) acc = vec_add<VEC>(acc, __ldg(G + (size_t)seg[e] * cv));
     grad_points[(cloud * n + i) * cv + l] = acc;
 }
 

@@ -401,7 +401,7 @@ __device__ __forceinline__ float4 blend3<float4>(float4 a, float4 b, float4 c, f
 }
 // grid.y = cloud: 32-bit index arithmetic inside a cloud.  TI_E output vectors per thread: the 3 * TI_E indices and weights
 // are loaded first, then the 3 * TI_E rows, then blended and stored with streaming stores (written once, never re-read here).
-constexpr int TI_E = 2;
+constexpr int TI_E = 4;
 template <typename VEC>
 __device__ __forceinline__ void ti_store(VEC* p, VEC v);
 template <>
@@ -512,8 +512,16 @@ __global__ void three_interpolate_grad_seg_kernel(int n, int cv, int m, const VE
     const VEC* __restrict__ G = grad_out + cloud * (size_t)n * cv + l;
     const float* __restrict__ W = weight + cloud * R;
     VEC acc = vec_zero3<VEC>();
-    for (int e = beg; e < end; ++e) {
-        const int src = seg[e];  // = 3*j + u
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {   // four contributions in flight; accumulated in ascending source order, as the sequential reference does
+        const int s0 = seg[e], s1 = seg[e + 1], s2 = seg[e + 2], s3 = seg[e + 3];  // = 3*j + u
+        const VEC g0 = __ldg(G + (size_t)(s0 / 3) * cv), g1 = __ldg(G + (size_t)(s1 / 3) * cv), g2 = __ldg(G + (size_t)(s2 / 3) * cv),
+                  g3 = __ldg(G + (size_t)(s3 / 3) * cv);
+        const float w0 = __ldg(W + s0), w1 = __ldg(W + s1), w2 = __ldg(W + s2), w3 = __ldg(W + s3);
+        acc = vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(acc, g0, w0), g1, w1), g2, w2), g3, w3);
+    }
+    for (; e < end; ++e) {
+        const int src = seg[e];
         acc = vec_madd_unfused<VEC>(acc, __ldg(G + (size_t)(src / 3) * cv), __ldg(W + src));
     }
     grad_points[(cloud * m + i) * cv + l] = acc;

@@ -30,10 +30,10 @@ float run(int b, int n, int split_len, float lvl2, const float* x1, const float*
     return ms;
 }
 
-template <int MODE, int NT>
+template <int MODE, int NT, int R = 1>
 float run_row(int b, int n, float lvl2, const float* x1, const float* x2, const float* w, float* scratch, float4* pA, float2* pZ) {
     SweepArgs a;
-    a.nr = n; a.nc = n; a.nrt = (n + NT - 1) / NT; a.nsplit = 1; a.split_len = n; a.nwords = (n + 31) / 32; a.npad = emd_npad(n); a.tma = (n % 4 == 0);
+    a.nr = n; a.nc = n; a.nrt = (n + NT * R - 1) / (NT * R); a.nsplit = 1; a.split_len = n; a.nwords = (n + 31) / 32; a.npad = emd_npad(n); a.tma = (n % 4 == 0);
     a.lvl2 = lvl2; a.lvl2b = lvl2 * 0.25f; a.init0 = 1e-9f;
     a.rows = x1; a.cands = x2; a.w = w; a.wb = w; a.rowfac = w; a.pairA = pA; a.pairZ = pZ;
     a.partial = nullptr; a.partial_b = nullptr;
@@ -41,15 +41,15 @@ float run_row(int b, int n, float lvl2, const float* x1, const float* x2, const 
     a.perm = nullptr; a.mask = nullptr;
     const unsigned grid = (unsigned)(b * a.nrt);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; ++i) emd_row_kernel<MODE, false, false, NT><<<grid, NT>>>(a);
+    for (int i = 0; i < 2; ++i) emd_row_kernel<MODE, false, false, NT, R><<<grid, NT>>>(a);
     cudaEventRecord(e0);
     const int it = 5;
-    for (int i = 0; i < it; ++i) emd_row_kernel<MODE, false, false, NT><<<grid, NT>>>(a);
+    for (int i = 0; i < it; ++i) emd_row_kernel<MODE, false, false, NT, R><<<grid, NT>>>(a);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     ms /= it;
     const double pp = (double)b * n * n * (MODE == 4 ? 2 : 1);
-    printf("  mode %d ROW kernel NT=%3d unroll %d (one chain per row)   grid=%6u (%5.1f CTAs/SM): %8.3f ms  %.2f Tpair-pass/s  MUFU %.1f%%\n", MODE, NT, EMD_ROW_UNROLL, grid,
+    printf("  mode %d ROW kernel NT=%3d rows/thread %d unroll %d   grid=%6u (%5.1f CTAs/SM): %8.3f ms  %.2f Tpair-pass/s  MUFU %.1f%%\n", MODE, NT, R, EMD_ROW_UNROLL, grid,
            grid / 148.0, ms, pp / ms / 1e9, 100.0 * pp / (ms * 1e-3) / (148.0 * 16 * 1.965e9));
     return ms;
 }
@@ -75,12 +75,14 @@ int main() {
         float4* pA; float2* pZ;
         cudaMalloc(&pA, (size_t)b * emd_npad(n) * 16); cudaMalloc(&pZ, (size_t)b * emd_npad(n) * 8);
         emd_pairs_kernel<<<dim3((unsigned)((emd_npad(n) + 255) / 256), (unsigned)b), 256>>>(n, emd_npad(n), x2, pA, pZ);
-        run_row<1, 128>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
         run_row<1, 64>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
         run_row<1, 32>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
-        run_row<4, 128>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<1, 64, 2>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<1, 32, 2>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
         run_row<4, 64>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
         run_row<4, 32>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<4, 64, 2>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
+        run_row<4, 32, 2>(b, n, lvl2, x1, x2, w, scratch, pA, pZ);
         cudaFree(pA); cudaFree(pZ);
         for (int sl : {512}) {
             if (sl > n || (n + sl - 1) / sl > 256) continue;
