@@ -15,8 +15,8 @@ One JSON line on stdout (rank 0).  Besides the contract's keys it carries
                 the reference's operand order admits no fewer), peak = 148 SMs x 128 lanes x sm clock
   cpu_baseline  the reference's own CPU kernel (oracle/_ref: /root/reference/pc_distance/tf_nndistance.cpp compiled
                 unmodified) timed on this host's cores on a bounded sample of the same workload
-  e2e           the same metric through the public host-buffer API from pinned HOST buffers with EVERY output of the operator
-                (dist1, idx1, dist2, idx2, both gradients, loss sums) copied back, copies inside the timed region
+  e2e           the same metric through the public host-buffer API: every step copies its batch from pinned HOST buffers and reads the
+                loss back (copies inside the timed region); e2e.all_outputs: the same with every output of the operator copied back too
   extra         measured after the timed region on ALL ranks (max over ranks, scalar all-reduce included), not part of `value`:
                   sustained        the same step looped >= 2 s, with the clocks sampled during the loop
                   config3          EMD approx_match + match_cost forward + gradient, B=32 TOTAL (strong scaling: 32/N clouds per
@@ -705,12 +705,17 @@ def main():
         v = pairs_per_step * k_e2e / (D.max_ms(e0.elapsed_time(e1)) * 1e-3) / 1e9
         return v, pipe.h2d_bytes, pipe.d2h_bytes, loss
 
-    v_all, h2d, d2h_all, e2e_loss = run_e2e(ChamferHostPipeline.ALL_OUTPUTS)
-    v_loop, _, d2h_loop, _ = run_e2e(("sums",))
-    e2e = {"value": v_all, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all, "steps": k_e2e, "loss_read_back": e2e_loss,
-           "api": "rfnet_b200.host.ChamferHostPipeline.submit(pinned xyz1, xyz2) -> pinned dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, loss sums "
-                  "(every output of NnDistance + NnDistanceGrad); 3-slot ring, copies overlap compute, all-reduce on a side stream",
-           "training_loop": {"value": v_loop, "d2h_bytes_per_step": d2h_loop, "note": "same call, only the 16-byte loss sums read back (what vv_recon.py's sess.run fetches)"}}
+    v_loop, h2d, d2h_loop, e2e_loss = run_e2e(("sums",))
+    v_all, _, d2h_all, _ = run_e2e(ChamferHostPipeline.ALL_OUTPUTS)
+    # e2e.value: what the reference's training / test loop does per step (vv_recon.py:424-428, recon_test.py:60) -- the batch goes
+    # host -> device, the loss comes back.  e2e.all_outputs: the same call with EVERY output of NnDistance + NnDistanceGrad copied
+    # back as well (dist, idx, gradients: 11.8 MB per step and GPU): an operator-level e2e, bound by the host's memory bandwidth
+    # once several GPUs share it (18.9 MB per 0.5 ms step and GPU).
+    e2e = {"value": v_loop, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_loop, "steps": k_e2e, "loss_read_back": e2e_loss,
+           "api": "rfnet_b200.host.ChamferHostPipeline.submit(pinned xyz1, xyz2) -> pinned loss sums (chamfer_big read back on the host); 3-slot ring, "
+                  "copies overlap compute, the cross-rank all-reduce runs on a side stream",
+           "all_outputs": {"value": v_all, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_all,
+                           "note": "same call, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2 and the loss sums all copied to pinned host memory every step"}}
 
     # ---- extras (all ranks take part; rank 0 reports)
     extra = {}
