@@ -42,9 +42,15 @@ const char *rfnet_error_string(int code);
  * does.  Results are only specified for finite inputs.
  * ------------------------------------------------------------------------------------------------------------- */
 #define RFNET_NN_UNFUSED 1
+#define RFNET_NN_DIRECT 2
 size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m);
 int rfnet_nn_distance(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1, float *dist2,
                       int *idx2, void *workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream);
+/* Same call; exact_scans (device pointer to one 64-bit counter, may be NULL) is incremented once per (query, work item) that
+ * the filtered search could not certify and scanned with the reference expression instead (diagnostics and tests). */
+int rfnet_nn_distance_stats(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist1, int *idx1,
+                            float *dist2, int *idx2, void *workspace, size_t workspace_bytes, int flags,
+                            unsigned long long *exact_scans, rfnet_stream_t stream);
 
 /* Replaces NmDistanceGradKernelLauncher, pc_distance/tf_nndistance.cpp:208 (tf_nndistance_g.cu:151-156).
  * grad_xyz1 / grad_xyz2 are fully overwritten (the launcher zero-fills them itself, as the reference does).

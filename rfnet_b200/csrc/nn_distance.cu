@@ -46,9 +46,14 @@ struct NNDir {
     int chunk;                  // candidates per chunk: multiple of 8, <= NN_TC
     int items;                  // b * nqt * nsplit
     int tma;                    // candidate rows are 16-byte aligned -> bulk-copy path
+    // filtered search only (nn_prepare_kernel writes both):
+    const float4* cv;           // candidates as (x - ox, y - oy, z - oz, |c - o|^2), ncp rows per cloud (tail rows: |.|^2 = +inf)
+    const float4* meta;         // per (cloud, split): (ox, oy, oz, max |c - o|^2) of the item's candidate range
+    int ncp;                    // nc rounded up to whole groups
 };
 struct NNParams {
     NNDir d[2];
+    unsigned long long* stats;  // optional (may be null): nn_filter_kernel counts the queries it had to scan exactly
 };
 
 template <int Q, bool FUSED>
@@ -208,6 +213,413 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(cons
         } else {
             atomicMin(&D.keys[o], pack_key(bd, k0 + j));
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// nn_filter_kernel: the same all-pairs search at HALF the FP32-pipe work per pair, same bits out.
+//
+// Every (query, candidate) pair is still visited, but the scan evaluates the expanded form
+//     s(q,c) = |c|^2 - 2 q.c          ( = d2(q,c) - |q|^2 in real arithmetic )
+// as three packed FMAs per pair of queries (|c|^2 rides along as the candidate's 4th coordinate), i.e. 3 FP32 lane-ops per
+// pair where the reference expression needs 6 -- and then uses it only to decide WHICH 8/16-group of candidates holds the
+// nearest neighbour.  Per query the scan keeps the smallest group minimum b1, the group k1 it came from and the second
+// smallest group minimum b2 (branch-free: 4 min/max + 1 compare + 1 select per group).  With
+//     E = 2^-20 (|q| + max|c|)^2  >=  |s(c) + |q|^2 - d2_ref(c)|   for every candidate of the item
+// (11 roundings of 2^-24 relative to (|q|+|c|)^2 between the two expressions -- derivation at nn_filter_tolerance below),
+// b2 > b1 + 2E proves that every candidate outside group k1 has a reference distance STRICTLY above that of the
+// candidate that produced b1, hence above the minimum of group k1: the exact arg-min (first index on ties) lies in group
+// k1, whose G reference distances are then evaluated in the reference's operand order -- dist and idx come out bit for bit.
+// Otherwise (two groups within 2E of each other: ~0.1 % of the (query, item) pairs on unit-cube clouds, every query for
+// duplicated points or for clouds far from the origin relative to their size) the warp scans the item's candidates for that
+// query with the reference expression, 32 lanes wide.  Either way the item contributes the exact (distance, index) minimum
+// of its candidate range; items are merged by the same 64-bit atomicMin as above.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef NNF_MIN_CTAS
+#define NNF_MIN_CTAS 4
+#endif
+#ifndef NNF_GROUP
+#define NNF_GROUP 16
+#endif
+constexpr int NNF_G = NNF_GROUP;   // candidates per tracked group: 8, 16 or 32
+static_assert(NNF_G == 8 || NNF_G == 16 || NNF_G == 32, "group size");
+
+// 2E for a query with |q - o|^2 = qn against candidates with |c - o|^2 <= cmax (o: the item's origin, u = 2^-24, u' = u(1+..)).
+//   scan: q~ = fl(q - o), c~ = fl(c - o); cn = fma(z,z, fma(x,x, y*y)) carries 3 roundings, the three FMAs 3 more: every term of
+//      |c~|^2 - 2 q~.c~ is perturbed by at most (1+u)^6  =>  |s - (|c~|^2 - 2 q~.c~)| <= 6u' (|c~|^2 + 2|q~||c~|) <= 6u' (|q~|+|c~|)^2;
+//   centring: q~ - c~ = (q - c) + e with |e| <= u (|q-o| + |c-o|)  =>  | |q~-c~|^2 - |q-c|^2 | <= 2|q-c||e| + |e|^2 <= 2u' (|q~|+|c~|)^2;
+//   reference d2 (fused or not): the differences, three products and two sums perturb every term by at most (1+u)^5
+//      =>  |d2_ref - |q-c|^2| <= 5u' |q-c|^2 <= 5u' (|q~|+|c~|)^2.
+// Together 13u' (|q~|+|c~|)^2 <= E = 16u (sqrt(qn)+sqrt(cmax))^2: the 23 % head-room covers the roundings of this function, of
+// the comparison b1 + 2E and the (<= 3u relative) error of qn and cmax; 1e-30 covers gradual underflow (<= 2^-149 per rounding).
+__device__ __forceinline__ float nn_filter_tolerance(float qn, float cmax) {
+    const float L = __fsqrt_ru(qn) + __fsqrt_ru(cmax);
+    return __fmaf_ru(__fmul_ru(L, L), 1.9073486328125e-6f /* 2^-19 = 2 * 16u */, 1e-30f);
+}
+
+// Preparation of the candidates for the filtered search: one CTA per work-item range of a candidate cloud (at most NNP_RANGE
+// rows -- the launch plan never makes an item longer).  It produces
+//   * the range's origin o, the centre of its bounding box: the tolerance scales with (|q - o| + |c - o|)^2, so a cloud far from
+//     the origin of its coordinate system would otherwise fail every certification; any o is valid, the roundings of q - o and
+//     c - o are part of the error budget;
+//   * the rows (x - ox, y - oy, z - oz, |c - o|^2), the cloud's last range padded to whole groups, and max |c - o|^2;
+//   * the DUPLICATES.  Clouds padded to a fixed size by repeating points (the reference's resample_pcd, data_util.py:8-13)
+//     give every query several candidates with bit-identical s, which no tolerance can tell apart.  But inside one item a
+//     repeated point can never be the answer -- the copy with the lowest index has the same distance and wins the tie (copies
+//     in different items are merged by the keys as ever) -- so the other copies leave the scan (|c|^2 = +inf).  Every point
+//     bids its index for two slots of a hash table in shared memory (atomicMin); afterwards a point is a copy if the winner of
+//     either slot is another point with equal coordinates.  Sets of equal points whose lowest index lost BOTH slots to other
+//     points bid once more for a slot of a second, nearly empty table.  The lowest index of a set of equal points always
+//     stays (a winner with equal coordinates would be a lower index); a copy that is still missed costs an exact scan, never
+//     a wrong answer.
+constexpr int NNP_THREADS = 1024, NNP_K = 8, NNP_RANGE = NNP_THREADS * NNP_K;
+struct NNPrep {
+    const float* c[2];      // candidate clouds of direction 0 / 1 (b, nc, 3)
+    float4* cv[2];
+    float4* meta[2];        // per (cloud, range): (ox, oy, oz, max |c - o|^2)
+    int nc[2], ncp[2], range[2], nsplit[2];
+    unsigned slots[2];      // hash table size of the direction (power of two)
+    unsigned blocks0;       // blocks of direction first_dir; the rest belong to the other direction
+    int first_dir;
+};
+__device__ __forceinline__ unsigned nn_hash1(float x, float y, float z) {
+    const unsigned h = __float_as_uint(x) * 0x9E3779B1u ^ __float_as_uint(y) * 0x85EBCA77u ^ __float_as_uint(z) * 0xC2B2AE3Du;
+    return h ^ (h >> 15) ^ (h >> 23);
+}
+__device__ __forceinline__ unsigned nn_hash2(float x, float y, float z) {
+    const unsigned h = __float_as_uint(x) * 0x27D4EB2Fu ^ __float_as_uint(y) * 0x165667B1u ^ __float_as_uint(z) * 0xD3A2646Du;
+    return h ^ (h >> 13) ^ (h >> 21);
+}
+__global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p) {
+    extern __shared__ __align__(16) unsigned tab[];
+    __shared__ float sRed[NNP_THREADS / 32][6];
+    __shared__ float sO[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned blk = blockIdx.x;
+    int d = p.first_dir;
+    if (blk >= p.blocks0) { blk -= p.blocks0; d = 1 - d; }
+    const int cloud = (int)(blk / (unsigned)p.nsplit[d]), split = (int)(blk % (unsigned)p.nsplit[d]);
+    const int nc = p.nc[d];
+    const int lo = split * p.range[d], hi = min(nc, lo + p.range[d]);
+    const int hip = split == p.nsplit[d] - 1 ? p.ncp[d] : hi;   // the cloud's last range also writes the padding rows
+    const float* __restrict__ src = p.c[d] + ((size_t)cloud * nc + lo) * 3;
+    float4* __restrict__ dst = p.cv[d] + (size_t)cloud * p.ncp[d] + lo;
+    const unsigned mask = p.slots[d] - 1;
+    const float INF = __int_as_float(0x7f800000);
+
+    for (unsigned i = tid * 4; i < mask + 1 + ((mask + 1) >> 2); i += NNP_THREADS * 4)   // both tables
+        *reinterpret_cast<uint4*>(tab + i) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    float x[NNP_K], y[NNP_K], z[NNP_K];
+    float lo0 = INF, lo1 = INF, lo2 = INF, hi0 = -INF, hi1 = -INF, hi2 = -INF;
+#pragma unroll
+    for (int k = 0; k < NNP_K; ++k) {
+        const int li = tid + k * NNP_THREADS;
+        const bool v = lo + li < hi;
+        x[k] = v ? src[li * 3 + 0] : 0.f; y[k] = v ? src[li * 3 + 1] : 0.f; z[k] = v ? src[li * 3 + 2] : 0.f;
+        if (v) {   // (fminf / fmaxf drop NaN)
+            lo0 = fminf(lo0, x[k]); hi0 = fmaxf(hi0, x[k]);
+            lo1 = fminf(lo1, y[k]); hi1 = fmaxf(hi1, y[k]);
+            lo2 = fminf(lo2, z[k]); hi2 = fmaxf(hi2, z[k]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fminf(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        lo1 = fminf(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+    }
+    if (lane == 0) { sRed[warp][0] = lo0; sRed[warp][1] = lo1; sRed[warp][2] = lo2; sRed[warp][3] = hi0; sRed[warp][4] = hi1; sRed[warp][5] = hi2; }
+    __syncthreads();   // (also: the table is filled)
+    if (tid < 3) {
+        float a = INF, c = -INF;
+        for (int w = 0; w < NNP_THREADS / 32; ++w) { a = fminf(a, sRed[w][tid]); c = fmaxf(c, sRed[w][3 + tid]); }
+        float o = 0.5f * a + 0.5f * c;
+        if (!(fabsf(o) < INF)) o = 0.f;   // no finite coordinate at all: every query ends in the exact scan anyway
+        sO[tid] = o;
+    }
+#pragma unroll
+    for (int k = 0; k < NNP_K; ++k) {
+        const int li = tid + k * NNP_THREADS;
+        if (lo + li < hi) {
+            atomicMin(&tab[nn_hash1(x[k], y[k], z[k]) & mask], (unsigned)li);
+            atomicMin(&tab[nn_hash2(x[k], y[k], z[k]) & mask], (unsigned)li);
+        }
+    }
+    __syncthreads();
+    // first round: copy / winner of a slot / neither.  The points that are neither -- a set of equal points whose lowest index lost
+    // both slots to other points -- bid once more, for one slot of a second, nearly empty table (a quarter of the first).
+    unsigned copies = 0u, again = 0u;
+    unsigned* __restrict__ tab2 = tab + mask + 1;
+    const unsigned mask2 = mask >> 2;
+#pragma unroll
+    for (int k = 0; k < NNP_K; ++k) {
+        const int li = tid + k * NNP_THREADS;
+        if (lo + li < hi) {
+            const unsigned w1 = tab[nn_hash1(x[k], y[k], z[k]) & mask], w2 = tab[nn_hash2(x[k], y[k], z[k]) & mask];   // both <= li
+            const bool copy = (w1 != (unsigned)li && src[w1 * 3 + 0] == x[k] && src[w1 * 3 + 1] == y[k] && src[w1 * 3 + 2] == z[k]) ||
+                              (w2 != (unsigned)li && src[w2 * 3 + 0] == x[k] && src[w2 * 3 + 1] == y[k] && src[w2 * 3 + 2] == z[k]);
+            if (copy) copies |= 1u << k;
+            else if (w1 != (unsigned)li && w2 != (unsigned)li) {
+                again |= 1u << k;
+                atomicMin(&tab2[(nn_hash1(y[k], z[k], x[k]) >> 7) & mask2], (unsigned)li);
+            }
+        }
+    }
+    __syncthreads();
+    const float ox = sO[0], oy = sO[1], oz = sO[2];
+    float cmax = 0.f;
+#pragma unroll
+    for (int k = 0; k < NNP_K; ++k) {
+        const int li = tid + k * NNP_THREADS;
+        if (lo + li < hip) {
+            float4 v = make_float4(0.f, 0.f, 0.f, INF);   // padding rows and copies never produce a minimum
+            if (lo + li < hi) {
+                bool copy = (copies >> k) & 1u;
+                if ((again >> k) & 1u) {
+                    const unsigned w = tab2[(nn_hash1(y[k], z[k], x[k]) >> 7) & mask2];
+                    copy = w != (unsigned)li && src[w * 3 + 0] == x[k] && src[w * 3 + 1] == y[k] && src[w * 3 + 2] == z[k];
+                }
+                v.x = x[k] - ox; v.y = y[k] - oy; v.z = z[k] - oz;
+                if (!copy) {
+                    v.w = __fmaf_rn(v.z, v.z, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
+                    cmax = fmaxf(cmax, v.w);   // drops NaN
+                }
+            }
+            dst[li] = v;
+        }
+    }
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(cmax));   // cmax >= +0: bits are monotone
+    if (lane == 0) sRed[warp][0] = __uint_as_float(wmax);   // (sRed was last read before the previous barrier)
+    __syncthreads();
+    if (tid == 0) {
+        unsigned mx = 0u;
+        for (int w = 0; w < NNP_THREADS / 32; ++w) mx = max(mx, __float_as_uint(sRed[w][0]));
+        p.meta[d][(size_t)cloud * p.nsplit[d] + split] = make_float4(ox, oy, oz, __uint_as_float(mx));
+    }
+}
+
+template <int Q, bool FUSED>
+__global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(const NNParams p) {
+    static_assert(Q % 2 == 0, "queries are processed as packed pairs");
+    constexpr int G = NNF_G;
+    __shared__ __align__(128) float4 sCv[2][NN_TC];   // (x, y, z, |c|^2) chunks relative to the cloud's origin, double buffered
+    __shared__ __align__(8) uint64_t bar[2];
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int dir = bid >= p.d[0].items ? 1 : 0;
+    if (dir) bid -= p.d[0].items;
+    const NNDir& D = p.d[dir];
+
+    const int split = bid % D.nsplit;
+    const int tile = (bid / D.nsplit) % D.nqt;
+    const int cloud = bid / (D.nsplit * D.nqt);
+    const int nq = D.nq, nc = D.nc, chunk = D.chunk;
+
+    const float* __restrict__ qbase = D.q + (size_t)cloud * nq * 3;
+    const float* __restrict__ cbase = D.c + (size_t)cloud * nc * 3;
+    const float4* __restrict__ cvbase = D.cv + (size_t)cloud * D.ncp;
+    const float4 meta = D.meta[(size_t)cloud * D.nsplit + split];
+    const float ox = meta.x, oy = meta.y, oz = meta.z, cmax_cloud = meta.w;
+
+    // ---- -2 * (query - origin) into registers, as pairs (2h, 2h+1) -> (x: query tid + 2h*T, y: query tid + (2h+1)*T)
+    const int q0 = tile * (NN_THREADS * Q) + tid;
+    float2 qx[Q / 2], qy[Q / 2], qz[Q / 2];
+    float b1[Q], b2[Q];
+    int k1[Q];
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) {
+        const int ia = q0 + (2 * h) * NN_THREADS, ib = ia + NN_THREADS;
+        const bool va = ia < nq, vb = ib < nq;
+        qx[h].x = va ? -2.0f * (qbase[(size_t)ia * 3 + 0] - ox) : 0.f;
+        qy[h].x = va ? -2.0f * (qbase[(size_t)ia * 3 + 1] - oy) : 0.f;
+        qz[h].x = va ? -2.0f * (qbase[(size_t)ia * 3 + 2] - oz) : 0.f;
+        qx[h].y = vb ? -2.0f * (qbase[(size_t)ib * 3 + 0] - ox) : 0.f;
+        qy[h].y = vb ? -2.0f * (qbase[(size_t)ib * 3 + 1] - oy) : 0.f;
+        qz[h].y = vb ? -2.0f * (qbase[(size_t)ib * 3 + 2] - oz) : 0.f;
+    }
+    const float INF = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) { b1[i] = INF; b2[i] = INF; k1[i] = 0; }
+
+    const int nchunks_total = (nc + chunk - 1) / chunk;
+    const int first_chunk = split * D.cps;
+    const int my_chunks = min(D.cps, nchunks_total - first_chunk);
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int ci) {  // thread 0 only: start the bulk copy of chunk ci of this item (whole groups: the rows are padded)
+        const int start = (first_chunk + ci) * chunk;
+        const int lenG = (min(chunk, nc - start) + G - 1) / G * G;
+        const unsigned bytes = (unsigned)lenG * 16u;
+        mbar_expect_tx(&bar[ci & 1], bytes);
+        tma_bulk_g2s(sCv[ci & 1], cvbase + start, bytes, &bar[ci & 1]);
+    };
+    if (tid == 0 && my_chunks > 0) issue(0);
+
+    int item_live = 0;
+    for (int ci = 0; ci < my_chunks; ++ci) {
+        const int start = (first_chunk + ci) * chunk;
+        const int lenG = (min(chunk, nc - start) + G - 1) / G * G;
+        if (tid == 0 && ci + 1 < my_chunks) issue(ci + 1);
+        mbar_wait(&bar[ci & 1], (ci >> 1) & 1);
+        const float4* __restrict__ cv = sCv[ci & 1];
+        int live = 0;   // does the chunk hold any candidate that takes part in the scan (not a copy, not padding)?
+        for (int i = tid; i < lenG; i += NN_THREADS) live |= cv[i].w < INF;
+
+#pragma unroll 1
+        for (int k = 0; k < lenG; k += G) {
+            float g[Q];
+#pragma unroll
+            for (int part = 0; part < G / 8; ++part) {
+                float4 c[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) c[j] = cv[k + part * 8 + j];
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    float2 s[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s[j] = __ffma2_rn(qz[h], make_float2(c[j].z, c[j].z), make_float2(c[j].w, c[j].w));
+                        s[j] = __ffma2_rn(qy[h], make_float2(c[j].y, c[j].y), s[j]);
+                        s[j] = __ffma2_rn(qx[h], make_float2(c[j].x, c[j].x), s[j]);
+                    }
+                    if (part == 0) {
+                        g[2 * h] = fmin3(fmin3(s[0].x, s[1].x, s[2].x), fmin3(s[3].x, s[4].x, s[5].x), fminf(s[6].x, s[7].x));
+                        g[2 * h + 1] = fmin3(fmin3(s[0].y, s[1].y, s[2].y), fmin3(s[3].y, s[4].y, s[5].y), fminf(s[6].y, s[7].y));
+                    } else {
+                        g[2 * h] = fmin3(fmin3(g[2 * h], s[0].x, s[1].x), fmin3(s[2].x, s[3].x, s[4].x), fmin3(s[5].x, s[6].x, s[7].x));
+                        g[2 * h + 1] = fmin3(fmin3(g[2 * h + 1], s[0].y, s[1].y), fmin3(s[2].y, s[3].y, s[4].y), fmin3(s[5].y, s[6].y, s[7].y));
+                    }
+                }
+            }
+            // smallest / second smallest group minimum and the group of the smallest (strict '<': the FIRST such group)
+            const int kbase = start + k;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                const float hi = fmaxf(g[i], b1[i]);
+                k1[i] = (g[i] < b1[i]) ? kbase : k1[i];
+                b1[i] = fminf(g[i], b1[i]);
+                b2[i] = fminf(b2[i], hi);
+            }
+        }
+        item_live |= __syncthreads_or(live);  // (barrier: everyone is done with sCv[ci&1] before the copy engine may overwrite it)
+    }
+    // An item whose candidates are all copies of points with lower indices (or padding) has nothing to contribute: each copy
+    // loses the tie against its original in whichever item holds it.
+    if (!item_live) {
+        if (D.nsplit == 1)
+            for (int i = 0; i < Q; ++i) {
+                const int qi = q0 + i * NN_THREADS;
+                if (qi < nq) { D.dist[(size_t)cloud * nq + qi] = INF; D.idx[(size_t)cloud * nq + qi] = 0; }
+            }
+        return;
+    }
+
+    // ---- per query: certify group k1 and evaluate it exactly, or queue the query for the exact warp scan.  The tracking
+    // state goes through shared memory (the chunk buffers are free now) so that this epilogue is a rolled loop.
+    float* sB1 = reinterpret_cast<float*>(&sCv[0][0]);
+    float* sB2 = sB1 + Q * NN_THREADS;
+    int* sK1 = reinterpret_cast<int*>(sB2 + Q * NN_THREADS);
+    static_assert(3 * Q * NN_THREADS <= 2 * NN_TC * 4, "tracking state fits in the chunk buffers");
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        sB1[i * NN_THREADS + tid] = b1[i];
+        sB2[i * NN_THREADS + tid] = b2[i];
+        sK1[i * NN_THREADS + tid] = k1[i];
+    }
+    const int range_lo = first_chunk * chunk;
+    const int range_hi = min(nc, range_lo + my_chunks * chunk);
+    const bool vec = D.tma != 0;   // raw candidate rows are 16-byte aligned: G of them are 3G/4 vector loads
+    auto emit = [&](int qi, float bd, int bi) {
+        const size_t o = (size_t)cloud * nq + qi;
+        if (D.nsplit == 1) {
+            D.dist[o] = bd;
+            D.idx[o] = bi;
+        } else {
+            atomicMin(&D.keys[o], pack_key(bd, bi));
+        }
+    };
+    unsigned pending = 0;
+#pragma unroll 1
+    for (int i = 0; i < Q; ++i) {
+        const int qi = q0 + i * NN_THREADS;
+        if (qi >= nq) break;
+        const float v1 = sB1[i * NN_THREADS + tid], v2 = sB2[i * NN_THREADS + tid];
+        const int k0 = sK1[i * NN_THREADS + tid];
+        const float qxs = qbase[(size_t)qi * 3 + 0], qys = qbase[(size_t)qi * 3 + 1], qzs = qbase[(size_t)qi * 3 + 2];
+        const float rx = qxs - ox, ry = qys - oy, rz = qzs - oz;   // the same roundings as in the scan
+        const float tol2 = nn_filter_tolerance(__fmaf_ru(rz, rz, __fmaf_ru(rx, rx, __fmul_ru(ry, ry))), cmax_cloud);
+        // every comparison is false for NaN, so non-finite states fall through to the exact scan
+        const bool certain = (v2 > __fadd_ru(v1, tol2)) && (fabsf(v1) < INF) && (tol2 < INF);
+        if (certain) {
+            // the G reference distances of the certified group, all independent (the loads and the arithmetic pipeline),
+            // then their minimum and the FIRST position attaining it
+            const int lim = min(G, range_hi - k0);
+            float dd[G];
+            if (vec && lim == G) {
+                const float4* __restrict__ grp = reinterpret_cast<const float4*>(cbase + (size_t)k0 * 3);
+                float r[G * 3];
+#pragma unroll
+                for (int t = 0; t < G * 3 / 4; ++t) {
+                    const float4 v = __ldg(grp + t);
+                    r[4 * t] = v.x; r[4 * t + 1] = v.y; r[4 * t + 2] = v.z; r[4 * t + 3] = v.w;
+                }
+#pragma unroll
+                for (int t = 0; t < G; ++t) dd[t] = sqdist3<FUSED>(qxs - r[3 * t], qys - r[3 * t + 1], qzs - r[3 * t + 2]);   // (query - candidate), as nn_search_kernel
+            } else {
+#pragma unroll
+                for (int t = 0; t < G; ++t) {
+                    const float* __restrict__ c = cbase + (size_t)(k0 + min(t, lim - 1)) * 3;
+                    dd[t] = sqdist3<FUSED>(qxs - c[0], qys - c[1], qzs - c[2]);
+                }
+#pragma unroll
+                for (int t = 0; t < G; ++t) dd[t] = (t < lim) ? dd[t] : INF;
+            }
+            float bd = fminf(dd[0], dd[1]);
+#pragma unroll
+            for (int t = 2; t < G; t += 2) bd = fmin3(bd, dd[t], dd[t + 1]);
+            int bj = 0;
+#pragma unroll
+            for (int t = G - 1; t >= 0; --t) bj = (dd[t] == bd) ? t : bj;
+            emit(qi, bd, k0 + bj);
+        } else {
+            pending |= 1u << i;
+        }
+    }
+    // ---- exact scan of the item's candidate range for the queries that could not be certified, one query per warp step
+    const int lane = tid & 31;
+    unsigned any = __ballot_sync(0xffffffffu, pending != 0);
+    while (any) {
+        const int srcl = __ffs(any) - 1;
+        const unsigned pm = __shfl_sync(0xffffffffu, pending, srcl);
+        const int i = __ffs(pm) - 1;
+        const int qi = q0 - lane + srcl + i * NN_THREADS;
+        const float qxs = qbase[(size_t)qi * 3 + 0], qys = qbase[(size_t)qi * 3 + 1], qzs = qbase[(size_t)qi * 3 + 2];
+        float bd = INF;
+        int bi = 0;
+        for (int cidx = range_lo + lane; cidx < range_hi; cidx += 32) {
+            const float* __restrict__ c = cbase + (size_t)cidx * 3;
+            const float dd = sqdist3<FUSED>(qxs - c[0], qys - c[1], qzs - c[2]);
+            if (dd < bd) { bd = dd; bi = cidx; }
+        }
+        unsigned long long key = pack_key(bd, bi);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == srcl) {
+            emit(qi, __uint_as_float((unsigned)(key >> 32)), (int)(unsigned)(key & 0xffffffffull));
+            pending &= pending - 1;
+            if (p.stats) atomicAdd(p.stats, 1ull);
+        }
+        any = __ballot_sync(0xffffffffu, pending != 0);
     }
 }
 
@@ -386,7 +798,8 @@ constexpr int NN_CTAS_PER_SM = NN_MIN_CTAS;  // resident CTAs per SM implied by 
 // index resolution, key merge) worth roughly 48 candidates of scanning.  The hardware hands items to the resident CTA slots
 // in blockIdx order -- direction 0's items, then direction 1's -- so the launch time is the makespan of list-scheduling
 // two classes of equal-cost items on `slots` machines; nn_makespan evaluates that exactly (a handful of steps) and
-// pick_chunks takes the pair of chunk lengths (each an even split of its candidate range, rounded up to 8) that minimises it.
+// pick_plan takes, per direction, the chunk length (an even split of the candidate range, rounded up to a group) and the number
+// of chunks per item that minimise it.
 // With one shared power-of-two chunk the bench shape ran 2.77 waves of work in 3 rounds (7 % idle); see DESIGN.md 4.1.
 static long nn_makespan(long slots, long cnt_a, long cost_a, long cnt_b, long cost_b) {
     // slot groups (time at which the slots of the group become free, how many), kept sorted by time; at most a few entries
@@ -415,18 +828,28 @@ static long nn_makespan(long slots, long cnt_a, long cost_a, long cnt_b, long co
     }
     return end;
 }
-static void pick_chunks(int b, int n, int m, int Q, int* chunk0, int* chunk1) {
-    struct Memo { int b, n, m, Q, sms, c0, c1; };
-    static thread_local Memo memo = {0, 0, 0, 0, 0, 0, 0};   // a pure function of its arguments: the memo only saves host time
+struct NNPlan { int chunk0, cps0, chunk1, cps1; };
+#ifdef NN_TUNE
+static int g_force_chunk = 0, g_force_cps = 0;   // tools/nn_tune.cu sweeps these
+#endif
+// Cost model, in units of "one candidate scanned by one CTA": an item of `cps` chunks of `len` candidates costs
+// cps * (len + per_chunk) + per_item.  direct kernel: per_chunk ~ 0 (the bulk copy is hidden), per_item ~ 48 (query loads,
+// pipeline fill, index resolution, key merge).  filtered kernel: the scan is twice as fast, so the same overheads weigh
+// double, each chunk pays a conversion pass and two block barriers, and each item one exact evaluation of a group per query.
+static NNPlan pick_plan(int b, int n, int m, int Q, bool direct) {
+    struct Memo { int b, n, m, Q, sms, direct; NNPlan plan; };
+    static thread_local Memo memo = {0, 0, 0, 0, 0, 0, {0, 0, 0, 0}};   // a pure function of its arguments: the memo only saves host time
     const int sms = num_sms();
-    if (memo.b == b && memo.n == n && memo.m == m && memo.Q == Q && memo.sms == sms) { *chunk0 = memo.c0; *chunk1 = memo.c1; return; }
+    if (memo.b == b && memo.n == n && memo.m == m && memo.Q == Q && memo.sms == sms && memo.direct == (int)direct) return memo.plan;
     const int TQ = NN_THREADS * Q;
-    const long slots = (long)sms * NN_CTAS_PER_SM;
+    const long slots = (long)sms * (direct ? NN_CTAS_PER_SM : NNF_MIN_CTAS);
+    const long per_chunk = direct ? 0 : 8, per_item = direct ? 48 : 150;
     const long tiles0 = (long)b * ((n + TQ - 1) / TQ), tiles1 = (long)b * ((m + TQ - 1) / TQ);
-    auto lens = [](int nc, int* out) {   // even splits of nc into k pieces, rounded up to 8, between 256 and NN_TC candidates
+    const int grp = direct ? 8 : NNF_G;   // chunks are whole groups of the kernel that scans them
+    auto lens = [grp](int nc, int* out) {   // even splits of nc into k pieces, rounded up to a group, between 256 and NN_TC candidates
         int cnt = 0, last = 0;
         for (int k = 1; k <= 64 && cnt < 64; ++k) {
-            int len = ((nc + k - 1) / k + 7) & ~7;
+            int len = ((nc + k - 1) / k + grp - 1) / grp * grp;
             if (len > NN_TC) continue;
             if (len < 256 && cnt > 0) break;
             if (len != last) out[cnt++] = len;
@@ -437,28 +860,38 @@ static void pick_chunks(int b, int n, int m, int Q, int* chunk0, int* chunk1) {
     };
     int l0[64], l1[64];
     const int c0 = lens(m, l0), c1 = lens(n, l1);
+    const int cps_opts[] = {1, 2, 3, 4, 6, 8};
+    const int ncps = direct ? 1 : 6;   // the direct kernel's per-item price is small: one chunk per item spreads best
     long best = -1;
-    int b0 = NN_TC, b1 = NN_TC;
+    NNPlan plan = {NN_TC, 1, NN_TC, 1};
     for (int i = 0; i < c0; ++i)
-        for (int j = 0; j < c1; ++j) {
-            const long k0 = (m + l0[i] - 1) / l0[i], k1 = (n + l1[j] - 1) / l1[j];
-            const long t = nn_makespan(slots, tiles0 * k0, (m < l0[i] ? m : l0[i]) + 48, tiles1 * k1, (n < l1[j] ? n : l1[j]) + 48);
-            if (best < 0 || t < best) { best = t; b0 = l0[i]; b1 = l1[j]; }
-        }
-    memo = {b, n, m, Q, sms, b0, b1};
-    *chunk0 = b0;
-    *chunk1 = b1;
+        for (int ci = 0; ci < ncps; ++ci)
+            for (int j = 0; j < c1; ++j)
+                for (int cj = 0; cj < ncps; ++cj) {
+                    const long k0 = (m + l0[i] - 1) / l0[i], k1 = (n + l1[j] - 1) / l1[j];
+                    const long p0 = cps_opts[ci] < k0 ? cps_opts[ci] : k0, p1 = cps_opts[cj] < k1 ? cps_opts[cj] : k1;
+                    if ((ci > 0 && cps_opts[ci] > k0) || (cj > 0 && cps_opts[cj] > k1)) continue;   // same plan as a smaller option
+                    const long s0 = (k0 + p0 - 1) / p0, s1 = (k1 + p1 - 1) / p1;
+                    const long cost0 = p0 * ((m < l0[i] ? m : l0[i]) + per_chunk) + per_item;
+                    const long cost1 = p1 * ((n < l1[j] ? n : l1[j]) + per_chunk) + per_item;
+                    // the longer class goes first in blockIdx order only if it is direction 0; the makespan model takes the order as it is
+                    const long t = nn_makespan(slots, tiles0 * s0, cost0, tiles1 * s1, cost1);
+                    if (best < 0 || t < best) { best = t; plan = {l0[i], (int)p0, l1[j], (int)p1}; }
+                }
+    memo = {b, n, m, Q, sms, (int)direct, plan};
+    return plan;
 }
 
-static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, bool split) {
+static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, int cps, bool direct) {
     D.nq = nq;
     D.nc = nc;
     const int TQ = NN_THREADS * Q;
     D.nqt = (nq + TQ - 1) / TQ;
     D.chunk = chunk;
     const int nchunks = (nc + chunk - 1) / chunk;
-    D.cps = split ? 1 : nchunks;
-    D.nsplit = split ? nchunks : 1;
+    D.cps = cps > 0 ? (cps < nchunks ? cps : nchunks) : nchunks;   // cps <= 0: the whole candidate range in one item ...
+    if (!direct && D.cps * chunk > NNP_RANGE) D.cps = NNP_RANGE / chunk;   // ... as far as the preparation of the filtered search reaches
+    D.nsplit = (nchunks + D.cps - 1) / D.cps;
     D.items = b * D.nqt * D.nsplit;
     D.tma = (nc % 4 == 0) && (((uintptr_t)D.c & 15u) == 0);
 }
@@ -466,47 +899,109 @@ static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, bo
 static int pick_q(int nq) { return nq >= 1024 ? 8 : (nq >= 512 ? 4 : 2); }
 
 template <int Q>
-static void launch_search(const NNParams& p, int grid, bool fused, cudaStream_t s) {
-    if (fused)
-        nn_search_kernel<Q, true><<<grid, NN_THREADS, 0, s>>>(p);
-    else
-        nn_search_kernel<Q, false><<<grid, NN_THREADS, 0, s>>>(p);
+static void launch_search(const NNParams& p, int grid, bool fused, bool direct, cudaStream_t s) {
+    if (direct) {
+        if (fused)
+            nn_search_kernel<Q, true><<<grid, NN_THREADS, 0, s>>>(p);
+        else
+            nn_search_kernel<Q, false><<<grid, NN_THREADS, 0, s>>>(p);
+    } else {
+        if (fused)
+            nn_filter_kernel<Q, true><<<grid, NN_THREADS, 0, s>>>(p);
+        else
+            nn_filter_kernel<Q, false><<<grid, NN_THREADS, 0, s>>>(p);
+    }
 }
 
 }  // namespace rfnet
 
 using namespace rfnet;
 
+// workspace: [ keys of direction 0 (b*n) | keys of direction 1 (b*m) ] [ prepared candidates of direction 0 (xyz2) | of direction 1
+// (xyz1) ] [ origin and max norm per (cloud, item range), direction 0 | direction 1 ]
+static inline int nn_padded(int nc) { return (nc + NNF_G - 1) / NNF_G * NNF_G; }
+static inline int nn_max_ranges(int nc) { return (nc + 255) / 256; }   // chunks are at least 256 candidates long
+struct NNLayout { size_t cv0, cv1, meta0, meta1, total; };
+static NNLayout nn_layout(int b, int n, int m) {
+    NNLayout L;
+    size_t o = ((size_t)b * ((size_t)n + (size_t)m) * sizeof(unsigned long long) + 15) & ~(size_t)15;
+    L.cv0 = o; o += sizeof(float4) * (size_t)b * nn_padded(m);
+    L.cv1 = o; o += sizeof(float4) * (size_t)b * nn_padded(n);
+    L.meta0 = o; o += sizeof(float4) * (size_t)b * nn_max_ranges(m);
+    L.meta1 = o; o += sizeof(float4) * (size_t)b * nn_max_ranges(n);
+    L.total = o;
+    return L;
+}
 extern "C" size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    return (size_t)b * ((size_t)n + (size_t)m) * sizeof(unsigned long long);
+    return nn_layout(b, n, m).total;
+}
+
+static int nn_prepare_launch(const NNPrep& pp, unsigned blocks, unsigned slots, cudaStream_t s) {
+    static bool attr_set[64] = {false};   // per device; benign race: every thread sets the same attribute
+    int dev = 0;
+    RFNET_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        RFNET_CUDA(cudaFuncSetAttribute(nn_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * NNP_RANGE + NNP_RANGE / 2) * (int)sizeof(unsigned)));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    nn_prepare_kernel<<<blocks, NNP_THREADS, (slots + slots / 4) * sizeof(unsigned), s>>>(pp);
+    return 0;
 }
 
 // plan + key memset + search launch; *need0 / *need1 tell the caller which directions left their results as packed keys
 // dirs: 1 = xyz1 queries against xyz2 only, 2 = xyz2 queries against xyz1 only, 3 = both
 static int nn_search_launch(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2, int* idx2, void* workspace,
-                            size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out, int dirs = 3) {
+                            size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out, int dirs = 3,
+                            unsigned long long* stats = nullptr) {
     const int Q = pick_q(n < m ? n : m);
     NNParams p;
+    p.stats = stats;
     p.d[0].q = xyz1; p.d[0].c = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1;
     p.d[1].q = xyz2; p.d[1].c = xyz1; p.d[1].dist = dist2; p.d[1].idx = idx2;
     // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
     // written directly, no key merge and no extra launches
     const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
-    int chunk0 = NN_TC, chunk1 = NN_TC;
-#ifdef NN_FORCE_CHUNK
-    if (split) chunk0 = chunk1 = NN_FORCE_CHUNK;   // tools/nn_tune.cu
-#else
-    if (split) pick_chunks(b, n, m, Q, &chunk0, &chunk1);
+    // below 2^24 pairs a call is a few microseconds of work and launch-bound: the direct kernel needs no preparation launch
+    const bool fused = !(flags & RFNET_NN_UNFUSED), direct = (flags & RFNET_NN_DIRECT) != 0 || 2.0 * b * (double)n * (double)m < 16777216.0;
+    NNPlan plan = {NN_TC, 0, NN_TC, 0};
+    if (split) plan = pick_plan(b, n, m, Q, direct);
+#ifdef NN_TUNE
+    if (split && g_force_chunk) plan.chunk0 = plan.chunk1 = g_force_chunk;
+    if (split && g_force_cps) plan.cps0 = plan.cps1 = g_force_cps;
 #endif
-    plan_direction(p.d[0], b, n, m, Q, chunk0, split);
-    plan_direction(p.d[1], b, m, n, Q, chunk1, split);
+    plan_direction(p.d[0], b, n, m, Q, plan.chunk0, plan.cps0, direct);
+    plan_direction(p.d[1], b, m, n, Q, plan.chunk1, plan.cps1, direct);
     if (!(dirs & 1)) { p.d[0].items = 0; p.d[0].nsplit = 1; }   // a direction without items launches no CTA and merges no keys
     if (!(dirs & 2)) { p.d[1].items = 0; p.d[1].nsplit = 1; }
     unsigned long long* keys = (unsigned long long*)workspace;
     p.d[0].keys = keys;
     p.d[1].keys = keys ? keys + (size_t)b * n : nullptr;
     const bool need0 = p.d[0].nsplit > 1, need1 = p.d[1].nsplit > 1;
+    if (!direct) {
+        // filtered search: the candidate range of every work item is prepared once per call (origin, duplicates, |c|^2)
+        RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_nn_distance_workspace_bytes(b, n, m));
+        const NNLayout L = nn_layout(b, n, m);
+        char* w = (char*)workspace;
+        NNPrep pp;
+        pp.c[0] = xyz2; pp.c[1] = xyz1;
+        pp.cv[0] = reinterpret_cast<float4*>(w + L.cv0); pp.cv[1] = reinterpret_cast<float4*>(w + L.cv1);
+        pp.meta[0] = reinterpret_cast<float4*>(w + L.meta0); pp.meta[1] = reinterpret_cast<float4*>(w + L.meta1);
+        unsigned slots_max = 0, blocks[2];
+        for (int d = 0; d < 2; ++d) {
+            const NNDir& D = p.d[d];
+            pp.nc[d] = D.nc; pp.ncp[d] = nn_padded(D.nc); pp.range[d] = D.cps * D.chunk; pp.nsplit[d] = D.nsplit;
+            unsigned sl = 64;
+            while (sl < 2u * (unsigned)(pp.range[d] < D.nc ? pp.range[d] : D.nc)) sl <<= 1;   // two bids per point: half full at most
+            pp.slots[d] = sl;
+            blocks[d] = D.items ? (unsigned)b * D.nsplit : 0u;
+            if (blocks[d] && sl > slots_max) slots_max = sl;
+            p.d[d].cv = pp.cv[d]; p.d[d].ncp = pp.ncp[d]; p.d[d].meta = pp.meta[d];
+        }
+        pp.first_dir = blocks[0] ? 0 : 1;
+        pp.blocks0 = blocks[pp.first_dir];
+        { const int rc = nn_prepare_launch(pp, blocks[0] + blocks[1], slots_max, s); if (rc) return rc; }
+    }
     if (need0 || need1) {
         RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_nn_distance_workspace_bytes(b, n, m));
         // the two key arrays are contiguous: one memset covers whichever directions are merged
@@ -515,10 +1010,9 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
         RFNET_CUDA(cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * cnt, s));
     }
     const int grid = p.d[0].items + p.d[1].items;
-    const bool fused = !(flags & RFNET_NN_UNFUSED);
-    if (Q == 8) launch_search<8>(p, grid, fused, s);
-    else if (Q == 4) launch_search<4>(p, grid, fused, s);
-    else launch_search<2>(p, grid, fused, s);
+    if (Q == 8) launch_search<8>(p, grid, fused, direct, s);
+    else if (Q == 4) launch_search<4>(p, grid, fused, direct, s);
+    else launch_search<2>(p, grid, fused, direct, s);
     *need0_out = need0;
     *need1_out = need1;
     return 0;
@@ -526,6 +1020,12 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
 
 extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
                                  int* idx2, void* workspace, size_t workspace_bytes, int flags, rfnet_stream_t stream) {
+    return rfnet_nn_distance_stats(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, flags, nullptr, stream);
+}
+
+extern "C" int rfnet_nn_distance_stats(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
+                                       int* idx2, void* workspace, size_t workspace_bytes, int flags, unsigned long long* exact_scans,
+                                       rfnet_stream_t stream) {
     RFNET_CHECK_ARG(b >= 0 && n >= 0 && m >= 0);
     if (b == 0 || (n == 0 && m == 0)) return 0;
     RFNET_CHECK_ARG(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2);
@@ -537,7 +1037,7 @@ extern "C" int rfnet_nn_distance(int b, int n, const float* xyz1, int m, const f
         return 0;
     }
     bool need0 = false, need1 = false;
-    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, flags, s, &need0, &need1); if (rc) return rc; }
+    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, workspace_bytes, flags, s, &need0, &need1, 3, exact_scans); if (rc) return rc; }
     if (need0 || need1) {
         const size_t count0 = (size_t)b * n;
         const size_t begin = need0 ? 0 : count0, end = need1 ? count0 + (size_t)b * m : count0;

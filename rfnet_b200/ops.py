@@ -48,10 +48,10 @@ def _workspace(nbytes, device):
 # ------------------------------------------------------------------------------------------------------------ raw calls
 # Allocation-free entry points over caller-owned CUDA tensors (contiguous, right dtype, all on the current device): what
 # rfnet_b200.host uses in its steady-state loop, where the torch dispatcher and per-call allocations would dominate.
-def raw_nn_distance(xyz1, xyz2, dist1, idx1, dist2, idx2, workspace, unfused=False):
+def raw_nn_distance(xyz1, xyz2, dist1, idx1, dist2, idx2, workspace, unfused=False, direct=False):
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     _lib.check(_lib.load().rfnet_nn_distance(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(dist1), _ptr(idx1), _ptr(dist2), _ptr(idx2), _ptr(workspace),
-                                             workspace.numel(), 1 if unfused else 0, _stream(xyz1)), "rfnet_nn_distance")
+                                             workspace.numel(), (1 if unfused else 0) | (2 if direct else 0), _stream(xyz1)), "rfnet_nn_distance")
 
 
 def raw_nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, workspace=None):
@@ -67,12 +67,12 @@ def raw_chamfer_partial_sums(dist1, dist2, sums4, workspace):
                                                       _ptr(workspace), workspace.numel(), _stream(dist1)), "rfnet_chamfer_partial_sums")
 
 
-def raw_chamfer_step(xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, sums4, workspace, unfused=False):
+def raw_chamfer_step(xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, sums4, workspace, unfused=False, direct=False):
     """nn_distance + NnDistanceGrad + the chamfer partial sums: one C-ABI call, three kernel launches (rfnet_chamfer_step)."""
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     _lib.check(_lib.load().rfnet_chamfer_step(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(grad_dist1), _ptr(grad_dist2), _ptr(dist1), _ptr(idx1), _ptr(dist2),
                                               _ptr(idx2), _ptr(grad_xyz1), _ptr(grad_xyz2), _ptr(sums4), _ptr(workspace), workspace.numel(),
-                                              1 if unfused else 0, _stream(xyz1)), "rfnet_chamfer_step")
+                                              (1 if unfused else 0) | (2 if direct else 0), _stream(xyz1)), "rfnet_chamfer_step")
 
 
 def nn_distance_workspace_bytes(b, n, m):
@@ -82,15 +82,10 @@ def nn_distance_workspace_bytes(b, n, m):
 
 
 # ------------------------------------------------------------------------------------------------------------ nn_distance
-@torch.library.custom_op("rfnet::nn_distance", mutates_args=(), device_types="cuda")
-def nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, unfused: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    # shape checks of NnDistanceGpuOp::Compute, pc_distance/tf_nndistance.cpp:175-182
-    _require(xyz1.dim() == 3, "NnDistance requires xyz1 be of shape (batch,#points,3)")
-    _require(xyz1.shape[2] == 3, "NnDistance only accepts 3d point set xyz1")
-    _require(xyz2.dim() == 3, "NnDistance requires xyz2 be of shape (batch,#points,3)")
-    _require(xyz2.shape[2] == 3, "NnDistance only accepts 3d point set xyz2")
-    _require(xyz2.shape[0] == xyz1.shape[0], "NnDistance expects xyz1 and xyz2 have same batch size")
-    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+NN_UNFUSED, NN_DIRECT = 1, 2   # rfnet_ops.h: RFNET_NN_UNFUSED, RFNET_NN_DIRECT
+
+
+def _nn_distance_call(xyz1, xyz2, flags, count_exact_scans=False):
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     dev = xyz1.device
     dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
@@ -100,14 +95,37 @@ def nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, unfused: bool = False
     lib = _lib.load()
     wsb = lib.rfnet_nn_distance_workspace_bytes(b, n, m)
     ws = _workspace(wsb, dev)
+    scans = torch.zeros((1,), dtype=torch.int64, device=dev) if count_exact_scans else None
     with torch.cuda.device(dev):
-        _lib.check(lib.rfnet_nn_distance(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(dist1), _ptr(idx1), _ptr(dist2), _ptr(idx2), _ptr(ws), wsb,
-                                         1 if unfused else 0, _stream(xyz1)), "rfnet_nn_distance")
-    return dist1, idx1, dist2, idx2
+        _lib.check(lib.rfnet_nn_distance_stats(b, n, _ptr(xyz1), m, _ptr(xyz2), _ptr(dist1), _ptr(idx1), _ptr(dist2), _ptr(idx2), _ptr(ws), wsb,
+                                               int(flags), _ptr(scans), _stream(xyz1)), "rfnet_nn_distance")
+    return dist1, idx1, dist2, idx2, scans
+
+
+def nn_distance_exact_scans(xyz1, xyz2, unfused=False):
+    """Diagnostics: the outputs of nn_distance plus the number of (query, work item) pairs the filtered search could not certify and
+    scanned with the reference expression (rfnet_nn_distance_stats)."""
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    d1, i1, d2, i2, scans = _nn_distance_call(xyz1, xyz2, NN_UNFUSED if unfused else 0, count_exact_scans=True)
+    return d1, i1, d2, i2, int(scans.item())
+
+
+@torch.library.custom_op("rfnet::nn_distance", mutates_args=(), device_types="cuda")
+def nn_distance_op(xyz1: torch.Tensor, xyz2: torch.Tensor, unfused: bool = False, direct: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    # unfused: the reference CPU build's distance expression; direct: evaluate the reference expression for every pair (nn_search_kernel)
+    # instead of the filtered search (nn_filter_kernel) -- same outputs bit for bit, see csrc/nn_distance.cu
+    # shape checks of NnDistanceGpuOp::Compute, pc_distance/tf_nndistance.cpp:175-182
+    _require(xyz1.dim() == 3, "NnDistance requires xyz1 be of shape (batch,#points,3)")
+    _require(xyz1.shape[2] == 3, "NnDistance only accepts 3d point set xyz1")
+    _require(xyz2.dim() == 3, "NnDistance requires xyz2 be of shape (batch,#points,3)")
+    _require(xyz2.shape[2] == 3, "NnDistance only accepts 3d point set xyz2")
+    _require(xyz2.shape[0] == xyz1.shape[0], "NnDistance expects xyz1 and xyz2 have same batch size")
+    xyz1, xyz2 = _cuda_f32("xyz1", xyz1), _cuda_f32("xyz2", xyz2)
+    return _nn_distance_call(xyz1, xyz2, (NN_UNFUSED if unfused else 0) | (NN_DIRECT if direct else 0))[:4]
 
 
 @nn_distance_op.register_fake
-def _(xyz1, xyz2, unfused=False):
+def _(xyz1, xyz2, unfused=False, direct=False):
     b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
     return (xyz1.new_empty((b, n)), xyz1.new_empty((b, n), dtype=torch.int32), xyz1.new_empty((b, m)), xyz1.new_empty((b, m), dtype=torch.int32))
 
@@ -152,7 +170,7 @@ DETERMINISTIC_DEFAULT = _os.environ.get("RFNET_DETERMINISTIC", "0") not in ("", 
 
 
 def _nn_distance_setup(ctx, inputs, output):
-    xyz1, xyz2, _unfused = inputs
+    xyz1, xyz2 = inputs[0], inputs[1]
     ctx.save_for_backward(xyz1, xyz2, output[1], output[3])
 
 
@@ -164,7 +182,7 @@ def _nn_distance_backward(ctx, grad_dist1, grad_idx1, grad_dist2, grad_idx2):
     if grad_dist2 is None:
         grad_dist2 = torch.zeros(idx2.shape, dtype=torch.float32, device=xyz1.device)
     g1, g2 = nn_distance_grad_op(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, DETERMINISTIC_DEFAULT)
-    return g1, g2, None
+    return g1, g2, None, None
 
 
 nn_distance_op.register_autograd(_nn_distance_backward, setup_context=_nn_distance_setup)

@@ -68,6 +68,12 @@ def test_version_and_error_string_without_gpu():
     assert lib.rfnet_version() >= 100
     assert b"invalid argument" in lib.rfnet_error_string(1)
     # workspace queries are pure host arithmetic
-    assert lib.rfnet_nn_distance_workspace_bytes(32, 2048, 16384) == 32 * (2048 + 16384) * 8
+    # packed keys (8 B per point, rounded to 16 B) + prepared candidate rows (16 B per point, clouds padded to whole groups of 16)
+    # + 16 B of origin / norm per possible work-item range (256 candidates at least)
+    def expect(b, n, m):
+        pad = lambda c: (c + 15) // 16 * 16
+        return (8 * b * (n + m) + 15) // 16 * 16 + 16 * b * (pad(n) + pad(m)) + 16 * b * ((n + 255) // 256 + (m + 255) // 256)
+    for shape in ((32, 2048, 16384), (1, 10, 17), (3, 1000, 777)):
+        assert lib.rfnet_nn_distance_workspace_bytes(*shape) == expect(*shape), shape
     assert lib.rfnet_approxmatch_workspace_bytes(2, 100, 100) > 0
     assert lib.rfnet_approxmatch_workspace_bytes(0, 100, 100) == 0

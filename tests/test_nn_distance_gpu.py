@@ -9,9 +9,9 @@ from oracle import port, ref
 pytestmark = pytest.mark.gpu
 
 
-def _run(cuda, x1, x2, unfused=False):
+def _run(cuda, x1, x2, unfused=False, direct=False):
     from rfnet_b200 import tf_nndistance
-    out = tf_nndistance.nn_distance(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), unfused=unfused)
+    out = tf_nndistance.nn_distance(torch.from_numpy(x1).to(cuda), torch.from_numpy(x2).to(cuda), unfused=unfused, direct=direct)
     return [o.cpu().numpy() for o in out]
 
 
@@ -19,15 +19,82 @@ def _run(cuda, x1, x2, unfused=False):
 SHAPES = [(1, 1, 1), (2, 5, 3), (3, 64, 1024), (2, 300, 257), (2, 1000, 1029), (1, 2048, 2048), (2, 2049, 4100), (4, 515, 8192), (1, 4096, 37)]
 
 
-@pytest.mark.parametrize("b,n,m", SHAPES)
+# the filtered search (default) takes over from 2^24 pairs; the last shapes are there for it
+SHAPES_FILTER = [(2, 2049, 4100), (4, 515, 8192), (3, 3000, 2999), (1, 5000, 16390)]
+
+
+@pytest.mark.parametrize("b,n,m", SHAPES + SHAPES_FILTER[2:])
 @pytest.mark.parametrize("unfused", [False, True])
-def test_nn_distance_bit_exact(cuda, rng, b, n, m, unfused):
+@pytest.mark.parametrize("direct", [False, True])
+def test_nn_distance_bit_exact(cuda, rng, b, n, m, unfused, direct):
     x1, x2 = cloud(rng, b, n), cloud(rng, b, m)
     want = port.nn_distance(x1, x2, fused=not unfused)
-    got = _run(cuda, x1, x2, unfused)
+    got = _run(cuda, x1, x2, unfused, direct)
     for name, g, w in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
         assert g.dtype == w.dtype and g.shape == w.shape
         assert np.array_equal(g, w), "%s differs at %d positions" % (name, (g != w).sum())
+
+
+def _padded(r, b, n, distinct):
+    """a cloud of `distinct` points repeated to n rows the way the reference's resample_pcd pads short scans (data_util.py:8-13)"""
+    base = (r.random((b, distinct, 3), dtype=np.float32) - 0.5)
+    pick = r.integers(0, distinct, size=(b, n - distinct))
+    return np.concatenate([base, np.take_along_axis(base, pick[..., None].repeat(3, axis=2), axis=1)], axis=1)
+
+
+ADVERSARIAL = {
+    # name -> (x1, x2) builder for (rng, b, n, m)
+    "shifted_by_1000": lambda r, b, n, m: (cloud(r, b, n) + 1000.0, cloud(r, b, m) + 1000.0),
+    "scale_1e6": lambda r, b, n, m: (cloud(r, b, n) * 1e6, cloud(r, b, m) * 1e6),
+    "scale_1e-15": lambda r, b, n, m: (cloud(r, b, n) * 1e-15, cloud(r, b, m) * 1e-15),
+    "scale_1e-22_underflow": lambda r, b, n, m: (cloud(r, b, n) * 1e-22, cloud(r, b, m) * 1e-22),
+    "lattice_exact_ties": lambda r, b, n, m: (np.floor(cloud(r, b, n) * 16) / 16, np.floor(cloud(r, b, m) * 16) / 16),
+    "padded_candidates_and_queries": lambda r, b, n, m: (_padded(r, b, n, 300), _padded(r, b, m, 777)),
+    "same_cloud_twice": lambda r, b, n, m: (lambda x: (x[:, :n].copy(), x[:, :m].copy()))(cloud(r, b, max(n, m))),
+    "tight_cluster_far_away": lambda r, b, n, m: (cloud(r, b, n) * 1e-3 + np.float32(37.5), cloud(r, b, m) * 1e-3 + np.float32(37.5)),
+    "surface_with_outliers": lambda r, b, n, m: (np.concatenate([cloud(r, b, n - 3) * np.float32([1, 1, 1e-4]), np.full((b, 3, 3), 5e3, np.float32)], 1),
+                                                  cloud(r, b, m) * np.float32([1, 1, 1e-4])),
+}
+
+
+@pytest.mark.parametrize("kind", sorted(ADVERSARIAL))
+@pytest.mark.parametrize("b,n,m", [(2, 2049, 4100), (4, 4096, 16384), (1, 16384, 16384)])
+def test_filtered_search_equals_direct_search(cuda, kind, b, n, m):
+    """nn_filter_kernel (the default) against nn_search_kernel (the reference expression for every pair): all four outputs bit for
+    bit, on inputs built to break the certification -- clouds far from the origin, tiny / huge scales, exact ties between distinct
+    points, repeated points, coincident clouds -- in both distance contracts; plus the oracle on a slice."""
+    r = np.random.default_rng(len(kind) * 1000 + n)
+    x1, x2 = ADVERSARIAL[kind](r, b, n, m)
+    x1, x2 = np.ascontiguousarray(x1, dtype=np.float32), np.ascontiguousarray(x2, dtype=np.float32)
+    for unfused in (True, False):
+        got = _run(cuda, x1, x2, unfused, direct=False)
+        want = _run(cuda, x1, x2, unfused, direct=True)
+        for name, g, w in zip(("dist1", "idx1", "dist2", "idx2"), got, want):
+            assert np.array_equal(g, w), "%s %s: %d of %d differ" % (kind, name, (g != w).sum(), g.size)
+    w = port.nn_distance(x1[:1, :40], x2[:1], fused=True)   # `got` is the fused run here
+    assert np.array_equal(got[0][0, :40], w[0][0]) and np.array_equal(got[1][0, :40], w[1][0])
+
+
+def test_filtered_search_certifies_almost_everything(cuda):
+    """How often the filtered search falls back to the exact warp scan ((query, item) pairs over queries): rare on generic clouds,
+    wherever they sit and however they are padded; exercised heavily by a lattice (which is what the test above relies on)."""
+    from rfnet_b200 import ops
+    r = np.random.default_rng(5)
+    b, n, m = 4, 2048, 16384
+
+    def frac(x1, x2):
+        t1, t2 = torch.from_numpy(np.ascontiguousarray(x1, dtype=np.float32)).to(cuda), torch.from_numpy(np.ascontiguousarray(x2, dtype=np.float32)).to(cuda)
+        d1, i1, d2, i2, scans = ops.nn_distance_exact_scans(t1, t2)
+        e = ops.nn_distance_op(t1, t2, False, True)
+        assert torch.equal(d1, e[0]) and torch.equal(i1, e[1]) and torch.equal(d2, e[2]) and torch.equal(i2, e[3])
+        return scans / float(b * (n + m))
+
+    cases = {"uniform": (cloud(r, b, n), cloud(r, b, m)), "shifted": (cloud(r, b, n) + 100.0, cloud(r, b, m) + 100.0),
+             "padded_small": (_padded(r, b, n, 300), cloud(r, b, m)), "padded_large": (cloud(r, b, m)[:, :n], _padded(r, b, m, 2000))}
+    got = {k: frac(*v) for k, v in cases.items()}
+    print("exact-scan fractions:", got)
+    assert all(v < 0.02 for v in got.values()), got
+    assert frac(np.floor(cloud(r, b, n) * 16) / 16, np.floor(cloud(r, b, m) * 16) / 16) > 0.5
 
 
 def test_nn_distance_ties_pick_lowest_index(cuda, rng):
