@@ -272,7 +272,8 @@ __device__ __forceinline__ float nn_filter_tolerance(float qn, float cmax) {
 //     points bid once more for a slot of a second, nearly empty table.  The lowest index of a set of equal points always
 //     stays (a winner with equal coordinates would be a lower index); a copy that is still missed costs an exact scan, never
 //     a wrong answer.
-constexpr int NNP_THREADS = 1024, NNP_K = 8, NNP_RANGE = NNP_THREADS * NNP_K;
+constexpr int NNP_THREADS = 512, NNP_K = 8, NNP_RANGE = NNP_THREADS * NNP_K;   // 4096 candidates per item at most
+struct NNFill { unsigned* ptr; size_t words; unsigned value; };   // buffers the preparation launch fills on the side (keys, zeroed gradients)
 struct NNPrep {
     const float* c[2];      // candidate clouds of direction 0 / 1 (b, nc, 3)
     float4* cv[2];
@@ -281,20 +282,36 @@ struct NNPrep {
     unsigned slots[2];      // hash table size of the direction (power of two)
     unsigned blocks0;       // blocks of direction first_dir; the rest belong to the other direction
     int first_dir;
+    NNFill fill[3];
 };
-__device__ __forceinline__ unsigned nn_hash1(float x, float y, float z) {
-    const unsigned h = __float_as_uint(x) * 0x9E3779B1u ^ __float_as_uint(y) * 0x85EBCA77u ^ __float_as_uint(z) * 0xC2B2AE3Du;
-    return h ^ (h >> 15) ^ (h >> 23);
+// three slot numbers from one multiply-xor mix of the coordinate bits (the high bits of a product depend on all bits of its factor)
+__device__ __forceinline__ unsigned nn_mix(float x, float y, float z) {
+    return __float_as_uint(x) * 0x9E3779B1u ^ __float_as_uint(y) * 0x85EBCA77u ^ __float_as_uint(z) * 0xC2B2AE3Du;
 }
-__device__ __forceinline__ unsigned nn_hash2(float x, float y, float z) {
-    const unsigned h = __float_as_uint(x) * 0x27D4EB2Fu ^ __float_as_uint(y) * 0x165667B1u ^ __float_as_uint(z) * 0xD3A2646Du;
-    return h ^ (h >> 13) ^ (h >> 21);
-}
+__device__ __forceinline__ unsigned nn_slot1(unsigned h) { return h >> 17; }
+__device__ __forceinline__ unsigned nn_slot2(unsigned h) { return (h * 0x27D4EB2Fu) >> 17; }
+__device__ __forceinline__ unsigned nn_slot3(unsigned h) { return (h * 0x165667B1u) >> 19; }
 __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p) {
     extern __shared__ __align__(16) unsigned tab[];
     __shared__ float sRed[NNP_THREADS / 32][6];
     __shared__ float sO[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- side job: this CTA's slice of the buffers the call needs filled (packed keys 0xff.., zeroed gradient outputs)
+#pragma unroll 1
+    for (int f = 0; f < 3; ++f) {
+        const NNFill F = p.fill[f];
+        if (F.words == 0) continue;
+        const size_t per = ((F.words + gridDim.x - 1) / gridDim.x + 3) & ~(size_t)3;
+        const size_t w0 = (size_t)blockIdx.x * per, w1 = w0 + per < F.words ? w0 + per : F.words;
+        if ((reinterpret_cast<uintptr_t>(F.ptr) & 15u) == 0) {
+            for (size_t i = w0 + (size_t)tid * 4; i < w1; i += (size_t)NNP_THREADS * 4) {
+                if (i + 4 <= w1) *reinterpret_cast<uint4*>(F.ptr + i) = make_uint4(F.value, F.value, F.value, F.value);
+                else for (size_t j = i; j < w1; ++j) F.ptr[j] = F.value;
+            }
+        } else {
+            for (size_t i = w0 + tid; i < w1; i += NNP_THREADS) F.ptr[i] = F.value;
+        }
+    }
     unsigned blk = blockIdx.x;
     int d = p.first_dir;
     if (blk >= p.blocks0) { blk -= p.blocks0; d = 1 - d; }
@@ -304,7 +321,8 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
     const int hip = split == p.nsplit[d] - 1 ? p.ncp[d] : hi;   // the cloud's last range also writes the padding rows
     const float* __restrict__ src = p.c[d] + ((size_t)cloud * nc + lo) * 3;
     float4* __restrict__ dst = p.cv[d] + (size_t)cloud * p.ncp[d] + lo;
-    const unsigned mask = p.slots[d] - 1;
+    const unsigned mask = p.slots[d] - 1, mask2 = mask >> 2;
+    unsigned* __restrict__ tab2 = tab + mask + 1;
     const float INF = __int_as_float(0x7f800000);
 
     for (unsigned i = tid * 4; i < mask + 1 + ((mask + 1) >> 2); i += NNP_THREADS * 4)   // both tables
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
         lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
     }
     if (lane == 0) { sRed[warp][0] = lo0; sRed[warp][1] = lo1; sRed[warp][2] = lo2; sRed[warp][3] = hi0; sRed[warp][4] = hi1; sRed[warp][5] = hi2; }
-    __syncthreads();   // (also: the table is filled)
+    __syncthreads();   // (also: the tables are filled)
     if (tid < 3) {
         float a = INF, c = -INF;
         for (int w = 0; w < NNP_THREADS / 32; ++w) { a = fminf(a, sRed[w][tid]); c = fmaxf(c, sRed[w][3 + tid]); }
@@ -337,31 +355,30 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
         if (!(fabsf(o) < INF)) o = 0.f;   // no finite coordinate at all: every query ends in the exact scan anyway
         sO[tid] = o;
     }
+    unsigned h[NNP_K];
 #pragma unroll
     for (int k = 0; k < NNP_K; ++k) {
         const int li = tid + k * NNP_THREADS;
+        h[k] = nn_mix(x[k], y[k], z[k]);
         if (lo + li < hi) {
-            atomicMin(&tab[nn_hash1(x[k], y[k], z[k]) & mask], (unsigned)li);
-            atomicMin(&tab[nn_hash2(x[k], y[k], z[k]) & mask], (unsigned)li);
+            atomicMin(&tab[nn_slot1(h[k]) & mask], (unsigned)li);
+            atomicMin(&tab[nn_slot2(h[k]) & mask], (unsigned)li);
         }
     }
     __syncthreads();
     // first round: copy / winner of a slot / neither.  The points that are neither -- a set of equal points whose lowest index lost
     // both slots to other points -- bid once more, for one slot of a second, nearly empty table (a quarter of the first).
+    auto same = [&](unsigned w, int k) { return src[w * 3 + 0] == x[k] && src[w * 3 + 1] == y[k] && src[w * 3 + 2] == z[k]; };
     unsigned copies = 0u, again = 0u;
-    unsigned* __restrict__ tab2 = tab + mask + 1;
-    const unsigned mask2 = mask >> 2;
 #pragma unroll
     for (int k = 0; k < NNP_K; ++k) {
         const int li = tid + k * NNP_THREADS;
         if (lo + li < hi) {
-            const unsigned w1 = tab[nn_hash1(x[k], y[k], z[k]) & mask], w2 = tab[nn_hash2(x[k], y[k], z[k]) & mask];   // both <= li
-            const bool copy = (w1 != (unsigned)li && src[w1 * 3 + 0] == x[k] && src[w1 * 3 + 1] == y[k] && src[w1 * 3 + 2] == z[k]) ||
-                              (w2 != (unsigned)li && src[w2 * 3 + 0] == x[k] && src[w2 * 3 + 1] == y[k] && src[w2 * 3 + 2] == z[k]);
-            if (copy) copies |= 1u << k;
+            const unsigned w1 = tab[nn_slot1(h[k]) & mask], w2 = tab[nn_slot2(h[k]) & mask];   // both <= li
+            if ((w1 != (unsigned)li && same(w1, k)) || (w2 != (unsigned)li && same(w2, k))) copies |= 1u << k;
             else if (w1 != (unsigned)li && w2 != (unsigned)li) {
                 again |= 1u << k;
-                atomicMin(&tab2[(nn_hash1(y[k], z[k], x[k]) >> 7) & mask2], (unsigned)li);
+                atomicMin(&tab2[nn_slot3(h[k]) & mask2], (unsigned)li);
             }
         }
     }
@@ -376,8 +393,8 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
             if (lo + li < hi) {
                 bool copy = (copies >> k) & 1u;
                 if ((again >> k) & 1u) {
-                    const unsigned w = tab2[(nn_hash1(y[k], z[k], x[k]) >> 7) & mask2];
-                    copy = w != (unsigned)li && src[w * 3 + 0] == x[k] && src[w * 3 + 1] == y[k] && src[w * 3 + 2] == z[k];
+                    const unsigned w = tab2[nn_slot3(h[k]) & mask2];
+                    copy = w != (unsigned)li && same(w, k);
                 }
                 v.x = x[k] - ox; v.y = y[k] - oy; v.z = z[k] - oz;
                 if (!copy) {
@@ -389,7 +406,7 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
         }
     }
     const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(cmax));   // cmax >= +0: bits are monotone
-    if (lane == 0) sRed[warp][0] = __uint_as_float(wmax);   // (sRed was last read before the previous barrier)
+    if (lane == 0) sRed[warp][0] = __uint_as_float(wmax);   // (sRed was last read two barriers ago)
     __syncthreads();
     if (tid == 0) {
         unsigned mx = 0u;
@@ -419,6 +436,23 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
     const float* __restrict__ qbase = D.q + (size_t)cloud * nq * 3;
     const float* __restrict__ cbase = D.c + (size_t)cloud * nc * 3;
     const float4* __restrict__ cvbase = D.cv + (size_t)cloud * D.ncp;
+    const int nchunks_total = (nc + chunk - 1) / chunk;
+    const int first_chunk = split * D.cps;
+    const int my_chunks = min(D.cps, nchunks_total - first_chunk);
+
+    auto issue = [&](int ci) {  // thread 0 only: start the bulk copy of chunk ci of this item (whole groups: the rows are padded)
+        const int start = (first_chunk + ci) * chunk;
+        const int lenG = (min(chunk, nc - start) + G - 1) / G * G;
+        const unsigned bytes = (unsigned)lenG * 16u;
+        mbar_expect_tx(&bar[ci & 1], bytes);
+        tma_bulk_g2s(sCv[ci & 1], cvbase + start, bytes, &bar[ci & 1]);
+    };
+    if (tid == 0) {   // the first chunk is on its way while the queries are loaded
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+        if (my_chunks > 0) issue(0);
+    }
     const float4 meta = D.meta[(size_t)cloud * D.nsplit + split];
     const float ox = meta.x, oy = meta.y, oz = meta.z, cmax_cloud = meta.w;
 
@@ -441,26 +475,7 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
     const float INF = __int_as_float(0x7f800000);
 #pragma unroll
     for (int i = 0; i < Q; ++i) { b1[i] = INF; b2[i] = INF; k1[i] = 0; }
-
-    const int nchunks_total = (nc + chunk - 1) / chunk;
-    const int first_chunk = split * D.cps;
-    const int my_chunks = min(D.cps, nchunks_total - first_chunk);
-
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto issue = [&](int ci) {  // thread 0 only: start the bulk copy of chunk ci of this item (whole groups: the rows are padded)
-        const int start = (first_chunk + ci) * chunk;
-        const int lenG = (min(chunk, nc - start) + G - 1) / G * G;
-        const unsigned bytes = (unsigned)lenG * 16u;
-        mbar_expect_tx(&bar[ci & 1], bytes);
-        tma_bulk_g2s(sCv[ci & 1], cvbase + start, bytes, &bar[ci & 1]);
-    };
-    if (tid == 0 && my_chunks > 0) issue(0);
+    __syncthreads();   // the barriers are initialised
 
     int item_live = 0;
     for (int ci = 0; ci < my_chunks; ++ci) {
@@ -953,7 +968,9 @@ static int nn_prepare_launch(const NNPrep& pp, unsigned blocks, unsigned slots, 
 // dirs: 1 = xyz1 queries against xyz2 only, 2 = xyz2 queries against xyz1 only, 3 = both
 static int nn_search_launch(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2, int* idx2, void* workspace,
                             size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out, int dirs = 3,
-                            unsigned long long* stats = nullptr) {
+                            unsigned long long* stats = nullptr, const NNFill* side_fill = nullptr, int n_side_fill = 0, bool* side_filled = nullptr) {
+    // side_fill: up to two buffers of the caller that need a constant fill before ITS next kernel; the preparation launch of the
+    // filtered search does it on the side (*side_filled = true), otherwise the caller issues its own memsets
     const int Q = pick_q(n < m ? n : m);
     NNParams p;
     p.stats = stats;
@@ -1000,9 +1017,16 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
         }
         pp.first_dir = blocks[0] ? 0 : 1;
         pp.blocks0 = blocks[pp.first_dir];
+        // the packed keys (0xff..: every real key is smaller) and the caller's buffers are filled by the same launch
+        for (int f = 0; f < 3; ++f) pp.fill[f] = NNFill{nullptr, 0, 0u};
+        if (need0 || need1) {
+            unsigned long long* first = need0 ? p.d[0].keys : p.d[1].keys;
+            pp.fill[0] = NNFill{reinterpret_cast<unsigned*>(first), 2 * ((need0 ? (size_t)b * n : 0) + (need1 ? (size_t)b * m : 0)), 0xffffffffu};
+        }
+        for (int f = 0; f < n_side_fill && f < 2; ++f) pp.fill[1 + f] = side_fill[f];
+        if (side_filled) *side_filled = true;
         { const int rc = nn_prepare_launch(pp, blocks[0] + blocks[1], slots_max, s); if (rc) return rc; }
-    }
-    if (need0 || need1) {
+    } else if (need0 || need1) {
         RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_nn_distance_workspace_bytes(b, n, m));
         // the two key arrays are contiguous: one memset covers whichever directions are merged
         unsigned long long* first = need0 ? p.d[0].keys : p.d[1].keys;
@@ -1245,11 +1269,14 @@ extern "C" int rfnet_chamfer_step(int b, int n, const float* xyz1, int m, const 
     RFNET_CHECK_ARG(workspace && workspace_bytes >= rfnet_chamfer_step_workspace_bytes(b, n, m));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t t1 = (size_t)b * n, t2 = (size_t)b * m;
-    RFNET_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * t1, s));
-    RFNET_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * t2, s));
-    bool need0 = false, need1 = false;
+    bool need0 = false, need1 = false, zeroed = false;
     const size_t key_bytes = rfnet_nn_distance_workspace_bytes(b, n, m);
-    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, key_bytes, flags, s, &need0, &need1); if (rc) return rc; }
+    const NNFill zero[2] = {{reinterpret_cast<unsigned*>(grad_xyz1), 3 * t1, 0u}, {reinterpret_cast<unsigned*>(grad_xyz2), 3 * t2, 0u}};
+    { const int rc = nn_search_launch(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, workspace, key_bytes, flags, s, &need0, &need1, 3, nullptr, zero, 2, &zeroed); if (rc) return rc; }
+    if (!zeroed) {
+        RFNET_CUDA(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * 3 * t1, s));
+        RFNET_CUDA(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * 3 * t2, s));
+    }
     float* partial = reinterpret_cast<float*>((char*)workspace + key_bytes);
     const unsigned blocks1 = (unsigned)((t1 + CE_THREADS - 1) / CE_THREADS), blocks2 = (unsigned)((t2 + CE_THREADS - 1) / CE_THREADS);
     chamfer_epilogue_kernel<<<blocks1 + blocks2, CE_THREADS, 0, s>>>(n, m, t1, t2, blocks1, need0 ? 1 : 0, need1 ? 1 : 0, (const unsigned long long*)workspace,
