@@ -36,7 +36,12 @@ const char *rfnet_error_string(int code);
  * tf_ops/CD/tf_nndistance_g.cu:127-130).  dist1[i,j] = min_k d2(xyz1[i,j], xyz2[i,k]), idx1 = first arg-min; same for
  * direction 2.  d2 is evaluated as fma(dz,dz, fma(dx,dx, dy*dy)) -- the contraction of the reference's GPU binary --
  * unless RFNET_NN_UNFUSED is set in flags, which gives ((dx*dx)+(dy*dy))+(dz*dz) as in the reference's CPU build
- * (pc_distance/tf_nndistance.cpp:21-43).  workspace may be NULL when rfnet_nn_distance_workspace_bytes() returns 0.
+ * (pc_distance/tf_nndistance.cpp:21-43).  workspace: rfnet_nn_distance_workspace_bytes() bytes, 16-byte aligned (NULL only when that is 0).
+ * flags: RFNET_NN_UNFUSED as above; RFNET_NN_DIRECT evaluates the distance expression for every pair (nn_search_kernel).  The
+ * default from 2^24 pairs per call is the FILTERED search (nn_prepare_kernel + nn_filter_kernel, csrc/nn_distance.cu): every pair
+ * is still visited, with the expanded form |c-o|^2 - 2(q-o).(c-o) at half the arithmetic, and the distance expression is
+ * evaluated only for the group of 16 candidates proven to hold the nearest neighbour (or for the whole candidate range of a
+ * query when no group can be certified).  Outputs are the same bits either way; the workspace is required for it.
  * Non-finite coordinates: a query whose distances are all NaN reports (+inf, 0) -- the reference reports (NaN-free seed
  * 1e38-style garbage / NaN depending on the build); three_nn ignores NaN distances exactly as the reference's strict '<'
  * does.  Results are only specified for finite inputs.

@@ -911,7 +911,11 @@ static void plan_direction(NNDir& D, int b, int nq, int nc, int Q, int chunk, in
     D.tma = (nc % 4 == 0) && (((uintptr_t)D.c & 15u) == 0);
 }
 
+#ifdef NN_FORCE_Q
+static int pick_q(int) { return NN_FORCE_Q; }   // tools/nn_tune.cu
+#else
 static int pick_q(int nq) { return nq >= 1024 ? 8 : (nq >= 512 ? 4 : 2); }
+#endif
 
 template <int Q>
 static void launch_search(const NNParams& p, int grid, bool fused, bool direct, cudaStream_t s) {

@@ -27,6 +27,11 @@ o = [torch.empty((3, 2048), dtype=f32, device=dev), torch.empty((3, 2048), dtype
      torch.empty((3, 5000), dtype=i32, device=dev), torch.empty((3, 2048, 3), device=dev), torch.empty((3, 5000, 3), device=dev), torch.empty(4, device=dev)]
 ws = torch.empty(ops.nn_distance_workspace_bytes(3, 2048, 5000), dtype=torch.uint8, device=dev)
 ops.raw_chamfer_step(a1, a2, torch.ones((3, 2048), device=dev), torch.ones((3, 5000), device=dev), *o, ws)   # fused chamfer step
+# filtered nn search: ragged sizes (plain-load resolve), a lattice (exact warp scans), repeated points (duplicate search, dead items)
+for a, c_ in ((rnd(2, 2049), rnd(2, 4099)), (torch.floor(rnd(2, 2048) * 8) / 8, torch.floor(rnd(2, 4096) * 8) / 8),
+              (rnd(2, 300).repeat(1, 8, 1), rnd(2, 4096))):
+    ops.nn_distance_exact_scans(a.contiguous(), c_.contiguous())
+    ops.nn_distance_op(a.contiguous(), c_.contiguous(), True, False)
 x = rnd(2, 5003)
 idx = tf_sampling.farthest_point_sample(300, x)         # pruned FPS, ragged last cluster
 q = tf_sampling.gather_point(x, idx)
