@@ -33,6 +33,20 @@ namespace rfnet {
 constexpr int NN_THREADS = NN_THREADS_VALUE;
 constexpr int NN_TC = 1024;  // max candidates per staged chunk (12 KiB per buffer)
 
+// Adds (x, y, z) to a 12-byte row of a float buffer whose base is 8-byte aligned: every row has one 8-byte aligned pair -- (x,y)
+// for even rows, (y,z) for odd rows -- which goes out as ONE vector reduction (red.global.add.v2.f32), the third value as a scalar
+// one: 2 reductions per row instead of 3.  The kernel is bound by the issue of these reductions (ncu: mio_throttle).
+__device__ __forceinline__ void red_add_row3(float* row, float x, float y, float z) {
+    if ((reinterpret_cast<uintptr_t>(row) & 7u) == 0) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row), "f"(x), "f"(y) : "memory");
+        atomicAdd(row + 2, z);
+    } else if ((reinterpret_cast<uintptr_t>(row + 1) & 7u) == 0) {
+        atomicAdd(row, x);
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row + 1), "f"(y), "f"(z) : "memory");
+    } else {   // a base that is only 4-byte aligned
+        atomicAdd(row, x); atomicAdd(row + 1, y); atomicAdd(row + 2, z);
+    }
+}
 struct NNDir {
     const float* q;             // queries    (b, nq, 3)
     const float* c;             // candidates (b, nc, 3)
@@ -692,9 +706,7 @@ __global__ void nn_grad_scatter_kernel(int n, int m, const float* __restrict__ x
         const float g = gd1[t] * 2.0f;
         const float* a = xyz1 + t * 3;
         const size_t oi = (cloud * m + j2) * 3;
-        atomicAdd(&g2[oi + 0], -(g * (a[0] - xyz2[oi + 0])));
-        atomicAdd(&g2[oi + 1], -(g * (a[1] - xyz2[oi + 1])));
-        atomicAdd(&g2[oi + 2], -(g * (a[2] - xyz2[oi + 2])));
+        red_add_row3(g2 + oi, -(g * (a[0] - xyz2[oi + 0])), -(g * (a[1] - xyz2[oi + 1])), -(g * (a[2] - xyz2[oi + 2])));
     } else if (t < total1 + total2) {
         const size_t u = t - total1;
         const size_t cloud = u / m;
@@ -702,9 +714,7 @@ __global__ void nn_grad_scatter_kernel(int n, int m, const float* __restrict__ x
         const float g = gd2[u] * 2.0f;
         const float* a = xyz2 + u * 3;
         const size_t oi = (cloud * n + j2) * 3;
-        atomicAdd(&g1[oi + 0], -(g * (a[0] - xyz1[oi + 0])));
-        atomicAdd(&g1[oi + 1], -(g * (a[1] - xyz1[oi + 1])));
-        atomicAdd(&g1[oi + 2], -(g * (a[2] - xyz1[oi + 2])));
+        red_add_row3(g1 + oi, -(g * (a[0] - xyz1[oi + 0])), -(g * (a[1] - xyz1[oi + 1])), -(g * (a[2] - xyz1[oi + 2])));
     }
 }
 
@@ -1118,8 +1128,8 @@ __global__ void __launch_bounds__(CE_THREADS) chamfer_epilogue_kernel(int n, int
         float* __restrict__ gown = (dir ? g2 : g1) + t * 3;
         float* __restrict__ goth = (dir ? g1 : g2) + oi;
         const float tx = g * (a[0] - o[0]), ty = g * (a[1] - o[1]), tz = g * (a[2] - o[2]);
-        atomicAdd(gown + 0, tx); atomicAdd(gown + 1, ty); atomicAdd(gown + 2, tz);
-        atomicAdd(goth + 0, -tx); atomicAdd(goth + 1, -ty); atomicAdd(goth + 2, -tz);
+        red_add_row3(gown, tx, ty, tz);
+        red_add_row3(goth, -tx, -ty, -tz);
     }
     root = warp_sum(root);
     if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = root;
