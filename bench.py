@@ -44,7 +44,7 @@ METRIC = "chamfer_nn_point_pairs_per_s"
 UNIT = "Gpairs/s"
 L2_BYTES = 126 * 1024 * 1024
 LANE_OPS_PER_PAIR = 6.0
-NN_FILTER_DRAM_BYTES = None   # dram bytes of one nn_filter_kernel launch at the bench shape (ncu --set full); filled in from profiles/r2_nn_filter_full.txt
+NN_FILTER_DRAM_BYTES = 17079040   # dram__bytes_read.sum + dram__bytes_write.sum of one nn_filter_kernel launch at the bench shape (profiles/r2_nn_filter_full.txt)
 HBM_PEAK_FALLBACK = 6544.0         # GB/s, MEASURED_PEAKS.json of this pool (used when the file is absent)
 
 
