@@ -993,8 +993,10 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
     // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
     // written directly, no key merge and no extra launches
     const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
-    // below 2^24 pairs a call is a few microseconds of work and launch-bound: the direct kernel needs no preparation launch
-    const bool fused = !(flags & RFNET_NN_UNFUSED), direct = (flags & RFNET_NN_DIRECT) != 0 || 2.0 * b * (double)n * (double)m < 16777216.0;
+    // below 2^24 pairs a call is a few microseconds of work and launch-bound: the direct kernel needs no preparation launch; and
+    // batches of tiny clouds (under 1024 points on both sides) are all per-item overhead, of which the direct kernel has less
+    const bool fused = !(flags & RFNET_NN_UNFUSED);
+    const bool direct = (flags & RFNET_NN_DIRECT) != 0 || 2.0 * b * (double)n * (double)m < 16777216.0 || (n < 1024 && m < 1024);
     NNPlan plan = {NN_TC, 0, NN_TC, 0};
     if (split) plan = pick_plan(b, n, m, Q, direct);
 #ifdef NN_TUNE
