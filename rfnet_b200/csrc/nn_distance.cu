@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(cons
 #define NNF_GROUP 16
 #endif
 constexpr int NNF_G = NNF_GROUP;   // candidates per tracked group: 8, 16 or 32
+constexpr int NNF_DIRECT_PENDING = 24;   // uncertified queries per warp (of 32 x Q) from which the warp switches to the direct loop
 static_assert(NNF_G == 8 || NNF_G == 16 || NNF_G == 32, "group size");
 
 // 2E for a query with |q - o|^2 = qn against candidates with |c - o|^2 <= cmax (o: the item's origin, u = 2^-24, u' = u(1+..)).
@@ -426,6 +427,77 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
         unsigned mx = 0u;
         for (int w = 0; w < NNP_THREADS / 32; ++w) mx = max(mx, __float_as_uint(sRed[w][0]));
         p.meta[d][(size_t)cloud * p.nsplit[d] + split] = make_float4(ox, oy, oz, __uint_as_float(mx));
+    }
+}
+
+// The direct kernel's loop for one warp of nn_filter_kernel (see there): Q queries per lane against candidates [range_lo, range_hi)
+// of the cloud, the reference expression for every pair, candidates broadcast from global memory.  Not inlined: it has its own
+// register allocation and stays out of the way of the filtered scan.
+template <int Q, bool FUSED>
+__device__ __noinline__ void nn_direct_scan_warp(const float* __restrict__ qbase, const float* __restrict__ cbase, int q0, int nq, int range_lo, int range_hi,
+                                                bool vec, bool direct_store, float* __restrict__ dist, int* __restrict__ idx, unsigned long long* __restrict__ keys) {
+    const float INF = __int_as_float(0x7f800000);
+    float2 rqx[Q / 2], rqy[Q / 2], rqz[Q / 2];
+    float best[Q];
+    int bestk[Q];
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) {
+        const int ia = q0 + (2 * h) * NN_THREADS, ib = ia + NN_THREADS;
+        const bool va = ia < nq, vb = ib < nq;
+        rqx[h].x = va ? qbase[(size_t)ia * 3 + 0] : 0.f; rqy[h].x = va ? qbase[(size_t)ia * 3 + 1] : 0.f; rqz[h].x = va ? qbase[(size_t)ia * 3 + 2] : 0.f;
+        rqx[h].y = vb ? qbase[(size_t)ib * 3 + 0] : 0.f; rqy[h].y = vb ? qbase[(size_t)ib * 3 + 1] : 0.f; rqz[h].y = vb ? qbase[(size_t)ib * 3 + 2] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) { best[i] = INF; bestk[i] = range_lo; }
+#pragma unroll 1
+    for (int k = range_lo; k < range_hi; k += 8) {
+        float cx[8], cy[8], cz[8];
+        if (vec && k + 8 <= range_hi) {
+            const float4* __restrict__ c4 = reinterpret_cast<const float4*>(cbase + (size_t)k * 3);
+            const float4 v0 = __ldg(c4), v1 = __ldg(c4 + 1), v2 = __ldg(c4 + 2), v3 = __ldg(c4 + 3), v4 = __ldg(c4 + 4), v5 = __ldg(c4 + 5);
+            cx[0] = v0.x; cy[0] = v0.y; cz[0] = v0.z; cx[1] = v0.w; cy[1] = v1.x; cz[1] = v1.y; cx[2] = v1.z; cy[2] = v1.w; cz[2] = v2.x;
+            cx[3] = v2.y; cy[3] = v2.z; cz[3] = v2.w; cx[4] = v3.x; cy[4] = v3.y; cz[4] = v3.z; cx[5] = v3.w; cy[5] = v4.x; cz[5] = v4.y;
+            cx[6] = v4.z; cy[6] = v4.w; cz[6] = v5.x; cx[7] = v5.y; cy[7] = v5.z; cz[7] = v5.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // rows past the end: +inf coordinates, +inf distances
+                const bool in = k + j < range_hi;
+                const float* __restrict__ c = cbase + (size_t)(in ? k + j : range_lo) * 3;
+                cx[j] = in ? c[0] : INF; cy[j] = in ? c[1] : INF; cz[j] = in ? c[2] : INF;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < Q / 2; ++h) {
+            float2 d[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                d[j] = sqdist3x2<FUSED>(__fadd2_rn(rqx[h], make_float2(-cx[j], -cx[j])), __fadd2_rn(rqy[h], make_float2(-cy[j], -cy[j])),
+                                        __fadd2_rn(rqz[h], make_float2(-cz[j], -cz[j])));
+            const float g0 = fmin3(fmin3(d[0].x, d[1].x, d[2].x), fmin3(d[3].x, d[4].x, d[5].x), fmin3(d[6].x, d[7].x, best[2 * h]));
+            bestk[2 * h] = (g0 < best[2 * h]) ? k : bestk[2 * h];
+            best[2 * h] = g0;
+            const float g1 = fmin3(fmin3(d[0].y, d[1].y, d[2].y), fmin3(d[3].y, d[4].y, d[5].y), fmin3(d[6].y, d[7].y, best[2 * h + 1]));
+            bestk[2 * h + 1] = (g1 < best[2 * h + 1]) ? k : bestk[2 * h + 1];
+            best[2 * h + 1] = g1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {   // the first position of the winning 8-group that attains the minimum (same operations, same bits)
+        const int qi = q0 + i * NN_THREADS;
+        if (qi < nq) {
+            const float qxs = qbase[(size_t)qi * 3 + 0], qys = qbase[(size_t)qi * 3 + 1], qzs = qbase[(size_t)qi * 3 + 2];
+            const int lim = min(8, range_hi - bestk[i]);
+            int j = 0;
+#pragma unroll
+            for (int t = 7; t >= 0; --t) {
+                if (t < lim) {
+                    const float* __restrict__ c = cbase + (size_t)(bestk[i] + t) * 3;
+                    j = (sqdist3<FUSED>(qxs - c[0], qys - c[1], qzs - c[2]) == best[i]) ? t : j;
+                }
+            }
+            if (direct_store) { dist[qi] = best[i]; idx[qi] = bestk[i] + j; }
+            else atomicMin(&keys[qi], pack_key(best[i], bestk[i] + j));
+        }
     }
 }
 
@@ -621,8 +693,18 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
             pending |= 1u << i;
         }
     }
-    // ---- exact scan of the item's candidate range for the queries that could not be certified, one query per warp step
     const int lane = tid & 31;
+    // ---- many uncertified queries in this warp (clouds full of distinct points at exactly equal distances, e.g. a lattice):
+    // one query per warp step below would cost ~25 scan steps each, so the warp runs the direct kernel's loop instead -- all
+    // Q queries of every lane against the item's candidates, the reference expression for every pair, candidates broadcast
+    // from global memory -- at twice the cost of the filtered scan it replaces, whatever the number of ties.
+    if (__reduce_add_sync(0xffffffffu, __popc(pending)) >= NNF_DIRECT_PENDING) {
+        nn_direct_scan_warp<Q, FUSED>(qbase, cbase, q0, nq, range_lo, range_hi, vec, D.nsplit == 1, D.dist + (size_t)cloud * nq, D.idx + (size_t)cloud * nq,
+                                      D.nsplit == 1 ? nullptr : D.keys + (size_t)cloud * nq);
+        if (p.stats && pending) atomicAdd(p.stats, (unsigned long long)__popc(pending));
+        pending = 0u;
+    }
+    // ---- exact scan of the item's candidate range for the queries that could not be certified, one query per warp step
     unsigned any = __ballot_sync(0xffffffffu, pending != 0);
     while (any) {
         const int srcl = __ffs(any) - 1;
