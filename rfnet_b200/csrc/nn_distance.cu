@@ -2,17 +2,22 @@
 //
 // Replaces NmDistanceKernel / NmDistanceGradKernel of the reference (tf_ops/CD/tf_nndistance_g.cu:4-156).
 //
-// Design (not a port -- the reference scans 512-candidate tiles with one query per thread and merges tiles through a
+// Two searches with bit-identical outputs (and one launch plan, pick_plan):
+//   nn_search_kernel                      the reference distance expression for every pair (RFNET_NN_DIRECT, and small calls)
+//   nn_prepare_kernel + nn_filter_kernel  the default: every pair visited with the expanded form |c|^2 - 2 q.c at half the FP32
+//                                         work, the reference expression only where it decides the result (see there)
+// Common design (not a port -- the reference scans 512-candidate tiles with one query per thread and merges tiles through a
 // global read-modify-write):
 //   * work item = (direction, cloud, tile of 128*Q queries, split of the candidate range); both directions in ONE launch;
 //     grid sized so that >= ~30 items per SM exist even at 4 clouds per GPU;
-//   * candidates are staged chunk by chunk in shared memory, raw (x,y,z) rows, by the TMA bulk-copy engine
-//     (cp.async.bulk + mbarrier, double buffered) -- plain loads when rows are not 16-byte aligned;
-//   * each thread keeps Q queries in registers as Q/2 packed pairs and evaluates two distances per instruction with
+//   * candidates are staged chunk by chunk in shared memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier, double
+//     buffered) -- raw (x,y,z) rows for the direct kernel (plain loads when rows are not 16-byte aligned), prepared
+//     (x, y, z, |c|^2) rows for the filtered one;
+//   * each thread keeps Q queries in registers as Q/2 packed pairs and evaluates two values per instruction with
 //     Blackwell's packed FP32 pipe (FADD2 / FMUL2 / FFMA2); candidates are warp-broadcast LDS.128;
-//   * min tracking is branch-free and costs 0.75 instruction per pair: eight distances and the running best are folded
-//     with four 3-input FMNMX3, one compare + one predicated move remember the 8-GROUP where the best strictly decreased;
-//     the index inside that group is recovered once per work item by re-evaluating its eight distances (same bits).
+//   * min tracking is branch-free: eight (sixteen) values and the running best are folded with 3-input FMNMX3, one compare
+//     + one predicated move remember the GROUP where the best strictly decreased; the index inside that group is recovered
+//     once per work item by evaluating its distances (same operations, same bits).
 //     (A first version branched to an index-selection slow path; ncu showed it taken in nearly every group, because 32
 //     lanes x 8 candidates almost always contain a new running minimum near the start of an item.)
 //   * splits are merged with a 64-bit atomicMin on (distance bits, index) keys, which is exactly the reference's
@@ -233,21 +238,22 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(cons
 // ---------------------------------------------------------------------------------------------------------------
 // nn_filter_kernel: the same all-pairs search at HALF the FP32-pipe work per pair, same bits out.
 //
-// Every (query, candidate) pair is still visited, but the scan evaluates the expanded form
-//     s(q,c) = |c|^2 - 2 q.c          ( = d2(q,c) - |q|^2 in real arithmetic )
-// as three packed FMAs per pair of queries (|c|^2 rides along as the candidate's 4th coordinate), i.e. 3 FP32 lane-ops per
-// pair where the reference expression needs 6 -- and then uses it only to decide WHICH 8/16-group of candidates holds the
-// nearest neighbour.  Per query the scan keeps the smallest group minimum b1, the group k1 it came from and the second
-// smallest group minimum b2 (branch-free: 4 min/max + 1 compare + 1 select per group).  With
-//     E = 2^-20 (|q| + max|c|)^2  >=  |s(c) + |q|^2 - d2_ref(c)|   for every candidate of the item
-// (11 roundings of 2^-24 relative to (|q|+|c|)^2 between the two expressions -- derivation at nn_filter_tolerance below),
+// Every (query, candidate) pair is still visited, but the scan evaluates the expanded form about the item's origin o
+//     s(q,c) = |c-o|^2 - 2 (q-o).(c-o)          ( = d2(q,c) - |q-o|^2 in real arithmetic )
+// as three packed FMAs per pair of queries (|c-o|^2 rides along as the candidate's 4th coordinate, nn_prepare_kernel), i.e.
+// 3 FP32 lane-ops per pair where the reference expression needs 6 -- and uses it only to decide WHICH group of 16 candidates
+// holds the nearest neighbour.  Per query the scan keeps the smallest group minimum b1, the group k1 it came from and the second
+// smallest group minimum b2 (branch-free: 8 FMNMX3 / FMNMX for the group minimum, then 3 min/max + 1 compare + 1 select).  With
+//     E = 2^-20 (|q-o| + max|c-o|)^2  >=  |s(c) + |q-o|^2 - d2_ref(c)|   for every candidate of the item
+// (13 roundings of 2^-24 relative to (|q-o|+|c-o|)^2 between the two expressions -- derivation at nn_filter_tolerance below),
 // b2 > b1 + 2E proves that every candidate outside group k1 has a reference distance STRICTLY above that of the
 // candidate that produced b1, hence above the minimum of group k1: the exact arg-min (first index on ties) lies in group
 // k1, whose G reference distances are then evaluated in the reference's operand order -- dist and idx come out bit for bit.
-// Otherwise (two groups within 2E of each other: ~0.1 % of the (query, item) pairs on unit-cube clouds, every query for
-// duplicated points or for clouds far from the origin relative to their size) the warp scans the item's candidates for that
-// query with the reference expression, 32 lanes wide.  Either way the item contributes the exact (distance, index) minimum
-// of its candidate range; items are merged by the same 64-bit atomicMin as above.
+// Otherwise (two groups within 2E of each other: 0.3-1.4 % of the (query, item) pairs on unit-cube clouds; every query when
+// distinct points sit at exactly equal distances) the warp scans the item's candidates for that query with the reference
+// expression, 32 lanes wide -- or, if that happens to many of its queries, runs the direct loop for its whole tile
+// (nn_direct_scan_warp).  Either way the item contributes the exact (distance, index) minimum of its candidate range; items
+// are merged by the same 64-bit atomicMin as above.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef NNF_MIN_CTAS
 #define NNF_MIN_CTAS 4
