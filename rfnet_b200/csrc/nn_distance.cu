@@ -956,7 +956,7 @@ static NNPlan pick_plan(int b, int n, int m, int Q, bool direct) {
     if (memo.b == b && memo.n == n && memo.m == m && memo.Q == Q && memo.sms == sms && memo.direct == (int)direct) return memo.plan;
     const int TQ = NN_THREADS * Q;
     const long slots = (long)sms * (direct ? NN_CTAS_PER_SM : NNF_MIN_CTAS);
-    const long per_chunk = direct ? 0 : 8, per_item = direct ? 48 : 150;
+    const long per_chunk = direct ? 0 : 8, per_item = direct ? 48 : 430;
     const long tiles0 = (long)b * ((n + TQ - 1) / TQ), tiles1 = (long)b * ((m + TQ - 1) / TQ);
     const int grp = direct ? 8 : NNF_G;   // chunks are whole groups of the kernel that scans them
     auto lens = [grp](int nc, int* out) {   // even splits of nc into k pieces, rounded up to a group, between 256 and NN_TC candidates
@@ -984,11 +984,22 @@ static NNPlan pick_plan(int b, int n, int m, int Q, bool direct) {
                     const long k0 = (m + l0[i] - 1) / l0[i], k1 = (n + l1[j] - 1) / l1[j];
                     const long p0 = cps_opts[ci] < k0 ? cps_opts[ci] : k0, p1 = cps_opts[cj] < k1 ? cps_opts[cj] : k1;
                     if ((ci > 0 && cps_opts[ci] > k0) || (cj > 0 && cps_opts[cj] > k1)) continue;   // same plan as a smaller option
+                    if (!direct && (cps_opts[ci] * l0[i] > NNP_RANGE || cps_opts[cj] * l1[j] > NNP_RANGE)) continue;   // longer than the preparation reaches
                     const long s0 = (k0 + p0 - 1) / p0, s1 = (k1 + p1 - 1) / p1;
                     const long cost0 = p0 * ((m < l0[i] ? m : l0[i]) + per_chunk) + per_item;
                     const long cost1 = p1 * ((n < l1[j] ? n : l1[j]) + per_chunk) + per_item;
-                    // the longer class goes first in blockIdx order only if it is direction 0; the makespan model takes the order as it is
-                    const long t = nn_makespan(slots, tiles0 * s0, cost0, tiles1 * s1, cost1);
+                    // direct kernel: the makespan of list-scheduling the two classes of items in blockIdx order (items of fixed duration).
+                    // filtered kernel: its CTAs share the SM's pipes, so the launch behaves like a throughput problem -- total work over
+                    // the slots -- plus a tail of about 0.6 of the longest item; per_item and the 0.6 are fitted to measured plans
+                    // (profiles/r2_nn_filter_plans.txt: 12 forced plans x 3 shapes, the fixed-duration model misranked them by up to 14 %)
+                    long t;
+                    if (direct) {
+                        t = nn_makespan(slots, tiles0 * s0, cost0, tiles1 * s1, cost1);
+                    } else {
+                        const long total = tiles0 * s0 * cost0 + tiles1 * s1 * cost1, longest = cost0 > cost1 ? cost0 : cost1;
+                        const long per_slot = (total + slots - 1) / slots;
+                        t = (per_slot > longest ? per_slot : longest) + longest * 6 / 10;
+                    }
                     if (best < 0 || t < best) { best = t; plan = {l0[i], (int)p0, l1[j], (int)p1}; }
                 }
     memo = {b, n, m, Q, sms, (int)direct, plan};
