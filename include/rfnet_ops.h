@@ -57,6 +57,11 @@ int rfnet_nn_distance_stats(int b, int n, const float *xyz1, int m, const float 
                             float *dist2, int *idx2, void *workspace, size_t workspace_bytes, int flags,
                             unsigned long long *exact_scans, rfnet_stream_t stream);
 
+/* The launch plan rfnet_nn_distance would use for (b, n, m, flags) on the current device, without launching anything (host
+ * arithmetic only; diagnostics and tests): out10 = { direct kernel?, queries per thread,  then per direction (xyz1 -> xyz2,
+ * xyz2 -> xyz1): candidates per chunk, chunks per work item, work items per query tile, work items }. */
+int rfnet_nn_distance_plan(int b, int n, int m, int flags, int *out10);
+
 /* Replaces NmDistanceGradKernelLauncher, pc_distance/tf_nndistance.cpp:208 (tf_nndistance_g.cu:151-156).
  * grad_xyz1 / grad_xyz2 are fully overwritten (the launcher zero-fills them itself, as the reference does).
  *

@@ -17,6 +17,7 @@ SIGNATURES = {
     "rfnet_nn_distance_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_nn_distance": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "rfnet_nn_distance_stats": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _z, _i, _p, _p]),
+    "rfnet_nn_distance_plan": (_i, [_i, _i, _i, _i, _p]),
     "rfnet_nn_distance_grad_workspace_bytes": (_z, [_i, _i, _i]),
     "rfnet_nn_distance_grad": (_i, [_i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "rfnet_chamfer_partial_sums_workspace_bytes": (_z, []),

@@ -1066,19 +1066,47 @@ extern "C" size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m) {
 }
 
 static int nn_prepare_launch(const NNPrep& pp, unsigned blocks, unsigned slots, cudaStream_t s) {
-    static bool attr_set[64] = {false};   // per device; benign race: every thread sets the same attribute
-    int dev = 0;
-    RFNET_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        RFNET_CUDA(cudaFuncSetAttribute(nn_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * NNP_RANGE + NNP_RANGE / 2) * (int)sizeof(unsigned)));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
+    // two hash tables in dynamic shared memory: `slots` and slots / 4 words (at most 2.5 x NNP_RANGE words = 40 KiB)
+    static_assert((2 * NNP_RANGE + NNP_RANGE / 2) * sizeof(unsigned) <= 48 * 1024, "fits the default dynamic shared-memory limit");
     nn_prepare_kernel<<<blocks, NNP_THREADS, (slots + slots / 4) * sizeof(unsigned), s>>>(pp);
     return 0;
 }
 
 // plan + key memset + search launch; *need0 / *need1 tell the caller which directions left their results as packed keys
 // dirs: 1 = xyz1 queries against xyz2 only, 2 = xyz2 queries against xyz1 only, 3 = both
+// The launch plan of a call: which kernel (return value: true = direct), and per direction the chunk length, chunks per item,
+// items.  A pure function of (b, n, m, flags) and the device's SM count.
+static bool nn_plan(NNParams& p, int b, int n, int m, int Q, int flags) {
+    // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
+    // written directly, no key merge and no extra launches
+    const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
+    // below 2^24 pairs a call is a few microseconds of work and launch-bound: the direct kernel needs no preparation launch; and
+    // batches of tiny clouds (under 1024 points on both sides) are all per-item overhead, of which the direct kernel has less
+    const bool direct = (flags & RFNET_NN_DIRECT) != 0 || 2.0 * b * (double)n * (double)m < 16777216.0 || (n < 1024 && m < 1024);
+    NNPlan plan = {NN_TC, 0, NN_TC, 0};
+    if (split) plan = pick_plan(b, n, m, Q, direct);
+#ifdef NN_TUNE
+    if (split && g_force_chunk) plan.chunk0 = plan.chunk1 = g_force_chunk;
+    if (split && g_force_cps) plan.cps0 = plan.cps1 = g_force_cps;
+#endif
+    plan_direction(p.d[0], b, n, m, Q, plan.chunk0, plan.cps0, direct);
+    plan_direction(p.d[1], b, m, n, Q, plan.chunk1, plan.cps1, direct);
+    return direct;
+}
+
+// Diagnostics / tests: the plan rfnet_nn_distance would use, without launching anything.
+// out = { direct, Q,  chunk0, chunks_per_item0, splits0, items0,  chunk1, chunks_per_item1, splits1, items1 }
+extern "C" int rfnet_nn_distance_plan(int b, int n, int m, int flags, int* out10) {
+    RFNET_CHECK_ARG(b > 0 && n > 0 && m > 0 && out10);
+    NNParams p;
+    p.d[0].c = p.d[1].c = nullptr;   // (alignment of the clouds is not part of the plan)
+    const int Q = pick_q(n < m ? n : m);
+    const bool direct = nn_plan(p, b, n, m, Q, flags);
+    out10[0] = direct ? 1 : 0; out10[1] = Q;
+    for (int d = 0; d < 2; ++d) { out10[2 + 4 * d] = p.d[d].chunk; out10[3 + 4 * d] = p.d[d].cps; out10[4 + 4 * d] = p.d[d].nsplit; out10[5 + 4 * d] = p.d[d].items; }
+    return 0;
+}
+
 static int nn_search_launch(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2, int* idx2, void* workspace,
                             size_t workspace_bytes, int flags, cudaStream_t s, bool* need0_out, bool* need1_out, int dirs = 3,
                             unsigned long long* stats = nullptr, const NNFill* side_fill = nullptr, int n_side_fill = 0, bool* side_filled = nullptr) {
@@ -1089,21 +1117,8 @@ static int nn_search_launch(int b, int n, const float* xyz1, int m, const float*
     p.stats = stats;
     p.d[0].q = xyz1; p.d[0].c = xyz2; p.d[0].dist = dist1; p.d[0].idx = idx1;
     p.d[1].q = xyz2; p.d[1].c = xyz1; p.d[1].dist = dist2; p.d[1].idx = idx2;
-    // small problems (< 2^27 pairs, a few tens of microseconds of work) are launch-bound: one item per query tile, results
-    // written directly, no key merge and no extra launches
-    const bool split = 2.0 * b * (double)n * (double)m >= 134217728.0;
-    // below 2^24 pairs a call is a few microseconds of work and launch-bound: the direct kernel needs no preparation launch; and
-    // batches of tiny clouds (under 1024 points on both sides) are all per-item overhead, of which the direct kernel has less
     const bool fused = !(flags & RFNET_NN_UNFUSED);
-    const bool direct = (flags & RFNET_NN_DIRECT) != 0 || 2.0 * b * (double)n * (double)m < 16777216.0 || (n < 1024 && m < 1024);
-    NNPlan plan = {NN_TC, 0, NN_TC, 0};
-    if (split) plan = pick_plan(b, n, m, Q, direct);
-#ifdef NN_TUNE
-    if (split && g_force_chunk) plan.chunk0 = plan.chunk1 = g_force_chunk;
-    if (split && g_force_cps) plan.cps0 = plan.cps1 = g_force_cps;
-#endif
-    plan_direction(p.d[0], b, n, m, Q, plan.chunk0, plan.cps0, direct);
-    plan_direction(p.d[1], b, m, n, Q, plan.chunk1, plan.cps1, direct);
+    const bool direct = nn_plan(p, b, n, m, Q, flags);
     if (!(dirs & 1)) { p.d[0].items = 0; p.d[0].nsplit = 1; }   // a direction without items launches no CTA and merges no keys
     if (!(dirs & 2)) { p.d[1].items = 0; p.d[1].nsplit = 1; }
     unsigned long long* keys = (unsigned long long*)workspace;

@@ -77,3 +77,34 @@ def test_version_and_error_string_without_gpu():
         assert lib.rfnet_nn_distance_workspace_bytes(*shape) == expect(*shape), shape
     assert lib.rfnet_approxmatch_workspace_bytes(2, 100, 100) > 0
     assert lib.rfnet_approxmatch_workspace_bytes(0, 100, 100) == 0
+
+
+def test_nn_distance_launch_plans_cover_the_clouds_and_fit_the_workspace():
+    """Host logic of the Chamfer search (no GPU): for a sweep of shapes the plan's work items tile the candidate range exactly
+    once, chunks are whole groups of the kernel that scans them, an item of the filtered search never exceeds what one
+    preparation CTA covers (4096 candidates), and the number of item ranges stays within the per-range records the workspace
+    reserves (one per 256 candidates)."""
+    import ctypes
+    from rfnet_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int * 10)()
+    shapes = [(b, n, m) for b in (1, 3, 4, 32, 64, 257) for n in (1, 5, 300, 1024, 2048, 2049, 5000, 16384, 40000) for m in (7, 1000, 2048, 4100, 16384, 65536)]
+    seen_filter = seen_direct = 0
+    for b, n, m in shapes:
+        for flags in (0, 2):
+            assert lib.rfnet_nn_distance_plan(b, n, m, flags, out) == 0
+            direct, q = out[0], out[1]
+            assert q in (2, 4, 8)
+            assert direct or flags == 0
+            seen_direct += direct
+            seen_filter += 1 - direct
+            for d, (nq, nc) in enumerate(((n, m), (m, n))):
+                chunk, cps, nsplit, items = out[2 + 4 * d], out[3 + 4 * d], out[4 + 4 * d], out[5 + 4 * d]
+                assert 0 < chunk <= 1024 and chunk % (8 if direct else 16) == 0
+                nchunks = -(-nc // chunk)
+                assert 1 <= cps <= nchunks and nsplit == -(-nchunks // cps), (b, n, m, flags, d)
+                assert items == b * -(-nq // (128 * q)) * nsplit
+                if not direct:
+                    assert cps * chunk <= 4096, (b, n, m, d)
+                    assert nsplit <= -(-nc // 256), (b, n, m, d)           # per-range records in the workspace
+    assert seen_filter > 50 and seen_direct > 50
