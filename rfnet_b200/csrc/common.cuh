@@ -37,6 +37,19 @@ static inline int num_sms() {
 
 static inline int launch_status() { return (int)cudaGetLastError(); }
 
+// Launch with programmatic stream serialization: the kernel must call pdl_wait() before it touches anything the previous kernel
+// of the stream wrote (or anything that kernel still reads and this one overwrites).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Squared distance in the reference's operand order.  Explicit intrinsics so -fmad never decides the contraction.
 //   fused   : fma(dz,dz, fma(dx,dx, dy*dy))     what nvcc emits for x*x+y*y+z*z in every reference CUDA kernel
@@ -124,6 +137,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ unsigned long long pack_key(float d, int idx) {
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
 }
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may become resident while the kernel before
+// it in the stream drains; pdl_wait() blocks until that kernel has completed and its writes are visible (a no-op for a kernel
+// launched the ordinary way), pdl_launch_dependents() lets the NEXT kernel's CTAs take the slots this grid frees.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(NNP_THREADS) nn_prepare_kernel(const NNPrep p)
     __shared__ float sRed[NNP_THREADS / 32][6];
     __shared__ float sO[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();   // the search's CTAs may take the slots this grid frees (they wait for its completion themselves)
+    pdl_wait();                // the previous call's kernels may still read what the fills below overwrite
     // ---- side job: this CTA's slice of the buffers the call needs filled (packed keys 0xff.., zeroed gradient outputs)
 #pragma unroll 1
     for (int f = 0; f < 3; ++f) {
@@ -514,6 +516,8 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
     __shared__ __align__(128) float4 sCv[2][NN_TC];   // (x, y, z, |c|^2) chunks relative to the cloud's origin, double buffered
     __shared__ __align__(8) uint64_t bar[2];
 
+    pdl_launch_dependents();
+    pdl_wait();   // nn_prepare_kernel's rows, origins and key fill
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
     const int dir = bid >= p.d[0].items ? 1 : 0;
@@ -743,6 +747,7 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
 // keys of direction 0 (count0 entries) are followed by those of direction 1: one launch unpacks whichever were merged
 __global__ void nn_unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ dist1, int* __restrict__ idx1, size_t count0,
                                       float* __restrict__ dist2, int* __restrict__ idx2, size_t begin, size_t end) {
+    pdl_wait();   // the search's keys
     const size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < end) {
         const unsigned long long k = keys[i];
@@ -1035,9 +1040,9 @@ static void launch_search(const NNParams& p, int grid, bool fused, bool direct, 
             nn_search_kernel<Q, false><<<grid, NN_THREADS, 0, s>>>(p);
     } else {
         if (fused)
-            nn_filter_kernel<Q, true><<<grid, NN_THREADS, 0, s>>>(p);
+            launch_pdl(nn_filter_kernel<Q, true>, dim3(grid), dim3(NN_THREADS), 0, s, p);
         else
-            nn_filter_kernel<Q, false><<<grid, NN_THREADS, 0, s>>>(p);
+            launch_pdl(nn_filter_kernel<Q, false>, dim3(grid), dim3(NN_THREADS), 0, s, p);
     }
 }
 
@@ -1068,7 +1073,7 @@ extern "C" size_t rfnet_nn_distance_workspace_bytes(int b, int n, int m) {
 static int nn_prepare_launch(const NNPrep& pp, unsigned blocks, unsigned slots, cudaStream_t s) {
     // two hash tables in dynamic shared memory: `slots` and slots / 4 words (at most 2.5 x NNP_RANGE words = 40 KiB)
     static_assert((2 * NNP_RANGE + NNP_RANGE / 2) * sizeof(unsigned) <= 48 * 1024, "fits the default dynamic shared-memory limit");
-    nn_prepare_kernel<<<blocks, NNP_THREADS, (slots + slots / 4) * sizeof(unsigned), s>>>(pp);
+    launch_pdl(nn_prepare_kernel, dim3(blocks), dim3(NNP_THREADS), (slots + slots / 4) * sizeof(unsigned), s, pp);
     return 0;
 }
 
@@ -1195,7 +1200,7 @@ extern "C" int rfnet_nn_distance_stats(int b, int n, const float* xyz1, int m, c
     if (need0 || need1) {
         const size_t count0 = (size_t)b * n;
         const size_t begin = need0 ? 0 : count0, end = need1 ? count0 + (size_t)b * m : count0;
-        nn_unpack_keys_kernel<<<(unsigned)((end - begin + 255) / 256), 256, 0, s>>>((const unsigned long long*)workspace, dist1, idx1, count0, dist2, idx2, begin, end);
+        launch_pdl(nn_unpack_keys_kernel, dim3((unsigned)((end - begin + 255) / 256)), dim3(256), 0, s, (const unsigned long long*)workspace, dist1, idx1, count0, dist2, idx2, begin, end);
     }
     return launch_status();
 }
@@ -1215,6 +1220,8 @@ __global__ void __launch_bounds__(CE_THREADS) chamfer_epilogue_kernel(int n, int
                                                                       float* __restrict__ dist2, int* __restrict__ idx2, float* __restrict__ g1,
                                                                       float* __restrict__ g2, float* __restrict__ partial) {
     __shared__ float sW[CE_THREADS / 32];
+    pdl_launch_dependents();
+    pdl_wait();   // the search's keys
     const int dir = blockIdx.x >= blocks1;
     const size_t t = (size_t)(blockIdx.x - (dir ? blocks1 : 0)) * CE_THREADS + threadIdx.x;
     const size_t total = dir ? total2 : total1;
@@ -1260,6 +1267,7 @@ __global__ void __launch_bounds__(512) chamfer_epilogue_final_kernel(size_t tota
                                                                      const float* __restrict__ partial, float* __restrict__ sums) {
     // warps 0-7: direction 0, warps 8-15: direction 1; thread-strided partials, then a fixed tree: deterministic
     __shared__ float sW[16];
+    pdl_wait();   // the epilogue's partial sums
     const int dir = threadIdx.x >> 8, tid = threadIdx.x & 255;
     const unsigned cnt = dir ? blocks2 : blocks1;
     const float* __restrict__ p = partial + (dir ? blocks1 : 0);
@@ -1288,6 +1296,7 @@ namespace rfnet {
 __global__ void merge_layer_kernel(int n_raw, int n_new, size_t total, int keyed, const unsigned long long* __restrict__ keys,
                                    const float* __restrict__ raw, const float* __restrict__ newp, const float* __restrict__ dec,
                                    int* __restrict__ idx, float* __restrict__ out) {
+    pdl_wait();   // the search's keys / indices
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int j;
@@ -1365,7 +1374,7 @@ extern "C" int rfnet_merge_layer(int b, int n_raw, const float* raw, int n_new, 
     { const int rc = nn_search_launch(b, n_raw, raw, n_new, newpts, nullptr, nullptr, out, idx, workspace, workspace_bytes, 0, s, &need0, &need1, 2); if (rc) return rc; }
     const size_t total = (size_t)b * n_new;
     const unsigned long long* keys = (const unsigned long long*)workspace + (size_t)b * n_raw;
-    merge_layer_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n_raw, n_new, total, need1 ? 1 : 0, keys, raw, newpts, decfactor, idx, out);
+    launch_pdl(merge_layer_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, n_raw, n_new, total, need1 ? 1 : 0, keys, raw, newpts, decfactor, idx, out);
     return launch_status();
 }
 
@@ -1409,9 +1418,9 @@ extern "C" int rfnet_chamfer_step(int b, int n, const float* xyz1, int m, const 
     }
     float* partial = reinterpret_cast<float*>((char*)workspace + key_bytes);
     const unsigned blocks1 = (unsigned)((t1 + CE_THREADS - 1) / CE_THREADS), blocks2 = (unsigned)((t2 + CE_THREADS - 1) / CE_THREADS);
-    chamfer_epilogue_kernel<<<blocks1 + blocks2, CE_THREADS, 0, s>>>(n, m, t1, t2, blocks1, need0 ? 1 : 0, need1 ? 1 : 0, (const unsigned long long*)workspace,
-                                                                       xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, partial);
-    chamfer_epilogue_final_kernel<<<1, 512, 0, s>>>(t1, t2, blocks1, blocks2, partial, sums4);
+    launch_pdl(chamfer_epilogue_kernel, dim3(blocks1 + blocks2), dim3(CE_THREADS), 0, s, n, m, t1, t2, blocks1, need0 ? 1 : 0, need1 ? 1 : 0,
+               (const unsigned long long*)workspace, xyz1, xyz2, grad_dist1, grad_dist2, dist1, idx1, dist2, idx2, grad_xyz1, grad_xyz2, partial);
+    launch_pdl(chamfer_epilogue_final_kernel, dim3(1), dim3(512), 0, s, t1, t2, blocks1, blocks2, (const float*)partial, sums4);
     return launch_status();
 }
 
