@@ -231,6 +231,9 @@ constexpr int EMD_ROW_UNROLL = EMD_ROW_UNROLL_VALUE;   // candidate pairs per un
 
 template <int MODE, bool UNIT, bool EXACT, int NT, int R = 1>
 __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ SweepArgs a) {
+    // (the dependents are released at the END of this kernel: CTAs of the next sweep that become resident while this one runs are
+    // placed on whatever SMs have room, and a sweep's CTAs live as long as the sweep -- measured 2.5x slower at 1 cloud of 16384 points)
+    pdl_wait();   // everything this kernel reads was written by the kernels before it in the stream
     constexpr bool P3 = MODE == 3 || MODE == 4;
     constexpr bool DUAL = MODE == 4;
     constexpr bool COORDS = !UNIT || DUAL;      // a unit-level single sweep needs the weights only
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ Swe
         }
         __syncthreads();   // everyone is done with this buffer before it is refilled
     }
+    pdl_launch_dependents();
 #pragma unroll
     for (int r = 0; r < R; ++r)
         if (valid[r]) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx[r], acc[r], accb[r]);
@@ -373,6 +377,9 @@ __global__ void __launch_bounds__(NT) emd_row_kernel(const __grid_constant__ Swe
 constexpr int PG_WARPS = 4;
 template <int MODE>
 __global__ void __launch_bounds__(PG_WARPS * 32) emd_pruned_kernel(const __grid_constant__ SweepArgs a) {
+    // (the dependents are released at the END of this kernel: CTAs of the next sweep that become resident while this one runs are
+    // placed on whatever SMs have room, and a sweep's CTAs live as long as the sweep -- measured 2.5x slower at 1 cloud of 16384 points)
+    pdl_wait();   // everything this kernel reads was written by the kernels before it in the stream
     constexpr bool P3 = MODE == 3;
     static_assert(MODE >= 1 && MODE <= 3, "one sharp level per pruned sweep");
     __shared__ int sList[PG_WARPS][64];
@@ -453,6 +460,7 @@ __global__ void __launch_bounds__(PG_WARPS * 32) emd_pruned_kernel(const __grid_
         }
     }
     if (count > 0) flush(count);
+    pdl_launch_dependents();
     if (valid) emd_apply<MODE>(a.remain, a.ratio, a.fac, ridx, acc, 0.f);
 }
 
@@ -702,6 +710,9 @@ struct PairArgs {
 };
 template <int ROLE, bool WRITE, bool COST, bool GRAD, bool GRAD2, bool EXACT>
 __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_constant__ PairArgs a) {
+    // (the dependents are released at the END of this kernel: CTAs of the next sweep that become resident while this one runs are
+    // placed on whatever SMs have room, and a sweep's CTAs live as long as the sweep -- measured 2.5x slower at 1 cloud of 16384 points)
+    pdl_wait();   // everything this kernel reads was written by the kernels before it in the stream
     static_assert(!WRITE || ROLE == 1, "the matrix is written k-contiguous: own = xyz1");
     static_assert(!GRAD2 || (ROLE == 1 && GRAD), "the one-pass form: grad1 in registers, grad2 through the per-warp slab");
     constexpr int LB = GRAD2 ? 4 : 2;                 // others per unrolled batch
@@ -891,6 +902,9 @@ __global__ void __launch_bounds__(MC_THREADS) matchcost_kernel(int n, int m, con
     }
 }
 __global__ void reduce_partials_kernel(int per_cloud, const float* __restrict__ partial, float* __restrict__ out) {
+    // (the dependents are released at the END of this kernel: CTAs of the next sweep that become resident while this one runs are
+    // placed on whatever SMs have room, and a sweep's CTAs live as long as the sweep -- measured 2.5x slower at 1 cloud of 16384 points)
+    pdl_wait();   // everything this kernel reads was written by the kernels before it in the stream
     __shared__ float sW[8];
     const int cloud = blockIdx.x;
     float s = 0.f;
@@ -1109,11 +1123,11 @@ __global__ void __launch_bounds__(GF_THREADS, 2) matchcostgrad_fused_kernel(int 
 template <int MODE, int NT>
 static void emd_launch_row(const SweepArgs& a, unsigned grid, bool unit, bool exact, cudaStream_t s) {
     if (exact) {
-        if (unit) emd_row_kernel<MODE, true, true, NT><<<grid, NT, 0, s>>>(a);
-        else emd_row_kernel<MODE, false, true, NT><<<grid, NT, 0, s>>>(a);
+        if (unit) launch_pdl(emd_row_kernel<MODE, true, true, NT>, dim3(grid), dim3(NT), 0, s, a);
+        else launch_pdl(emd_row_kernel<MODE, false, true, NT>, dim3(grid), dim3(NT), 0, s, a);
     } else {
-        if (unit) emd_row_kernel<MODE, true, false, NT><<<grid, NT, 0, s>>>(a);
-        else emd_row_kernel<MODE, false, false, NT><<<grid, NT, 0, s>>>(a);
+        if (unit) launch_pdl(emd_row_kernel<MODE, true, false, NT>, dim3(grid), dim3(NT), 0, s, a);
+        else launch_pdl(emd_row_kernel<MODE, false, false, NT>, dim3(grid), dim3(NT), 0, s, a);
     }
 }
 template <int Q, int MODE>
@@ -1149,7 +1163,7 @@ static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b,
             constexpr int PM = MODE == 4 ? 1 : MODE;
             const int nclusters = (nr + EMD_CLUSTER - 1) / EMD_CLUSTER;
             a.nrt = (nclusters + PG_WARPS - 1) / PG_WARPS;
-            emd_pruned_kernel<PM><<<(unsigned)(b * a.nrt), PG_WARPS * 32, 0, s>>>(a);
+            launch_pdl(emd_pruned_kernel<PM>, dim3((unsigned)(b * a.nrt)), dim3(PG_WARPS * 32), 0, s, a);
             return;
         }
         // 64-thread CTAs beat 128-thread ones at every size (profiles/r2_emd_tune.txt); one-warp CTAs when even those leave fewer
@@ -1178,8 +1192,8 @@ static void emd_sweep(int b, int nr, int nc, int flags, float lvl2, float lvl2b,
 // ---- final pass launcher ----------------------------------------------------------------------------------------
 template <int ROLE, bool WRITE, bool COST, bool GRAD, bool GRAD2>
 static void emd_launch_pair(const PairArgs& a, dim3 grid, bool exact, cudaStream_t s) {
-    if (exact) emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, true><<<grid, MT_THREADS, 0, s>>>(a);
-    else emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, false><<<grid, MT_THREADS, 0, s>>>(a);
+    if (exact) launch_pdl(emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, true>, grid, dim3(MT_THREADS), 0, s, a);
+    else launch_pdl(emd_pair_kernel<ROLE, WRITE, COST, GRAD, GRAD2, false>, grid, dim3(MT_THREADS), 0, s, a);
 }
 static dim3 emd_pair_grid(int b, int n_own, int n_oth) {
     const int ot = emd_pair_tile(n_oth);
@@ -1199,6 +1213,9 @@ static size_t emd_grad2_partials(int b, int n_own, int n_oth) {   // one slice p
     return (size_t)b * g.x * (MT_THREADS / 32) * n_oth * 3;
 }
 __global__ void emd_grad_reduce_kernel(int n, int nt, size_t bn, const float* __restrict__ partial, float* __restrict__ grad) {
+    // (the dependents are released at the END of this kernel: CTAs of the next sweep that become resident while this one runs are
+    // placed on whatever SMs have room, and a sweep's CTAs live as long as the sweep -- measured 2.5x slower at 1 cloud of 16384 points)
+    pdl_wait();   // everything this kernel reads was written by the kernels before it in the stream
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over bn*3
     if (t >= bn * 3) return;
     const size_t cloud = t / ((size_t)n * 3), r = t % ((size_t)n * 3);
@@ -1280,8 +1297,8 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
         pa.grad_partial = g1.y > 1 ? gp1 : grad1;
         pa.grad2_partial = gp2;
         emd_launch_pair<1, false, true, true, true>(pa, g1, exact, s);
-        if (g1.y > 1) emd_grad_reduce_kernel<<<(unsigned)((bn * 3 + 255) / 256), 256, 0, s>>>(n, (int)g1.y, bn, gp1, grad1);
-        emd_grad_reduce_kernel<<<(unsigned)((bm * 3 + 255) / 256), 256, 0, s>>>(m, (int)(g1.x * (MT_THREADS / 32)), bm, gp2, grad2);
+        if (g1.y > 1) launch_pdl(emd_grad_reduce_kernel, dim3((unsigned)((bn * 3 + 255) / 256)), dim3(256), 0, s, n, (int)g1.y, bn, (const float*)gp1, grad1);
+        launch_pdl(emd_grad_reduce_kernel, dim3((unsigned)((bm * 3 + 255) / 256)), dim3(256), 0, s, m, (int)(g1.x * (MT_THREADS / 32)), bm, (const float*)gp2, grad2);
     } else if (match && cost) {
         emd_launch_pair<1, true, true, false, false>(pa, g1, exact, s);
     } else if (cost) {
@@ -1289,7 +1306,7 @@ static int emd_run(int b, int n, int m, const float* xyz1, const float* xyz2, fl
     } else {
         emd_launch_pair<1, true, false, false, false>(pa, g1, exact, s);
     }
-    if (cost) reduce_partials_kernel<<<b, 256, 0, s>>>((int)(g1.x * g1.y), extra, cost);
+    if (cost) launch_pdl(reduce_partials_kernel, dim3(b), dim3(256), 0, s, (int)(g1.x * g1.y), (const float*)extra, cost);
     return launch_status();
 }
 
