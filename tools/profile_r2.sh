@@ -18,7 +18,8 @@ $NCU --metrics gpu__time_duration.sum -c 300 --csv --log-file gpurun_out/r2_benc
 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r2_emd16k_b4_launches.csv python tools/emd_one.py 4 16384 > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/r2_emd2k_b32_launches.csv python tools/emd_one.py 32 2048 > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file gpurun_out/r2_config4_launches.csv python tools/profile_targets.py config4 > /dev/null 2>&1
-full nn_search -k regex:nn_search -s 3 -c 1 -- python bench.py --steps 2 --warmup 3 --no-extra
+full nn_filter -k regex:nn_filter -s 3 -c 1 -- python bench.py --steps 2 --warmup 3 --no-extra
+full nn_search -k regex:nn_search -s 1 -c 1 -- python bench.py --steps 2 --warmup 3 --no-extra   # the direct kernel (bench times it beside the default)
 full chamfer_epilogue -k regex:chamfer_epilogue -s 4 -c 2 -- python bench.py --steps 2 --warmup 3 --no-extra
 full emd_row -k regex:emd_row_kernel -s 17 -c 3 -- python tools/emd_one.py 4 16384
 full emd_row_b32 -k regex:emd_row_kernel -s 17 -c 3 -- python tools/emd_one.py 32 16384
