@@ -285,3 +285,15 @@ def three_interpolate_grad(points, idx, weight, grad_out):
 
 def ball_threshold(r):
     return float(lib().rfo_ball_threshold(float(np.float32(r))))
+
+
+def nn_filter_bound_ratio(q, c, origin, fused=True):
+    """max over all (query, candidate) pairs of |s + |q-o|^2 - d2_ref| / E for the expanded form the filtered NN search of
+    rfnet_b200 scans (float32, the kernel's operation order) -- a numerical check of its error bound (<= 1 means it holds);
+    test infrastructure only."""
+    q, pq = _f(q)
+    c, pc = _f(c)
+    o, po = _f(np.asarray(origin, dtype=np.float32))
+    fn = lib().rfo_nn_filter_bound_ratio
+    fn.restype = ctypes.c_double
+    return float(fn(q.shape[0], pq, c.shape[0], pc, po, int(bool(fused))))

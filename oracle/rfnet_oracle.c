@@ -583,3 +583,39 @@ RFO_API void rfo_selection_sort(int b, int n, int m, int k, const float *dist, i
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Check of the error bound behind rfnet_b200's filtered nearest-neighbour search (csrc/nn_distance.cu: nn_filter_tolerance).
+ * NOT a restatement of the reference: it replays, in the kernel's float32 operation order, the expanded form
+ *     s = fma(-2(qx-ox), cx-ox, fma(-2(qy-oy), cy-oy, fma(-2(qz-oz), cz-oz, |c-o|^2))),  |c-o|^2 = fma(z,z, fma(x,x, y*y))
+ * for n queries x m candidates about the origin o, and compares  s + |q-o|^2  (the squared norm taken in double from the
+ * ROUNDED differences, as the derivation does) with the reference distance expression d2 (fused or unfused, sqdist above).
+ * Returns max over all pairs of  |s + |q~|^2 - d2| / E,  E = 2^-20 (|q~| + max|c~|)^2 + 5e-31  -- the kernel certifies with 2E,
+ * so the bound holds iff the result is <= 1.
+ * ------------------------------------------------------------------------------------------------------------- */
+double rfo_nn_filter_bound_ratio(int n, const float *q, int m, const float *c, const float *origin, int fused) {
+    const float ox = origin[0], oy = origin[1], oz = origin[2];
+    double cmax = 0.0;
+    for (int j = 0; j < m; j++) {
+        const float x = c[3 * j] - ox, y = c[3 * j + 1] - oy, z = c[3 * j + 2] - oz;
+        const float cn = fmaf(z, z, fmaf(x, x, y * y));
+        if ((double)cn > cmax) cmax = (double)cn;
+    }
+    double worst = 0.0;
+    for (int i = 0; i < n; i++) {
+        const float rx = q[3 * i] - ox, ry = q[3 * i + 1] - oy, rz = q[3 * i + 2] - oz;   /* the kernel's roundings */
+        const float ax = -2.0f * rx, ay = -2.0f * ry, az = -2.0f * rz;
+        const double qn = (double)rx * rx + (double)ry * ry + (double)rz * rz;
+        const double L = sqrt(qn) + sqrt(cmax);
+        const double E = ldexp(L * L, -20) + 5e-31;
+        for (int j = 0; j < m; j++) {
+            const float x = c[3 * j] - ox, y = c[3 * j + 1] - oy, z = c[3 * j + 2] - oz;
+            const float cn = fmaf(z, z, fmaf(x, x, y * y));
+            const float s = fmaf(ax, x, fmaf(ay, y, fmaf(az, z, cn)));
+            const float d2 = sqdist(c + 3 * j, q + 3 * i, fused);
+            const double r = fabs((double)s + qn - (double)d2) / E;
+            if (r > worst) worst = r;
+        }
+    }
+    return worst;
+}

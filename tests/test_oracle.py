@@ -166,3 +166,31 @@ def test_oracle_selection_sort(rng):
         assert np.array_equal(out[..., :k], np.sort(d, axis=-1, kind="stable")[..., :k])
         assert np.array_equal(np.take_along_axis(d, outi, axis=-1), out)                        # a permutation of the row
         assert np.array_equal(np.sort(outi, axis=-1), np.broadcast_to(np.arange(33), d.shape))
+
+
+def test_nn_filter_error_bound_holds_numerically():
+    """The certificate of rfnet_b200's filtered nearest-neighbour search rests on  |s + |q-o|^2 - d2_ref| <= E = 2^-20 (|q-o| + max|c-o|)^2
+    (csrc/nn_distance.cu: nn_filter_tolerance; 13 roundings of 2^-24 by the derivation there).  Replayed here in the kernel's float32
+    operation order on the CPU over scales, offsets, origins inside and outside the data, lattices and near-coincident points: the
+    worst observed ratio must stay below 1 (the derivation says <= 13/16), for both distance contracts."""
+    from oracle import port
+    rng = np.random.default_rng(99)
+    worst = 0.0
+    cases = []
+    for scale in (1.0, 1e-3, 1e4, 1e-12, 1e12):
+        for offset in (0.0, 3.0, -250.0):
+            q = ((rng.random((200, 3), dtype=np.float32) - 0.5) + np.float32(offset)) * np.float32(scale)
+            c = ((rng.random((600, 3), dtype=np.float32) - 0.5) + np.float32(offset)) * np.float32(scale)
+            centre = 0.5 * (c.min(0) + c.max(0))
+            cases += [(q, c, centre), (q, c, c[0]), (q, c, centre + np.float32(0.3 * scale))]
+    lat_q = (np.floor((rng.random((200, 3), dtype=np.float32) - 0.5) * 16) / 16).astype(np.float32)
+    lat_c = (np.floor((rng.random((600, 3), dtype=np.float32) - 0.5) * 16) / 16).astype(np.float32)
+    cases.append((lat_q, lat_c, np.zeros(3, np.float32)))
+    near = (rng.random((600, 3), dtype=np.float32) - 0.5)
+    cases.append((near[:200] + np.float32(1e-6), near, 0.5 * (near.min(0) + near.max(0))))     # queries a hair away from candidates
+    for q, c, o in cases:
+        for fused in (True, False):
+            r = port.nn_filter_bound_ratio(q, c, o, fused)
+            assert r <= 1.0, "error bound violated: ratio %.3f" % r
+            worst = max(worst, r)
+    assert 0.0 < worst <= 13.0 / 16.0 + 0.05, worst
