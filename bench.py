@@ -607,7 +607,7 @@ def main():
 
     def step(i):
         part = parts[i & 1]
-        # one C-ABI call: search, then gradient + unpack + sqrt partial sums, then the fixed-order reduction (3 launches)
+        # one C-ABI call: search, then gradient + unpack + sqrt partial sums, then the fixed-order reduction (4 launches with the preparation of the filtered search)
         ops.raw_chamfer_step(d1s[i % nsets], d2s[i % nsets], gd1, gd2, o["d1"], o["i1"], o["d2"], o["i2"], o["g1"], o["g2"], part, ws)
         if world > 1:
             # the path's only collective: 16 bytes over NCCL/NVLink, on NCCL's own stream.  Nothing on the device consumes

@@ -72,7 +72,7 @@ class ChamferHostPipeline:
             ops.raw_nn_distance_grad(self.x1[k], self.x2[k], self.gd1, r["idx1"], self.gd2, r["idx2"], r["grad1"], r["grad2"], r["ws"])
             ops.raw_chamfer_partial_sums(r["dist1"], r["dist2"], r["sums"], r["ws"])
         else:
-            # search + one epilogue (unpack, gradient, sqrt partial sums) + one reduction: three launches
+            # search + one epilogue (unpack, gradient, sqrt partial sums) + one reduction (+ the preparation kernel of the filtered search): four launches
             ops.raw_chamfer_step(self.x1[k], self.x2[k], self.gd1, self.gd2, r["dist1"], r["idx1"], r["dist2"], r["idx2"], r["grad1"], r["grad2"],
                                  r["sums"], r["ws"])
         self.ev_compute[k].record(compute)
