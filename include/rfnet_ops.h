@@ -83,8 +83,8 @@ size_t rfnet_chamfer_partial_sums_workspace_bytes(void);
 int rfnet_chamfer_partial_sums(int b, int n, int m, const float *dist1, const float *dist2, float *sums4,
                                void *workspace, size_t workspace_bytes, rfnet_stream_t stream);
 
-/* One training step of the reference's chamfer_big (vv_recon.py:381-385, forward and backward) in one call and three
- * kernel launches: nn_distance, NnDistanceGrad for the given upstream gradients grad_dist1 (b,n) / grad_dist2 (b,m), and the
+/* One training step of the reference's chamfer_big (vv_recon.py:381-385, forward and backward) in one call and four
+ * kernel launches (preparation + search, one epilogue, one reduction; no memset): nn_distance, NnDistanceGrad for the given upstream gradients grad_dist1 (b,n) / grad_dist2 (b,m), and the
  * loss partial sums sums4 (as rfnet_chamfer_partial_sums).  Outputs are exactly those of the three separate calls:
  * dist/idx bit-identical; gradients by the reference's float-reduction formulation (last bits depend on thread timing). */
 size_t rfnet_chamfer_step_workspace_bytes(int b, int n, int m);
