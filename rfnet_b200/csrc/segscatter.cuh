@@ -56,6 +56,7 @@ static __global__ void csr_count_kernel(int n, unsigned R, const int* __restrict
 // one CTA of 1024 threads per cloud: exclusive scan of the counts (n arbitrary), cursor := offset.  Each thread owns a
 // run of consecutive targets, so there is a single block-wide scan of 1024 partial sums whatever n is.
 static __global__ void __launch_bounds__(1024) csr_scan_kernel(int n, int* __restrict__ cursor, int* __restrict__ offset) {
+    pdl_wait();   // the previous kernel of the CSR build (programmatic dependent launch: only the launch latency overlaps)
     __shared__ int warp_tot[32];
     const size_t cloud = blockIdx.x;
     int* cnt = cursor + cloud * n;
@@ -94,6 +95,7 @@ static __global__ void __launch_bounds__(1024) csr_scan_kernel(int n, int* __res
 }
 
 static __global__ void csr_fill_kernel(int n, unsigned R, const int* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ list) {
+    pdl_wait();   // the previous kernel of the CSR build (programmatic dependent launch: only the launch latency overlaps)
     const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const size_t cloud = blockIdx.y;
@@ -107,6 +109,7 @@ static __global__ void csr_fill_kernel(int n, unsigned R, const int* __restrict_
 constexpr int kSegThread = 16;
 static __global__ void csr_sort_short_kernel(int n, unsigned R, size_t queue_len, const int* __restrict__ offset, int* __restrict__ list,
                                              int* __restrict__ long_count, int* __restrict__ vlong_count, int2* __restrict__ long_list) {
+    pdl_wait();   // the previous kernel of the CSR build (programmatic dependent launch: only the launch latency overlaps)
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (unsigned)n) return;
     const size_t cloud = blockIdx.y;
@@ -130,6 +133,7 @@ static __global__ void csr_sort_short_kernel(int n, unsigned R, size_t queue_len
 // persistent warps over the queue of long segments.  The rank of an entry is the number of smaller entries.
 static __global__ void __launch_bounds__(256) csr_sort_long_kernel(int n, unsigned R, const int* __restrict__ offset, int* __restrict__ list,
                                                                    const int* __restrict__ long_count, const int2* __restrict__ long_list) {
+    pdl_wait();   // the previous kernel of the CSR build (programmatic dependent launch: only the launch latency overlaps)
     __shared__ int seg_smem[8 * kSegSmem];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = *long_count;
@@ -155,6 +159,7 @@ static __global__ void __launch_bounds__(256) csr_sort_long_kernel(int n, unsign
 // one CTA per very long segment (kSegSmem < L <= kSegSortMax): bitonic network over shared memory, padded with INT_MAX
 static __global__ void __launch_bounds__(512) csr_sort_vlong_kernel(int n, unsigned R, size_t queue_len, const int* __restrict__ offset, int* __restrict__ list,
                                                                     const int* __restrict__ vlong_count, const int2* __restrict__ long_list) {
+    pdl_wait();   // the previous kernel of the CSR build (programmatic dependent launch: only the launch latency overlaps)
     __shared__ int s[kSegSortMax];
     const int total = *vlong_count;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -192,15 +197,15 @@ static inline int csr_build(Csr c, int b, int n, size_t R, const int* idx, cudaS
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
         csr_count_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor);
     }
-    csr_scan_kernel<<<b, 1024, 0, s>>>(n, c.cursor, c.offset);
+    launch_pdl(csr_scan_kernel, dim3(b), dim3(1024), 0, s, n, c.cursor, c.offset);
     if (R) {
         dim3 g((unsigned)((R + 255) / 256), (unsigned)b);
-        csr_fill_kernel<<<g, 256, 0, s>>>(n, (unsigned)R, idx, c.cursor, c.list);
+        launch_pdl(csr_fill_kernel, g, dim3(256), 0, s, n, (unsigned)R, idx, c.cursor, c.list);
         dim3 gs((unsigned)((n + 255) / 256), (unsigned)b);
         const size_t queue_len = (size_t)b * n;
-        csr_sort_short_kernel<<<gs, 256, 0, s>>>(n, (unsigned)R, queue_len, c.offset, c.list, c.long_count, c.vlong_count, c.long_list);
-        csr_sort_long_kernel<<<num_sms(), 256, 0, s>>>(n, (unsigned)R, c.offset, c.list, c.long_count, c.long_list);
-        csr_sort_vlong_kernel<<<num_sms(), 512, 0, s>>>(n, (unsigned)R, queue_len, c.offset, c.list, c.vlong_count, c.long_list);
+        launch_pdl(csr_sort_short_kernel, gs, dim3(256), 0, s, n, (unsigned)R, queue_len, (const int*)c.offset, c.list, c.long_count, c.vlong_count, c.long_list);
+        launch_pdl(csr_sort_long_kernel, dim3(num_sms()), dim3(256), 0, s, n, (unsigned)R, (const int*)c.offset, c.list, c.long_count, c.long_list);
+        launch_pdl(csr_sort_vlong_kernel, dim3(num_sms()), dim3(512), 0, s, n, (unsigned)R, queue_len, (const int*)c.offset, c.list, c.vlong_count, c.long_list);
     }
     return launch_status();
 }
