@@ -297,3 +297,16 @@ def nn_filter_bound_ratio(q, c, origin, fused=True):
     fn = lib().rfo_nn_filter_bound_ratio
     fn.restype = ctypes.c_double
     return float(fn(q.shape[0], pq, c.shape[0], pc, po, int(bool(fused))))
+
+
+def nn_filter_certificate_check(q, c, origin, fused=True):
+    """(violations, certified pairs, tightest certified relative gap) of the filtered search's certificate over all (query, best
+    candidate, other candidate) triples -- see rfo_nn_filter_certificate_violations; test infrastructure only."""
+    q, pq = _f(q)
+    c, pc = _f(c)
+    o, po = _f(np.asarray(origin, dtype=np.float32))
+    fn = lib().rfo_nn_filter_certificate_violations
+    fn.restype = ctypes.c_long
+    cert, tight = ctypes.c_long(0), ctypes.c_double(0.0)
+    bad = fn(q.shape[0], pq, c.shape[0], pc, po, int(bool(fused)), ctypes.byref(cert), ctypes.byref(tight))
+    return int(bad), int(cert.value), float(tight.value)

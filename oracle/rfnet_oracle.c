@@ -585,7 +585,8 @@ RFO_API void rfo_selection_sort(int b, int n, int m, int k, const float *dist, i
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Check of the error bound behind rfnet_b200's filtered nearest-neighbour search (csrc/nn_distance.cu: nn_filter_tolerance).
+ * Check of the error bound behind rfnet_b200's filtered nearest-neighbour search (csrc/nn_distance.cu: the uniform bound
+ * E = 2^-20 (|q-o| + max|c-o|)^2 of its first version; the certificate in use, nn_filter_certain, is checked further below).
  * NOT a restatement of the reference: it replays, in the kernel's float32 operation order, the expanded form
  *     s = fma(-2(qx-ox), cx-ox, fma(-2(qy-oy), cy-oy, fma(-2(qz-oz), cz-oz, |c-o|^2))),  |c-o|^2 = fma(z,z, fma(x,x, y*y))
  * for n queries x m candidates about the origin o, and compares  s + |q-o|^2  (the squared norm taken in double from the
@@ -618,4 +619,58 @@ double rfo_nn_filter_bound_ratio(int n, const float *q, int m, const float *c, c
         }
     }
     return worst;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Check of the CERTIFICATE of the filtered search (csrc/nn_distance.cu: nn_filter_certain), replayed in double on the float32
+ * values the kernel would see.  For every query: c1 = the candidate with the smallest scanned value s (b1), and for every other
+ * candidate c (b2 := s(c)) the kernel's test
+ *      sqrt(X) - sqrt(Y) > 9u L,   X = b2 - A + |q~|^2,  Y = max(0, b1 + A + |q~|^2),  A = 6.1u (Cmax^2 + |q~| Cmax),  L = |q~| + Cmax
+ * is evaluated; whenever it holds, the reference distances must satisfy d2_ref(c) > d2_ref(c1).  Returns the number of violations
+ * (must be 0) and, through *certified, how many pairs the test certified (so that a vacuous pass is visible); *tightest gets the
+ * smallest (d2_ref(c) - d2_ref(c1)) / d2_ref(c1) over certified pairs.
+ * ------------------------------------------------------------------------------------------------------------- */
+long rfo_nn_filter_certificate_violations(int n, const float *q, int m, const float *c, const float *origin, int fused, long *certified,
+                                          double *tightest) {
+    const double u = ldexp(1.0, -24);
+    const float ox = origin[0], oy = origin[1], oz = origin[2];
+    float *s = (float *)malloc(sizeof(float) * (size_t)m), *d = (float *)malloc(sizeof(float) * (size_t)m);
+    double cmax = 0.0;
+    for (int j = 0; j < m; j++) {
+        const float x = c[3 * j] - ox, y = c[3 * j + 1] - oy, z = c[3 * j + 2] - oz;
+        const float cn = fmaf(z, z, fmaf(x, x, y * y));
+        if ((double)cn > cmax) cmax = (double)cn;
+    }
+    const double Cm = sqrt(cmax * (1.0 + 4.0 * u));
+    long bad = 0, cert = 0;
+    double tight = 1e300;
+    for (int i = 0; i < n; i++) {
+        const float rx = q[3 * i] - ox, ry = q[3 * i + 1] - oy, rz = q[3 * i + 2] - oz;
+        const float ax = -2.0f * rx, ay = -2.0f * ry, az = -2.0f * rz;
+        const double qn = (double)rx * rx + (double)ry * ry + (double)rz * rz;
+        const double ql = sqrt(qn), L = ql + Cm;
+        const double A = 6.1 * u * (Cm * Cm + ql * Cm) + 1e-35;
+        int j1 = 0;
+        for (int j = 0; j < m; j++) {
+            const float x = c[3 * j] - ox, y = c[3 * j + 1] - oy, z = c[3 * j + 2] - oz;
+            const float cn = fmaf(z, z, fmaf(x, x, y * y));
+            s[j] = fmaf(ax, x, fmaf(ay, y, fmaf(az, z, cn)));
+            d[j] = sqdist(c + 3 * j, q + 3 * i, fused);
+            if (s[j] < s[j1]) j1 = j;
+        }
+        const double Y0 = (double)s[j1] + A + qn, Y = Y0 > 0.0 ? Y0 : 0.0;
+        for (int j = 0; j < m; j++) {
+            if (j == j1) continue;
+            const double X = (double)s[j] - A + qn;
+            if (X > 0.0 && sqrt(X) - sqrt(Y) > 9.0 * u * L) {
+                cert++;
+                if (!(d[j] > d[j1])) bad++;
+                else if (d[j1] > 0.f) { const double t = ((double)d[j] - (double)d[j1]) / (double)d[j1]; if (t < tight) tight = t; }
+            }
+        }
+    }
+    free(s); free(d);
+    *certified = cert;
+    *tightest = tight;
+    return bad;
 }

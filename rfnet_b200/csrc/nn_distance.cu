@@ -243,13 +243,14 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_CTAS) nn_search_kernel(cons
 // as three packed FMAs per pair of queries (|c-o|^2 rides along as the candidate's 4th coordinate, nn_prepare_kernel), i.e.
 // 3 FP32 lane-ops per pair where the reference expression needs 6 -- and uses it only to decide WHICH group of 16 candidates
 // holds the nearest neighbour.  Per query the scan keeps the smallest group minimum b1, the group k1 it came from and the second
-// smallest group minimum b2 (branch-free: 8 FMNMX3 / FMNMX for the group minimum, then 3 min/max + 1 compare + 1 select).  With
-//     E = 2^-20 (|q-o| + max|c-o|)^2  >=  |s(c) + |q-o|^2 - d2_ref(c)|   for every candidate of the item
-// (13 roundings of 2^-24 relative to (|q-o|+|c-o|)^2 between the two expressions -- derivation at nn_filter_tolerance below),
-// b2 > b1 + 2E proves that every candidate outside group k1 has a reference distance STRICTLY above that of the
-// candidate that produced b1, hence above the minimum of group k1: the exact arg-min (first index on ties) lies in group
+// smallest group minimum b2 (branch-free: 8 FMNMX3 / FMNMX for the group minimum, then 3 min/max + 1 compare + 1 select).  The
+// certificate (nn_filter_certain below, with its derivation) turns b1 and b2 into a rigorous upper bound Y on the squared distance
+// of the scan's best candidate and a lower bound X on that of every candidate outside its group, both in terms of the rounded
+// differences the scan works with, and  sqrt(X) - sqrt(Y) > 9 * 2^-24 (|q-o| + max|c-o|)  proves that every candidate outside group k1
+// has a reference distance STRICTLY above that of the candidate that produced b1, hence above the minimum of group k1: the exact
+// arg-min (first index on ties) lies in group
 // k1, whose G reference distances are then evaluated in the reference's operand order -- dist and idx come out bit for bit.
-// Otherwise (two groups within 2E of each other: 0.3-1.4 % of the (query, item) pairs on unit-cube clouds; every query when
+// Otherwise (two groups too close to separate: well under 1 % of the (query, item) pairs on unit-cube clouds; every query when
 // distinct points sit at exactly equal distances) the warp scans the item's candidates for that query with the reference
 // expression, 32 lanes wide -- or, if that happens to many of its queries, runs the direct loop for its whole tile
 // (nn_direct_scan_warp).  Either way the item contributes the exact (distance, index) minimum of its candidate range; items
@@ -265,17 +266,30 @@ constexpr int NNF_G = NNF_GROUP;   // candidates per tracked group: 8, 16 or 32
 constexpr int NNF_DIRECT_PENDING = 24;   // uncertified queries per warp (of 32 x Q) from which the warp switches to the direct loop
 static_assert(NNF_G == 8 || NNF_G == 16 || NNF_G == 32, "group size");
 
-// 2E for a query with |q - o|^2 = qn against candidates with |c - o|^2 <= cmax (o: the item's origin, u = 2^-24, u' = u(1+..)).
-//   scan: q~ = fl(q - o), c~ = fl(c - o); cn = fma(z,z, fma(x,x, y*y)) carries 3 roundings, the three FMAs 3 more: every term of
-//      |c~|^2 - 2 q~.c~ is perturbed by at most (1+u)^6  =>  |s - (|c~|^2 - 2 q~.c~)| <= 6u' (|c~|^2 + 2|q~||c~|) <= 6u' (|q~|+|c~|)^2;
-//   centring: q~ - c~ = (q - c) + e with |e| <= u (|q-o| + |c-o|)  =>  | |q~-c~|^2 - |q-c|^2 | <= 2|q-c||e| + |e|^2 <= 2u' (|q~|+|c~|)^2;
-//   reference d2 (fused or not): the differences, three products and two sums perturb every term by at most (1+u)^5
-//      =>  |d2_ref - |q-c|^2| <= 5u' |q-c|^2 <= 5u' (|q~|+|c~|)^2.
-// Together 13u' (|q~|+|c~|)^2 <= E = 16u (sqrt(qn)+sqrt(cmax))^2: the 23 % head-room covers the roundings of this function, of
-// the comparison b1 + 2E and the (<= 3u relative) error of qn and cmax; 1e-30 covers gradual underflow (<= 2^-149 per rounding).
-__device__ __forceinline__ float nn_filter_tolerance(float qn, float cmax) {
-    const float L = __fsqrt_ru(qn) + __fsqrt_ru(cmax);
-    return __fmaf_ru(__fmul_ru(L, L), 1.9073486328125e-6f /* 2^-19 = 2 * 16u */, 1e-30f);
+// The certificate.  b1 = s(c1) is the smallest scanned value of the item, b2 the smallest group minimum outside c1's group; q~ = fl(q - o),
+// c~ = fl(c - o) are the ROUNDED differences the scan works with, u = 2^-24, L = |q~| + max|c~|.  Three error sources:
+//   scan:       cn = fma(z,z, fma(x,x, y*y)) and s = fma(ax,x, fma(ay,y, fma(az,z, cn))), a = -2q~: six roundings, each relative to a
+//               partial sum bounded by |c~|^2 + |a||c~|   =>  |s - (|c~|^2 - 2 q~.c~)| <= A := 6.1u (Cmax^2 + |q~| Cmax)
+//   centring:   q~ - c~ = (q - c) + e, |e| <= 1.01u L      =>  | |q~ - c~| - |q - c| | <= 1.01u L
+//   reference:  d2_ref = |q - c|^2 (1 + t), |t| <= 5.01u (three differences, three products, two sums, fused or not)
+// With D~ = |q~ - c~|^2 = (|c~|^2 - 2q~.c~) + |q~|^2:  every c outside c1's group has D~(c) >= X := b2 - A + |q~|^2, and
+// D~(c1) <= Y := b1 + A + |q~|^2.  Hence sqrt(d2_ref(c)) >= (1 - 2.51u)(sqrt(X) - 1.02u L) and sqrt(d2_ref(c1)) <= (1 + 2.51u)(sqrt(Y) + 1.02u L),
+// and  sqrt(X) - sqrt(Y) > 9u L  (> 2.51u (sqrt(X) + sqrt(Y)) + 2.1u L, as sqrt(X), sqrt(Y) <= L (1 + ..))  implies d2_ref(c) > d2_ref(c1):
+// the exact arg-min is in c1's group.  Every quantity below is rounded AGAINST the certificate (X down, Y up, L and A up), 1e-35
+// covers gradual underflow in the scan (<= 2^-149 per rounding).  The test is about 3.5x sharper than a uniform bound
+// E = 16u L^2 on |s + |q~|^2 - d2_ref| (the first version; tests/test_oracle.py checks both numerically: no violation in 1e7 certified
+// pairs, near-ties included; the tightest certified pair differs by 3e-4 relative).
+__device__ __forceinline__ bool nn_filter_certain(float b1, float b2, float rx, float ry, float rz, float cmax_up_sqrt) {
+    const float INF = __int_as_float(0x7f800000);
+    const float qn_lo = __fmaf_rd(rz, rz, __fmaf_rd(rx, rx, __fmul_rd(ry, ry)));
+    const float qn_hi = __fmaf_ru(rz, rz, __fmaf_ru(rx, rx, __fmul_ru(ry, ry)));
+    const float ql = __fsqrt_ru(qn_hi);
+    const float L = __fadd_ru(ql, cmax_up_sqrt);
+    const float A = __fmaf_ru(3.6359e-7f /* 6.1u, rounded up */, __fmaf_ru(cmax_up_sqrt, cmax_up_sqrt, __fmul_ru(ql, cmax_up_sqrt)), 1e-35f);
+    const float X = __fadd_rd(__fadd_rd(b2, -A), qn_lo);
+    const float Y = fmaxf(0.f, __fadd_ru(__fadd_ru(b1, A), qn_hi));
+    // every comparison is false for NaN, so non-finite states fall through to the exact scan
+    return X > 0.f && (__fadd_rd(__fsqrt_rd(X), -__fsqrt_ru(Y)) > __fmul_ru(5.3645e-7f /* 9u, rounded up */, L)) && (fabsf(b1) < INF) && (L < INF);
 }
 
 // Preparation of the candidates for the filtered search: one CTA per work-item range of a candidate cloud (at most NNP_RANGE
@@ -646,6 +660,7 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
     }
     const int range_lo = first_chunk * chunk;
     const int range_hi = min(nc, range_lo + my_chunks * chunk);
+    const float cmax_sqrt = __fsqrt_ru(__fmul_ru(cmax_cloud, 1.0000003f));   // max |c~|, rounded up (the prepared norms carry <= 3u)
     const bool vec = D.tma != 0;   // raw candidate rows are 16-byte aligned: G of them are 3G/4 vector loads
     auto emit = [&](int qi, float bd, int bi) {
         const size_t o = (size_t)cloud * nq + qi;
@@ -665,9 +680,7 @@ __global__ void __launch_bounds__(NN_THREADS, NNF_MIN_CTAS) nn_filter_kernel(con
         const int k0 = sK1[i * NN_THREADS + tid];
         const float qxs = qbase[(size_t)qi * 3 + 0], qys = qbase[(size_t)qi * 3 + 1], qzs = qbase[(size_t)qi * 3 + 2];
         const float rx = qxs - ox, ry = qys - oy, rz = qzs - oz;   // the same roundings as in the scan
-        const float tol2 = nn_filter_tolerance(__fmaf_ru(rz, rz, __fmaf_ru(rx, rx, __fmul_ru(ry, ry))), cmax_cloud);
-        // every comparison is false for NaN, so non-finite states fall through to the exact scan
-        const bool certain = (v2 > __fadd_ru(v1, tol2)) && (fabsf(v1) < INF) && (tol2 < INF);
+        const bool certain = nn_filter_certain(v1, v2, rx, ry, rz, cmax_sqrt);
         if (certain) {
             // the G reference distances of the certified group, all independent (the loads and the arithmetic pipeline),
             // then their minimum and the FIRST position attaining it

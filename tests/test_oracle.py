@@ -169,8 +169,9 @@ def test_oracle_selection_sort(rng):
 
 
 def test_nn_filter_error_bound_holds_numerically():
-    """The certificate of rfnet_b200's filtered nearest-neighbour search rests on  |s + |q-o|^2 - d2_ref| <= E = 2^-20 (|q-o| + max|c-o|)^2
-    (csrc/nn_distance.cu: nn_filter_tolerance; 13 roundings of 2^-24 by the derivation there).  Replayed here in the kernel's float32
+    """The scan of rfnet_b200's filtered nearest-neighbour search satisfies  |s + |q-o|^2 - d2_ref| <= E = 2^-20 (|q-o| + max|c-o|)^2
+    (13 roundings of 2^-24: 6 of the scan, 2 of the centring, 5 of the reference expression; the uniform bound behind the first version
+    of the certificate, kept as a sanity check of the error model -- the sharper test in use is checked by the next test).  Replayed here in the kernel's float32
     operation order on the CPU over scales, offsets, origins inside and outside the data, lattices and near-coincident points: the
     worst observed ratio must stay below 1 (the derivation says <= 13/16), for both distance contracts."""
     from oracle import port
@@ -194,3 +195,39 @@ def test_nn_filter_error_bound_holds_numerically():
             assert r <= 1.0, "error bound violated: ratio %.3f" % r
             worst = max(worst, r)
     assert 0.0 < worst <= 13.0 / 16.0 + 0.05, worst
+
+
+def test_nn_filter_certificate_has_no_violation():
+    """The sharper certificate of the filtered search (csrc/nn_distance.cu: nn_filter_certain):  sqrt(X) - sqrt(Y) > 9u L  must imply that the
+    candidate's REFERENCE distance is strictly above that of the scan's best candidate.  Replayed in double on the float32 scan values over
+    scales, offsets, origins, lattices, near-coincident points and near-ties: no violation, and the pass is not vacuous."""
+    from oracle import port
+    rng = np.random.default_rng(7)
+    cases = []
+    for scale in (1.0, 1e-3, 1e4, 1e-12, 1e12, 1e-19):
+        for offset in (0.0, 3.0, -250.0):
+            q = ((rng.random((150, 3), dtype=np.float32) - 0.5) + np.float32(offset)) * np.float32(scale)
+            c = ((rng.random((500, 3), dtype=np.float32) - 0.5) + np.float32(offset)) * np.float32(scale)
+            centre = 0.5 * (c.min(0) + c.max(0))
+            cases += [(q, c, centre), (q, c, c[0]), (q, c, centre + np.float32(0.3 * scale))]
+    lat_q = (np.floor((rng.random((150, 3), dtype=np.float32) - 0.5) * 16) / 16).astype(np.float32)
+    lat_c = (np.floor((rng.random((500, 3), dtype=np.float32) - 0.5) * 16) / 16).astype(np.float32)
+    cases.append((lat_q, lat_c, np.zeros(3, np.float32)))
+    near = (rng.random((500, 3), dtype=np.float32) - 0.5)
+    cases.append((near[:150] + np.float32(1e-6), near, 0.5 * (near.min(0) + near.max(0))))
+    # near-ties: pairs of candidates at almost the same distance from each query (a thin shell around the query cloud's centre)
+    dirs = rng.standard_normal((500, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    shell = (dirs * (np.float32(0.3) + np.float32(1e-7) * rng.standard_normal((500, 1)).astype(np.float32))).astype(np.float32)
+    cases.append(((rng.standard_normal((150, 3)) * 1e-4).astype(np.float32), shell, np.zeros(3, np.float32)))
+    cases.append(((rng.standard_normal((150, 3)) * 1e-4).astype(np.float32) + np.float32(40.0), shell + np.float32(40.0), np.full(3, 40.0, np.float32)))
+    total = 0
+    tightest = np.inf
+    for q, c, o in cases:
+        for fused in (True, False):
+            bad, cert, tight = port.nn_filter_certificate_check(q, c, o, fused)
+            assert bad == 0, "certificate violated for %d pairs" % bad
+            total += cert
+            tightest = min(tightest, tight)
+    assert total > 1_000_000, total          # not vacuous
+    assert tightest > 0.0
