@@ -314,7 +314,7 @@ template <>
 __device__ __forceinline__ float4 vec_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 template <typename VEC>
-__global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC* __restrict__ grad_out, const int* __restrict__ offset,
+__global__ void __launch_bounds__(256, 8) group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC* __restrict__ grad_out, const int* __restrict__ offset,
                                             const int* __restrict__ list, VEC* __restrict__ grad_points) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (target point, channel vector) of this cloud
     const unsigned i = t / (unsigned)cv;
@@ -325,13 +325,27 @@ __global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC
     const int* __restrict__ seg = list + cloud * R;
     const VEC* __restrict__ G = grad_out + cloud * (size_t)R * cv + l;
     VEC acc = vec_zero<VEC>();
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {   // four source rows in flight; added in ascending order, as the sequential reference does
-        const int s0 = seg[e], s1 = seg[e + 1], s2 = seg[e + 2], s3 = seg[e + 3];
-        const VEC g0 = __ldg(G + (size_t)s0 * cv), g1 = __ldg(G + (size_t)s1 * cv), g2 = __ldg(G + (size_t)s2 * cv), g3 = __ldg(G + (size_t)s3 * cv);
-        acc = vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(acc, g0), g1), g2), g3);
+    // four source rows in flight, the entry numbers of the NEXT four loaded before the current rows are waited for; added in ascending
+    // order, as the sequential reference does.  Segments are short here (4 on average at config 4) and the kernel lives on occupancy:
+    // an 8-deep version at 72 registers ran 28 % slower than this one.
+    constexpr int GPG_U = 4;
+    int cur[GPG_U];
+#pragma unroll
+    for (int u = 0; u < GPG_U; ++u) cur[u] = beg + u < end ? seg[beg + u] : -1;
+    for (int e = beg; e < end; e += GPG_U) {
+        VEC g[GPG_U];
+#pragma unroll
+        for (int u = 0; u < GPG_U; ++u)
+            if (cur[u] >= 0) g[u] = __ldg(G + (size_t)cur[u] * cv);
+        int nxt[GPG_U];
+#pragma unroll
+        for (int u = 0; u < GPG_U; ++u) nxt[u] = e + GPG_U + u < end ? seg[e + GPG_U + u] : -1;
+#pragma unroll
+        for (int u = 0; u < GPG_U; ++u)
+            if (cur[u] >= 0) acc = vec_add<VEC>(acc, g[u]);
+#pragma unroll
+        for (int u = 0; u < GPG_U; ++u) cur[u] = nxt[u];
     }
-    for (; e < end; ++e) acc = vec_add<VEC>(acc, __ldg(G + (size_t)seg[e] * cv));
     grad_points[(cloud * n + i) * cv + l] = acc;
 }
 
@@ -344,6 +358,36 @@ __global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC
 // gives) finished with a REDUX-free shuffle tree on (value, position), then lane 0 swaps.  Rows longer than the shared
 // budget run the same code on the output row in global memory.
 // ---------------------------------------------------------------------------------------------------------------
+// k steps of selection sort with swaps on one row (values + positions, shared or global memory), by one warp: lane-strided arg-min
+// (first minimum: lowest position among equals, as the strict '<' scan from min = s gives), shuffle tree on (value, position), lane 0
+// swaps.  NaN as in the reference: nothing compares below a NaN, so a NaN at position s stays there (the step does nothing) and a NaN
+// elsewhere is never selected.
+__device__ __forceinline__ void ss_plain_sort(float* val, int* pos, int n, int k, int lane) {
+    for (int s = 0; s < k; ++s) {
+        const float vs = val[s];
+        if (vs != vs) continue;   // warp-uniform
+        float bv = 0.f;
+        int bp = 0x7fffffff;   // "no element"
+        for (int t = s + lane; t < n; t += 32) {
+            const float v = val[t];
+            if (v == v && (bp == 0x7fffffff || v < bv)) { bv = v; bp = t; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, off);
+            // keep the smaller value; among equals the lower position; an empty lane never wins
+            const bool take = op != 0x7fffffff && (bp == 0x7fffffff || ov < bv || (ov == bv && op < bp));
+            if (take) { bv = ov; bp = op; }
+        }
+        if (lane == 0 && bp != s) {
+            const float tv = val[bp]; val[bp] = val[s]; val[s] = tv;
+            const int tp = pos[bp]; pos[bp] = pos[s]; pos[s] = tp;
+        }
+        __syncwarp();
+    }
+}
+
 constexpr int SS_WARPS = 4;
 __global__ void __launch_bounds__(SS_WARPS * 32) selection_sort_kernel(int n, int k, size_t rows, int smem_rows, const float* __restrict__ dist,
                                                                        int* __restrict__ outi, float* __restrict__ out) {
@@ -361,35 +405,165 @@ __global__ void __launch_bounds__(SS_WARPS * 32) selection_sort_kernel(int n, in
         pos[i] = i;
     }
     __syncwarp();
-    for (int s = 0; s < k; ++s) {
-        float bv = 0.f;
-        int bp = 0x7fffffff;   // "no element"
-        for (int t = s + lane; t < n; t += 32) {
-            const float v = val[t];
-            if (bp == 0x7fffffff || v < bv) { bv = v; bp = t; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int op = __shfl_xor_sync(0xffffffffu, bp, off);
-            // keep the smaller value; among equals the lower position; an empty lane never wins
-            const bool take = op != 0x7fffffff && (bp == 0x7fffffff || ov < bv || (ov == bv && op < bp));
-            if (take) { bv = ov; bp = op; }
-        }
-        // the reference's scan starts from min = s and only moves on a strictly smaller value: identical to the first
-        // minimum unless the row holds NaNs (a NaN at s is never displaced there; here the comparison tree may differ)
-        if (lane == 0 && bp != s) {
-            const float tv = val[bp]; val[bp] = val[s]; val[s] = tv;
-            const int tp = pos[bp]; pos[bp] = pos[s]; pos[s] = tp;
-        }
-        __syncwarp();
-    }
+    ss_plain_sort(val, pos, n, k, lane);
     if (smem_rows) {
         for (int i = lane; i < n; i += 32) {
             o[i] = val[i];
             oi[i] = pos[i];
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// selection_sort for k <= 128: the same result without running the selection sort over the row.
+//
+// k steps of selection sort touch few positions: step s swaps position s with the position of the current minimum of [s, n).
+// Let T be any value with at least k row entries <= T.  Every selected minimum is one of the k smallest entries, hence <= T, and
+// an entry only ever moves to position s < k (selected) or to the position a selected entry just left (displaced).  So the set
+//     P = [0, k)  U  { t : row[t] <= T }
+// is closed under the swaps, every minimum search over [s, n) finds its answer inside P (ties included: ALL entries equal to
+// the minimum are <= T, and the reference's strict '<' scan takes the one at the lowest current position), and everything
+// outside P keeps its value and its index.  A warp therefore
+//   (1) streams the row once: out = dist, outi = 0..n-1 (vector loads and stores), each lane keeping its j = ceil(k/32) smallest
+//       values; T = the largest of the lanes' j-th smallest (at least 32 j >= k entries are <= T; ~6 % of a random row at k = 32);
+//   (2) re-reads the row (cache hits) and compacts P in position order into shared memory (ballot + popcount);
+//   (3) runs the k steps on that list: slot s is position s; arg-min over slots >= s on an order-preserving integer key
+//       (two REDUX: smallest key, then the lowest slot holding it), lane 0 swaps (key, entry id);
+//   (4) writes back the slots whose entry changed.
+// A row whose P exceeds SSF_CAP slots (masses of equal values) runs the plain selection sort on its output row instead.
+// NaN: the reference never moves a NaN out of position s (nothing compares below it) and never selects one; reproduced by
+// skipping step s when slot s holds a NaN and giving NaN the largest key.  -0.0 and +0.0 compare equal, as in the reference.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SSF_WARPS = 8;
+constexpr int SSF_CAP = 384;     // slots per row list
+constexpr int SSF_JMAX = 4;      // k <= 32 * SSF_JMAX
+
+__device__ __forceinline__ unsigned ss_key(float v) {
+    // order-preserving map float -> unsigned with -0 == +0 and every NaN on top
+    if (v != v) return 0xffffffffu;
+    const unsigned u = (unsigned)__float_as_int(v + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <int J>
+__device__ __forceinline__ void ss_insert(float (&a)[J], float v) {
+    // a[0] <= ... <= a[J-1] keeps the J smallest values seen; NaN counts as +inf
+    v = (v != v) ? __int_as_float(0x7f800000) : v;
+#pragma unroll
+    for (int i = J - 1; i > 0; --i) a[i] = fminf(a[i], fmaxf(a[i - 1], v));
+    a[0] = fminf(a[0], v);
+}
+
+template <int J>
+__global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int n, int k, size_t rows, const float* __restrict__ dist,
+                                                                             int* __restrict__ outi, float* __restrict__ out) {
+    __shared__ int s_pos[SSF_WARPS][SSF_CAP];        // position (= original index) of list entry e
+    __shared__ float s_val[SSF_WARPS][SSF_CAP];      // its value
+    __shared__ unsigned s_key[SSF_WARPS][SSF_CAP];   // key of the entry currently in slot i
+    __shared__ int s_id[SSF_WARPS][SSF_CAP];         // ... and which entry that is
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t row = (size_t)blockIdx.x * SSF_WARPS + warp;
+    if (row >= rows) return;
+    const float* __restrict__ src = dist + row * n;
+    float* o = out + row * n;
+    int* oi = outi + row * n;
+    const float inf = __int_as_float(0x7f800000);
+
+    // (1) copy + threshold
+    float a[J];
+#pragma unroll
+    for (int i = 0; i < J; ++i) a[i] = inf;
+    const bool vec = (n & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)o) | ((uintptr_t)oi)) & 15u) == 0;
+    if (vec) {
+        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        int4* oi4 = reinterpret_cast<int4*>(oi);
+#pragma unroll 4
+        for (int i = lane; i < (n >> 2); i += 32) {
+            const float4 v = __ldg(s4 + i);
+            o4[i] = v;
+            oi4[i] = make_int4(4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3);
+            ss_insert<J>(a, v.x); ss_insert<J>(a, v.y); ss_insert<J>(a, v.z); ss_insert<J>(a, v.w);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) {
+            const float v = __ldg(src + i);
+            o[i] = v;
+            oi[i] = i;
+            ss_insert<J>(a, v);
+        }
+    }
+    float T = inf;
+    if (n > SSF_CAP) {   // every lane saw at least SSF_CAP / 32 >= J entries
+        T = a[J - 1];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, off));
+    }
+    __syncwarp();
+
+    // (2) the list P in position order
+    int cnt = 0;
+#pragma unroll 4
+    for (int base = 0; base < n; base += 32) {
+        const int t = base + lane;
+        const float v = t < n ? __ldg(src + t) : inf;
+        const bool in = t < n && (t < k || v <= T);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (in && slot < SSF_CAP) {
+            s_pos[warp][slot] = t;
+            s_val[warp][slot] = v;
+            s_key[warp][slot] = ss_key(v);
+            s_id[warp][slot] = slot;
+        }
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+
+    if (cnt > SSF_CAP) {
+        // too many entries at or below the threshold: plain selection sort on the output row (ss_plain_sort, as selection_sort_kernel)
+        ss_plain_sort(o, oi, n, k, lane);
+        return;
+    }
+
+    // (3) k steps on the list; slot s is position s because [0, k) leads the list
+    for (int s = 0; s < k; ++s) {
+        unsigned bk = 0xffffffffu;
+        int bs = 0x7fffffff;
+        for (int i = s + lane; i < cnt; i += 32) {
+            const unsigned key = s_key[warp][i];
+            if (key < bk || bs == 0x7fffffff) { bk = key; bs = i; }   // ascending i: the first of equals stays
+        }
+        const unsigned mk = __reduce_min_sync(0xffffffffu, bk);
+        const int ms = __reduce_min_sync(0xffffffffu, (bk == mk && bs != 0x7fffffff) ? bs : 0x7fffffff);
+        if (lane == 0 && ms != s) {
+            const unsigned ks = s_key[warp][s];
+            if (ks != 0xffffffffu) {   // a NaN at position s stays there (nothing compares below it)
+                const int is = s_id[warp][s], im = s_id[warp][ms];
+                s_key[warp][s] = mk; s_id[warp][s] = im;
+                s_key[warp][ms] = ks; s_id[warp][ms] = is;
+            }
+        }
+        __syncwarp();
+    }
+
+    // (4) write back what moved
+    for (int i = lane; i < cnt; i += 32) {
+        const int e = s_id[warp][i];
+        if (e != i) {
+            const int p = s_pos[warp][i];
+            o[p] = s_val[warp][e];
+            oi[p] = s_pos[warp][e];
+        }
+    }
+}
+
+template <int J>
+static void launch_selection_sort_fast(int n, int k, size_t rows, const float* dist, int* outi, float* out, cudaStream_t s) {
+    const size_t blocks = (rows + SSF_WARPS - 1) / SSF_WARPS;
+    selection_sort_fast_kernel<J><<<(unsigned)blocks, SSF_WARPS * 32, 0, s>>>(n, k, rows, dist, outi, out);
 }
 
 }  // namespace rfnet
@@ -526,6 +700,14 @@ extern "C" int rfnet_selection_sort(int b, int n, int m, int k, const float* dis
     if (k > n) k = n;
     const size_t blocks = (rows + SS_WARPS - 1) / SS_WARPS;
     RFNET_CHECK_ARG(blocks <= 0x7fffffffull);
+    if (k <= 32 * SSF_JMAX) {
+        const int j = (k + 31) / 32;
+        if (j == 1) launch_selection_sort_fast<1>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        else if (j == 2) launch_selection_sort_fast<2>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        else if (j == 3) launch_selection_sort_fast<3>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        else launch_selection_sort_fast<4>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        return launch_status();
+    }
     const size_t smem = (size_t)SS_WARPS * n * 8;   // value + position per entry, one row per warp
     const int in_smem = smem <= 160 * 1024;
     if (in_smem && smem > 48 * 1024)

@@ -445,6 +445,59 @@ __global__ void __launch_bounds__(256) three_interpolate_kernel(int m, int cv, i
         if (i0[u] >= 0) ti_store<VEC>(O + e0 + u * 256u, blend3<VEC>(a[u], b[u], c[u], w0[u], w1[u], w2[u]));
 }
 
+// Staged variant for wide rows (c % 16 == 0, known cloud slice fits shared memory).  The plain kernel above gathers every output
+// vector's three source rows through L2: 3x the output volume in L2 reads (403 MB for 134 MB written at config 4; ncu: L2-bound,
+// DRAM at 20 %).  Here a CTA owns a 16-channel slice of ONE cloud's known points in shared memory (m x 64 B) and streams a contiguous
+// range of unknown points through it: the gathers are LDS.128, L2 carries the slice once per CTA, and HBM sees the algorithmic
+// bytes.  The grid is persistent -- groups x slices CTAs, one per SM; the CTAs of a group walk the same rows at the same pace, each
+// writing its 64-byte part of a row, so the 256-byte output rows complete in L2 close together.  Same expression, same bits.
+constexpr int TIS_THREADS = 1024;
+constexpr int TIS_CSV = 4;   // float4 per row slice
+constexpr int TIS_U = 4;     // rows per thread and step: a CTA keeps 1024 rows (64 KB of output) in flight per memory round trip
+__global__ void __launch_bounds__(TIS_THREADS, 1) three_interpolate_staged_kernel(int b, int m, int cv, int n, const float4* __restrict__ points,
+                                                                                  const int* __restrict__ idx, const float* __restrict__ weight,
+                                                                                  float4* __restrict__ out, unsigned long long rows_per_group) {
+    extern __shared__ __align__(16) float4 tis_rows[];   // [m][TIS_CSV]
+    const int nslice = cv / TIS_CSV;
+    const int slice = blockIdx.x % nslice;
+    const unsigned long long group = blockIdx.x / nslice;
+    const unsigned long long total = (unsigned long long)b * (unsigned)n;
+    unsigned long long r0 = group * rows_per_group;
+    const unsigned long long r1 = min(total, r0 + rows_per_group);
+    const int v = threadIdx.x & (TIS_CSV - 1), rt = threadIdx.x / TIS_CSV;
+    constexpr int RPS = TIS_THREADS / TIS_CSV;   // rows per step and unroll slot
+    while (r0 < r1) {
+        const unsigned long long cloud = r0 / (unsigned)n;
+        const unsigned long long cend = min(r1, (cloud + 1) * (unsigned)n);
+        __syncthreads();   // the previous cloud's readers are done
+        const float4* __restrict__ P = points + cloud * (size_t)m * cv + slice * TIS_CSV;
+#pragma unroll 8
+        for (int t = threadIdx.x; t < m * TIS_CSV; t += TIS_THREADS) tis_rows[t] = __ldg(P + (size_t)(t / TIS_CSV) * cv + (t & (TIS_CSV - 1)));
+        __syncthreads();
+        for (unsigned long long base = r0; base < cend; base += RPS * TIS_U) {
+            int i0[TIS_U], i1[TIS_U], i2[TIS_U];
+            float w0[TIS_U], w1[TIS_U], w2[TIS_U];
+#pragma unroll
+            for (int u = 0; u < TIS_U; ++u) {
+                const unsigned long long r = base + u * RPS + rt;
+                i0[u] = -1;
+                if (r < cend) {
+                    i0[u] = __ldg(idx + r * 3); i1[u] = __ldg(idx + r * 3 + 1); i2[u] = __ldg(idx + r * 3 + 2);
+                    w0[u] = __ldg(weight + r * 3); w1[u] = __ldg(weight + r * 3 + 1); w2[u] = __ldg(weight + r * 3 + 2);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TIS_U; ++u)
+                if (i0[u] >= 0) {
+                    const unsigned long long r = base + u * RPS + rt;
+                    const float4 a = tis_rows[i0[u] * TIS_CSV + v], bb = tis_rows[i1[u] * TIS_CSV + v], c = tis_rows[i2[u] * TIS_CSV + v];
+                    __stcs(out + r * cv + slice * TIS_CSV + v, blend3<float4>(a, bb, c, w0[u], w1[u], w2[u]));
+                }
+        }
+        r0 = cend;
+    }
+}
+
 // grad_points[i, i_t, l] += grad_out[i,j,l] * w_t  after zero-fill             (tf_interpolate.cpp:131-153, :258)
 __global__ void three_interpolate_grad_kernel(int n, int c, int m, const float* __restrict__ grad_out, const int* __restrict__ idx,
                                               const float* __restrict__ weight, float* __restrict__ grad_points) {
@@ -512,17 +565,30 @@ __global__ void three_interpolate_grad_seg_kernel(int n, int cv, int m, const VE
     const VEC* __restrict__ G = grad_out + cloud * (size_t)n * cv + l;
     const float* __restrict__ W = weight + cloud * R;
     VEC acc = vec_zero3<VEC>();
-    int e = beg;
-    for (; e + 4 <= end; e += 4) {   // four contributions in flight; accumulated in ascending source order, as the sequential reference does
-        const int s0 = seg[e], s1 = seg[e + 1], s2 = seg[e + 2], s3 = seg[e + 3];  // = 3*j + u
-        const VEC g0 = __ldg(G + (size_t)(s0 / 3) * cv), g1 = __ldg(G + (size_t)(s1 / 3) * cv), g2 = __ldg(G + (size_t)(s2 / 3) * cv),
-                  g3 = __ldg(G + (size_t)(s3 / 3) * cv);
-        const float w0 = __ldg(W + s0), w1 = __ldg(W + s1), w2 = __ldg(W + s2), w3 = __ldg(W + s3);
-        acc = vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(vec_madd_unfused<VEC>(acc, g0, w0), g1, w1), g2, w2), g3, w3);
-    }
-    for (; e < end; ++e) {
-        const int src = seg[e];
-        acc = vec_madd_unfused<VEC>(acc, __ldg(G + (size_t)(src / 3) * cv), __ldg(W + src));
+    // TIG_U contributions in flight, the entry numbers of the NEXT batch loaded before the current batch's rows are waited for (a
+    // first version chained entry -> row loads four at a time: 13 dependent memory round trips for a segment of 24; ncu: long-scoreboard
+    // bound at 30 % of DRAM).  Accumulated in ascending source order, as the sequential reference does.
+    constexpr int TIG_U = 8;
+    int cur[TIG_U];
+#pragma unroll
+    for (int u = 0; u < TIG_U; ++u) cur[u] = beg + u < end ? seg[beg + u] : -1;   // = 3*j + u
+    for (int e = beg; e < end; e += TIG_U) {
+        VEC g[TIG_U];
+        float w[TIG_U];
+#pragma unroll
+        for (int u = 0; u < TIG_U; ++u)
+            if (cur[u] >= 0) {
+                g[u] = __ldg(G + (size_t)(cur[u] / 3) * cv);
+                w[u] = __ldg(W + cur[u]);
+            }
+        int nxt[TIG_U];
+#pragma unroll
+        for (int u = 0; u < TIG_U; ++u) nxt[u] = e + TIG_U + u < end ? seg[e + TIG_U + u] : -1;
+#pragma unroll
+        for (int u = 0; u < TIG_U; ++u)
+            if (cur[u] >= 0) acc = vec_madd_unfused<VEC>(acc, g[u], w[u]);
+#pragma unroll
+        for (int u = 0; u < TIG_U; ++u) cur[u] = nxt[u];
     }
     grad_points[(cloud * m + i) * cv + l] = acc;
 }
@@ -567,7 +633,21 @@ extern "C" int rfnet_three_interpolate(int b, int m, int c, int n, const float* 
     RFNET_CHECK_ARG(m > 0 && points && idx && weight && out);
     cudaStream_t s = (cudaStream_t)stream;
     RFNET_CHECK_ARG(b <= 65535 && (size_t)n * c < 0x7fffffffull);
-    if (c % 4 == 0 && (((uintptr_t)points | (uintptr_t)out) & 15u) == 0) {
+    const bool aligned = (((uintptr_t)points | (uintptr_t)out) & 15u) == 0;
+    const size_t slice_bytes = (size_t)m * TIS_CSV * sizeof(float4);
+    if (aligned && c % (4 * TIS_CSV) == 0 && slice_bytes <= 200 * 1024) {
+        // staged: worth it once a CTA streams several times more rows than it stages
+        const int nslice = c / (4 * TIS_CSV);
+        const int groups = num_sms() / nslice > 0 ? num_sms() / nslice : 1;
+        const unsigned long long rpg = (rows + groups - 1) / groups;
+        if (rpg >= 4ull * (unsigned)m) {
+            RFNET_CUDA(cudaFuncSetAttribute(three_interpolate_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
+            three_interpolate_staged_kernel<<<(unsigned)(groups * nslice), TIS_THREADS, slice_bytes, s>>>(b, m, c / 4, n, (const float4*)points, idx, weight,
+                                                                                                     (float4*)out, rpg);
+            return launch_status();
+        }
+    }
+    if (c % 4 == 0 && aligned) {
         dim3 grid((unsigned)(((size_t)n * (c / 4) + 256 * TI_E - 1) / (256 * TI_E)), (unsigned)b);
         three_interpolate_kernel<float4><<<grid, 256, 0, s>>>(m, c / 4, n, (const float4*)points, idx, weight, (float4*)out);
     } else {

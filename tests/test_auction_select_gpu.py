@@ -95,6 +95,42 @@ def test_select_top_k_vs_oracle(cuda, rng, b, m, n, k):
     assert np.array_equal(outi.cpu().numpy(), wi) and np.array_equal(out.cpu().numpy(), wo)
 
 
+@pytest.mark.parametrize("kind", ["quantised", "constant", "two_values", "sorted", "reversed", "signed_zeros", "nan", "inf"])
+@pytest.mark.parametrize("n,k", [(2048, 32), (1000, 33), (999, 128), (4096, 129), (385, 64), (384, 7), (50, 50)])
+def test_select_top_k_adversarial_rows(cuda, rng, kind, n, k):
+    """The list-based kernel (k <= 128) on rows built to break it: masses of equal values (list overflow -> plain sort of the row), equal
+    values straddling the threshold, monotone rows, -0.0 / +0.0, NaN and infinities; k = 129 takes the whole-row kernel.  Bit-exact with the
+    oracle's swap sequence, tail included."""
+    from rfnet_b200 import tf_grouping
+    b, m = 2, 37
+    d = rng.random((b, m, n), dtype=np.float32)
+    if kind == "quantised":
+        d = np.floor(d * 8).astype(np.float32) / 8
+    elif kind == "constant":
+        d[:] = np.float32(0.25)
+        d[0, :, n // 2] = 0.125
+    elif kind == "two_values":
+        d = (d > 0.97).astype(np.float32)           # ~3 % ones, the rest zeros: every minimum is a tie
+    elif kind == "sorted":
+        d = np.sort(d, axis=-1)
+    elif kind == "reversed":
+        d = np.sort(d, axis=-1)[..., ::-1].copy()
+    elif kind == "signed_zeros":
+        d[..., ::3] = 0.0
+        d[..., 1::7] = -0.0
+    elif kind == "nan":
+        d[..., 3] = np.nan                           # inside [0, k) for k > 3: stays where it is
+        d[0, :, min(n - 1, 200)] = np.nan
+        d[1, 5, :] = np.nan
+    elif kind == "inf":
+        d[..., ::5] = np.inf
+        d[..., 2::11] = -np.inf
+    wi, wo = port.select_top_k(k, d)
+    outi, out = tf_grouping.select_top_k(k, t(d, cuda))
+    assert np.array_equal(outi.cpu().numpy(), wi)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), wo.view(np.uint32))   # bit patterns: NaN and the sign of zero included
+
+
 @pytest.mark.skipif(not ref.available("gpu"), reason="oracle/_ref/libref_gpu.so not built")
 def test_select_top_k_vs_reference_cuda_kernel(cuda, rng):
     from rfnet_b200 import tf_grouping
