@@ -314,7 +314,7 @@ template <>
 __device__ __forceinline__ float4 vec_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 template <typename VEC>
-__global__ void __launch_bounds__(256, 8) group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC* __restrict__ grad_out, const int* __restrict__ offset,
+__global__ void group_point_grad_seg_kernel(int n, int cv, unsigned R, const VEC* __restrict__ grad_out, const int* __restrict__ offset,
                                             const int* __restrict__ list, VEC* __restrict__ grad_points) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (target point, channel vector) of this cloud
     const unsigned i = t / (unsigned)cv;
@@ -325,27 +325,13 @@ __global__ void __launch_bounds__(256, 8) group_point_grad_seg_kernel(int n, int
     const int* __restrict__ seg = list + cloud * R;
     const VEC* __restrict__ G = grad_out + cloud * (size_t)R * cv + l;
     VEC acc = vec_zero<VEC>();
-    // four source rows in flight, the entry numbers of the NEXT four loaded before the current rows are waited for; added in ascending
-    // order, as the sequential reference does.  Segments are short here (4 on average at config 4) and the kernel lives on occupancy:
-    // an 8-deep version at 72 registers ran 28 % slower than this one.
-    constexpr int GPG_U = 4;
-    int cur[GPG_U];
-#pragma unroll
-    for (int u = 0; u < GPG_U; ++u) cur[u] = beg + u < end ? seg[beg + u] : -1;
-    for (int e = beg; e < end; e += GPG_U) {
-        VEC g[GPG_U];
-#pragma unroll
-        for (int u = 0; u < GPG_U; ++u)
-            if (cur[u] >= 0) g[u] = __ldg(G + (size_t)cur[u] * cv);
-        int nxt[GPG_U];
-#pragma unroll
-        for (int u = 0; u < GPG_U; ++u) nxt[u] = e + GPG_U + u < end ? seg[e + GPG_U + u] : -1;
-#pragma unroll
-        for (int u = 0; u < GPG_U; ++u)
-            if (cur[u] >= 0) acc = vec_add<VEC>(acc, g[u]);
-#pragma unroll
-        for (int u = 0; u < GPG_U; ++u) cur[u] = nxt[u];
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {   // four source rows in flight; added in ascending order, as the sequential reference does
+        const int s0 = seg[e], s1 = seg[e + 1], s2 = seg[e + 2], s3 = seg[e + 3];
+        const VEC g0 = __ldg(G + (size_t)s0 * cv), g1 = __ldg(G + (size_t)s1 * cv), g2 = __ldg(G + (size_t)s2 * cv), g3 = __ldg(G + (size_t)s3 * cv);
+        acc = vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(vec_add<VEC>(acc, g0), g1), g2), g3);
     }
+    for (; e < end; ++e) acc = vec_add<VEC>(acc, __ldg(G + (size_t)seg[e] * cv));
     grad_points[(cloud * n + i) * cv + l] = acc;
 }
 
@@ -538,6 +524,7 @@ __global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int
         }
         const unsigned mk = __reduce_min_sync(0xffffffffu, bk);
         const int ms = __reduce_min_sync(0xffffffffu, (bk == mk && bs != 0x7fffffff) ? bs : 0x7fffffff);
+        __syncwarp();   // every lane's reads of this step precede lane 0's writes (the reductions imply it; this states it)
         if (lane == 0 && ms != s) {
             const unsigned ks = s_key[warp][s];
             if (ks != 0xffffffffu) {   // a NaN at position s stays there (nothing compares below it)

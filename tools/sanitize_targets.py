@@ -39,5 +39,16 @@ bi, bc = tf_grouping.query_ball_point(0.15, 16, x, q)
 d3, i3 = tf_interpolate.three_nn(x, q)
 ml, mr = tf_auctionmatch.auction_match(rnd(2, 600), rnd(2, 600))
 si, so = tf_grouping.select_top_k(5, torch.rand((2, 7, 300), generator=g).to(dev))
+# list-based select_top_k: vector and scalar row copies, two thresholds per lane, list overflow (plain sort of the row), whole-row kernel
+for n_, k_ in ((1000, 40), (999, 7), (2048, 129)):
+    tf_grouping.select_top_k(k_, torch.rand((2, 9, n_), generator=g).to(dev))
+tf_grouping.select_top_k(16, (torch.rand((1, 9, 1200), generator=g) > 0.9).float().to(dev))
+# staged three_interpolate (a 16-channel slice of the known points in shared memory) + the planned / standalone gradients
+kn, un = rnd(2, 16), rnd(2, 8192)
+d3s, i3s = tf_interpolate.three_nn(un, kn)
+feats = torch.rand((2, 16, 32), generator=g).to(dev).requires_grad_(True)
+tf_interpolate.three_interpolate(feats, i3s, torch.rand((2, 8192, 3), generator=g).to(dev)).sum().backward()
+pts = torch.rand((2, 5003, 8), generator=g).to(dev).requires_grad_(True)
+tf_grouping.group_point(pts, bi).sum().backward()     # CSR gradient with prefetched entry numbers
 torch.cuda.synchronize()
 print("sanitize targets ok", float(m.sum()), float(c.sum()), int(idx.sum()), int(bc.sum()), int(i3.sum()), int(ml.sum()), int(si.sum()))
