@@ -411,18 +411,22 @@ __global__ void __launch_bounds__(SS_WARPS * 32) selection_sort_kernel(int n, in
 // is closed under the swaps, every minimum search over [s, n) finds its answer inside P (ties included: ALL entries equal to
 // the minimum are <= T, and the reference's strict '<' scan takes the one at the lowest current position), and everything
 // outside P keeps its value and its index.  A warp therefore
-//   (1) streams the row once: out = dist, outi = 0..n-1 (vector loads and stores), each lane keeping its j = ceil(k/32) smallest
-//       values; T = the largest of the lanes' j-th smallest (at least 32 j >= k entries are <= T; ~6 % of a random row at k = 32);
+//   (1) streams the row once: out = dist, outi = 0..n-1 (vector loads and stores), each lane keeping its J = ceil(k/32) + 1 smallest
+//       values; T = the k-th smallest of those 32 J values (they are row entries, so at least k row entries are <= T), found by
+//       bisection on their integer keys with ballots -- for a random row |P| - k is a handful beyond k (a first version took the
+//       largest of the lanes' minima: ~6 % of the row);
 //   (2) re-reads the row (cache hits) and compacts P in position order into shared memory (ballot + popcount);
-//   (3) runs the k steps on that list: slot s is position s; arg-min over slots >= s on an order-preserving integer key
-//       (two REDUX: smallest key, then the lowest slot holding it), lane 0 swaps (key, entry id);
+//   (3) runs the k steps on that list: slot s is position s; arg-min over slots >= s on an order-preserving integer key (two REDUX:
+//       smallest key, then the lowest slot holding it).  Lists of up to 128 slots keep their keys in registers (four slots per lane,
+//       the displaced key travels by one shuffle, lane 0 keeps the slot -> entry map in shared memory); longer ones scan shared memory;
 //   (4) writes back the slots whose entry changed.
 // A row whose P exceeds SSF_CAP slots (masses of equal values) runs the plain selection sort on its output row instead.
 // NaN: the reference never moves a NaN out of position s (nothing compares below it) and never selects one; reproduced by
 // skipping step s when slot s holds a NaN and giving NaN the largest key.  -0.0 and +0.0 compare equal, as in the reference.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SSF_WARPS = 8;
-constexpr int SSF_CAP = 384;     // slots per row list
+constexpr int SSF_CAP = 256;     // slots per row list
+constexpr int SSF_REG = 4;       // slots per lane of the register-resident step loop
 constexpr int SSF_JMAX = 4;      // k <= 32 * SSF_JMAX
 
 __device__ __forceinline__ unsigned ss_key(float v) {
@@ -430,6 +434,9 @@ __device__ __forceinline__ unsigned ss_key(float v) {
     if (v != v) return 0xffffffffu;
     const unsigned u = (unsigned)__float_as_int(v + 0.0f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ss_unkey(unsigned key) {   // inverse of ss_key on non-NaN keys
+    return __int_as_float((int)((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key));
 }
 
 template <int J>
@@ -441,13 +448,13 @@ __device__ __forceinline__ void ss_insert(float (&a)[J], float v) {
     a[0] = fminf(a[0], v);
 }
 
-template <int J>
+template <int J>   // values kept per lane: ceil(k / 32) + 1
 __global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int n, int k, size_t rows, const float* __restrict__ dist,
                                                                              int* __restrict__ outi, float* __restrict__ out) {
     __shared__ int s_pos[SSF_WARPS][SSF_CAP];        // position (= original index) of list entry e
     __shared__ float s_val[SSF_WARPS][SSF_CAP];      // its value
-    __shared__ unsigned s_key[SSF_WARPS][SSF_CAP];   // key of the entry currently in slot i
-    __shared__ int s_id[SSF_WARPS][SSF_CAP];         // ... and which entry that is
+    __shared__ unsigned s_key[SSF_WARPS][SSF_CAP];   // key of the entry currently in slot i (lists longer than 32 * SSF_REG only)
+    __shared__ int s_id[SSF_WARPS][SSF_CAP];         // which entry slot i currently holds
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t row = (size_t)blockIdx.x * SSF_WARPS + warp;
     if (row >= rows) return;
@@ -482,10 +489,20 @@ __global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int
         }
     }
     float T = inf;
-    if (n > SSF_CAP) {   // every lane saw at least SSF_CAP / 32 >= J entries
-        T = a[J - 1];
+    if (n > SSF_CAP) {   // every lane saw at least SSF_CAP / 32 >= J entries: the 32 J kept values are row entries, 32 J >= k + 32
+        unsigned key[J];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, off));
+        for (int i = 0; i < J; ++i) key[i] = ss_key(a[i]);
+        // the smallest K with at least k keys <= K, i.e. the k-th smallest key
+        unsigned lo = __reduce_min_sync(0xffffffffu, key[0]), hi = __reduce_max_sync(0xffffffffu, key[J - 1]);
+        while (lo < hi) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < J; ++i) c += __popc(__ballot_sync(0xffffffffu, key[i] <= mid));
+            if (c >= k) hi = mid; else lo = mid + 1;
+        }
+        T = ss_unkey(lo);   // +inf when fewer than k kept values are finite: everything is listed, the list overflows, plain sort
     }
     __syncwarp();
 
@@ -501,8 +518,6 @@ __global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int
         if (in && slot < SSF_CAP) {
             s_pos[warp][slot] = t;
             s_val[warp][slot] = v;
-            s_key[warp][slot] = ss_key(v);
-            s_id[warp][slot] = slot;
         }
         cnt += __popc(bal);
     }
@@ -513,27 +528,66 @@ __global__ void __launch_bounds__(SSF_WARPS * 32) selection_sort_fast_kernel(int
         ss_plain_sort(o, oi, n, k, lane);
         return;
     }
+    for (int i = lane; i < cnt; i += 32) s_id[warp][i] = i;
 
     // (3) k steps on the list; slot s is position s because [0, k) leads the list
-    for (int s = 0; s < k; ++s) {
-        unsigned bk = 0xffffffffu;
-        int bs = 0x7fffffff;
-        for (int i = s + lane; i < cnt; i += 32) {
-            const unsigned key = s_key[warp][i];
-            if (key < bk || bs == 0x7fffffff) { bk = key; bs = i; }   // ascending i: the first of equals stays
-        }
-        const unsigned mk = __reduce_min_sync(0xffffffffu, bk);
-        const int ms = __reduce_min_sync(0xffffffffu, (bk == mk && bs != 0x7fffffff) ? bs : 0x7fffffff);
-        __syncwarp();   // every lane's reads of this step precede lane 0's writes (the reductions imply it; this states it)
-        if (lane == 0 && ms != s) {
-            const unsigned ks = s_key[warp][s];
-            if (ks != 0xffffffffu) {   // a NaN at position s stays there (nothing compares below it)
+    if (cnt <= 32 * SSF_REG) {
+        // keys in registers: lane holds slots lane + 32 r.  Only lane 0 touches s_id until the write-back.
+        unsigned kr[SSF_REG];
+#pragma unroll
+        for (int r = 0; r < SSF_REG; ++r) kr[r] = lane + 32 * r < cnt ? ss_key(s_val[warp][lane + 32 * r]) : 0xffffffffu;
+        __syncwarp();
+        for (int s = 0; s < k; ++s) {
+            unsigned bk = 0xffffffffu;
+            int bs = 0x7fffffff;
+#pragma unroll
+            for (int r = 0; r < SSF_REG; ++r) {
+                const int slot = lane + 32 * r;
+                if (slot >= s && kr[r] < bk) { bk = kr[r]; bs = slot; }   // ascending slot: the first of equals stays
+            }
+            const unsigned mk = __reduce_min_sync(0xffffffffu, bk);
+            if (mk == 0xffffffffu) continue;   // only NaN left at or behind s: the reference's scan moves nothing
+            const int ms = __reduce_min_sync(0xffffffffu, bk == mk ? bs : 0x7fffffff);
+            const int rs = s >> 5, rm = ms >> 5;   // warp-uniform
+            unsigned ksel = kr[0];
+#pragma unroll
+            for (int r = 1; r < SSF_REG; ++r) ksel = rs == r ? kr[r] : ksel;
+            const unsigned ks = __shfl_sync(0xffffffffu, ksel, s & 31);
+            if (ms == s || ks == 0xffffffffu) continue;   // already in place / a NaN at position s stays there
+            if (lane == (ms & 31)) {
+#pragma unroll
+                for (int r = 0; r < SSF_REG; ++r) kr[r] = rm == r ? ks : kr[r];
+            }
+            if (lane == 0) {
                 const int is = s_id[warp][s], im = s_id[warp][ms];
-                s_key[warp][s] = mk; s_id[warp][s] = im;
-                s_key[warp][ms] = ks; s_id[warp][ms] = is;
+                s_id[warp][s] = im;
+                s_id[warp][ms] = is;
             }
         }
         __syncwarp();
+    } else {
+        for (int i = lane; i < cnt; i += 32) s_key[warp][i] = ss_key(s_val[warp][i]);
+        __syncwarp();
+        for (int s = 0; s < k; ++s) {
+            unsigned bk = 0xffffffffu;
+            int bs = 0x7fffffff;
+            for (int i = s + lane; i < cnt; i += 32) {
+                const unsigned key = s_key[warp][i];
+                if (key < bk || bs == 0x7fffffff) { bk = key; bs = i; }   // ascending i: the first of equals stays
+            }
+            const unsigned mk = __reduce_min_sync(0xffffffffu, bk);
+            const int ms = __reduce_min_sync(0xffffffffu, (bk == mk && bs != 0x7fffffff) ? bs : 0x7fffffff);
+            __syncwarp();   // every lane's reads of this step precede lane 0's writes (the reductions imply it; this states it)
+            if (lane == 0 && ms != s) {
+                const unsigned ks = s_key[warp][s];
+                if (ks != 0xffffffffu) {   // a NaN at position s stays there (nothing compares below it)
+                    const int is = s_id[warp][s], im = s_id[warp][ms];
+                    s_key[warp][s] = mk; s_id[warp][s] = im;
+                    s_key[warp][ms] = ks; s_id[warp][ms] = is;
+                }
+            }
+            __syncwarp();
+        }
     }
 
     // (4) write back what moved
@@ -688,11 +742,11 @@ extern "C" int rfnet_selection_sort(int b, int n, int m, int k, const float* dis
     const size_t blocks = (rows + SS_WARPS - 1) / SS_WARPS;
     RFNET_CHECK_ARG(blocks <= 0x7fffffffull);
     if (k <= 32 * SSF_JMAX) {
-        const int j = (k + 31) / 32;
-        if (j == 1) launch_selection_sort_fast<1>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
-        else if (j == 2) launch_selection_sort_fast<2>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        const int j = (k + 31) / 32 + 1;   // values kept per lane
+        if (j == 2) launch_selection_sort_fast<2>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
         else if (j == 3) launch_selection_sort_fast<3>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
-        else launch_selection_sort_fast<4>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        else if (j == 4) launch_selection_sort_fast<4>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
+        else launch_selection_sort_fast<5>(n, k, rows, dist, outi, out, (cudaStream_t)stream);
         return launch_status();
     }
     const size_t smem = (size_t)SS_WARPS * n * 8;   // value + position per entry, one row per warp
