@@ -210,6 +210,23 @@ def test_three_interpolate_and_grad(cuda, rng, c):
     assert np.array_equal(gg, want)    # same (j, u) order and unfused arithmetic as threeinterpolate_grad_cpu: bit-exact
 
 
+@pytest.mark.parametrize("b,n,m,c", [(2, 6000, 24, 32), (3, 5001, 16, 16), (1, 60000, 300, 64), (2, 9000, 64, 48)])
+def test_three_interpolate_staged_slices(cuda, rng, b, n, m, c):
+    """Shapes that take three_interpolate_staged_kernel (rows of >= 16 channels, many unknown points per known point): a CTA keeps a
+    16-channel slice of one cloud's known points in shared memory and streams a range of unknown points that may straddle clouds.
+    Same expression as the plain gather kernel and the reference's CPU code: bit-exact, gradient included."""
+    from rfnet_b200 import ops, tf_interpolate
+    pts = rng.standard_normal((b, m, c)).astype(np.float32)
+    idx = rng.integers(0, m, size=(b, n, 3)).astype(np.int32)
+    idx[:, ::7, 1] = idx[:, ::7, 0]                              # repeated neighbours
+    w = rng.random((b, n, 3)).astype(np.float32)
+    got = tf_interpolate.three_interpolate(t(pts, cuda), t(idx, cuda), t(w, cuda)).cpu().numpy()
+    assert np.array_equal(got, port.three_interpolate(pts, idx, w))
+    go = rng.standard_normal((b, n, c)).astype(np.float32)
+    gg = ops.three_interpolate_grad_op(t(pts, cuda), t(idx, cuda), t(w, cuda), t(go, cuda)).cpu().numpy()
+    assert np.array_equal(gg, port.three_interpolate_grad(pts, idx, w, go))
+
+
 def test_three_interpolate_gradient_check_like_reference(cuda):
     """tf_interpolate_op_test.py:9-21: points (1,8,16), xyz1 (1,128,3), xyz2 (1,8,3), weights 1/3; gradient error < 1e-4."""
     from rfnet_b200 import tf_interpolate
