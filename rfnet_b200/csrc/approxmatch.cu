@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
     static_assert(!WRITE || ROLE == 1, "the matrix is written k-contiguous: own = xyz1");
     static_assert(!GRAD2 || (ROLE == 1 && GRAD), "the one-pass form: grad1 in registers, grad2 through the per-warp slab");
     constexpr int LB = GRAD2 ? 4 : 2;                 // others per unrolled batch
-    __shared__ float sG2[GRAD2 ? MT_THREADS / 32 : 1][GRAD2 ? LB * 3 * 32 : 1];
+    __shared__ __align__(16) float sG2[GRAD2 ? MT_THREADS / 32 : 1][GRAD2 ? LB * 3 * 32 : 4];
     __shared__ __align__(16) float4 sP[MT_L];       // x, y, z of the other point
     __shared__ __align__(16) float sF[MT_L][12];    // its factors, j = 0..9 (+2 pad)
     __shared__ float sW[MT_THREADS / 32];
@@ -760,9 +760,9 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
                 if (GRAD2) {   // a ragged tail still has to clear its slab rows
                     const int lane_ = threadIdx.x & 31, r_ = u * 3;
                     float* slab_ = sG2[threadIdx.x >> 5];
-                    slab_[(r_ + 0) * 32 + ((lane_ + r_ + 0) & 31)] = 0.f;
-                    slab_[(r_ + 1) * 32 + ((lane_ + r_ + 1) & 31)] = 0.f;
-                    slab_[(r_ + 2) * 32 + ((lane_ + r_ + 2) & 31)] = 0.f;
+                    slab_[(r_ + 0) * 32 + lane_] = 0.f;
+                    slab_[(r_ + 1) * 32 + lane_] = 0.f;
+                    slab_[(r_ + 2) * 32 + lane_] = 0.f;
                 }
                 continue;
             }
@@ -824,13 +824,13 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
                     gz = __ffma2_rn(dz, ns, gz);
                     if (GRAD2) {
                         // the other point's gradient, sum over k of match * (other - own) * rsqrt: this lane's two k's go to the
-                        // warp's slab (rotated: conflict-free lane-wise writes and row-wise reads), reduced below every LB rows
+                        // warp's slab (one row of 32 lane partials per (other point, component)), reduced below every LB rows
                         const float2 px = __fmul2_rn(dxg, s), py = __fmul2_rn(dy, s), pz = __fmul2_rn(dz, s);
                         const int lane_ = threadIdx.x & 31, r_ = u * 3;
                         float* slab_ = sG2[threadIdx.x >> 5];
-                        slab_[(r_ + 0) * 32 + ((lane_ + r_ + 0) & 31)] = px.x + px.y;
-                        slab_[(r_ + 1) * 32 + ((lane_ + r_ + 1) & 31)] = py.x + py.y;
-                        slab_[(r_ + 2) * 32 + ((lane_ + r_ + 2) & 31)] = pz.x + pz.y;
+                        slab_[(r_ + 0) * 32 + lane_] = px.x + px.y;
+                        slab_[(r_ + 1) * 32 + lane_] = py.x + py.y;
+                        slab_[(r_ + 2) * 32 + lane_] = pz.x + pz.y;
                     }
                 }
             }
@@ -838,11 +838,27 @@ __global__ void __launch_bounds__(MT_THREADS) emd_pair_kernel(const __grid_const
         if (GRAD2) {
             const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
             __syncwarp();
-            if (lane_ < LB * 3 && lb + lane_ / 3 < nl) {   // one (other point, component) per lane: the 32 lane partials in lane order
-                float t = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) t += sG2[warp_][lane_ * 32 + ((i + lane_) & 31)];
-                a.grad2_partial[(((size_t)cloud * (gridDim.x * (MT_THREADS / 32)) + blockIdx.x * (MT_THREADS / 32) + warp_) * n_oth + l0 + lb) * 3 + lane_] = t;
+            {
+                // all 32 lanes: lane (g, c) = (lane / 8, lane % 8) adds columns 4c..4c+3 of the three slab rows of other point lb + g (one
+                // LDS.128 each, a quarter-warp reads one whole row: no bank conflicts), then three butterfly steps inside the 8-lane group
+                // join the eight column chunks -- 8 issue slots per other point where 12 lanes walking 32 columns each cost 32.
+                // A fixed order, the same for every call: deterministic and batch-invariant as before.
+                static_assert(!GRAD2 || LB == 4, "four other points x eight column chunks = one warp");
+                const int g_ = lane_ >> 3, c_ = lane_ & 7;
+                const float4 v0 = *reinterpret_cast<const float4*>(&sG2[warp_][(3 * g_ + 0) * 32 + 4 * c_]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&sG2[warp_][(3 * g_ + 1) * 32 + 4 * c_]);
+                const float4 v2 = *reinterpret_cast<const float4*>(&sG2[warp_][(3 * g_ + 2) * 32 + 4 * c_]);
+                float t0 = (v0.x + v0.y) + (v0.z + v0.w), t1 = (v1.x + v1.y) + (v1.z + v1.w), t2 = (v2.x + v2.y) + (v2.z + v2.w);
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+                }
+                if (c_ == 0 && lb + g_ < nl) {
+                    float* gp2 = a.grad2_partial + (((size_t)cloud * (gridDim.x * (MT_THREADS / 32)) + blockIdx.x * (MT_THREADS / 32) + warp_) * n_oth + l0 + lb + g_) * 3;
+                    gp2[0] = t0; gp2[1] = t1; gp2[2] = t2;
+                }
             }
             __syncwarp();
         }
