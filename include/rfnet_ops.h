@@ -219,7 +219,8 @@ int rfnet_knn_point(int b, int n, int m, int k, const float *xyz1, const float *
 /* select_top_k.  Replaces selectionSortLauncher, tf_ops/grouping/tf_grouping.cpp:112 (defined tf_grouping_g.cu:129-132).
  * dist (b,m,n) -> outi (b,m,n), out (b,m,n): per row a copy of dist / 0..n-1 after k steps of selection sort with swaps,
  * so the first k entries are the k smallest (ascending, first index among equals) and the tail is permuted exactly as the
- * reference leaves it.  k > n is clamped to n (the reference reads out of bounds). */
+ * reference leaves it.  k > n is clamped to n (the reference reads out of bounds).  NaN entries behave as under the reference's
+ * strict '<': never selected, and a NaN at position s < k stays there; -0.0 and +0.0 compare equal.  out / outi must not alias dist. */
 int rfnet_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, rfnet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -231,3 +231,73 @@ def test_nn_filter_certificate_has_no_violation():
             tightest = min(tightest, tight)
     assert total > 1_000_000, total          # not vacuous
     assert tightest > 0.0
+
+
+def _select_list_model(row, k, lanes=32, cap=256):
+    """numpy model of selection_sort_fast_kernel (csrc/grouping.cu): threshold = k-th smallest of the lanes' J smallest values, closed
+    candidate list P = [0,k) U {t : row[t] <= T} in position order, k steps on the list, write-back of the moved slots.  Returns
+    (outi, out, list length) or None where the kernel falls back to the plain selection sort (list overflow)."""
+    n = row.shape[0]
+    k = min(k, n)
+    out, outi = row.copy(), np.arange(n, dtype=np.int32)
+
+    def key(v):           # order-preserving key: -0 == +0, NaN on top
+        if np.isnan(v):
+            return 0xFFFFFFFF
+        u = int(np.float32(v + np.float32(0.0)).view(np.uint32))
+        return (~u & 0xFFFFFFFF) if u & 0x80000000 else (u | 0x80000000)
+
+    T = np.float32(np.inf)
+    if n > cap:
+        J = (k + 31) // 32 + 1
+        kept = []
+        for lane in range(lanes):
+            vals = np.where(np.isnan(row[lane::lanes]), np.float32(np.inf), row[lane::lanes])
+            kept += sorted(vals.tolist())[:J] + [float("inf")] * max(0, J - len(vals))
+        T = np.float32(sorted(kept, key=lambda v: key(np.float32(v)))[k - 1])
+    with np.errstate(invalid="ignore"):
+        member = (np.arange(n) < k) | (row <= T)
+    pos = np.nonzero(member)[0]
+    if len(pos) > cap:
+        return None
+    slot_key = [key(row[p]) for p in pos]
+    slot_id = list(range(len(pos)))
+    for s in range(k):
+        rest = slot_key[s:]
+        mk = min(rest)
+        if mk == 0xFFFFFFFF or slot_key[s] == 0xFFFFFFFF:
+            continue
+        ms = s + rest.index(mk)                       # lowest slot among equals = lowest current position
+        if ms != s:
+            slot_key[s], slot_key[ms] = slot_key[ms], slot_key[s]
+            slot_id[s], slot_id[ms] = slot_id[ms], slot_id[s]
+    for i, e in enumerate(slot_id):
+        if e != i:
+            out[pos[i]] = row[pos[e]]
+            outi[pos[i]] = pos[e]
+    return outi, out, len(pos)
+
+
+def test_select_list_algorithm_model_equals_selection_sort():
+    """The algorithm behind rfnet_selection_sort for k <= 128 (a closed candidate list instead of sorting the row), modelled in numpy and
+    held to the oracle's swap-by-swap selection sort, tail included: random rows, ties, monotone rows, signed zeros, NaN, infinities."""
+    from oracle import port
+    rng = np.random.default_rng(5)
+    lengths = []
+    for n, k in ((300, 5), (300, 40), (1000, 32), (1000, 33), (999, 128), (2048, 16), (257, 100)):
+        rows = [rng.random(n, dtype=np.float32) for _ in range(3)]
+        rows.append((np.floor(rng.random(n) * 64) / 64).astype(np.float32))                 # ties
+        rows.append(np.sort(rng.random(n, dtype=np.float32)))
+        rows.append(np.sort(rng.random(n, dtype=np.float32))[::-1].copy())
+        z = rng.random(n, dtype=np.float32); z[::3] = 0.0; z[1::7] = -0.0; rows.append(z)
+        q = rng.random(n, dtype=np.float32); q[3] = np.nan; q[n // 2] = np.nan; rows.append(q)
+        f = rng.random(n, dtype=np.float32); f[::5] = np.inf; f[2::11] = -np.inf; rows.append(f)
+        for row in rows:
+            wi, wo = port.select_top_k(k, row[None, None, :])
+            got = _select_list_model(row, k)
+            if got is None:
+                continue
+            gi, go, length = got
+            lengths.append((length - min(k, n)) / n)
+            assert np.array_equal(gi, wi[0, 0]) and np.array_equal(go.view(np.uint32), wo[0, 0].view(np.uint32)), (n, k)
+    assert len(lengths) > 40 and float(np.median(lengths)) < 0.1      # the list stays short: k plus a few per cent of the row
